@@ -1,0 +1,160 @@
+/*
+ * ngp_b200.h -- C ABI of libngp_b200.so: hand-written sm_100a kernels for jaxngp's NeRF hot path.
+ *
+ * Every op is an XLA *legacy* GPU custom call, the exact ABI the reference registers
+ * (deps/volume-rendering-jax/lib/ffi.cc:17-51, deps/jax-tcnn/lib/ffi.cc:25-30):
+ *
+ *     void op(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len);
+ *
+ * `buffers` = operands in lowering order followed by results, all device pointers owned by the
+ * caller; results arrive uninitialised and every promised byte is defined by the op; `opaque` is
+ * the raw little-endian bytes of the descriptor struct (deps/serde-helper/serde.h:30-40).  Ops only
+ * enqueue work on `stream`: no host synchronisation, no allocation on the data path (one cached
+ * scratch block per stream is created on first use), re-entrant across host threads.
+ *
+ * Errors never cross the boundary as C++ exceptions (the reference throws through XLA's C
+ * callback, volrend.h:9-16): a failed call records a thread-local status, readable with
+ * ngp_b200_last_status()/ngp_b200_last_error(), and enqueues nothing.
+ *
+ * Section A are drop-ins for the reference's registered targets (same names in the registry, same
+ * descriptors byte for byte, same buffer order).  Section B are additions of this library (the
+ * pure-JAX HashGridEncoder of models/encoders.py as one kernel pair, the density-grid update,
+ * fused training helpers); they use the same calling convention so that one binding serves all.
+ *
+ * All `file:line` citations are relative to the reference checkout (blurgyy/jaxngp).
+ */
+#ifndef NGP_B200_H_
+#define NGP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __DRIVER_TYPES_H__
+typedef struct CUstream_st *cudaStream_t;
+#endif
+
+#define NGP_B200_ABI_VERSION 1
+
+/* ------------------------------------------------------------------ descriptors (section A)
+ * Byte-identical to deps/volume-rendering-jax/lib/impl/volrend.h:23-118 and
+ * deps/jax-tcnn/lib/impl/tcnnutils.h:11-29. */
+typedef struct { uint32_t n_bytes; } NgpPackbitsDescriptor;                       /* volrend.h:116-118 */
+typedef struct { uint32_t length; } NgpMorton3DDescriptor;                        /* volrend.h:110-113 */
+typedef struct {                                                                   /* volrend.h:57-85  */
+    uint32_t n_rays, total_samples, diagonal_n_steps, K, G;
+    float bound, stepsize_portion;
+} NgpMarchingDescriptor;
+typedef struct {                                                                   /* volrend.h:88-108 */
+    uint32_t n_total_rays, n_rays, diagonal_n_steps, K, G, march_steps_cap;
+    float bound, stepsize_portion;
+} NgpMarchingInferenceDescriptor;
+typedef struct { uint32_t n_rays, total_samples; } NgpIntegratingDescriptor;       /* volrend.h:23-29  */
+typedef struct {                                                                   /* volrend.h:32-43  */
+    uint32_t n_rays, total_samples;
+    float near_distance;
+} NgpIntegratingBackwardDescriptor;
+typedef struct { uint32_t n_total_rays, n_rays, march_steps_cap; } NgpIntegratingInferenceDescriptor; /* volrend.h:46-55 */
+typedef struct {                                                                   /* tcnnutils.h:11-29 */
+    uint32_t n_coords, L, F, N_min;
+    float per_level_scale;
+} NgpHashGridDescriptor;
+
+/* ------------------------------------------------------------------ section A: drop-in targets */
+
+/* replaces volrendjax::pack_density_into_bits (volrend.h:121-126, packbits.cu:36-72)
+ * in : density_threshold f32[N], density_grid f32[N]      out: occupied_mask bool[N], bitfield u8[N/8] */
+void ngp_pack_density_into_bits(cudaStream_t, void **, const char *, size_t);
+
+/* replaces volrendjax::march_rays (volrend.h:128-133, marching.cu:435-522)
+ * in : rays_o f32[n,3], rays_d f32[n,3], t_starts f32[n], t_ends f32[n], noises f32[n], bitfield u8[K*G^3/8]
+ * out: next_sample_write_location u32[1], number_of_exceeded_samples u32[1], ray_is_valid bool[n],
+ *      rays_n_samples u32[n], rays_sample_startidx u32[n], idcs u32[S], xyzs f32[S,3], dirs f32[S,3],
+ *      dss f32[S], z_vals f32[S]
+ * Sample ranges are handed out in RAY ORDER (deterministic); the reference hands them out in
+ * atomic arrival order (marching.cu:205).  See DESIGN.md "march_rays compaction". */
+void ngp_march_rays(cudaStream_t, void **, const char *, size_t);
+
+/* replaces volrendjax::march_rays_inference (volrend.h:135-140, marching.cu:524-604)
+ * in : rays_o f32[N,3], rays_d f32[N,3], t_starts f32[N], t_ends f32[N], bitfield u8[..],
+ *      next_ray_index_in u32[1], terminated bool[n], indices_in u32[n]
+ * out: next_ray_index u32[1], indices_out u32[n], n_samples u32[n], t_starts_out f32[n],
+ *      xyzs f32[n,cap,3], dss f32[n,cap], z_vals f32[n,cap]
+ * No stream synchronisation (the reference has one, marching.cu:562); fresh rays are handed to
+ * terminated slots in slot order. */
+void ngp_march_rays_inference(cudaStream_t, void **, const char *, size_t);
+
+/* replace volrendjax::morton3d / morton3d_invert (volrend.h:143-154, marching.cu:606-665)
+ * morton3d: in xyzs u32[len,3], out idcs u32[len];  invert: in idcs u32[len], out xyzs u32[len,3] */
+void ngp_morton3d(cudaStream_t, void **, const char *, size_t);
+void ngp_morton3d_invert(cudaStream_t, void **, const char *, size_t);
+
+/* replaces volrendjax::integrate_rays (volrend.h:156-161, integrating.cu:325-377)
+ * in : rays_sample_startidx u32[n], rays_n_samples u32[n], bgs f32[n,3], dss f32[S], z_vals f32[S], drgbs f32[S,4]
+ * out: measured_batch_size u32[1], final_rgbds f32[n,4], final_opacities f32[n] */
+void ngp_integrate_rays(cudaStream_t, void **, const char *, size_t);
+
+/* replaces volrendjax::integrate_rays_backward (volrend.h:163-168, integrating.cu:379-446)
+ * in : startidx, n_samples, bgs, dss, z_vals, drgbs, final_rgbds f32[n,4], final_opacities f32[n], dL_dfinal_rgbds f32[n,4]
+ * out: dL_dbgs f32[n,3], dL_dz_vals f32[S], dL_ddrgbs f32[S,4] */
+void ngp_integrate_rays_backward(cudaStream_t, void **, const char *, size_t);
+
+/* replaces volrendjax::integrate_rays_inference (volrend.h:170-175, integrating.cu:448-507)
+ * in : rays_bg f32[N,3], rays_rgbd f32[N,4], rays_T f32[N], n_samples u32[n], indices u32[n],
+ *      dss f32[n,cap], z_vals f32[n,cap], drgbs f32[n,cap,4]
+ * out: terminate_cnt u32[1], terminated bool[n], rays_rgbd_out f32[n,4], rays_T_out f32[n] */
+void ngp_integrate_rays_inference(cudaStream_t, void **, const char *, size_t);
+
+/* replaces jaxtcnn::hashgrid_encode (tcnnutils.h:31-36, hashgrid.cu:20-88; tiny-cuda-nn v1.6
+ * kernel_grid<float,3,F,CoherentPrime> semantics: f32-on-device level scale, index % level size)
+ * in : offset_table u32[L+1], coords_rm f32[3,n], params f32[rows,F]
+ * out: encoded_rm f32[L*F,n], dy_dcoords_rm f32[3*L*F,n] (stored as float3 per (feature,point)) */
+void ngp_hashgrid_encode(cudaStream_t, void **, const char *, size_t);
+
+/* replaces jaxtcnn::hashgrid_encode_backward (tcnnutils.h:38-43, hashgrid.cu:90-174)
+ * in : offset_table u32[L+1], coords_rm f32[3,n], dL_dy_rm f32[L*F,n], dy_dcoords_rm f32[3*L*F,n]
+ * out: dL_dparams f32[rows,F], dL_dcoords_rm f32[3,n] */
+void ngp_hashgrid_encode_backward(cudaStream_t, void **, const char *, size_t);
+
+/* ------------------------------------------------------------------ section B: additions */
+
+#define NGP_HG_MAX_LEVELS 32
+
+/* One kernel pair for the pure-JAX HashGridEncoder.__call__ (models/encoders.py:82-256): the level
+ * table is computed by the host exactly as encoders.py:89-103 does and travels in the descriptor.
+ * wrap_T != 0 reproduces `indices mod T` on every level (encoders.py:187); 0 = modulo level size. */
+typedef struct {
+    uint32_t n_points, dim, L, F;
+    uint32_t wrap_T;
+    uint32_t table_dtype; /* 0 = f32 rows (API dtype), 1 = f16 rows (storage variant) */
+    float bound;
+    uint32_t hashed_mask; /* bit l set = level l uses the spatial hash */
+    float scales[NGP_HG_MAX_LEVELS];
+    uint32_t res[NGP_HG_MAX_LEVELS];
+    uint32_t offsets[NGP_HG_MAX_LEVELS + 1];
+} NgpHashGridA1Descriptor;
+
+/* in : pos f32[n,dim], table (f32|f16)[rows,F]          out: enc f32[n,L*F] */
+void ngp_hashgrid_a1_forward(cudaStream_t, void **, const char *, size_t);
+/* in : pos f32[n,dim], d_enc f32[n,L*F]                 out: d_table f32[rows,F] (zero-filled, then scatter-added) */
+void ngp_hashgrid_a1_backward(cudaStream_t, void **, const char *, size_t);
+
+/* packbits with a scalar threshold read from device memory (drops the broadcast array the
+ * reference materialises, packbits/__init__.py:25-28).
+ * in : threshold f32[1], density f32[N]                  out: occupied_mask bool[N], bitfield u8[N/8] */
+void ngp_packbits_scalar(cudaStream_t, void **, const char *, size_t);
+
+/* ------------------------------------------------------------------ status */
+int ngp_b200_abi_version(void);
+/* 0 = last call on this host thread succeeded; otherwise a cudaError_t or a negative ngp code */
+int ngp_b200_last_status(void);
+const char *ngp_b200_last_error(void);
+void ngp_b200_clear_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGP_B200_H_ */

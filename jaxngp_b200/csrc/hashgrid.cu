@@ -1,0 +1,485 @@
+// hashgrid.cu -- multiresolution hash-grid encoder, forward gather and gradient scatter, sm_100a.
+//
+// Two front-ends over the same device code:
+//   * ngp_hashgrid_a1_{forward,backward}: the pure-JAX HashGridEncoder.__call__ of
+//     models/encoders.py:82-256 (row-major [n, L*F] output, host-computed f32 level scales,
+//     `index mod T` on every level, corner order irrelevant to the sum), 2-D and 3-D.
+//   * ngp_hashgrid_encode{,_backward}: the jax-tcnn custom calls (deps/jax-tcnn/lib/impl/
+//     hashgrid.cu:20-174), i.e. tiny-cuda-nn v1.6 kernel_grid semantics (SoA [L*F, n] output,
+//     f32-on-device scale = exp2f(l*log2f(b))*N_min-1, pos = fma(scale, x, .5), `index % level
+//     size`, dy_dx side output).  tiny-cuda-nn is not vendored by the reference: parity unpinned.
+//
+// Mapping: one thread = one (point, level).  With L = 16 a warp covers 2 points x 16 levels, so the
+// row-major output row of a point is written by 16 consecutive lanes (full 128 B lines), the
+// position loads are broadcasts, and the 8 corner fetches of each lane are independent 8-byte
+// (F=2 f32) / 4-byte (F=2 f16) vector loads issued back to back: 256 gathers in flight per warp.
+// The whole table (48.8 MB at T=2^19) is L2-resident on B200 (126 MB), so the kernel is bound by
+// L2 sector throughput, not HBM; see DESIGN.md section 5 for the roofline arithmetic.
+//
+// Backward: same mapping, `red.global.add.v2.f32` (one 8-byte L2 reduction per corner instead of
+// two scalar atomics), after a zero-fill of the gradient table.
+#include "common.cuh"
+
+namespace ngp {
+namespace {
+
+constexpr int kBlock = 256;
+constexpr uint32_t kPrime1 = 2654435761u, kPrime2 = 805459861u;  // encoders.py:169
+
+struct LevelMeta {
+    float scale;
+    uint32_t res, offset, wrap, hashed;
+};
+
+template <int DIM>
+__device__ __forceinline__ uint32_t grid_row(const uint32_t (&v)[DIM], const LevelMeta &m) {
+    uint32_t idx;
+    if (m.hashed) {  // encoders.py:157-177
+        idx = v[0] ^ (v[1] * kPrime1);
+        if (DIM == 3) idx ^= v[2] * kPrime2;
+    } else {  // encoders.py:134-155 (uint32 wrap-around arithmetic)
+        idx = v[0] + v[1] * m.res;
+        if (DIM == 3) idx += v[2] * m.res * m.res;
+    }
+    // `mod wrap` (encoders.py:187); power-of-two wraps are a mask, others rarely exceed the range
+    if ((m.wrap & (m.wrap - 1u)) == 0u) idx &= m.wrap - 1u;
+    else if (idx >= m.wrap) idx %= m.wrap;
+    return idx + m.offset;
+}
+
+template <typename TT, int F>
+struct RowIO;
+template <>
+struct RowIO<float, 2> {
+    static __device__ __forceinline__ void load(const float *t, uint32_t row, float (&f)[2]) {
+        float2 v = __ldg(reinterpret_cast<const float2 *>(t) + row);
+        f[0] = v.x; f[1] = v.y;
+    }
+};
+template <>
+struct RowIO<float, 4> {
+    static __device__ __forceinline__ void load(const float *t, uint32_t row, float (&f)[4]) {
+        float4 v = __ldg(reinterpret_cast<const float4 *>(t) + row);
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+    }
+};
+template <>
+struct RowIO<__half, 2> {
+    static __device__ __forceinline__ void load(const __half *t, uint32_t row, float (&f)[2]) {
+        __half2 h = __ldg(reinterpret_cast<const __half2 *>(t) + row);
+        float2 v = __half22float2(h);
+        f[0] = v.x; f[1] = v.y;
+    }
+};
+template <>
+struct RowIO<__half, 4> {
+    static __device__ __forceinline__ void load(const __half *t, uint32_t row, float (&f)[4]) {
+        uint2 raw = __ldg(reinterpret_cast<const uint2 *>(t) + row);
+        float2 a = __half22float2(*reinterpret_cast<__half2 *>(&raw.x));
+        float2 b = __half22float2(*reinterpret_cast<__half2 *>(&raw.y));
+        f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+    }
+};
+
+__device__ __forceinline__ LevelMeta a1_level(const NgpHashGridA1Descriptor &d, uint32_t level) {
+    LevelMeta m;
+    m.scale = d.scales[level];
+    m.res = d.res[level];
+    m.offset = d.offsets[level];
+    m.wrap = d.wrap_T ? d.wrap_T : d.offsets[level + 1] - d.offsets[level];
+    m.hashed = (d.hashed_mask >> level) & 1u;
+    return m;
+}
+
+// cell base and fractional offsets of a point at one level (encoders.py:87,116-123,204,216-218)
+template <int DIM>
+__device__ __forceinline__ void a1_cell(const float *__restrict__ pos, uint32_t point, float bound, float scale,
+                                        uint32_t (&base)[DIM], float (&fr)[DIM]) {
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        float p01 = __fdiv_rn(__fadd_rn(__ldg(pos + (size_t)point * DIM + k), bound), __fmul_rn(2.f, bound));
+        float ps = __fadd_rn(__fmul_rn(p01, scale), .5f);  // mul then add, as the XLA-CPU reference path
+        float fl = floorf(ps);
+        base[k] = (uint32_t)(int)fl;
+        fr[k] = ps - fl;
+    }
+}
+
+template <int DIM, int F, typename TT>
+__global__ void __launch_bounds__(kBlock) hashgrid_a1_forward_kernel(const __grid_constant__ NgpHashGridA1Descriptor d,
+                                                                      const float *__restrict__ pos,
+                                                                      const TT *__restrict__ table,
+                                                                      float *__restrict__ enc) {
+    __shared__ LevelMeta s_meta[NGP_HG_MAX_LEVELS];
+    if (threadIdx.x < d.L) s_meta[threadIdx.x] = a1_level(d, threadIdx.x);
+    __syncthreads();
+    const uint64_t tid = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    const uint32_t point = (uint32_t)(tid / d.L), level = (uint32_t)(tid % d.L);
+    if (point >= d.n_points) return;
+    const LevelMeta m = s_meta[level];
+
+    uint32_t base[DIM];
+    float fr[DIM];
+    a1_cell<DIM>(pos, point, d.bound, m.scale, base, fr);
+
+    constexpr int NC = 1 << DIM;
+    uint32_t rows[NC];
+    float w[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        uint32_t v[DIM];
+        float wc = 1.f;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) {
+            const uint32_t bit = (c >> (DIM - 1 - k)) & 1;  // last axis fastest, encoders.py:16-33
+            v[k] = base[k] + bit;
+            wc *= bit ? fr[k] : 1.f - fr[k];  // encoders.py:204-213 (clip is a no-op for frac in [0,1))
+        }
+        rows[c] = grid_row<DIM>(v, m);
+        w[c] = wc;
+    }
+    float vals[NC][F];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) RowIO<TT, F>::load(table, rows[c], vals[c]);
+    float acc[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[f] = fmaf(w[c], vals[c][f], acc[f]);
+
+    float *out = enc + ((size_t)point * d.L + level) * F;  // [n, L*F], level-major / feature-minor (:233)
+    if (F == 2) *reinterpret_cast<float2 *>(out) = make_float2(acc[0], acc[1]);
+    else *reinterpret_cast<float4 *>(out) = make_float4(acc[0], acc[1], acc[F - 2], acc[F - 1]);
+}
+
+template <int DIM, int F>
+__global__ void __launch_bounds__(kBlock) hashgrid_a1_backward_kernel(const __grid_constant__ NgpHashGridA1Descriptor d,
+                                                                       const float *__restrict__ pos,
+                                                                       const float *__restrict__ d_enc,
+                                                                       float *__restrict__ d_table) {
+    __shared__ LevelMeta s_meta[NGP_HG_MAX_LEVELS];
+    if (threadIdx.x < d.L) s_meta[threadIdx.x] = a1_level(d, threadIdx.x);
+    __syncthreads();
+    const uint64_t tid = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    const uint32_t point = (uint32_t)(tid / d.L), level = (uint32_t)(tid % d.L);
+    if (point >= d.n_points) return;
+    const LevelMeta m = s_meta[level];
+
+    float g[F];
+    const float *gin = d_enc + ((size_t)point * d.L + level) * F;
+    if (F == 2) {
+        float2 v = __ldg(reinterpret_cast<const float2 *>(gin));
+        g[0] = v.x; g[1] = v.y;
+    } else {
+        float4 v = __ldg(reinterpret_cast<const float4 *>(gin));
+        g[0] = v.x; g[1] = v.y; g[F - 2] = v.z; g[F - 1] = v.w;
+    }
+    bool any = false;
+#pragma unroll
+    for (int f = 0; f < F; ++f) any |= (g[f] != 0.f);
+    if (!any) return;  // padded / masked samples carry exact zeros
+
+    uint32_t base[DIM];
+    float fr[DIM];
+    a1_cell<DIM>(pos, point, d.bound, m.scale, base, fr);
+    constexpr int NC = 1 << DIM;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        uint32_t v[DIM];
+        float wc = 1.f;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) {
+            const uint32_t bit = (c >> (DIM - 1 - k)) & 1;
+            v[k] = base[k] + bit;
+            wc *= bit ? fr[k] : 1.f - fr[k];
+        }
+        float *dst = d_table + (size_t)grid_row<DIM>(v, m) * F;
+        if (F == 2) red_add_v2(dst, wc * g[0], wc * g[1]);
+        else red_add_v4(dst, wc * g[0], wc * g[1], wc * g[F - 2], wc * g[F - 1]);
+    }
+}
+
+// ---------------------------------------------------------------- tiny-cuda-nn compatible path
+// kernel_grid<float,3,F,CoherentPrime> (tiny-cuda-nn v1.6 include/tiny-cuda-nn/encodings/grid.h),
+// as launched at deps/jax-tcnn/lib/impl/hashgrid.cu:53-85: Linear interpolation, GridType::Hash,
+// max_level = 1e3, quantize_threshold = 0.
+struct TcnnLevel {
+    float scale;
+    uint32_t res, offset, size;
+};
+
+__device__ __forceinline__ TcnnLevel tcnn_level(const uint32_t *__restrict__ offset_table, uint32_t level,
+                                                uint32_t N_min, float log2_per_level_scale) {
+    TcnnLevel m;
+    m.offset = __ldg(offset_table + level);
+    m.size = __ldg(offset_table + level + 1) - m.offset;
+    m.scale = exp2f((float)level * log2_per_level_scale) * (float)N_min - 1.0f;  // grid_scale()
+    m.res = (uint32_t)ceilf(m.scale) + 1u;                                        // grid_resolution()
+    return m;
+}
+
+__device__ __forceinline__ uint32_t tcnn_index(const uint32_t (&v)[3], const TcnnLevel &m) {  // grid_index()
+    uint32_t stride = 1, index = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (stride <= m.size) {
+            index += v[k] * stride;
+            stride *= m.res;
+        }
+    }
+    if (m.size < stride) index = v[0] ^ (v[1] * kPrime1) ^ (v[2] * kPrime2);  // coherent prime hash
+    return index % m.size + m.offset;
+}
+
+template <int F>
+__global__ void __launch_bounds__(kBlock) hashgrid_tcnn_forward_kernel(
+    NgpHashGridDescriptor d, float log2_b, const uint32_t *__restrict__ offset_table,
+    const float *__restrict__ coords_rm, const float *__restrict__ params, float *__restrict__ encoded_rm,
+    float *__restrict__ dy_dcoords_rm) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    const uint32_t level = blockIdx.y;
+    if (i >= d.n_coords) return;
+    const TcnnLevel m = tcnn_level(offset_table, level, d.N_min, log2_b);
+    uint32_t base[3];
+    float fr[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float p = fmaf(m.scale, __ldg(coords_rm + (size_t)k * d.n_coords + i), 0.5f);  // pos_fract()
+        float fl = floorf(p);
+        base[k] = (uint32_t)(int)fl;
+        fr[k] = p - fl;
+    }
+    float vals[8][F];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint32_t v[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[k] = base[k] + ((c >> k) & 1);  // tcnn: bit k of the corner = axis k
+        RowIO<float, F>::load(params, tcnn_index(v, m), vals[c]);
+    }
+    float acc[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float w = 1.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w *= ((c >> k) & 1) ? fr[k] : 1.f - fr[k];
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[f] = fmaf(w, vals[c][f], acc[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < F; ++f) encoded_rm[(size_t)(level * F + f) * d.n_coords + i] = acc[f];
+
+    // dy_dx: one float3 per (level*F+f, point), as tcnn's vector_fullp_t<3> array
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+        float grad[3];
+#pragma unroll
+        for (int gd = 0; gd < 3; ++gd) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                if ((c >> gd) & 1) continue;  // c has bit gd clear; partner = c | (1 << gd)
+                float w = m.scale;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (k != gd) w *= ((c >> k) & 1) ? fr[k] : 1.f - fr[k];
+                s += w * (vals[c | (1 << gd)][f] - vals[c][f]);
+            }
+            grad[gd] = s;
+        }
+        float *dst = dy_dcoords_rm + ((size_t)(level * F + f) * d.n_coords + i) * 3;
+        dst[0] = grad[0]; dst[1] = grad[1]; dst[2] = grad[2];
+    }
+}
+
+template <int F>
+__global__ void __launch_bounds__(kBlock) hashgrid_tcnn_backward_kernel(
+    NgpHashGridDescriptor d, float log2_b, const uint32_t *__restrict__ offset_table,
+    const float *__restrict__ coords_rm, const float *__restrict__ dL_dy_rm, float *__restrict__ dL_dparams) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    const uint32_t level = blockIdx.y;
+    if (i >= d.n_coords) return;
+    const TcnnLevel m = tcnn_level(offset_table, level, d.N_min, log2_b);
+    uint32_t base[3];
+    float fr[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float p = fmaf(m.scale, __ldg(coords_rm + (size_t)k * d.n_coords + i), 0.5f);
+        float fl = floorf(p);
+        base[k] = (uint32_t)(int)fl;
+        fr[k] = p - fl;
+    }
+    float g[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) g[f] = __ldg(dL_dy_rm + (size_t)(level * F + f) * d.n_coords + i);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint32_t v[3];
+        float w = 1.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v[k] = base[k] + ((c >> k) & 1);
+            w *= ((c >> k) & 1) ? fr[k] : 1.f - fr[k];
+        }
+        float *dst = dL_dparams + (size_t)tcnn_index(v, m) * F;
+        if (F == 2) red_add_v2(dst, w * g[0], w * g[1]);
+        else red_add_v4(dst, w * g[0], w * g[1], w * g[F - 2], w * g[F - 1]);
+    }
+}
+
+// kernel_grid_backward_input<float,3>: dL/dx[d] = sum_k dL/dy[k] * dy_dx[k][d]
+__global__ void __launch_bounds__(kBlock) hashgrid_tcnn_backward_input_kernel(
+    uint32_t n, uint32_t LF, const float *__restrict__ dL_dy_rm, const float *__restrict__ dy_dcoords_rm,
+    float *__restrict__ dL_dcoords_rm) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (uint32_t k = 0; k < LF; ++k) {
+        const float g = __ldg(dL_dy_rm + (size_t)k * n + i);
+        const float *j = dy_dcoords_rm + ((size_t)k * n + i) * 3;
+        a0 = fmaf(g, __ldg(j + 0), a0);
+        a1 = fmaf(g, __ldg(j + 1), a1);
+        a2 = fmaf(g, __ldg(j + 2), a2);
+    }
+    dL_dcoords_rm[i] = a0;
+    dL_dcoords_rm[(size_t)n + i] = a1;
+    dL_dcoords_rm[2 * (size_t)n + i] = a2;
+}
+
+// zero-fill `rows x F` floats where rows = offset_table[L] lives in device memory
+__global__ void __launch_bounds__(kBlock) zero_rows_kernel(const uint32_t *__restrict__ offset_table, uint32_t L,
+                                                            uint32_t F, float *__restrict__ out) {
+    const size_t n = (size_t)__ldg(offset_table + L) * F;
+    const size_t n4 = ((uintptr_t)out % 16 == 0) ? n / 4 : 0;
+    for (size_t i = (size_t)blockIdx.x * kBlock + threadIdx.x; i < n4; i += (size_t)gridDim.x * kBlock)
+        reinterpret_cast<float4 *>(out)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t i = n4 * 4 + (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (size_t)gridDim.x * kBlock) out[i] = 0.f;
+}
+
+bool a1_validate(const NgpHashGridA1Descriptor *d, const char *op) {
+    if (d->L == 0 || d->L > NGP_HG_MAX_LEVELS || (d->dim != 2 && d->dim != 3) || (d->F != 2 && d->F != 4) ||
+        d->table_dtype > 1) {
+        set_error(NGP_ERR_ARGUMENT, "%s: unsupported L=%u dim=%u F=%u table_dtype=%u", op, d->L, d->dim, d->F,
+                  d->table_dtype);
+        return false;
+    }
+    return true;
+}
+
+}  // namespace
+}  // namespace ngp
+
+extern "C" {
+
+void ngp_hashgrid_a1_forward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *d = descriptor<NgpHashGridA1Descriptor>(opaque, opaque_len, "hashgrid_a1_forward");
+    if (!d || !a1_validate(d, "hashgrid_a1_forward") || d->n_points == 0) return;
+    BufferCursor b{buffers};
+    const float *pos = b.next<const float>();
+    const void *table = b.next<const void>();
+    float *enc = b.next<float>();
+    const unsigned blocks = div_up((unsigned long long)d->n_points * d->L, kBlock);
+#define NGP_FWD(DIM, F, TT) \
+    hashgrid_a1_forward_kernel<DIM, F, TT><<<blocks, kBlock, 0, stream>>>(*d, pos, static_cast<const TT *>(table), enc)
+    if (d->table_dtype == 0) {
+        if (d->dim == 3 && d->F == 2) NGP_FWD(3, 2, float);
+        else if (d->dim == 3) NGP_FWD(3, 4, float);
+        else if (d->F == 2) NGP_FWD(2, 2, float);
+        else NGP_FWD(2, 4, float);
+    } else {
+        if (d->dim == 3 && d->F == 2) NGP_FWD(3, 2, __half);
+        else if (d->dim == 3) NGP_FWD(3, 4, __half);
+        else if (d->F == 2) NGP_FWD(2, 2, __half);
+        else NGP_FWD(2, 4, __half);
+    }
+#undef NGP_FWD
+    check_launch("hashgrid_a1_forward");
+}
+
+void ngp_hashgrid_a1_backward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *d = descriptor<NgpHashGridA1Descriptor>(opaque, opaque_len, "hashgrid_a1_backward");
+    if (!d || !a1_validate(d, "hashgrid_a1_backward")) return;
+    BufferCursor b{buffers};
+    const float *pos = b.next<const float>();
+    const float *d_enc = b.next<const float>();
+    float *d_table = b.next<float>();
+    NGP_CUDA_OK(cudaMemsetAsync(d_table, 0, (size_t)d->offsets[d->L] * d->F * sizeof(float), stream),
+                "hashgrid_a1_backward");
+    if (d->n_points == 0) return;
+    const unsigned blocks = div_up((unsigned long long)d->n_points * d->L, kBlock);
+    if (d->dim == 3 && d->F == 2) hashgrid_a1_backward_kernel<3, 2><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
+    else if (d->dim == 3) hashgrid_a1_backward_kernel<3, 4><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
+    else if (d->F == 2) hashgrid_a1_backward_kernel<2, 2><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
+    else hashgrid_a1_backward_kernel<2, 4><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
+    check_launch("hashgrid_a1_backward");
+}
+
+void ngp_hashgrid_encode(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *d = descriptor<NgpHashGridDescriptor>(opaque, opaque_len, "hashgrid_encode");
+    if (!d) return;
+    if (d->F != 2 && d->F != 4) {  // hashgrid.cu:81-85 throws here
+        set_error(NGP_ERR_ARGUMENT, "hashgrid_encode: supported values of F (n_features_per_level) are [2, 4], got %u", d->F);
+        return;
+    }
+    if (d->n_coords == 0 || d->L == 0) return;
+    BufferCursor b{buffers};
+    const uint32_t *offset_table = b.next<const uint32_t>();
+    const float *coords_rm = b.next<const float>();
+    const float *params = b.next<const float>();
+    float *encoded_rm = b.next<float>();
+    float *dy_dcoords_rm = b.next<float>();
+    const dim3 grid(div_up(d->n_coords, kBlock), d->L, 1);
+    const float log2_b = log2f(d->per_level_scale);  // hashgrid.cu:60
+    if (d->F == 2)
+        hashgrid_tcnn_forward_kernel<2><<<grid, kBlock, 0, stream>>>(*d, log2_b, offset_table, coords_rm, params, encoded_rm, dy_dcoords_rm);
+    else
+        hashgrid_tcnn_forward_kernel<4><<<grid, kBlock, 0, stream>>>(*d, log2_b, offset_table, coords_rm, params, encoded_rm, dy_dcoords_rm);
+    check_launch("hashgrid_encode");
+}
+
+void ngp_hashgrid_encode_backward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *d = descriptor<NgpHashGridDescriptor>(opaque, opaque_len, "hashgrid_encode_backward");
+    if (!d) return;
+    if (d->F != 2 && d->F != 4) {
+        set_error(NGP_ERR_ARGUMENT, "hashgrid_encode_backward: supported values of F are 2, 4, got %u", d->F);
+        return;
+    }
+    if (d->L == 0) return;
+    BufferCursor b{buffers};
+    const uint32_t *offset_table = b.next<const uint32_t>();
+    const float *coords_rm = b.next<const float>();
+    const float *dL_dy_rm = b.next<const float>();
+    const float *dy_dcoords_rm = b.next<const float>();
+    float *dL_dparams = b.next<float>();
+    float *dL_dcoords_rm = b.next<float>();
+    // The reference sizes a host-side memset from a host copy of the offset table that an
+    // un-synchronised D2H memcpy may still be filling (hashgrid.cu:115-117).  The table size is not
+    // in the descriptor, so the zero-fill runs on the device and reads offset_table[L] there.
+    zero_rows_kernel<<<148 * 8, kBlock, 0, stream>>>(offset_table, d->L, d->F, dL_dparams);
+    if (!check_launch("hashgrid_encode_backward(zero)")) return;
+    if (d->n_coords == 0) return;
+    const dim3 grid(div_up(d->n_coords, kBlock), d->L, 1);
+    const float log2_b = log2f(d->per_level_scale);
+    if (d->F == 2)
+        hashgrid_tcnn_backward_kernel<2><<<grid, kBlock, 0, stream>>>(*d, log2_b, offset_table, coords_rm, dL_dy_rm, dL_dparams);
+    else
+        hashgrid_tcnn_backward_kernel<4><<<grid, kBlock, 0, stream>>>(*d, log2_b, offset_table, coords_rm, dL_dy_rm, dL_dparams);
+    if (!check_launch("hashgrid_encode_backward")) return;
+    hashgrid_tcnn_backward_input_kernel<<<div_up(d->n_coords, kBlock), kBlock, 0, stream>>>(
+        d->n_coords, d->L * d->F, dL_dy_rm, dy_dcoords_rm, dL_dcoords_rm);
+    check_launch("hashgrid_encode_backward(input)");
+}
+
+}  // extern "C"

@@ -1,0 +1,339 @@
+// integrating.cu -- volume-rendering integrator (forward, backward, resumable inference) for sm_100a.
+//
+// Replaces deps/volume-rendering-jax/lib/impl/integrating.cu:24-322,325-507.
+//
+// The reference walks each ray with one thread (scalar, uncoalesced loads, a latency chain of
+// n_samples global loads).  Here a warp walks a ray: each lane loads one sample with full-width
+// coalesced accesses (float4 for drgbs) and evaluates its alpha in parallel; only the
+// transmittance recurrence T <- T * (1 - alpha) is replayed in sample order through shuffles, with
+// the same two rounded operations per sample as the reference, so the early-stop decision
+// (T <= 1e-4) and therefore `measured_batch_size` are integer-exact.  Colour/depth sums are
+// warp-tree reductions (abs error ~1e-7, tolerance 1e-4).
+#include "common.cuh"
+
+namespace ngp {
+namespace {
+
+constexpr float kTThreshold = 1e-4f;  // integrating.cu:12
+constexpr int kBlock = 128;
+constexpr int kRaysPerWarp = 8;  // a warp owns 8 consecutive rays and walks the non-empty ones in turn
+
+struct Chunk {
+    float alpha, one_minus, Tb;  // this lane's sample: alpha, 1-alpha, transmittance before it
+    bool active;                 // sample is composited (T before it > threshold)
+};
+
+// Replays T_{k+1} = T_k * (1 - alpha_k) over the (up to 32) samples held by the lanes, in order,
+// stopping like `for (; T > T_THRESHOLD && idx < n; ++idx)` (integrating.cu:61).
+__device__ __forceinline__ void transmittance_chain(float one_minus, uint32_t count, uint32_t lane, float &T,
+                                                    float &Tb, bool &active, uint32_t &processed) {
+    active = false;
+    Tb = 0.f;
+#pragma unroll 8
+    for (uint32_t k = 0; k < 32; ++k) {
+        float a = __shfl_sync(0xffffffffu, one_minus, k);
+        if (k < count && T > kTThreshold) {
+            if (lane == k) {
+                Tb = T;
+                active = true;
+            }
+            T = __fmul_rn(T, a);
+            ++processed;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) integrate_rays_kernel(
+    uint32_t n_rays, const uint32_t *__restrict__ rays_sample_startidx, const uint32_t *__restrict__ rays_n_samples,
+    const float *__restrict__ bgs, const float *__restrict__ dss, const float *__restrict__ z_vals,
+    const float4 *__restrict__ drgbs, uint32_t *__restrict__ measured_batch_size, float4 *__restrict__ final_rgbds,
+    float *__restrict__ final_opacities) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps_total = gridDim.x * (kBlock / 32);
+    const uint32_t warp_global = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    const uint32_t n_groups = (n_rays + kRaysPerWarp - 1) / kRaysPerWarp;
+    uint32_t composited = 0;
+
+    for (uint32_t grp = warp_global; grp < n_groups; grp += warps_total) {
+        const uint32_t my_ray = grp * kRaysPerWarp + lane;
+        uint32_t my_start = 0, my_n = 0;
+        if (lane < kRaysPerWarp && my_ray < n_rays) {
+            my_start = __ldg(rays_sample_startidx + my_ray);
+            my_n = __ldg(rays_n_samples + my_ray);
+        }
+        for (uint32_t q = 0; q < kRaysPerWarp; ++q) {
+            const uint32_t ray = grp * kRaysPerWarp + q;
+            if (ray >= n_rays) break;
+            const uint32_t start = __shfl_sync(0xffffffffu, my_start, q);
+            const uint32_t n = __shfl_sync(0xffffffffu, my_n, q);
+            float T = 1.f, r = 0.f, g = 0.f, b = 0.f, depth = 0.f;
+            for (uint32_t c = 0; c < n && T > kTThreshold; c += 32) {
+                const uint32_t count = min(32u, n - c);
+                float one_minus = 1.f, alpha = 0.f, z = 0.f;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (lane < count) {
+                    const uint32_t s = start + c + lane;
+                    v = __ldg(drgbs + s);
+                    z = __ldg(z_vals + s);
+                    alpha = 1.f - __expf(-v.x * __ldg(dss + s));  // integrating.cu:64
+                    one_minus = 1.f - alpha;
+                }
+                float Tb;
+                bool active;
+                transmittance_chain(one_minus, count, lane, T, Tb, active, composited);
+                const float w = active ? Tb * alpha : 0.f;
+                r += w * v.y;
+                g += w * v.z;
+                b += w * v.w;
+                depth += w * z;
+            }
+            r = warp_sum(r);
+            g = warp_sum(g);
+            b = warp_sum(b);
+            depth = warp_sum(depth);
+            if (lane == 0) {
+                const float opacity = 1.f - T;
+                final_opacities[ray] = opacity;
+                float4 out;
+                if (T <= kTThreshold) {  // integrating.cu:85-90
+                    const float idenom = 1.f / opacity;
+                    out = make_float4(r * idenom, g * idenom, b * idenom, depth * idenom);
+                } else {  // integrating.cu:91-96
+                    out = make_float4(r + T * __ldg(bgs + 3 * (size_t)ray + 0), g + T * __ldg(bgs + 3 * (size_t)ray + 1),
+                                      b + T * __ldg(bgs + 3 * (size_t)ray + 2), depth);
+                }
+                final_rgbds[ray] = out;
+            }
+        }
+    }
+    // `composited` is identical on all lanes (the chain is replicated); one atomic per warp
+    if (lane == 0 && composited) atomicAdd(measured_batch_size, composited);
+}
+
+__device__ __forceinline__ float warp_incl_scan(float v, uint32_t lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        float u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(kBlock) integrate_rays_backward_kernel(
+    uint32_t n_rays, float near_distance, const uint32_t *__restrict__ rays_sample_startidx,
+    const uint32_t *__restrict__ rays_n_samples, const float *__restrict__ bgs, const float *__restrict__ dss,
+    const float *__restrict__ z_vals, const float4 *__restrict__ drgbs, const float4 *__restrict__ final_rgbds,
+    const float *__restrict__ final_opacities, const float4 *__restrict__ dL_dfinal_rgbds,
+    float *__restrict__ dL_dbgs, float *__restrict__ dL_dz_vals, float4 *__restrict__ dL_ddrgbs) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps_total = gridDim.x * (kBlock / 32);
+    const uint32_t warp_global = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    const uint32_t n_groups = (n_rays + kRaysPerWarp - 1) / kRaysPerWarp;
+
+    for (uint32_t grp = warp_global; grp < n_groups; grp += warps_total) {
+        const uint32_t my_ray = grp * kRaysPerWarp + lane;
+        uint32_t my_start = 0, my_n = 0;
+        if (lane < kRaysPerWarp && my_ray < n_rays) {
+            my_start = __ldg(rays_sample_startidx + my_ray);
+            my_n = __ldg(rays_n_samples + my_ray);
+        }
+        for (uint32_t q = 0; q < kRaysPerWarp; ++q) {
+            const uint32_t ray = grp * kRaysPerWarp + q;
+            if (ray >= n_rays) break;
+            const uint32_t start = __shfl_sync(0xffffffffu, my_start, q);
+            const uint32_t n = __shfl_sync(0xffffffffu, my_n, q);
+            const float4 dfin = __ldg(dL_dfinal_rgbds + ray);
+            float T = 1.f;
+            if (n > 0) {
+                const float4 fin = __ldg(final_rgbds + ray);
+                const float opac = __ldg(final_opacities + ray);
+                const bool terminated = opac >= 1.f - kTThreshold;  // integrating.cu:158
+                const float bgw = terminated ? 0.f : 1.f - opac;
+                const float bg0 = __ldg(bgs + 3 * (size_t)ray + 0) * bgw, bg1 = __ldg(bgs + 3 * (size_t)ray + 1) * bgw,
+                            bg2 = __ldg(bgs + 3 * (size_t)ray + 2) * bgw;
+                float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;  // running composited colour / depth
+                uint32_t dummy = 0;
+                for (uint32_t c = 0; c < n && T > kTThreshold; c += 32) {
+                    const uint32_t count = min(32u, n - c);
+                    float one_minus = 1.f, alpha = 0.f, z = 0.f, dt = 0.f;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const uint32_t s = start + c + lane;
+                    if (lane < count) {
+                        v = __ldg(drgbs + s);
+                        z = __ldg(z_vals + s);
+                        dt = __ldg(dss + s);
+                        alpha = 1.f - __expf(-v.x * dt);  // integrating.cu:181
+                        one_minus = 1.f - alpha;
+                    }
+                    float Tb;
+                    bool active;
+                    transmittance_chain(one_minus, count, lane, T, Tb, active, dummy);
+                    const float w = active ? Tb * alpha : 0.f;
+                    const float Ta = Tb * one_minus;  // transmittance after this sample, integrating.cu:193
+                    const float ir = cr + warp_incl_scan(w * v.y, lane);
+                    const float ig = cg + warp_incl_scan(w * v.z, lane);
+                    const float ib = cb + warp_incl_scan(w * v.w, lane);
+                    const float id = cd + warp_incl_scan(w * z, lane);
+                    cr = __shfl_sync(0xffffffffu, ir, 31);
+                    cg = __shfl_sync(0xffffffffu, ig, 31);
+                    cb = __shfl_sync(0xffffffffu, ib, 31);
+                    cd = __shfl_sync(0xffffffffu, id, 31);
+                    if (active) {
+                        dL_dz_vals[s] = w * dfin.w;  // integrating.cu:196
+                        float acc = dfin.x * (Ta * v.y - (fin.x - ir) - bg0) + dfin.y * (Ta * v.z - (fin.y - ig) - bg1) +
+                                    dfin.z * (Ta * v.w - (fin.z - ib) - bg2) + dfin.w * (Ta * z - (fin.w - id));
+                        const float dsig = dt * acc;                                            // :199-215
+                        const float reg = (v.x > 4e-5f && z < near_distance) ? 1e-4f : 0.f;     // :221
+                        const float scal = fminf(z * z, 1.f);                                   // :225
+                        dL_ddrgbs[s] = make_float4(scal * dsig + reg, w * dfin.x, w * dfin.y, w * dfin.z);
+                    }
+                }
+            }
+            if (lane == 0 && T > kTThreshold) {  // integrating.cu:235-239
+                dL_dbgs[3 * (size_t)ray + 0] = T * dfin.x;
+                dL_dbgs[3 * (size_t)ray + 1] = T * dfin.y;
+                dL_dbgs[3 * (size_t)ray + 2] = T * dfin.z;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) integrate_rays_inference_kernel(
+    NgpIntegratingInferenceDescriptor p, const float *__restrict__ rays_bg, const float4 *__restrict__ rays_rgbd,
+    const float *__restrict__ rays_T, const uint32_t *__restrict__ n_samples, const uint32_t *__restrict__ indices,
+    const float *__restrict__ dss, const float *__restrict__ z_vals, const float4 *__restrict__ drgbs,
+    uint32_t *__restrict__ terminate_cnt, uint8_t *__restrict__ terminated, float4 *__restrict__ rays_rgbd_out,
+    float *__restrict__ rays_T_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool term = false;
+    if (i < p.n_rays) {
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+        float T_out = 0.f;
+        const uint32_t ns = __ldg(n_samples + i), ray = __ldg(indices + i);
+        if (ray < p.n_total_rays) {
+            const uint32_t cap = p.march_steps_cap;
+            const float *__restrict__ rds = dss + (size_t)i * cap;
+            const float *__restrict__ rz = z_vals + (size_t)i * cap;
+            const float4 *__restrict__ rc = drgbs + (size_t)i * cap;
+            float T = __ldg(rays_T + ray);
+            float4 acc = __ldg(rays_rgbd + ray);
+            for (uint32_t s = 0; T > kTThreshold && s < ns; ++s) {  // integrating.cu:278-291
+                const float4 v = __ldg(rc + s);
+                const float alpha = 1.f - __expf(-v.x * __ldg(rds + s));
+                const float w = T * alpha;
+                acc.x += w * v.y;
+                acc.y += w * v.z;
+                acc.z += w * v.w;
+                acc.w += w * __ldg(rz + s);
+                T *= (1.f - alpha);
+            }
+            if (T <= kTThreshold) {  // integrating.cu:293-301
+                const float idenom = 1.f / (1.f - T);
+                term = true;
+                T_out = 0.f;
+                out = make_float4(acc.x * idenom, acc.y * idenom, acc.z * idenom, acc.w * idenom);
+            } else {  // integrating.cu:302-314
+                term = ns < cap;
+                T_out = T;
+                out = acc;
+                if (term) {
+                    out.x = acc.x + T * __ldg(rays_bg + 3 * (size_t)ray + 0);
+                    out.y = acc.y + T * __ldg(rays_bg + 3 * (size_t)ray + 1);
+                    out.z = acc.z + T * __ldg(rays_bg + 3 * (size_t)ray + 2);
+                }
+            }
+        }
+        terminated[i] = term ? 1 : 0;
+        rays_rgbd_out[i] = out;
+        rays_T_out[i] = T_out;
+    }
+    const uint32_t votes = __popc(__ballot_sync(0xffffffffu, term));
+    if ((threadIdx.x & 31u) == 0 && votes) atomicAdd(terminate_cnt, votes);
+}
+
+}  // namespace
+}  // namespace ngp
+
+extern "C" {
+
+void ngp_integrate_rays(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *desc = descriptor<NgpIntegratingDescriptor>(opaque, opaque_len, "integrate_rays");
+    if (!desc) return;
+    BufferCursor b{buffers};
+    const uint32_t *start = b.next<const uint32_t>();
+    const uint32_t *ns = b.next<const uint32_t>();
+    const float *bgs = b.next<const float>();
+    const float *dss = b.next<const float>();
+    const float *z_vals = b.next<const float>();
+    const float4 *drgbs = b.next<const float4>();
+    uint32_t *mbs = b.next<uint32_t>();
+    float4 *final_rgbds = b.next<float4>();
+    float *final_opacities = b.next<float>();
+    NGP_CUDA_OK(cudaMemsetAsync(mbs, 0, sizeof(uint32_t), stream), "integrate_rays");
+    if (desc->n_rays == 0) return;
+    const unsigned groups = div_up(desc->n_rays, kRaysPerWarp);
+    const unsigned blocks = min(div_up(groups, kBlock / 32), 148u * 16u);
+    integrate_rays_kernel<<<blocks, kBlock, 0, stream>>>(desc->n_rays, start, ns, bgs, dss, z_vals, drgbs, mbs,
+                                                         final_rgbds, final_opacities);
+    check_launch("integrate_rays");
+}
+
+void ngp_integrate_rays_backward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *desc = descriptor<NgpIntegratingBackwardDescriptor>(opaque, opaque_len, "integrate_rays_backward");
+    if (!desc) return;
+    BufferCursor b{buffers};
+    const uint32_t *start = b.next<const uint32_t>();
+    const uint32_t *ns = b.next<const uint32_t>();
+    const float *bgs = b.next<const float>();
+    const float *dss = b.next<const float>();
+    const float *z_vals = b.next<const float>();
+    const float4 *drgbs = b.next<const float4>();
+    const float4 *final_rgbds = b.next<const float4>();
+    const float *final_opacities = b.next<const float>();
+    const float4 *dL_dfinal = b.next<const float4>();
+    float *dL_dbgs = b.next<float>();
+    float *dL_dz = b.next<float>();
+    float4 *dL_dd = b.next<float4>();
+    // samples that are not composited (after early stop, or unused slots) get zero gradient
+    NGP_CUDA_OK(cudaMemsetAsync(dL_dbgs, 0, (size_t)desc->n_rays * 3 * sizeof(float), stream), "integrate_rays_backward");
+    NGP_CUDA_OK(cudaMemsetAsync(dL_dz, 0, (size_t)desc->total_samples * sizeof(float), stream), "integrate_rays_backward");
+    NGP_CUDA_OK(cudaMemsetAsync(dL_dd, 0, (size_t)desc->total_samples * 4 * sizeof(float), stream), "integrate_rays_backward");
+    if (desc->n_rays == 0) return;
+    const unsigned groups = div_up(desc->n_rays, kRaysPerWarp);
+    const unsigned blocks = min(div_up(groups, kBlock / 32), 148u * 16u);
+    integrate_rays_backward_kernel<<<blocks, kBlock, 0, stream>>>(desc->n_rays, desc->near_distance, start, ns, bgs,
+                                                                  dss, z_vals, drgbs, final_rgbds, final_opacities,
+                                                                  dL_dfinal, dL_dbgs, dL_dz, dL_dd);
+    check_launch("integrate_rays_backward");
+}
+
+void ngp_integrate_rays_inference(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *desc = descriptor<NgpIntegratingInferenceDescriptor>(opaque, opaque_len, "integrate_rays_inference");
+    if (!desc) return;
+    BufferCursor b{buffers};
+    const float *rays_bg = b.next<const float>();
+    const float4 *rays_rgbd = b.next<const float4>();
+    const float *rays_T = b.next<const float>();
+    const uint32_t *ns = b.next<const uint32_t>();
+    const uint32_t *indices = b.next<const uint32_t>();
+    const float *dss = b.next<const float>();
+    const float *z_vals = b.next<const float>();
+    const float4 *drgbs = b.next<const float4>();
+    uint32_t *terminate_cnt = b.next<uint32_t>();
+    uint8_t *terminated = b.next<uint8_t>();
+    float4 *rgbd_out = b.next<float4>();
+    float *T_out = b.next<float>();
+    NGP_CUDA_OK(cudaMemsetAsync(terminate_cnt, 0, sizeof(uint32_t), stream), "integrate_rays_inference");
+    if (desc->n_rays == 0) return;
+    integrate_rays_inference_kernel<<<div_up(desc->n_rays, kBlock), kBlock, 0, stream>>>(
+        *desc, rays_bg, rays_rgbd, rays_T, ns, indices, dss, z_vals, drgbs, terminate_cnt, terminated, rgbd_out, T_out);
+    check_launch("integrate_rays_inference");
+}
+
+}  // extern "C"

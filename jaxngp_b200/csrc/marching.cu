@@ -1,0 +1,514 @@
+// marching.cu -- occupancy-grid ray marching for sm_100a.
+//
+// Replaces deps/volume-rendering-jax/lib/impl/marching.cu:101-397,435-604.
+//
+// Numerics: every floating-point operation that decides where a sample lands is pinned with
+// round-to-nearest intrinsics in exactly the shape nvcc gives the reference source (FFMA for
+// o + t*d, for t_start + ds*noise and for the two contractions inside the next-voxel distance;
+// IEEE division for 1/d, 1/G, pos/mip_bound and the ds lower bound) -- read off the reference SASS,
+// see DESIGN.md section 4 -- so sample counts, grid indices, positions and z values are bit-equal
+// to the reference kernels'.
+//
+// Structure (training march): one kernel.  A CTA takes a tile of 128 consecutive rays (dynamic
+// ticket), counts each ray's occupied steps, scans the counts and obtains the tile's exclusive
+// prefix by decoupled look-back, so sample ranges are handed out in ray order without a second
+// launch or a host round trip.  The first tile whose inclusive prefix reaches `total_samples`
+// publishes a cut; tiles behind the cut stop marching (they poll the cut flag) -- this is the
+// reference's "budget already full" early-out (marching.cu:135) made deterministic.  Rays that got a
+// range then re-march and write their samples; a tail kernel zero-fills the unused sample slots
+// (observable API, marching/__init__.py:60-68).  The reference zero-fills everything with 10
+// memsets before its kernel (marching.cu:474-483).
+#include "common.cuh"
+
+namespace ngp {
+namespace {
+
+constexpr float kTwoSqrt3 = 3.4641015529632568359f;  // 2 * (float)SQRT3, volrend.h:18
+
+struct Grid {
+    uint32_t K, G, G3;
+    float Gf, inv_G, bound, portion, ds_lo, ds_hi;
+    const uint32_t *__restrict__ bits;  // bitfield viewed as little-endian 32-bit words
+};
+
+__device__ __forceinline__ Grid make_grid(uint32_t steps, uint32_t K, uint32_t G, float bound, float portion,
+                                          const uint8_t *bitfield) {
+    Grid g;
+    g.K = K;
+    g.G = G;
+    g.G3 = G * G * G;
+    g.Gf = (float)G;
+    g.inv_G = __fdiv_rn(1.f, g.Gf);                                                    // marching.cu:158
+    g.bound = bound;
+    g.portion = portion;
+    g.ds_lo = __fdiv_rn(__fmul_rn(fminf(bound, 1.f), kTwoSqrt3), (float)steps);        // marching.cu:20
+    g.ds_hi = __fmul_rn(__fmul_rn(bound, kTwoSqrt3), g.inv_G);                         // marching.cu:21
+    g.bits = reinterpret_cast<const uint32_t *>(bitfield);
+    return g;
+}
+
+__device__ __forceinline__ float calc_ds(const Grid &g, float t) {  // marching.cu:15-23
+    return fminf(fmaxf(__fmul_rn(t, g.portion), g.ds_lo), g.ds_hi);
+}
+
+__device__ __forceinline__ uint32_t mip_of(float v, uint32_t K) {  // marching.cu:25-39
+    int e;
+    frexpf(v, &e);
+    return (uint32_t)min(max(e, 0), (int)K - 1);
+}
+
+struct Ray {
+    float ox, oy, oz, dx, dy, dz, ix, iy, iz;
+};
+
+__device__ __forceinline__ Ray load_ray(const float *__restrict__ rays_o, const float *__restrict__ rays_d, uint32_t r) {
+    Ray ray;
+    ray.ox = __ldg(rays_o + 3 * (size_t)r + 0);
+    ray.oy = __ldg(rays_o + 3 * (size_t)r + 1);
+    ray.oz = __ldg(rays_o + 3 * (size_t)r + 2);
+    ray.dx = __ldg(rays_d + 3 * (size_t)r + 0);
+    ray.dy = __ldg(rays_d + 3 * (size_t)r + 1);
+    ray.dz = __ldg(rays_d + 3 * (size_t)r + 2);
+    ray.ix = __fdiv_rn(1.f, ray.dx);  // marching.cu:157
+    ray.iy = __fdiv_rn(1.f, ray.dy);
+    ray.iz = __fdiv_rn(1.f, ray.dz);
+    return ray;
+}
+
+struct Step {
+    float px, py, pz, ds, t_next;
+    bool occupied;
+};
+
+// distance along one axis to the next voxel boundary (marching.cu:182-183)
+__device__ __forceinline__ float axis_delta(float gp, float d, float inv_d, float pos, float inv_G, float mip_bound) {
+    float ng = floorf(__fmaf_rn(copysignf(1.f, d), .5f, __fadd_rn(gp, .5f)));
+    float a = __fmaf_rn(ng, inv_G, -.5f);
+    a = __fadd_rn(a, a);
+    return __fmul_rn(__fmaf_rn(mip_bound, a, -pos), inv_d);
+}
+
+// One marching step at parameter t (marching.cu:166-190)
+template <bool kWantSkip>
+__device__ __forceinline__ Step march_step(const Grid &g, const Ray &r, float t) {
+    Step s;
+    s.px = __fmaf_rn(t, r.dx, r.ox);
+    s.py = __fmaf_rn(t, r.dy, r.oy);
+    s.pz = __fmaf_rn(t, r.dz, r.oz);
+    s.ds = calc_ds(g, t);
+    uint32_t cascade = 0;
+    if (g.K > 1) {  // marching.cu:79-98
+        float linf = fmaxf(fabsf(s.px), fmaxf(fabsf(s.py), fabsf(s.pz)));
+        cascade = max(mip_of(linf, g.K), mip_of(__fmul_rn(s.ds, g.Gf), g.K));
+    }
+    float mip_bound = fminf((float)(1u << cascade), g.bound);
+    float gx = __fmul_rn(__fmul_rn(__fadd_rn(__fdiv_rn(s.px, mip_bound), 1.f), .5f), g.Gf);
+    float gy = __fmul_rn(__fmul_rn(__fadd_rn(__fdiv_rn(s.py, mip_bound), 1.f), .5f), g.Gf);
+    float gz = __fmul_rn(__fmul_rn(__fadd_rn(__fdiv_rn(s.pz, mip_bound), 1.f), .5f), g.Gf);
+    int gmax = (int)g.G - 1;
+    uint32_t ux = (uint32_t)min(max(__float2int_rd(gx), 0), gmax);  // marching.cu:41-50
+    uint32_t uy = (uint32_t)min(max(__float2int_rd(gy), 0), gmax);
+    uint32_t uz = (uint32_t)min(max(__float2int_rd(gz), 0), gmax);
+    uint32_t idx = cascade * g.G3 + morton3d_encode(ux, uy, uz);
+    s.occupied = (__ldg(g.bits + (idx >> 5)) >> (idx & 31u)) & 1u;  // == byte[idx>>3] & (1 << (idx&7))
+    s.t_next = __fadd_rn(t, s.ds);
+    if (kWantSkip && !s.occupied) {
+        float ax = axis_delta(gx, r.dx, r.ix, s.px, g.inv_G, mip_bound);
+        float ay = axis_delta(gy, r.dy, r.iy, s.py, g.inv_G, mip_bound);
+        float az = axis_delta(gz, r.dz, r.iz, s.pz, g.inv_G, mip_bound);
+        float next_t = __fadd_rn(t, fmaxf(0.f, fminf(ax, fminf(ay, az))));
+        while (s.t_next < next_t) s.t_next = __fadd_rn(s.t_next, calc_ds(g, s.t_next));
+    }
+    return s;
+}
+
+// ---------------------------------------------------------------- training march
+constexpr int kTile = 128;  // rays per CTA
+constexpr uint64_t kFlagAgg = 1ull << 62, kFlagIncl = 2ull << 62, kValueMask = (1ull << 62) - 1;
+
+struct MarchScratch {
+    uint32_t ticket;
+    uint32_t cut_inv;  // 0 = no cut yet; else 0xFFFFFFFF - (index of a tile whose inclusive prefix >= total_samples)
+    unsigned long long status[1];  // [num_tiles]
+};
+
+__device__ __forceinline__ bool behind_cut(const MarchScratch *ws, uint32_t tile) {
+    uint32_t v = *reinterpret_cast<const volatile uint32_t *>(&ws->cut_inv);
+    return v != 0 && (0xFFFFFFFFu - v) < tile;
+}
+
+__global__ void __launch_bounds__(kTile) march_rays_kernel(
+    NgpMarchingDescriptor p, MarchScratch *__restrict__ ws, uint32_t num_tiles,
+    const float *__restrict__ rays_o, const float *__restrict__ rays_d, const float *__restrict__ t_starts,
+    const float *__restrict__ t_ends, const float *__restrict__ noises, const uint8_t *__restrict__ bitfield,
+    uint32_t *__restrict__ next_sample_write_location, uint32_t *__restrict__ number_of_exceeded_samples,
+    uint8_t *__restrict__ ray_is_valid, uint32_t *__restrict__ rays_n_samples,
+    uint32_t *__restrict__ rays_sample_startidx, uint32_t *__restrict__ idcs, float *__restrict__ xyzs,
+    float *__restrict__ dirs, float *__restrict__ dss, float *__restrict__ z_vals) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warp_sum[kTile / 32];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_abandon;
+
+    if (threadIdx.x == 0) {
+        s_tile = atomicAdd(&ws->ticket, 1u);
+        s_abandon = 0;
+    }
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t i = tile * kTile + threadIdx.x;
+    const bool in_range = i < p.n_rays;
+    const Grid g = make_grid(p.diagonal_n_steps, p.K, p.G, p.bound, p.stepsize_portion, bitfield);
+
+    // ---- pass 1: count occupied steps
+    Ray ray = {};
+    float t_start = 0.f, t_end = 0.f, t0 = 0.f;
+    uint32_t n = 0;
+    bool hit_box = false, abandoned = false;
+    if (in_range) {
+        t_start = __ldg(t_starts + i);
+        t_end = __ldg(t_ends + i);
+        hit_box = t_end > t_start;  // marching.cu:151
+    }
+    if (hit_box) {
+        ray = load_ray(rays_o, rays_d, i);
+        t0 = __fmaf_rn(calc_ds(g, t_start), __ldg(noises + i), t_start);  // marching.cu:164
+        const float max_steps = __fmul_rn((float)p.diagonal_n_steps, p.bound);  // marching.cu:165
+        float t = t0;
+        uint32_t it = 0;
+        while ((float)n < max_steps && t < t_end) {
+            Step s = march_step<true>(g, ray, t);
+            n += s.occupied;
+            t = s.t_next;
+            if ((++it & 15u) == 0 && behind_cut(ws, tile)) {
+                abandoned = true;
+                break;
+            }
+        }
+    }
+    if (abandoned) s_abandon = 1;
+
+    // ---- block scan of the counts
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t warp_base = 0, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kTile / 32; ++w) {
+        uint32_t v = s_warp_sum[w];
+        if (w < (int)warp) warp_base += v;
+        tile_total += v;
+    }
+    const uint32_t excl_in_tile = warp_base + incl - n;
+
+    // ---- decoupled look-back for the tile's exclusive prefix (thread 0)
+    if (threadIdx.x == 0) {
+        volatile unsigned long long *status = ws->status;
+        unsigned long long prefix = 0;
+        bool give_up = s_abandon != 0;
+        if (!give_up) {
+            if (tile == 0) {
+                status[0] = kFlagIncl | tile_total;
+            } else {
+                status[tile] = kFlagAgg | tile_total;
+                __threadfence();
+                for (int64_t j = (int64_t)tile - 1; j >= 0; --j) {
+                    unsigned long long st;
+                    while ((st = status[j]) == 0) {
+                        if (behind_cut(ws, tile)) { give_up = true; break; }
+                    }
+                    if (give_up) break;
+                    prefix += st & kValueMask;
+                    if (st & kFlagIncl) break;
+                }
+                if (!give_up) {
+                    status[tile] = kFlagIncl | (prefix + tile_total);
+                }
+            }
+            if (!give_up) {
+                __threadfence();
+                if (prefix + tile_total >= p.total_samples) atomicMax(&ws->cut_inv, 0xFFFFFFFFu - tile);
+                if (tile == num_tiles - 1 && prefix + tile_total < p.total_samples) {
+                    // no cut anywhere: the counters are the plain totals
+                    *next_sample_write_location = (uint32_t)(prefix + tile_total);
+                    *number_of_exceeded_samples = 0u;
+                }
+            }
+        }
+        if (give_up) s_abandon = 1;
+        s_prefix = prefix;
+    }
+    __syncthreads();
+    if (!in_range) return;
+
+    const bool tile_abandoned = s_abandon != 0;
+    const unsigned long long start64 = s_prefix + excl_in_tile;
+    bool valid = false;
+    uint32_t n_out = 0, start_out = 0;
+    if (!tile_abandoned && start64 < p.total_samples && hit_box) {  // else: marching.cu:135 / :151
+        const uint32_t start = (uint32_t)start64;
+        if (n == 0) {
+            valid = true;  // marching.cu:196-199
+        } else {
+            if (start64 + n >= p.total_samples) {  // this is the ray at which the budget fills
+                *next_sample_write_location = start + n;
+                *number_of_exceeded_samples = (start64 + n > p.total_samples) ? n : 0u;
+            }
+            if (start64 + n <= p.total_samples) {
+                valid = true;
+                n_out = n;
+                start_out = start;
+            }
+        }
+    }
+    ray_is_valid[i] = valid ? 1 : 0;
+    rays_n_samples[i] = n_out;
+    rays_sample_startidx[i] = start_out;
+    if (n_out == 0) return;
+
+    // ---- pass 2: march again and write (marching.cu:224-267)
+    uint32_t *__restrict__ o_idcs = idcs + start_out;
+    float *__restrict__ o_xyzs = xyzs + (size_t)start_out * 3;
+    float *__restrict__ o_dirs = dirs + (size_t)start_out * 3;
+    float *__restrict__ o_dss = dss + start_out;
+    float *__restrict__ o_z = z_vals + start_out;
+    uint32_t steps = 0;
+    float t = t0;
+    while (steps < n_out && t < t_end) {
+        Step s = march_step<true>(g, ray, t);
+        if (s.occupied) {
+            o_idcs[steps] = i;
+            o_xyzs[steps * 3 + 0] = s.px;
+            o_xyzs[steps * 3 + 1] = s.py;
+            o_xyzs[steps * 3 + 2] = s.pz;
+            o_dirs[steps * 3 + 0] = ray.dx;
+            o_dirs[steps * 3 + 1] = ray.dy;
+            o_dirs[steps * 3 + 2] = ray.dz;
+            o_dss[steps] = s.ds;
+            o_z[steps] = t;
+            ++steps;
+        }
+        t = s.t_next;
+    }
+}
+
+// zero the sample slots nobody wrote: [next - exceeded, total_samples)
+__global__ void __launch_bounds__(256) march_rays_tail_kernel(
+    uint32_t total_samples, const uint32_t *__restrict__ next_loc, const uint32_t *__restrict__ exceeded,
+    uint32_t *__restrict__ idcs, float *__restrict__ xyzs, float *__restrict__ dirs, float *__restrict__ dss,
+    float *__restrict__ z_vals) {
+    const uint32_t used = min(*next_loc - *exceeded, total_samples);
+    for (uint32_t s = used + blockIdx.x * blockDim.x + threadIdx.x; s < total_samples; s += gridDim.x * blockDim.x) {
+        idcs[s] = 0u;
+        dss[s] = 0.f;
+        z_vals[s] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            xyzs[(size_t)s * 3 + k] = 0.f;
+            dirs[(size_t)s * 3 + k] = 0.f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- inference march
+constexpr int kInferBlock = 128;
+
+__global__ void __launch_bounds__(kInferBlock) march_rays_inference_kernel(
+    NgpMarchingInferenceDescriptor p, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+    const float *__restrict__ t_starts, const float *__restrict__ t_ends, const uint8_t *__restrict__ bitfield,
+    const uint32_t *__restrict__ next_ray_index_in, const uint8_t *__restrict__ terminated,
+    const uint32_t *__restrict__ indices_in, uint32_t *__restrict__ next_ray_index,
+    uint32_t *__restrict__ indices_out, uint32_t *__restrict__ n_samples, float *__restrict__ t_starts_out,
+    float *__restrict__ xyzs, float *__restrict__ dss, float *__restrict__ z_vals) {
+    __shared__ uint32_t s_partial[kInferBlock / 32];
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+
+    // Rank of this slot among the terminated slots, in slot order: fresh rays are handed out
+    // deterministically (the reference uses atomicAdd arrival order, marching.cu:300).
+    // Slots before this block are counted directly from the flags (n_rays is a few thousand).
+    uint32_t before = 0;
+    const uint32_t block_begin = blockIdx.x * blockDim.x;
+    for (uint32_t j = threadIdx.x; j < block_begin; j += blockDim.x) before += terminated[j] ? 1u : 0u;
+    before = warp_sum_u32(before);
+    if (lane == 0) s_partial[warp] = before;
+    __syncthreads();
+    uint32_t base = 0;
+#pragma unroll
+    for (int w = 0; w < kInferBlock / 32; ++w) base += s_partial[w];
+    __syncthreads();
+    const bool mine = i < p.n_rays && terminated[i];
+    const uint32_t ballot = __ballot_sync(0xffffffffu, mine);
+    if (lane == 0) s_partial[warp] = __popc(ballot);
+    __syncthreads();
+    uint32_t rank = base + __popc(ballot & ((1u << lane) - 1u));
+    uint32_t block_total = 0;
+#pragma unroll
+    for (int w = 0; w < kInferBlock / 32; ++w) {
+        if (w < (int)warp) rank += s_partial[w];
+        block_total += s_partial[w];
+    }
+    const uint32_t counter_in = __ldg(next_ray_index_in);
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *next_ray_index = counter_in + base + block_total;
+    if (i >= p.n_rays) return;
+
+    const uint32_t cap = p.march_steps_cap;
+    float *__restrict__ o_xyzs = xyzs + (size_t)i * cap * 3;
+    float *__restrict__ o_dss = dss + (size_t)i * cap;
+    float *__restrict__ o_z = z_vals + (size_t)i * cap;
+
+    const uint32_t ray_idx = mine ? counter_in + rank : __ldg(indices_in + i);
+    indices_out[i] = ray_idx;
+    uint32_t steps = 0;
+    float t = 0.f;
+    bool live = ray_idx < p.n_total_rays;
+    float t_end = 0.f;
+    if (live) {
+        t = __ldg(t_starts + ray_idx);
+        t_end = __ldg(t_ends + ray_idx);
+        live = !(t_end < t);  // marching.cu:317 (strict)
+    }
+    if (live) {
+        const Grid g = make_grid(p.diagonal_n_steps, p.K, p.G, p.bound, p.stepsize_portion, bitfield);
+        const Ray ray = load_ray(rays_o, rays_d, ray_idx);
+        while (steps < cap && t < t_end) {
+            Step s = march_step<true>(g, ray, t);
+            if (s.occupied) {
+                o_xyzs[steps * 3 + 0] = s.px;
+                o_xyzs[steps * 3 + 1] = s.py;
+                o_xyzs[steps * 3 + 2] = s.pz;
+                o_dss[steps] = s.ds;
+                o_z[steps] = t;
+                ++steps;
+            }
+            t = s.t_next;
+        }
+        if (t >= t_end) {  // far-plane sample, marching.cu:367-394
+            Step s = march_step<false>(g, ray, t_end);
+            if (s.occupied) {
+                if (steps > 0 && __fadd_rn(o_dss[steps - 1], o_z[steps - 1]) >= t_end)
+                    o_dss[steps - 1] = __fadd_rn(t_end, -o_z[steps - 1]);
+                if (steps < cap) {
+                    o_xyzs[steps * 3 + 0] = s.px;
+                    o_xyzs[steps * 3 + 1] = s.py;
+                    o_xyzs[steps * 3 + 2] = s.pz;
+                    o_dss[steps] = s.ds;
+                    o_z[steps] = t_end;
+                    ++steps;
+                } else {
+                    t = t_end;
+                }
+            }
+        }
+    } else {
+        t = 0.f;  // the reference leaves the memset zeros for rays it skips
+    }
+    n_samples[i] = steps;
+    t_starts_out[i] = live ? t : 0.f;
+    for (uint32_t s = steps; s < cap; ++s) {  // zero the unused tail (reference: memsets, marching.cu:565-570)
+        o_xyzs[s * 3 + 0] = 0.f;
+        o_xyzs[s * 3 + 1] = 0.f;
+        o_xyzs[s * 3 + 2] = 0.f;
+        o_dss[s] = 0.f;
+        o_z[s] = 0.f;
+    }
+}
+
+}  // namespace
+}  // namespace ngp
+
+extern "C" {
+
+void ngp_march_rays(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *desc = descriptor<NgpMarchingDescriptor>(opaque, opaque_len, "march_rays");
+    if (!desc) return;
+    if (desc->K == 0 || desc->G == 0 || desc->G > 1024) {
+        set_error(NGP_ERR_ARGUMENT, "march_rays: expected K > 0 and 0 < G <= 1024, got K=%u G=%u", desc->K, desc->G);
+        return;
+    }
+    BufferCursor b{buffers};
+    const float *rays_o = b.next<const float>();
+    const float *rays_d = b.next<const float>();
+    const float *t_starts = b.next<const float>();
+    const float *t_ends = b.next<const float>();
+    const float *noises = b.next<const float>();
+    const uint8_t *bitfield = b.next<const uint8_t>();
+    uint32_t *next_loc = b.next<uint32_t>();
+    uint32_t *exceeded = b.next<uint32_t>();
+    uint8_t *valid = b.next<uint8_t>();
+    uint32_t *rays_n = b.next<uint32_t>();
+    uint32_t *rays_start = b.next<uint32_t>();
+    uint32_t *idcs = b.next<uint32_t>();
+    float *xyzs = b.next<float>();
+    float *dirs = b.next<float>();
+    float *dss = b.next<float>();
+    float *z_vals = b.next<float>();
+
+    const uint32_t num_tiles = div_up(desc->n_rays, kTile);
+    if (num_tiles == 0) {
+        NGP_CUDA_OK(cudaMemsetAsync(next_loc, 0, sizeof(uint32_t), stream), "march_rays");
+        NGP_CUDA_OK(cudaMemsetAsync(exceeded, 0, sizeof(uint32_t), stream), "march_rays");
+    } else {
+        const size_t ws_bytes = sizeof(MarchScratch) + (size_t)num_tiles * sizeof(unsigned long long);
+        auto *ws = static_cast<MarchScratch *>(workspace(stream, ws_bytes));
+        if (!ws) return;
+        NGP_CUDA_OK(cudaMemsetAsync(ws, 0, ws_bytes, stream), "march_rays");
+        march_rays_kernel<<<num_tiles, kTile, 0, stream>>>(*desc, ws, num_tiles, rays_o, rays_d, t_starts, t_ends,
+                                                           noises, bitfield, next_loc, exceeded, valid, rays_n,
+                                                           rays_start, idcs, xyzs, dirs, dss, z_vals);
+        if (!check_launch("march_rays")) return;
+    }
+    if (desc->total_samples) {
+        const unsigned blocks = min(div_up(desc->total_samples, 256u), 148u * 8u);
+        march_rays_tail_kernel<<<blocks, 256, 0, stream>>>(desc->total_samples, next_loc, exceeded, idcs, xyzs, dirs,
+                                                           dss, z_vals);
+        check_launch("march_rays(tail)");
+    }
+}
+
+void ngp_march_rays_inference(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *desc = descriptor<NgpMarchingInferenceDescriptor>(opaque, opaque_len, "march_rays_inference");
+    if (!desc) return;
+    if (desc->K == 0 || desc->G == 0 || desc->G > 1024) {
+        set_error(NGP_ERR_ARGUMENT, "march_rays_inference: expected K > 0 and 0 < G <= 1024, got K=%u G=%u",
+                  desc->K, desc->G);
+        return;
+    }
+    BufferCursor b{buffers};
+    const float *rays_o = b.next<const float>();
+    const float *rays_d = b.next<const float>();
+    const float *t_starts = b.next<const float>();
+    const float *t_ends = b.next<const float>();
+    const uint8_t *bitfield = b.next<const uint8_t>();
+    const uint32_t *next_in = b.next<const uint32_t>();
+    const uint8_t *terminated = b.next<const uint8_t>();
+    const uint32_t *indices_in = b.next<const uint32_t>();
+    uint32_t *next_out = b.next<uint32_t>();
+    uint32_t *indices_out = b.next<uint32_t>();
+    uint32_t *n_samples = b.next<uint32_t>();
+    float *t_starts_out = b.next<float>();
+    float *xyzs = b.next<float>();
+    float *dss = b.next<float>();
+    float *z_vals = b.next<float>();
+    if (desc->n_rays == 0) {
+        NGP_CUDA_OK(cudaMemcpyAsync(next_out, next_in, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream),
+                    "march_rays_inference");
+        return;
+    }
+    march_rays_inference_kernel<<<div_up(desc->n_rays, kInferBlock), kInferBlock, 0, stream>>>(
+        *desc, rays_o, rays_d, t_starts, t_ends, bitfield, next_in, terminated, indices_in, next_out, indices_out,
+        n_samples, t_starts_out, xyzs, dss, z_vals);
+    check_launch("march_rays_inference");
+}
+
+}  // extern "C"

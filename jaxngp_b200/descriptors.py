@@ -1,0 +1,76 @@
+"""Opaque descriptor factories: the wire format is the raw little-endian bytes of the POD structs in
+include/ngp_b200.h, byte-identical to the reference's (deps/volume-rendering-jax/lib/ffi.cc:55-207,
+deps/jax-tcnn/lib/ffi.cc:31-56 via serde-helper/serde.h:30-33).  Same names, arguments, validation.
+"""
+import struct
+
+HG_MAX_LEVELS = 32
+
+
+def _u32(x, name):
+    x = int(x)
+    if not 0 <= x < 2 ** 32:
+        raise ValueError(f"{name} must fit in uint32, got {x}")
+    return x
+
+
+def make_packbits_descriptor(n_bytes):
+    if n_bytes == 0:  # ffi.cc:57-59
+        raise RuntimeError("expected n_bytes to be a positive integer, got 0")
+    return struct.pack("<I", _u32(n_bytes, "n_bytes"))
+
+
+def make_morton3d_descriptor(length):
+    return struct.pack("<I", _u32(length, "length"))
+
+
+def make_marching_descriptor(n_rays, total_samples, diagonal_n_steps, K, G, bound, stepsize_portion):
+    if K == 0:  # ffi.cc:79-81
+        raise RuntimeError("expected K to be a positive integer, got 0")
+    return struct.pack("<5I2f", _u32(n_rays, "n_rays"), _u32(total_samples, "total_samples"),
+                       _u32(diagonal_n_steps, "diagonal_n_steps"), _u32(K, "K"), _u32(G, "G"),
+                       float(bound), float(stepsize_portion))
+
+
+def make_marching_inference_descriptor(n_total_rays, n_rays, diagonal_n_steps, K, G, march_steps_cap,
+                                       bound, stepsize_portion):
+    if K == 0:  # ffi.cc:114-116
+        raise RuntimeError("expected K to be a positive integer, got 0")
+    return struct.pack("<6I2f", _u32(n_total_rays, "n_total_rays"), _u32(n_rays, "n_rays"),
+                       _u32(diagonal_n_steps, "diagonal_n_steps"), _u32(K, "K"), _u32(G, "G"),
+                       _u32(march_steps_cap, "march_steps_cap"), float(bound), float(stepsize_portion))
+
+
+def make_integrating_descriptor(n_rays, total_samples):
+    return struct.pack("<2I", _u32(n_rays, "n_rays"), _u32(total_samples, "total_samples"))
+
+
+def make_integrating_backward_descriptor(n_rays, total_samples, near_distance):
+    return struct.pack("<2If", _u32(n_rays, "n_rays"), _u32(total_samples, "total_samples"), float(near_distance))
+
+
+def make_integrating_inference_descriptor(n_total_rays, n_rays, march_steps_cap):
+    return struct.pack("<3I", _u32(n_total_rays, "n_total_rays"), _u32(n_rays, "n_rays"),
+                       _u32(march_steps_cap, "march_steps_cap"))
+
+
+def make_hashgrid_descriptor(n_coords, L, F, N_min, per_level_scale):
+    return struct.pack("<4If", _u32(n_coords, "n_coords"), _u32(L, "L"), _u32(F, "F"), _u32(N_min, "N_min"),
+                       float(per_level_scale))
+
+
+def make_hashgrid_a1_descriptor(n_points, dim, L, F, wrap_T, table_dtype, bound, hashed, scales, res, offsets):
+    """NgpHashGridA1Descriptor (include/ngp_b200.h): level table of models/encoders.py:89-103."""
+    if not 0 < L <= HG_MAX_LEVELS:
+        raise ValueError(f"L must be in (0, {HG_MAX_LEVELS}], got {L}")
+    mask = 0
+    for l, h in enumerate(hashed):
+        mask |= (1 << l) if h else 0
+    pad = HG_MAX_LEVELS - L
+    return struct.pack(
+        f"<6IfI{HG_MAX_LEVELS}f{HG_MAX_LEVELS}I{HG_MAX_LEVELS + 1}I",
+        _u32(n_points, "n_points"), _u32(dim, "dim"), _u32(L, "L"), _u32(F, "F"), _u32(wrap_T, "wrap_T"),
+        _u32(table_dtype, "table_dtype"), float(bound), mask,
+        *([float(s) for s in scales] + [0.0] * pad),
+        *([int(r) for r in res] + [0] * pad),
+        *([int(o) for o in offsets] + [0] * pad))
