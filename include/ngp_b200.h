@@ -147,6 +147,18 @@ void ngp_hashgrid_a1_backward(cudaStream_t, void **, const char *, size_t);
  * in : threshold f32[1], density f32[N]                  out: occupied_mask bool[N], bitfield u8[N/8] */
 void ngp_packbits_scalar(cudaStream_t, void **, const char *, size_t);
 
+/* Adam step of app/nerf/_utils.py:19-77 over a flat f32 buffer [hash table | MLP weights]; elements
+ * at index >= decay_begin also receive the reference's (additive) decayed-weights term.
+ * in : step u32[1] (device-resident count of completed steps), params f32[n] (updated in place),
+ *      grads f32[n], m f32[n], v f32[n] (updated in place) */
+typedef struct {
+    uint64_t n, decay_begin;
+    float lr_init, lr_end, decay_rate;
+    uint32_t transition_steps, transition_begin, staircase;
+    float b1, b2, eps, eps_root, weight_decay, grad_scale;
+} NgpAdamDescriptor;
+void ngp_adam_step(cudaStream_t, void **, const char *, size_t);
+
 /* ------------------------------------------------------------------ status */
 int ngp_b200_abi_version(void);
 /* 0 = last call on this host thread succeeded; otherwise a cudaError_t or a negative ngp code */

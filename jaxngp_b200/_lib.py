@@ -21,7 +21,7 @@ OPS = (
     "ngp_pack_density_into_bits", "ngp_packbits_scalar", "ngp_march_rays", "ngp_march_rays_inference",
     "ngp_morton3d", "ngp_morton3d_invert", "ngp_integrate_rays", "ngp_integrate_rays_backward",
     "ngp_integrate_rays_inference", "ngp_hashgrid_encode", "ngp_hashgrid_encode_backward",
-    "ngp_hashgrid_a1_forward", "ngp_hashgrid_a1_backward",
+    "ngp_hashgrid_a1_forward", "ngp_hashgrid_a1_backward", "ngp_adam_step",
 )
 STATUS_SYMBOLS = ("ngp_b200_abi_version", "ngp_b200_last_status", "ngp_b200_last_error", "ngp_b200_clear_error")
 
@@ -76,9 +76,9 @@ def call(name, buffers, opaque, stream=None):
     """Enqueue custom call `name` on `stream` (default: torch's current stream)."""
     global launch_count
     L = lib()
+    arr = (C.c_void_p * len(buffers))(*[_ptr(b) for b in buffers])
     if stream is None:
         stream = torch.cuda.current_stream().cuda_stream
-    arr = (C.c_void_p * len(buffers))(*[_ptr(b) for b in buffers])
     getattr(L, name)(C.c_void_p(stream), arr, opaque, len(opaque))
     launch_count += 1
     st = L.ngp_b200_last_status()

@@ -74,3 +74,11 @@ def make_hashgrid_a1_descriptor(n_points, dim, L, F, wrap_T, table_dtype, bound,
         *([float(s) for s in scales] + [0.0] * pad),
         *([int(r) for r in res] + [0] * pad),
         *([int(o) for o in offsets] + [0] * pad))
+
+
+def make_adam_descriptor(n, decay_begin, lr_init, lr_end, decay_rate, transition_steps, transition_begin, staircase,
+                         b1, b2, eps, eps_root, weight_decay, grad_scale=1.0):
+    """NgpAdamDescriptor (include/ngp_b200.h): optimizer constants of app/nerf/_utils.py:19-77."""
+    return struct.pack("<2Q3f3I6f", int(n), int(decay_begin), float(lr_init), float(lr_end), float(decay_rate),
+                       int(transition_steps), int(transition_begin), int(bool(staircase)), float(b1), float(b2),
+                       float(eps), float(eps_root), float(weight_decay), float(grad_scale))

@@ -1,0 +1,55 @@
+"""Ray-sharded data parallelism: what each rank owns and the one exchange per step.
+
+Training: every rank draws its own ray batch (disjoint index streams), runs the whole step locally and
+all-reduces ONE flat gradient buffer [hash-table grad | MLP grads]; the optimizer divides by the world
+size (NgpAdamDescriptor.grad_scale), so replicas stay bit-identical without a parameter broadcast.
+Inference: image rows are dealt to ranks in interleaved tiles; the only collective is the final gather.
+"""
+import torch
+import torch.distributed as dist
+
+
+def allreduce_flat_gradients(flat_grads: torch.Tensor, group=None) -> torch.Tensor:
+    """SUM all-reduce of the flat gradient buffer, in place (NCCL on GPUs, gloo in the CPU tests)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return flat_grads
+
+
+def allreduce_density_grid(grid: torch.Tensor, group=None) -> torch.Tensor:
+    """MAX all-reduce of the density grid after each rank updated its own share of the cells."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(grid, op=dist.ReduceOp.MAX, group=group)
+    return grid
+
+
+def tile_rows(height: int, rank: int, world_size: int, tile: int = 32):
+    """Row indices of the image owned by `rank`: interleaved `tile`-row bands (empty-space rays are cheap,
+    so contiguous slabs would be unbalanced)."""
+    rows = torch.arange(height)
+    return rows[((rows // tile) % world_size) == rank]
+
+
+def gather_image(local_rows: torch.Tensor, local_pixels: torch.Tensor, height: int, group=None) -> torch.Tensor:
+    """All-gather the per-rank row bands into the full image [height, W, C] on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        out = torch.empty((height,) + tuple(local_pixels.shape[1:]), dtype=local_pixels.dtype, device=local_pixels.device)
+        out[local_rows] = local_pixels
+        return out
+    counts = [torch.zeros(1, dtype=torch.int64, device=local_pixels.device) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([local_rows.numel()], dtype=torch.int64, device=local_pixels.device), group=group)
+    max_rows = int(max(int(c) for c in counts))
+    pad_rows = torch.full((max_rows,), -1, dtype=torch.int64, device=local_pixels.device)
+    pad_rows[: local_rows.numel()] = local_rows.to(local_pixels.device)
+    pad_pix = torch.zeros((max_rows,) + tuple(local_pixels.shape[1:]), dtype=local_pixels.dtype, device=local_pixels.device)
+    pad_pix[: local_rows.numel()] = local_pixels
+    all_rows = [torch.empty_like(pad_rows) for _ in range(world)]
+    all_pix = [torch.empty_like(pad_pix) for _ in range(world)]
+    dist.all_gather(all_rows, pad_rows, group=group)
+    dist.all_gather(all_pix, pad_pix, group=group)
+    out = torch.empty((height,) + tuple(local_pixels.shape[1:]), dtype=local_pixels.dtype, device=local_pixels.device)
+    for r, p in zip(all_rows, all_pix):
+        ok = r >= 0
+        out[r[ok]] = p[ok]
+    return out

@@ -1,0 +1,231 @@
+"""Device-resident training state and step for the reference's NeRF training path
+(app/nerf/_utils.py:80-170 ``train_step``, app/nerf/train.py:28-96 ``train_epoch``), ray-sharded data
+parallel over NCCL when launched with one process per GPU.
+
+Per step (shapes at BASELINE config C2: n_rays = total_samples = 2^18):
+  perm[n_rays] -> rays (o, d) -> near/far -> march_rays* -> hash-grid encode* -> MLP -> integrate_rays*
+  -> Huber(0.1) over valid rays -> integrate_rays_backward* -> MLP backward -> hash-grid scatter*
+  -> [all-reduce of the flat gradient buffer across ranks] -> Adam*            (* = this package's kernels)
+
+All parameters live in ONE flat f32 buffer [hash table | MLP weights] with matching flat gradient and
+Adam-moment buffers, so data parallelism is a single ``all_reduce`` and the optimizer a single launch.
+"""
+import torch
+
+from . import _lib, descriptors, dp, encoders, nerf as nerf_mod, renderers, synthetic
+from .volrendjax import integrate_rays, march_rays, morton3d_invert, packbits
+
+
+def huber(pred, target, delta=0.1):
+    """optax.huber_loss (app/nerf/_utils.py:153)."""
+    err = (pred - target).abs()
+    quad = torch.clamp(err, max=delta)
+    return 0.5 * quad * quad + delta * (err - quad)
+
+
+class Scene:
+    """Device-resident training set: transforms [V, 12] f32 and RGBA pixels [V*H*W, 4] u8
+    (utils/types.py:924-1116 SceneData), rendered from the procedural field of synthetic.py."""
+
+    def __init__(self, device, n_views=100, width=synthetic.W, height=synthetic.H):
+        self.cam = synthetic.camera()
+        if (width, height) != (synthetic.W, synthetic.H):
+            s = width / synthetic.W
+            self.cam = dict(width=width, height=height, fx=self.cam["fx"] * s, fy=self.cam["fy"] * s, cx=width / 2,
+                            cy=height / 2, near=synthetic.NEAR)
+        self.n_views, self.width, self.height = n_views, width, height
+        self.transforms = torch.from_numpy(synthetic.poses(n_views)).to(device)
+        self.bitfield_gt = torch.from_numpy(synthetic.occupancy_bitfield()).to(device)
+        self.rgbas_u8 = self._render_ground_truth(device)
+
+    @property
+    def n_pixels(self):
+        return self.n_views * self.width * self.height
+
+    def rays(self, perm):
+        """app/nerf/_utils.py:93-115."""
+        hw = self.width * self.height
+        view, pix = perm // hw, perm % hw
+        d_cam = renderers.make_ray_directions(pix % self.width, pix // self.width, self.cam)
+        tf = self.transforms[view]
+        d_world = (d_cam[:, None, :] * tf[:, :9].reshape(-1, 3, 3)).sum(-1)
+        return tf[:, 9:].contiguous(), d_world.contiguous()
+
+    @torch.no_grad()
+    def _render_ground_truth(self, device, chunk=1 << 17, budget=1 << 25):
+        """Renders every training pixel of the analytic field with this package's own march and
+        integrate kernels (bg = 0) and stores straight-alpha RGBA like the blender PNGs."""
+        out = torch.empty(self.n_pixels, 4, dtype=torch.uint8, device=device)
+        lo = torch.tensor([-0.7, -0.3, -0.6], device=device)
+        hi = torch.tensor([-0.2, 0.3, 0.1], device=device)
+        for begin in range(0, self.n_pixels, chunk):
+            perm = torch.arange(begin, min(begin + chunk, self.n_pixels), device=device)
+            o, d = self.rays(perm)
+            ts, te = renderers.make_near_far_from_bound(synthetic.BOUND, o, d)
+            _, _, rn, rs, _, xyzs, _, dss, zs = march_rays(budget, synthetic.DIAGONAL_N_STEPS, synthetic.K, synthetic.G,
+                                                           synthetic.BOUND, synthetic.STEPSIZE_PORTION, o, d, ts, te,
+                                                           0.0, self.bitfield_gt)
+            inside = ((xyzs ** 2).sum(-1) < 0.45 ** 2) | ((xyzs > lo) & (xyzs < hi)).all(-1)
+            drgbs = torch.cat([torch.where(inside, synthetic.SIGMA_INSIDE, 0.0)[:, None],
+                               0.5 + 0.5 * xyzs.clamp(-1, 1)], dim=-1).contiguous()
+            _, rgbd, opac = integrate_rays(synthetic.NEAR, rs, rn, torch.zeros(3, device=device), dss, zs, drgbs)
+            # integrate_rays renormalises terminated rays by opacity (integrating.cu:85-90): undo that to get
+            # premultiplied colour, then store straight alpha
+            premult = torch.where((opac >= 1 - 1e-4)[:, None], rgbd[:, :3] * opac[:, None], rgbd[:, :3])
+            straight = premult / opac.clamp(min=1e-6)[:, None]
+            rgba = torch.cat([straight.clamp(0, 1), opac[:, None]], dim=-1)
+            out[begin:begin + perm.shape[0]] = (rgba * 255 + 0.5).to(torch.uint8)
+        return out
+
+
+class Trainer:
+    def __init__(self, device="cuda:0", n_rays=1 << 18, total_samples=1 << 18, lr=1e-2, seed=1000000007, rank=0,
+                 world_size=1, process_group=None, scene=None, T=1 << 19, use_graph=True):
+        self.device = torch.device(device)
+        self.n_rays, self.total_samples = n_rays, total_samples
+        self.rank, self.world_size, self.pg = rank, world_size, process_group
+        torch.backends.cuda.matmul.allow_tf32 = True  # XLA's default f32 dot precision on Ampere+
+        gen = torch.Generator(device=self.device).manual_seed(seed)  # same init on every rank
+        self.nerf = nerf_mod.NeRF(bound=synthetic.BOUND, inference=False, device=self.device, generator=gen, T=T)
+        self.levels = self.nerf.position_encoder.levels
+        self._flatten_parameters()
+        self.scene = scene if scene is not None else Scene(self.device)
+        # occupancy grid state (utils/types.py:93-144): all-ones bitfield at step 0
+        G3 = synthetic.K * synthetic.G ** 3
+        self.density_grid = torch.zeros(G3, dtype=torch.float32, device=self.device)
+        self.occupancy = torch.full((G3 // 8,), 0xFF, dtype=torch.uint8, device=self.device)
+        self.occ_mask = torch.ones(G3, dtype=torch.bool, device=self.device)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.step = 0
+        torch.cuda.manual_seed(seed + 1 + rank)  # per-rank perturbation / background streams (graph-safe default generator)
+        self.noise_gen = None
+        self.adam_desc = descriptors.make_adam_descriptor(
+            n=self.flat_params.numel(), decay_begin=self.table_numel, lr_init=lr, lr_end=lr / 100, decay_rate=1 / 3,
+            transition_steps=10_000, transition_begin=10_000, staircase=True, b1=0.9, b2=0.99, eps=1e-15,
+            eps_root=1e-15, weight_decay=1e-6, grad_scale=1.0 / world_size)
+        self.use_graph = use_graph
+        self._graph = None
+        self._static_perm = torch.zeros(n_rays, dtype=torch.int32, device=self.device)
+        self._static_out = None
+
+    # -- flat parameter / gradient / moment buffers ---------------------------------------------
+    def _flatten_parameters(self):
+        enc = self.nerf.position_encoder
+        mlp = self.nerf.mlp_parameters()
+        self.table_numel = enc.latents.numel()
+        assert self.table_numel % 4 == 0
+        total = self.table_numel + sum(p.numel() for p in mlp)
+        total_padded = total + (-total) % 4
+        self.flat_params = torch.zeros(total_padded, dtype=torch.float32, device=self.device)
+        self.flat_grads = torch.zeros_like(self.flat_params)
+        self.adam_m = torch.zeros_like(self.flat_params)
+        self.adam_v = torch.zeros_like(self.flat_params)
+        off = 0
+        views = []
+        for p in [enc.latents] + mlp:
+            n = p.numel()
+            self.flat_params[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat_params[off:off + n].view_as(p)
+            views.append((off, n))
+            off += n
+        self.table = enc.latents.data
+        self.table_grad = self.flat_grads[: self.table_numel].view_as(self.table)
+        self.mlp_params = mlp
+        self.mlp_grad_views = [self.flat_grads[o:o + n].view_as(p) for (o, n), p in zip(views[1:], mlp)]
+
+    # -- one training step ------------------------------------------------------------------------
+    def _step_body(self, perm, noises=None, bg=None, apply=True):
+        sc, dev = self.scene, self.device
+        perm = perm.to(torch.int64)
+        o, d = sc.rays(perm)
+        t_starts, t_ends = renderers.make_near_far_from_bound(synthetic.BOUND, o, d)
+        if noises is None:
+            noises = torch.rand(self.n_rays, device=dev)  # cuda.py:118-122
+        if bg is None:
+            bg = torch.rand(self.n_rays, 3, device=dev)  # random_bg, _utils.py:134-136
+        mb, ray_is_valid, rays_n, rays_start, _, xyzs, dirs, dss, z_vals = march_rays(
+            self.total_samples, synthetic.DIAGONAL_N_STEPS, synthetic.K, synthetic.G, synthetic.BOUND,
+            synthetic.STEPSIZE_PORTION, o, d, t_starts, t_ends, noises, self.occupancy)
+        # hash-grid gather outside autograd: its backward writes straight into the flat gradient buffer
+        enc = encoders.hashgrid_forward(self.levels, xyzs, synthetic.BOUND, self.table).requires_grad_(True)
+        n = self.nerf
+        x = torch.relu(enc @ n.density_w0) @ n.density_w1
+        density = nerf_mod.trunc_exp(x[:, :1])
+        h = torch.cat([x, nerf_mod.sh4(dirs)], dim=-1)
+        rgb = torch.sigmoid(torch.relu(torch.relu(h @ n.rgb_w0) @ n.rgb_w1) @ n.rgb_w2)
+        drgbs = torch.cat([density, rgb], dim=-1)
+        effective, final_rgbds, _ = integrate_rays(synthetic.NEAR, rays_start, rays_n, bg, dss, z_vals, drgbs)
+        gt = sc.rgbas_u8[perm].to(torch.float32) / 255  # _utils.py:165
+        gt_rgb = gt[:, :3] * gt[:, 3:] + bg * (1 - gt[:, 3:])  # utils/data.py:443-464
+        n_valid = ray_is_valid.sum()
+        loss = torch.where(ray_is_valid, huber(final_rgbds[:, :3], gt_rgb).mean(-1), 0.0).sum() / n_valid  # :151-156
+        grads = torch.autograd.grad(loss, [enc] + self.mlp_params)
+        encoders.hashgrid_backward(self.levels, xyzs, synthetic.BOUND, grads[0].contiguous(), out=self.table_grad)
+        for view, g in zip(self.mlp_grad_views, grads[1:]):
+            view.copy_(g)
+        if self.world_size > 1:  # one collective per step over [table grad | MLP grads]
+            dp.allreduce_flat_gradients(self.flat_grads, self.pg)
+        if apply:
+            _lib.call("ngp_adam_step", [self.step_dev, self.flat_params, self.flat_grads, self.adam_m, self.adam_v],
+                      self.adam_desc)
+            self.step_dev += 1
+        return dict(loss=loss.detach(), n_valid_rays=n_valid, measured_batch_size_before_compaction=mb,
+                    measured_batch_size=effective)
+
+    def train_step(self, perm):
+        """perm: int32 [n_rays] indices into the scene's pixels (device tensor).  Returns device-side
+        metrics (no host synchronisation)."""
+        self.step += 1
+        if not self.use_graph:
+            return self._step_body(perm)
+        self._static_perm.copy_(perm, non_blocking=True)
+        if self._graph is None:
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up on the capture stream (scratch blocks, cuBLAS handles)
+                    self._step_body(self._static_perm)
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph, stream=side):
+                    self._static_out = self._step_body(self._static_perm)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            self.step += 2
+        self._graph.replay()
+        return self._static_out
+
+    # -- density grid update (utils/types.py:1149-1239), torch arm -------------------------------
+    @torch.no_grad()
+    def update_ogrid(self, update_all=None, commit=True):
+        G, dev = synthetic.G, self.device
+        if update_all is None:
+            update_all = self.step < 256  # utils/types.py:1391-1392
+        G3 = G ** 3
+        grid = self.density_grid if commit else self.density_grid.clone()
+        grid *= 0.95  # :1162 (all cells alive in the synthetic scene)
+        if update_all:
+            idx = torch.arange(G3, dtype=torch.int32, device=dev)
+        else:
+            M = max(1, G3 // 2)
+            first = torch.randint(0, G3, (max(1, M // 2),), device=dev, generator=self.noise_gen)
+            occ = self.occ_mask.nonzero().squeeze(-1)
+            if occ.numel() == 0:
+                occ = torch.arange(G3, device=dev)
+            second = occ[torch.randint(0, occ.numel(), (max(1, M // 2),), device=dev, generator=self.noise_gen)]
+            idx = torch.cat([first, second]).to(torch.int32)
+        coords = morton3d_invert(idx).to(torch.float32) / (G - 1) * 2 - 1  # :1193-1194
+        half = synthetic.BOUND / G
+        coords = coords * (synthetic.BOUND - half)
+        coords = coords + (torch.rand(coords.shape, device=dev, generator=self.noise_gen) * 2 - 1) * half  # :1199-1206
+        dens = []
+        for part in coords.split(self.total_samples):
+            enc = encoders.hashgrid_forward(self.levels, part.contiguous(), synthetic.BOUND, self.table)
+            x = torch.relu(enc @ self.nerf.density_w0) @ self.nerf.density_w1
+            dens.append(torch.exp(x[:, 0]))
+        dens = torch.cat(dens)
+        grid.scatter_reduce_(0, idx.to(torch.int64), dens, reduce="amax")  # atomic max
+        thr = torch.minimum(torch.tensor(synthetic.DENSITY_THRESHOLD, device=dev), grid.mean())  # :1229-1230
+        occ_mask, occupancy = packbits(thr, grid)
+        if commit:  # in place: a captured CUDA graph keeps reading the same buffers
+            self.occ_mask.copy_(occ_mask)
+            self.occupancy.copy_(occupancy)
+        return occ_mask, occupancy

@@ -519,10 +519,11 @@ void orc_hashgrid_backward(uint32_t n, uint32_t dim, uint32_t L, uint32_t F, con
                            double *d_table) {
     uint32_t nc = 1u << dim;
     memset(d_table, 0, (size_t)offsets[L] * F * sizeof(double));
-    /* parallel over levels: rows of different levels are disjoint except for the mod-T spill
-     * (Q1) of dense levels into their successor, so stay serial whenever wrap_T is in use */
+    /* parallel over points with atomic adds (rows are shared between points, and dense levels
+     * spill into their successor's rows under wrap_T, Q1) */
     for (uint32_t l = 0; l < L; ++l) {
         uint32_t wrap = wrap_T ? wrap_T : (offsets[l + 1] - offsets[l]);
+#pragma omp parallel for schedule(static)
         for (uint32_t p = 0; p < n; ++p) {
             float fr[3];
             uint32_t base[3];
@@ -544,8 +545,11 @@ void orc_hashgrid_backward(uint32_t n, uint32_t dim, uint32_t L, uint32_t F, con
                     w *= wk;
                 }
                 uint32_t row = hg_index(dim, v, res[l], hashed[l], wrap, offsets[l]);
-                for (uint32_t f = 0; f < F; ++f)
-                    d_table[(size_t)row * F + f] += (double)w * (double)d_enc[(size_t)p * L * F + l * F + f];
+                for (uint32_t f = 0; f < F; ++f) {
+                    double upd = (double)w * (double)d_enc[(size_t)p * L * F + l * F + f];
+#pragma omp atomic
+                    d_table[(size_t)row * F + f] += upd;
+                }
             }
         }
     }

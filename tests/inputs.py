@@ -7,7 +7,7 @@ from jaxngp_b200 import synthetic as S
 def march_case(name):
     """Returns (static kwargs, array kwargs) for march_rays."""
     if name == "scene":  # NeRF-synthetic-shaped, nothing overflows
-        r = S.training_rays(4096, seed=1000000007)
+        r = S.training_rays(2048, seed=1000000007)
         st = dict(total_samples=1 << 19, diagonal_n_steps=1024, K=1, G=128, bound=1.0, stepsize_portion=0.0)
         bits = S.occupancy_bitfield()
     elif name == "overflow":  # the budget fills after a few dozen rays
@@ -26,6 +26,14 @@ def march_case(name):
         bits = rng.integers(0, 256, size=3 * 32 ** 3 // 8, dtype=np.uint8) & rng.integers(0, 256, size=3 * 32 ** 3 // 8, dtype=np.uint8)
     elif name == "dense":  # all-ones bitfield (state at step 0, utils/types.py:123-126): per-ray cap 1024*bound bites
         r = S.training_rays(512, seed=3)
+        # a few rays along the cube diagonal: 2*sqrt(3)/ds = 1024 steps, so the per-ray cap bites
+        diag = np.float32(1 / np.sqrt(3))
+        for k, sgn in enumerate(((1, 1, 1), (-1, 1, 1), (1, -1, -1), (-1, -1, 1))):
+            sg = np.asarray(sgn, np.float32)
+            r["rays_d"][k] = sg * diag
+            r["rays_o"][k] = -sg * np.float32(1.3)
+            r["noises"][k] = np.float32(0.01 * k)
+        r["t_starts"], r["t_ends"] = S.near_far(r["rays_o"], r["rays_d"])
         st = dict(total_samples=1 << 19, diagonal_n_steps=1024, K=1, G=128, bound=1.0, stepsize_portion=0.0)
         bits = np.full(128 ** 3 // 8, 0xFF, np.uint8)
     elif name == "miss":  # rays that never enter the box, and an empty grid

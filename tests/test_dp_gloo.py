@@ -1,0 +1,53 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: flat-gradient all-reduce, density-grid
+max-reduce, disjoint per-rank ray streams, and tile-sharded image gather."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from jaxngp_b200 import dp
+    import bench
+    flat = torch.full((1000,), float(rank + 1))
+    dp.allreduce_flat_gradients(flat)
+    grid = torch.arange(16, dtype=torch.float32) * (1 if rank == 0 else -1) + rank
+    dp.allreduce_density_grid(grid)
+    H, Wd = 100, 7
+    rows = dp.tile_rows(H, rank, world, tile=8)
+    local = (rows[:, None] * Wd + torch.arange(Wd)[None]).to(torch.float32)[..., None]
+    img = dp.gather_image(rows, local, H)
+    perms = bench.host_perms(2, rank)
+    q.put((rank, flat.sum().item(), grid.tolist(), img[..., 0].tolist(), rows.tolist(), perms[:, :64].tolist()))
+    dist.destroy_process_group()
+
+
+def test_dp_host_logic_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, s0, g0, img0, rows0, p0), (r1, s1, g1, img1, rows1, p1) = res
+    assert s0 == s1 == 3000.0                      # SUM over ranks, identical on both
+    assert g0 == g1 == [max(i, -i + 1) for i in range(16)]
+    assert sorted(rows0 + rows1) == list(range(100)) and not set(rows0) & set(rows1)
+    expect = (np.arange(100)[:, None] * 7 + np.arange(7)[None]).tolist()
+    assert img0 == expect and img1 == expect      # every rank ends with the whole image
+    assert p0 != p1                                # disjoint ray streams per rank
