@@ -53,6 +53,10 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.window = [None, None]
+
+    def mark(self, which):
+        self.window[which] = time.time()
 
     def start(self):
         try:
@@ -65,21 +69,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        rows = [r for r in self.rows if len(r) >= 7 and r[0].isdigit()]
+        allrows = [r for r in self.rows if len(r) >= 8 and r[1].isdigit()]
+        t0, t1 = self.window
+        rows = [r[1:] for r in allrows if t0 is not None and t1 is not None and t0 <= r[0] <= t1 + 0.1]
+        in_window = len(rows)
+        if not rows:  # timed region shorter than the sampling period: take the samples nearest to it
+            rows = [r[1:] for r in sorted(allrows, key=lambda r: abs(r[0] - (t1 or 0)))[:3]]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
         return {"sm_mhz": float(np.median([float(r[0]) for r in rows])), "sm_max_mhz": float(rows[0][1]),
                 "power_w": float(np.median([float(r[2]) for r in rows if r[2].replace(".", "").isdigit()] or [0])),
-                "samples": len(rows), "reasons": reasons}
+                "samples": len(rows), "samples_inside_timed_region": in_window, "reasons": reasons}
 
 
 def host_perms(n_steps, rank, seed=1000000007):
@@ -103,7 +112,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 3)
-    tr = Trainer(device=dev, n_rays=N_RAYS, total_samples=TOTAL_SAMPLES, rank=rank, world_size=world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # started early: nvidia-smi needs a moment before its first sample
+    tr = Trainer(device=dev, n_rays=N_RAYS, total_samples=TOTAL_SAMPLES, rank=rank, world_size=world,
+                 use_graph=not args.no_graph)
     tr.occupancy.copy_(tr.scene.bitfield_gt)  # converged occupancy of the analytic scene (see DESIGN.md "bench state")
     perms_host = torch.from_numpy(host_perms(W + K, rank)).pin_memory()
     perms_dev = perms_host.to(dev)
@@ -142,11 +155,19 @@ def run_ours(args):
     for k in range(W):  # warm-up (captures the step's CUDA graph)
         tr.train_step(perms_dev[k])
     tr.update_ogrid(update_all=False, commit=False)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    if args.profile:  # ncu --profile-from-start off: only these steps are captured
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for k in range(args.profile):
+            tr.train_step(perms_dev[W + k])
+        tr.update_ogrid(update_all=False, commit=False)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    sampler.mark(0)
     ms, samples, _, _ = timed(K, W, e2e=False)
     ms_e2e, samples_e2e, loss, _ = timed(K, W, e2e=True)
+    sampler.mark(1)
     clocks = sampler.stop() if rank == 0 else None
 
     # launches per step: count the kernels of one eager (un-graphed) step with the torch profiler's CUPTI view
@@ -172,7 +193,7 @@ def run_ours(args):
                    "n_rays_per_gpu": N_RAYS, "total_samples_per_gpu": TOTAL_SAMPLES, "ogrid_update_every": OGRID_EVERY,
                    "parallelism": f"ray-sharded dp{world}, one NCCL all-reduce of the flat gradient per step",
                    "l2": "per-step working set (table+grads+moments+activations ~0.5 GB) exceeds the 126 MB L2; no flush",
-                   "cuda_graph": True},
+                   "cuda_graph": not args.no_graph},
         "samples_per_step": samples / K,
         "e2e": {"value": samples_e2e / (ms_e2e / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": N_RAYS * 4, "d2h_bytes_per_step": 4, "loss": loss},
@@ -435,6 +456,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu launch lists)")
+    ap.add_argument("--profile", type=int, default=0, help="run N steps between cudaProfilerStart/Stop and exit")
     ap.add_argument("--with-ref-gpu", action="store_true", help="also time the reference's CUDA ops arm in a subprocess")
     args = ap.parse_args()
     if args.impl == "reference":

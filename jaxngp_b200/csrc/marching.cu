@@ -9,10 +9,10 @@
 // see DESIGN.md section 4 -- so sample counts, grid indices, positions and z values are bit-equal
 // to the reference kernels'.
 //
-// Structure (training march): one kernel.  A CTA takes a tile of 128 consecutive rays (dynamic
-// ticket), counts each ray's occupied steps, scans the counts and obtains the tile's exclusive
-// prefix by decoupled look-back, so sample ranges are handed out in ray order without a second
-// launch or a host round trip.  The first tile whose inclusive prefix reaches `total_samples`
+// Structure (training march): one persistent kernel, one warp per ray.  A CTA takes a tile of 8
+// consecutive rays (dynamic ticket), counts each ray's occupied steps, and obtains the tile's
+// exclusive prefix by decoupled look-back, so sample ranges are handed out in ray order without a
+// second launch or a host round trip.  The first tile whose inclusive prefix reaches `total_samples`
 // publishes a cut; tiles behind the cut stop marching (they poll the cut flag) -- this is the
 // reference's "budget already full" early-out (marching.cu:135) made deterministic.  Rays that got a
 // range then re-march and write their samples; a tail kernel zero-fills the unused sample slots
@@ -123,7 +123,17 @@ __device__ __forceinline__ Step march_step(const Grid &g, const Ray &r, float t)
 }
 
 // ---------------------------------------------------------------- training march
-constexpr int kTile = 128;  // rays per CTA
+//
+// One WARP per ray.  The parameter sequence a ray can visit is fixed by its start:
+// t_{k+1} = t_k + ds(t_k) (the same rounded additions whether the reference takes a sample step or
+// walks to the next voxel, marching.cu:178-189), and the reference visits a subsequence of it:
+// after an occupied point the next one, after an empty point the first t_j >= next_t.  So a warp
+// evaluates 32 consecutive chain points at once (32 independent bitfield lookups in flight instead
+// of a 600-deep dependent chain per thread), then replays the visit rule over the 32 results with
+// ballots -- runs of occupied points are consumed in one go, skips with one shuffle + one ballot.
+// Same visited set, same samples, bit for bit; ~30x shorter critical path per ray.
+constexpr int kRaysPerTile = 8;   // warps per CTA, one ray each
+constexpr int kMarchBlock = kRaysPerTile * 32;
 constexpr uint64_t kFlagAgg = 1ull << 62, kFlagIncl = 2ull << 62, kValueMask = (1ull << 62) - 1;
 
 struct MarchScratch {
@@ -137,7 +147,145 @@ __device__ __forceinline__ bool behind_cut(const MarchScratch *ws, uint32_t tile
     return v != 0 && (0xFFFFFFFFu - v) < tile;
 }
 
-__global__ void __launch_bounds__(kTile) march_rays_kernel(
+struct EvalPoint {
+    float px, py, pz, ds, next_t;
+    bool occupied;
+};
+
+// occupancy at chain point t, and (if empty) the parameter of the next voxel boundary
+__device__ __forceinline__ EvalPoint eval_point(const Grid &g, const Ray &r, float t) {
+    EvalPoint s;
+    s.px = __fmaf_rn(t, r.dx, r.ox);
+    s.py = __fmaf_rn(t, r.dy, r.oy);
+    s.pz = __fmaf_rn(t, r.dz, r.oz);
+    s.ds = calc_ds(g, t);
+    uint32_t cascade = 0;
+    if (g.K > 1) {
+        float linf = fmaxf(fabsf(s.px), fmaxf(fabsf(s.py), fabsf(s.pz)));
+        cascade = max(mip_of(linf, g.K), mip_of(__fmul_rn(s.ds, g.Gf), g.K));
+    }
+    const float mip_bound = fminf((float)(1u << cascade), g.bound);
+    // pos / mip_bound: when mip_bound is a power of two the quotient is an exact scaling, so the
+    // multiplication by its (exact) reciprocal rounds identically to the IEEE division
+    const uint32_t mb_bits = __float_as_uint(mip_bound);
+    float qx, qy, qz;
+    if ((mb_bits & 0x007FFFFFu) == 0u) {
+        const float inv = __uint_as_float(0x7F000000u - mb_bits);  // 2^-e for 2^e
+        qx = __fmul_rn(s.px, inv);
+        qy = __fmul_rn(s.py, inv);
+        qz = __fmul_rn(s.pz, inv);
+    } else {
+        qx = __fdiv_rn(s.px, mip_bound);
+        qy = __fdiv_rn(s.py, mip_bound);
+        qz = __fdiv_rn(s.pz, mip_bound);
+    }
+    const float gx = __fmul_rn(__fmul_rn(__fadd_rn(qx, 1.f), .5f), g.Gf);
+    const float gy = __fmul_rn(__fmul_rn(__fadd_rn(qy, 1.f), .5f), g.Gf);
+    const float gz = __fmul_rn(__fmul_rn(__fadd_rn(qz, 1.f), .5f), g.Gf);
+    const int gmax = (int)g.G - 1;
+    const uint32_t ux = (uint32_t)min(max(__float2int_rd(gx), 0), gmax);
+    const uint32_t uy = (uint32_t)min(max(__float2int_rd(gy), 0), gmax);
+    const uint32_t uz = (uint32_t)min(max(__float2int_rd(gz), 0), gmax);
+    const uint32_t idx = cascade * g.G3 + morton3d_encode(ux, uy, uz);
+    s.occupied = (__ldg(g.bits + (idx >> 5)) >> (idx & 31u)) & 1u;
+    s.next_t = 0.f;
+    if (!s.occupied) {
+        const float ax = axis_delta(gx, r.dx, r.ix, s.px, g.inv_G, mip_bound);
+        const float ay = axis_delta(gy, r.dy, r.iy, s.py, g.inv_G, mip_bound);
+        const float az = axis_delta(gz, r.dz, r.iz, s.pz, g.inv_G, mip_bound);
+        s.next_t = __fadd_rn(t, fmaxf(0.f, fminf(ax, fminf(ay, az))));
+    }
+    return s;
+}
+
+struct SampleSink {
+    uint32_t *idcs;
+    float *xyzs, *dirs, *dss, *z_vals;
+};
+
+// Marches one ray with the whole warp.  `limit` = most samples this ray may emit (count pass: the
+// per-ray cap diagonal_n_steps*bound, marching.cu:165; write pass: the count found in pass 1).
+// Returns the number of samples; in the count pass returns 0xFFFFFFFF if the tile fell behind the cut.
+template <bool kWrite>
+__device__ __forceinline__ uint32_t march_ray_warp(const Grid &g, const Ray &r, float t0, float t_end, uint32_t limit,
+                                                   uint32_t ray_index, const SampleSink &out,
+                                                   const MarchScratch *ws, uint32_t tile) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const bool const_ds = g.portion == 0.f;  // ds(t) == ds_lo clamped: no dependence on t
+    const float ds0 = calc_ds(g, 0.f);
+    uint32_t n = 0;
+    float t_base = t0;
+    bool pending = false;
+    float pend_t = 0.f;
+    while (n < limit) {
+        // chain: lane j holds t_base advanced j times
+        float t = t_base;
+        if (const_ds) {
+#pragma unroll
+            for (int i = 0; i < 31; ++i) {
+                const float tn = __fadd_rn(t, ds0);
+                if (i < (int)lane) t = tn;
+            }
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < 31; ++i) {
+                const float tn = __fadd_rn(t, calc_ds(g, t));
+                if (i < (int)lane) t = tn;
+            }
+        }
+        const float t_last = __shfl_sync(0xffffffffu, t, 31);
+        const float t_next_base = __fadd_rn(t_last, calc_ds(g, t_last));
+        const bool in = t < t_end;
+        const uint32_t V = __ballot_sync(0xffffffffu, in);
+        if (V == 0u) break;
+        uint32_t v = 0;
+        bool skip_eval = false;
+        if (pending) {  // still walking towards a voxel boundary found in an earlier chunk
+            const uint32_t m = __ballot_sync(0xffffffffu, t >= pend_t);
+            if (m == 0u) { v = 32; skip_eval = true; }
+            else { v = __ffs(m) - 1; pending = false; }
+        }
+        if (!skip_eval) {
+            const EvalPoint s = eval_point(g, r, t);
+            const uint32_t O = __ballot_sync(0xffffffffu, s.occupied && in);
+            bool done = false;
+            while (v < 32u) {
+                if (!((V >> v) & 1u) || n >= limit) { done = true; break; }
+                if ((O >> v) & 1u) {
+                    const uint32_t rest = O >> v;  // consecutive occupied points starting at v
+                    uint32_t run = (rest == (0xFFFFFFFFu >> v)) ? 32u - v : (uint32_t)__ffs(~rest) - 1u;
+                    run = min(run, limit - n);
+                    if (kWrite && lane >= v && lane < v + run) {
+                        const uint32_t w = n + (lane - v);
+                        out.idcs[w] = ray_index;
+                        out.xyzs[w * 3 + 0] = s.px;
+                        out.xyzs[w * 3 + 1] = s.py;
+                        out.xyzs[w * 3 + 2] = s.pz;
+                        out.dirs[w * 3 + 0] = r.dx;
+                        out.dirs[w * 3 + 1] = r.dy;
+                        out.dirs[w * 3 + 2] = r.dz;
+                        out.dss[w] = s.ds;
+                        out.z_vals[w] = t;
+                    }
+                    n += run;
+                    v += run;
+                } else {
+                    const float nt = __shfl_sync(0xffffffffu, s.next_t, v);
+                    const uint32_t above = (v == 31u) ? 0u : (0xFFFFFFFFu << (v + 1u));
+                    const uint32_t m = __ballot_sync(0xffffffffu, t >= nt) & above;
+                    if (m == 0u) { pending = true; pend_t = nt; v = 32; }
+                    else v = __ffs(m) - 1;
+                }
+            }
+            if (done) break;
+        }
+        t_base = t_next_base;
+        if (!kWrite && behind_cut(ws, tile)) return 0xFFFFFFFFu;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(kMarchBlock) march_rays_kernel(
     NgpMarchingDescriptor p, MarchScratch *__restrict__ ws, uint32_t num_tiles,
     const float *__restrict__ rays_o, const float *__restrict__ rays_d, const float *__restrict__ t_starts,
     const float *__restrict__ t_ends, const float *__restrict__ noises, const uint8_t *__restrict__ bitfield,
@@ -146,155 +294,128 @@ __global__ void __launch_bounds__(kTile) march_rays_kernel(
     uint32_t *__restrict__ rays_sample_startidx, uint32_t *__restrict__ idcs, float *__restrict__ xyzs,
     float *__restrict__ dirs, float *__restrict__ dss, float *__restrict__ z_vals) {
     __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_warp_sum[kTile / 32];
+    __shared__ uint32_t s_count[kRaysPerTile];
     __shared__ unsigned long long s_prefix;
     __shared__ int s_abandon;
 
-    if (threadIdx.x == 0) {
-        s_tile = atomicAdd(&ws->ticket, 1u);
-        s_abandon = 0;
-    }
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint32_t i = tile * kTile + threadIdx.x;
-    const bool in_range = i < p.n_rays;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const Grid g = make_grid(p.diagonal_n_steps, p.K, p.G, p.bound, p.stepsize_portion, bitfield);
+    // per-ray cap: `(float)n < diagonal_n_steps * bound` (marching.cu:165) <=> n < ceil(that product)
+    const float max_steps_f = __fmul_rn((float)p.diagonal_n_steps, p.bound);
+    const uint32_t cap = max_steps_f > 0.f ? (uint32_t)fminf(ceilf(max_steps_f), 4294967040.f) : 0u;
 
-    // ---- pass 1: count occupied steps
-    Ray ray = {};
-    float t_start = 0.f, t_end = 0.f, t0 = 0.f;
-    uint32_t n = 0;
-    bool hit_box = false, abandoned = false;
-    if (in_range) {
-        t_start = __ldg(t_starts + i);
-        t_end = __ldg(t_ends + i);
-        hit_box = t_end > t_start;  // marching.cu:151
-    }
-    if (hit_box) {
-        ray = load_ray(rays_o, rays_d, i);
-        t0 = __fmaf_rn(calc_ds(g, t_start), __ldg(noises + i), t_start);  // marching.cu:164
-        const float max_steps = __fmul_rn((float)p.diagonal_n_steps, p.bound);  // marching.cu:165
-        float t = t0;
-        uint32_t it = 0;
-        while ((float)n < max_steps && t < t_end) {
-            Step s = march_step<true>(g, ray, t);
-            n += s.occupied;
-            t = s.t_next;
-            if ((++it & 15u) == 0 && behind_cut(ws, tile)) {
-                abandoned = true;
-                break;
+    for (;;) {  // persistent: tiles are taken in ticket order, so earlier rays are never starved by later ones
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_tile = atomicAdd(&ws->ticket, 1u);
+            s_abandon = 0;
+        }
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= num_tiles) return;
+        const uint32_t i = tile * kRaysPerTile + warp;
+        const bool in_range = i < p.n_rays;
+
+        // ---- pass 1: count occupied steps (warp-cooperative)
+        Ray ray = {};
+        float t_end = 0.f, t0 = 0.f;
+        uint32_t n = 0;
+        bool hit_box = false;
+        if (in_range) {
+            const float t_start = __ldg(t_starts + i);
+            t_end = __ldg(t_ends + i);
+            hit_box = t_end > t_start;  // marching.cu:151
+            if (hit_box) {
+                ray = load_ray(rays_o, rays_d, i);
+                t0 = __fmaf_rn(calc_ds(g, t_start), __ldg(noises + i), t_start);  // marching.cu:164
             }
         }
-    }
-    if (abandoned) s_abandon = 1;
-
-    // ---- block scan of the counts
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t incl = n;
+        bool abandoned = behind_cut(ws, tile);
+        if (hit_box && !abandoned) {
+            n = march_ray_warp<false>(g, ray, t0, t_end, cap, i, SampleSink{}, ws, tile);
+            if (n == 0xFFFFFFFFu) { abandoned = true; n = 0; }
+        }
+        if (lane == 0) {
+            s_count[warp] = n;
+            if (abandoned) s_abandon = 1;
+        }
+        __syncthreads();
+        uint32_t excl_in_tile = 0, tile_total = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_warp_sum[warp] = incl;
-    __syncthreads();
-    uint32_t warp_base = 0, tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < kTile / 32; ++w) {
-        uint32_t v = s_warp_sum[w];
-        if (w < (int)warp) warp_base += v;
-        tile_total += v;
-    }
-    const uint32_t excl_in_tile = warp_base + incl - n;
+        for (int w = 0; w < kRaysPerTile; ++w) {
+            const uint32_t c = s_count[w];
+            if (w < (int)warp) excl_in_tile += c;
+            tile_total += c;
+        }
 
-    // ---- decoupled look-back for the tile's exclusive prefix (thread 0)
-    if (threadIdx.x == 0) {
-        volatile unsigned long long *status = ws->status;
-        unsigned long long prefix = 0;
-        bool give_up = s_abandon != 0;
-        if (!give_up) {
-            if (tile == 0) {
-                status[0] = kFlagIncl | tile_total;
-            } else {
-                status[tile] = kFlagAgg | tile_total;
-                __threadfence();
-                for (int64_t j = (int64_t)tile - 1; j >= 0; --j) {
-                    unsigned long long st;
-                    while ((st = status[j]) == 0) {
-                        if (behind_cut(ws, tile)) { give_up = true; break; }
+        // ---- decoupled look-back for the tile's exclusive prefix (thread 0)
+        if (threadIdx.x == 0) {
+            volatile unsigned long long *status = ws->status;
+            unsigned long long prefix = 0;
+            bool give_up = s_abandon != 0;
+            if (!give_up) {
+                if (tile == 0) {
+                    status[0] = kFlagIncl | tile_total;
+                } else {
+                    status[tile] = kFlagAgg | tile_total;
+                    __threadfence();
+                    for (int64_t j = (int64_t)tile - 1; j >= 0; --j) {
+                        unsigned long long st;
+                        while ((st = status[j]) == 0) {
+                            if (behind_cut(ws, tile)) { give_up = true; break; }
+                        }
+                        if (give_up) break;
+                        prefix += st & kValueMask;
+                        if (st & kFlagIncl) break;
                     }
-                    if (give_up) break;
-                    prefix += st & kValueMask;
-                    if (st & kFlagIncl) break;
+                    if (!give_up) status[tile] = kFlagIncl | (prefix + tile_total);
                 }
                 if (!give_up) {
-                    status[tile] = kFlagIncl | (prefix + tile_total);
+                    __threadfence();
+                    if (prefix + tile_total >= p.total_samples) atomicMax(&ws->cut_inv, 0xFFFFFFFFu - tile);
+                    if (tile == num_tiles - 1 && prefix + tile_total < p.total_samples) {
+                        *next_sample_write_location = (uint32_t)(prefix + tile_total);  // no cut anywhere
+                        *number_of_exceeded_samples = 0u;
+                    }
                 }
             }
-            if (!give_up) {
-                __threadfence();
-                if (prefix + tile_total >= p.total_samples) atomicMax(&ws->cut_inv, 0xFFFFFFFFu - tile);
-                if (tile == num_tiles - 1 && prefix + tile_total < p.total_samples) {
-                    // no cut anywhere: the counters are the plain totals
-                    *next_sample_write_location = (uint32_t)(prefix + tile_total);
-                    *number_of_exceeded_samples = 0u;
+            if (give_up) s_abandon = 1;
+            s_prefix = prefix;
+        }
+        __syncthreads();
+        if (!in_range) continue;
+
+        const bool tile_abandoned = s_abandon != 0;
+        const unsigned long long start64 = s_prefix + excl_in_tile;
+        bool valid = false;
+        uint32_t n_out = 0, start_out = 0;
+        if (!tile_abandoned && start64 < p.total_samples && hit_box) {  // else: marching.cu:135 / :151
+            const uint32_t start = (uint32_t)start64;
+            if (n == 0) {
+                valid = true;  // marching.cu:196-199
+            } else {
+                if (start64 + n >= p.total_samples && lane == 0) {  // the ray at which the budget fills
+                    *next_sample_write_location = start + n;
+                    *number_of_exceeded_samples = (start64 + n > p.total_samples) ? n : 0u;
+                }
+                if (start64 + n <= p.total_samples) {
+                    valid = true;
+                    n_out = n;
+                    start_out = start;
                 }
             }
         }
-        if (give_up) s_abandon = 1;
-        s_prefix = prefix;
-    }
-    __syncthreads();
-    if (!in_range) return;
-
-    const bool tile_abandoned = s_abandon != 0;
-    const unsigned long long start64 = s_prefix + excl_in_tile;
-    bool valid = false;
-    uint32_t n_out = 0, start_out = 0;
-    if (!tile_abandoned && start64 < p.total_samples && hit_box) {  // else: marching.cu:135 / :151
-        const uint32_t start = (uint32_t)start64;
-        if (n == 0) {
-            valid = true;  // marching.cu:196-199
-        } else {
-            if (start64 + n >= p.total_samples) {  // this is the ray at which the budget fills
-                *next_sample_write_location = start + n;
-                *number_of_exceeded_samples = (start64 + n > p.total_samples) ? n : 0u;
-            }
-            if (start64 + n <= p.total_samples) {
-                valid = true;
-                n_out = n;
-                start_out = start;
-            }
+        if (lane == 0) {
+            ray_is_valid[i] = valid ? 1 : 0;
+            rays_n_samples[i] = n_out;
+            rays_sample_startidx[i] = start_out;
         }
-    }
-    ray_is_valid[i] = valid ? 1 : 0;
-    rays_n_samples[i] = n_out;
-    rays_sample_startidx[i] = start_out;
-    if (n_out == 0) return;
-
-    // ---- pass 2: march again and write (marching.cu:224-267)
-    uint32_t *__restrict__ o_idcs = idcs + start_out;
-    float *__restrict__ o_xyzs = xyzs + (size_t)start_out * 3;
-    float *__restrict__ o_dirs = dirs + (size_t)start_out * 3;
-    float *__restrict__ o_dss = dss + start_out;
-    float *__restrict__ o_z = z_vals + start_out;
-    uint32_t steps = 0;
-    float t = t0;
-    while (steps < n_out && t < t_end) {
-        Step s = march_step<true>(g, ray, t);
-        if (s.occupied) {
-            o_idcs[steps] = i;
-            o_xyzs[steps * 3 + 0] = s.px;
-            o_xyzs[steps * 3 + 1] = s.py;
-            o_xyzs[steps * 3 + 2] = s.pz;
-            o_dirs[steps * 3 + 0] = ray.dx;
-            o_dirs[steps * 3 + 1] = ray.dy;
-            o_dirs[steps * 3 + 2] = ray.dz;
-            o_dss[steps] = s.ds;
-            o_z[steps] = t;
-            ++steps;
+        // ---- pass 2: march again and write (marching.cu:224-267)
+        if (n_out) {
+            SampleSink sink{idcs + start_out, xyzs + (size_t)start_out * 3, dirs + (size_t)start_out * 3,
+                            dss + start_out, z_vals + start_out};
+            march_ray_warp<true>(g, ray, t0, t_end, n_out, i, sink, ws, tile);
         }
-        t = s.t_next;
     }
 }
 
@@ -452,7 +573,7 @@ void ngp_march_rays(cudaStream_t stream, void **buffers, const char *opaque, siz
     float *dss = b.next<float>();
     float *z_vals = b.next<float>();
 
-    const uint32_t num_tiles = div_up(desc->n_rays, kTile);
+    const uint32_t num_tiles = div_up(desc->n_rays, kRaysPerTile);
     if (num_tiles == 0) {
         NGP_CUDA_OK(cudaMemsetAsync(next_loc, 0, sizeof(uint32_t), stream), "march_rays");
         NGP_CUDA_OK(cudaMemsetAsync(exceeded, 0, sizeof(uint32_t), stream), "march_rays");
@@ -461,7 +582,9 @@ void ngp_march_rays(cudaStream_t stream, void **buffers, const char *opaque, siz
         auto *ws = static_cast<MarchScratch *>(workspace(stream, ws_bytes));
         if (!ws) return;
         NGP_CUDA_OK(cudaMemsetAsync(ws, 0, ws_bytes, stream), "march_rays");
-        march_rays_kernel<<<num_tiles, kTile, 0, stream>>>(*desc, ws, num_tiles, rays_o, rays_d, t_starts, t_ends,
+        // persistent grid: 4 CTAs of 8 warps per SM keep ~4.7k rays in flight, in ray order
+        const unsigned grid = min(num_tiles, 148u * 4u);
+        march_rays_kernel<<<grid, kMarchBlock, 0, stream>>>(*desc, ws, num_tiles, rays_o, rays_d, t_starts, t_ends,
                                                            noises, bitfield, next_loc, exceeded, valid, rays_n,
                                                            rays_start, idcs, xyzs, dirs, dss, z_vals);
         if (!check_launch("march_rays")) return;
