@@ -450,6 +450,9 @@ def run_subprocess_json(extra):
 
 
 def main():
+    if os.environ.get("NGP_FAULT_DUMP"):  # debugging aid: print every thread's stack and exit if we are still running
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["NGP_FAULT_DUMP"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=48)

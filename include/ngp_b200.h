@@ -147,6 +147,20 @@ void ngp_hashgrid_a1_backward(cudaStream_t, void **, const char *, size_t);
  * in : threshold f32[1], density f32[N]                  out: occupied_mask bool[N], bitfield u8[N/8] */
 void ngp_packbits_scalar(cudaStream_t, void **, const char *, size_t);
 
+/* Density-grid update, utils/types.py:1149-1239 (NeRFState.update_ogrid_density / threshold_ogrid).
+ * sample_positions: in idx u32[M] (Morton cell indices inside the cascade), uniforms f32[M,3] in [0,1)
+ *                   out coords f32[M,3]                                              (:1193-1206)
+ * decay_max       : in density f32[N], idx u32[M], new_density f32[M]; out density f32[N] (may alias the
+ *                   input): alive cells * decay, then max with the new values        (:1162-1164,1219-1221)
+ * threshold       : in density f32[n_cells] (alive cells of the cascades the mean runs over)
+ *                   out thr f32[1] = min(thr_max, mean)                              (:1229-1230,143-144) */
+typedef struct { uint32_t n_points, G; float mip_bound; } NgpOgridSampleDescriptor;
+typedef struct { uint32_t n_cells, n_updates; float decay; } NgpOgridUpdateDescriptor;
+typedef struct { uint32_t n_cells; float thr_max; } NgpOgridThresholdDescriptor;
+void ngp_ogrid_sample_positions(cudaStream_t, void **, const char *, size_t);
+void ngp_ogrid_decay_max(cudaStream_t, void **, const char *, size_t);
+void ngp_ogrid_threshold(cudaStream_t, void **, const char *, size_t);
+
 /* Adam step of app/nerf/_utils.py:19-77 over a flat f32 buffer [hash table | MLP weights]; elements
  * at index >= decay_begin also receive the reference's (additive) decayed-weights term.
  * in : step u32[1] (device-resident count of completed steps), params f32[n] (updated in place),

@@ -16,8 +16,8 @@
 // The whole table (48.8 MB at T=2^19) is L2-resident on B200 (126 MB), so the kernel is bound by
 // L2 sector throughput, not HBM; see DESIGN.md section 5 for the roofline arithmetic.
 //
-// Backward: same mapping, `red.global.add.v2.f32` (one 8-byte L2 reduction per corner instead of
-// two scalar atomics), after a zero-fill of the gradient table.
+// Backward: level-major warps with run aggregation (see the kernel), `red.global.add.v2.f32` (one
+// 8-byte L2 reduction per corner instead of two scalar atomics), after a zero-fill of the table grad.
 #include "common.cuh"
 
 namespace ngp {
@@ -154,6 +154,13 @@ __global__ void __launch_bounds__(kBlock) hashgrid_a1_forward_kernel(const __gri
     else *reinterpret_cast<float4 *>(out) = make_float4(acc[0], acc[1], acc[F - 2], acc[F - 1]);
 }
 
+// Backward: level-major warps.  A CTA owns 256 consecutive points; warp w walks levels w, w+8 and its
+// lanes are 32 CONSECUTIVE points at ONE level.  Samples arrive ray by ray (march_rays emits each
+// ray's samples contiguously), so neighbouring lanes usually sit in the same grid cell on the coarse
+// and middle levels: runs of lanes with an identical cell are summed with a segmented shuffle
+// reduction and only the run's first lane issues the 8 reductions.  L2 reductions are issued per
+// active lane (~1.3 cycles each), so this removes ~55 % of them on ray-ordered samples; on
+// incoherent points the run detection costs three shuffles and a vote per level.
 template <int DIM, int F>
 __global__ void __launch_bounds__(kBlock) hashgrid_a1_backward_kernel(const __grid_constant__ NgpHashGridA1Descriptor d,
                                                                        const float *__restrict__ pos,
@@ -162,42 +169,93 @@ __global__ void __launch_bounds__(kBlock) hashgrid_a1_backward_kernel(const __gr
     __shared__ LevelMeta s_meta[NGP_HG_MAX_LEVELS];
     if (threadIdx.x < d.L) s_meta[threadIdx.x] = a1_level(d, threadIdx.x);
     __syncthreads();
-    const uint64_t tid = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
-    const uint32_t point = (uint32_t)(tid / d.L), level = (uint32_t)(tid % d.L);
-    if (point >= d.n_points) return;
-    const LevelMeta m = s_meta[level];
-
-    float g[F];
-    const float *gin = d_enc + ((size_t)point * d.L + level) * F;
-    if (F == 2) {
-        float2 v = __ldg(reinterpret_cast<const float2 *>(gin));
-        g[0] = v.x; g[1] = v.y;
-    } else {
-        float4 v = __ldg(reinterpret_cast<const float4 *>(gin));
-        g[0] = v.x; g[1] = v.y; g[F - 2] = v.z; g[F - 1] = v.w;
-    }
-    bool any = false;
-#pragma unroll
-    for (int f = 0; f < F; ++f) any |= (g[f] != 0.f);
-    if (!any) return;  // padded / masked samples carry exact zeros
-
-    uint32_t base[DIM];
-    float fr[DIM];
-    a1_cell<DIM>(pos, point, d.bound, m.scale, base, fr);
     constexpr int NC = 1 << DIM;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        uint32_t v[DIM];
-        float wc = 1.f;
+    constexpr int kWarps = kBlock / 32;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tile_begin = blockIdx.x * kBlock;
+
+    for (uint32_t sub = 0; sub < kWarps; ++sub) {
+        const uint32_t point = tile_begin + sub * 32u + lane;
+        const bool in_range = point < d.n_points;
+        float p01[DIM];
 #pragma unroll
         for (int k = 0; k < DIM; ++k) {
-            const uint32_t bit = (c >> (DIM - 1 - k)) & 1;
-            v[k] = base[k] + bit;
-            wc *= bit ? fr[k] : 1.f - fr[k];
+            const float x = in_range ? __ldg(pos + (size_t)point * DIM + k) : 0.f;
+            p01[k] = __fdiv_rn(__fadd_rn(x, d.bound), __fmul_rn(2.f, d.bound));  // encoders.py:87
         }
-        float *dst = d_table + (size_t)grid_row<DIM>(v, m) * F;
-        if (F == 2) red_add_v2(dst, wc * g[0], wc * g[1]);
-        else red_add_v4(dst, wc * g[0], wc * g[1], wc * g[F - 2], wc * g[F - 1]);
+        for (uint32_t level = warp; level < d.L; level += kWarps) {
+            const LevelMeta m = s_meta[level];
+            float g[F];
+#pragma unroll
+            for (int f = 0; f < F; ++f) g[f] = 0.f;
+            if (in_range) {
+                const float *gin = d_enc + ((size_t)point * d.L + level) * F;
+                if (F == 2) {
+                    const float2 v = __ldg(reinterpret_cast<const float2 *>(gin));
+                    g[0] = v.x; g[1] = v.y;
+                } else {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(gin));
+                    g[0] = v.x; g[1] = v.y; g[F - 2] = v.z; g[F - 1] = v.w;
+                }
+            }
+            bool active = false;  // padded / masked samples carry exact zeros: nothing to add
+#pragma unroll
+            for (int f = 0; f < F; ++f) active |= (g[f] != 0.f);
+
+            uint32_t base[DIM];
+            float fr[DIM];
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                const float ps = __fadd_rn(__fmul_rn(p01[k], m.scale), .5f);  // encoders.py:218
+                const float fl = floorf(ps);
+                base[k] = (uint32_t)(int)fl;
+                fr[k] = ps - fl;
+            }
+            // runs of consecutive active lanes in the same cell
+            bool same_as_prev = lane > 0;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) same_as_prev &= (__shfl_up_sync(0xffffffffu, base[k], 1) == base[k]);
+            const uint32_t A = __ballot_sync(0xffffffffu, active);
+            const bool prev_active = lane > 0 && ((A >> (lane - 1)) & 1u);
+            const bool head = active && !(same_as_prev && prev_active);
+            const uint32_t H = __ballot_sync(0xffffffffu, head);
+            const uint32_t above = (lane == 31u) ? 0u : (0xFFFFFFFFu << (lane + 1u));
+            const uint32_t stops = (H | ~A) & above;
+            const uint32_t seg_end = stops ? (uint32_t)__ffs(stops) - 1u : 32u;
+
+            float v[NC][F];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                float wc = active ? 1.f : 0.f;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) wc *= ((c >> (DIM - 1 - k)) & 1) ? fr[k] : 1.f - fr[k];
+#pragma unroll
+                for (int f = 0; f < F; ++f) v[c][f] = wc * g[f];
+            }
+#pragma unroll
+            for (uint32_t dist = 1; dist < 32; dist <<= 1) {
+                const bool take = active && lane + dist < seg_end;
+                if (!__any_sync(0xffffffffu, take)) break;  // no run in this warp is longer than `dist`
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+#pragma unroll
+                    for (int f = 0; f < F; ++f) {
+                        const float o = __shfl_down_sync(0xffffffffu, v[c][f], dist);
+                        if (take) v[c][f] += o;
+                    }
+            }
+            if (head) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    uint32_t vert[DIM];
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) vert[k] = base[k] + ((c >> (DIM - 1 - k)) & 1);
+                    float *dst = d_table + (size_t)grid_row<DIM>(vert, m) * F;
+                    if (F == 2) red_add_v2(dst, v[c][0], v[c][1]);
+                    else red_add_v4(dst, v[c][0], v[c][1], v[c][F - 2], v[c][F - 1]);
+                }
+            }
+        }
     }
 }
 
@@ -414,7 +472,7 @@ void ngp_hashgrid_a1_backward(cudaStream_t stream, void **buffers, const char *o
     NGP_CUDA_OK(cudaMemsetAsync(d_table, 0, (size_t)d->offsets[d->L] * d->F * sizeof(float), stream),
                 "hashgrid_a1_backward");
     if (d->n_points == 0) return;
-    const unsigned blocks = div_up((unsigned long long)d->n_points * d->L, kBlock);
+    const unsigned blocks = div_up(d->n_points, kBlock);  // one CTA per 256 points, all levels
     if (d->dim == 3 && d->F == 2) hashgrid_a1_backward_kernel<3, 2><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
     else if (d->dim == 3) hashgrid_a1_backward_kernel<3, 4><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
     else if (d->F == 2) hashgrid_a1_backward_kernel<2, 2><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);

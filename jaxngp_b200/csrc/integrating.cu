@@ -16,7 +16,7 @@ namespace {
 
 constexpr float kTThreshold = 1e-4f;  // integrating.cu:12
 constexpr int kBlock = 128;
-constexpr int kRaysPerWarp = 8;  // a warp owns 8 consecutive rays and walks the non-empty ones in turn
+constexpr int kRaysPerWarp = 32;  // a warp owns 32 consecutive rays: empty ones are finished lane-parallel, the rest walked in turn
 
 struct Chunk {
     float alpha, one_minus, Tb;  // this lane's sample: alpha, 1-alpha, transmittance before it
@@ -57,13 +57,20 @@ __global__ void __launch_bounds__(kBlock) integrate_rays_kernel(
     for (uint32_t grp = warp_global; grp < n_groups; grp += warps_total) {
         const uint32_t my_ray = grp * kRaysPerWarp + lane;
         uint32_t my_start = 0, my_n = 0;
-        if (lane < kRaysPerWarp && my_ray < n_rays) {
+        if (my_ray < n_rays) {
             my_start = __ldg(rays_sample_startidx + my_ray);
             my_n = __ldg(rays_n_samples + my_ray);
+            if (my_n == 0) {  // nothing to composite: T = 1, opacity 0, colour = background (integrating.cu:91-96)
+                final_opacities[my_ray] = 0.f;
+                final_rgbds[my_ray] = make_float4(__ldg(bgs + 3 * (size_t)my_ray + 0), __ldg(bgs + 3 * (size_t)my_ray + 1),
+                                                  __ldg(bgs + 3 * (size_t)my_ray + 2), 0.f);
+            }
         }
-        for (uint32_t q = 0; q < kRaysPerWarp; ++q) {
+        uint32_t todo = __ballot_sync(0xffffffffu, my_n != 0);
+        while (todo) {  // the warp walks the non-empty rays of its group one at a time
+            const uint32_t q = __ffs(todo) - 1;
+            todo &= todo - 1;
             const uint32_t ray = grp * kRaysPerWarp + q;
-            if (ray >= n_rays) break;
             const uint32_t start = __shfl_sync(0xffffffffu, my_start, q);
             const uint32_t n = __shfl_sync(0xffffffffu, my_n, q);
             float T = 1.f, r = 0.f, g = 0.f, b = 0.f, depth = 0.f;
@@ -133,18 +140,26 @@ __global__ void __launch_bounds__(kBlock) integrate_rays_backward_kernel(
     for (uint32_t grp = warp_global; grp < n_groups; grp += warps_total) {
         const uint32_t my_ray = grp * kRaysPerWarp + lane;
         uint32_t my_start = 0, my_n = 0;
-        if (lane < kRaysPerWarp && my_ray < n_rays) {
+        if (my_ray < n_rays) {
             my_start = __ldg(rays_sample_startidx + my_ray);
             my_n = __ldg(rays_n_samples + my_ray);
+            if (my_n == 0) {  // T stays 1: the whole colour gradient flows to the background (integrating.cu:235-239)
+                const float4 dfin = __ldg(dL_dfinal_rgbds + my_ray);
+                dL_dbgs[3 * (size_t)my_ray + 0] = dfin.x;
+                dL_dbgs[3 * (size_t)my_ray + 1] = dfin.y;
+                dL_dbgs[3 * (size_t)my_ray + 2] = dfin.z;
+            }
         }
-        for (uint32_t q = 0; q < kRaysPerWarp; ++q) {
+        uint32_t todo = __ballot_sync(0xffffffffu, my_n != 0);
+        while (todo) {
+            const uint32_t q = __ffs(todo) - 1;
+            todo &= todo - 1;
             const uint32_t ray = grp * kRaysPerWarp + q;
-            if (ray >= n_rays) break;
             const uint32_t start = __shfl_sync(0xffffffffu, my_start, q);
             const uint32_t n = __shfl_sync(0xffffffffu, my_n, q);
             const float4 dfin = __ldg(dL_dfinal_rgbds + ray);
             float T = 1.f;
-            if (n > 0) {
+            {
                 const float4 fin = __ldg(final_rgbds + ray);
                 const float opac = __ldg(final_opacities + ray);
                 const bool terminated = opac >= 1.f - kTThreshold;  // integrating.cu:158

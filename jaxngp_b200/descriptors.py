@@ -82,3 +82,15 @@ def make_adam_descriptor(n, decay_begin, lr_init, lr_end, decay_rate, transition
     return struct.pack("<2Q3f3I6f", int(n), int(decay_begin), float(lr_init), float(lr_end), float(decay_rate),
                        int(transition_steps), int(transition_begin), int(bool(staircase)), float(b1), float(b2),
                        float(eps), float(eps_root), float(weight_decay), float(grad_scale))
+
+
+def make_ogrid_sample_descriptor(n_points, G, mip_bound):
+    return struct.pack("<2If", _u32(n_points, "n_points"), _u32(G, "G"), float(mip_bound))
+
+
+def make_ogrid_update_descriptor(n_cells, n_updates, decay):
+    return struct.pack("<2If", _u32(n_cells, "n_cells"), _u32(n_updates, "n_updates"), float(decay))
+
+
+def make_ogrid_threshold_descriptor(n_cells, thr_max):
+    return struct.pack("<If", _u32(n_cells, "n_cells"), float(thr_max))

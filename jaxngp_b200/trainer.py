@@ -12,8 +12,8 @@ Adam-moment buffers, so data parallelism is a single ``all_reduce`` and the opti
 """
 import torch
 
-from . import _lib, descriptors, dp, encoders, nerf as nerf_mod, renderers, synthetic
-from .volrendjax import integrate_rays, march_rays, morton3d_invert, packbits
+from . import _lib, descriptors, dp, encoders, nerf as nerf_mod, ogrid, renderers, synthetic
+from .volrendjax import integrate_rays, march_rays
 
 
 def huber(pred, target, delta=0.1):
@@ -91,10 +91,7 @@ class Trainer:
         self._flatten_parameters()
         self.scene = scene if scene is not None else Scene(self.device)
         # occupancy grid state (utils/types.py:93-144): all-ones bitfield at step 0
-        G3 = synthetic.K * synthetic.G ** 3
-        self.density_grid = torch.zeros(G3, dtype=torch.float32, device=self.device)
-        self.occupancy = torch.full((G3 // 8,), 0xFF, dtype=torch.uint8, device=self.device)
-        self.occ_mask = torch.ones(G3, dtype=torch.bool, device=self.device)
+        self.grid = ogrid.OccupancyDensityGrid(synthetic.K, synthetic.G, device=self.device)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.step = 0
         torch.cuda.manual_seed(seed + 1 + rank)  # per-rank perturbation / background streams (graph-safe default generator)
@@ -107,6 +104,14 @@ class Trainer:
         self._graph = None
         self._static_perm = torch.zeros(n_rays, dtype=torch.int32, device=self.device)
         self._static_out = None
+
+    @property
+    def occupancy(self):
+        return self.grid.occupancy
+
+    @property
+    def occ_mask(self):
+        return self.grid.occ_mask
 
     # -- flat parameter / gradient / moment buffers ---------------------------------------------
     def _flatten_parameters(self):
@@ -145,7 +150,7 @@ class Trainer:
             bg = torch.rand(self.n_rays, 3, device=dev)  # random_bg, _utils.py:134-136
         mb, ray_is_valid, rays_n, rays_start, _, xyzs, dirs, dss, z_vals = march_rays(
             self.total_samples, synthetic.DIAGONAL_N_STEPS, synthetic.K, synthetic.G, synthetic.BOUND,
-            synthetic.STEPSIZE_PORTION, o, d, t_starts, t_ends, noises, self.occupancy)
+            synthetic.STEPSIZE_PORTION, o, d, t_starts, t_ends, noises, self.grid.occupancy)
         # hash-grid gather outside autograd: its backward writes straight into the flat gradient buffer
         enc = encoders.hashgrid_forward(self.levels, xyzs, synthetic.BOUND, self.table).requires_grad_(True)
         n = self.nerf
@@ -163,21 +168,31 @@ class Trainer:
         encoders.hashgrid_backward(self.levels, xyzs, synthetic.BOUND, grads[0].contiguous(), out=self.table_grad)
         for view, g in zip(self.mlp_grad_views, grads[1:]):
             view.copy_(g)
+        out = dict(loss=loss.detach(), n_valid_rays=n_valid, measured_batch_size_before_compaction=mb,
+                   measured_batch_size=effective)
+        if apply and self.world_size == 1:
+            self._optimizer_step()
+        return out
+
+    def _optimizer_step(self):
+        """[all-reduce of the flat gradient] + Adam.  With more than one rank this part stays outside the
+        CUDA graph: the collective is issued eagerly on the current stream between the captured
+        compute graph and the optimizer launch."""
         if self.world_size > 1:  # one collective per step over [table grad | MLP grads]
             dp.allreduce_flat_gradients(self.flat_grads, self.pg)
-        if apply:
-            _lib.call("ngp_adam_step", [self.step_dev, self.flat_params, self.flat_grads, self.adam_m, self.adam_v],
-                      self.adam_desc)
-            self.step_dev += 1
-        return dict(loss=loss.detach(), n_valid_rays=n_valid, measured_batch_size_before_compaction=mb,
-                    measured_batch_size=effective)
+        _lib.call("ngp_adam_step", [self.step_dev, self.flat_params, self.flat_grads, self.adam_m, self.adam_v],
+                  self.adam_desc)
+        self.step_dev += 1
 
     def train_step(self, perm):
         """perm: int32 [n_rays] indices into the scene's pixels (device tensor).  Returns device-side
         metrics (no host synchronisation)."""
         self.step += 1
         if not self.use_graph:
-            return self._step_body(perm)
+            out = self._step_body(perm)
+            if self.world_size > 1:
+                self._optimizer_step()
+            return out
         self._static_perm.copy_(perm, non_blocking=True)
         if self._graph is None:
             side = torch.cuda.Stream(device=self.device)
@@ -185,47 +200,37 @@ class Trainer:
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up on the capture stream (scratch blocks, cuBLAS handles)
                     self._step_body(self._static_perm)
+                    if self.world_size > 1:
+                        self._optimizer_step()
                 self._graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self._graph, stream=side):
                     self._static_out = self._step_body(self._static_perm)
             torch.cuda.current_stream(self.device).wait_stream(side)
             self.step += 2
         self._graph.replay()
+        if self.world_size > 1:
+            self._optimizer_step()
         return self._static_out
 
-    # -- density grid update (utils/types.py:1149-1239), torch arm -------------------------------
+    # -- density grid update (utils/types.py:1149-1239) --------------------------------------------
+    def _density_fn(self, xyz):
+        enc = encoders.hashgrid_forward(self.levels, xyz.contiguous(), synthetic.BOUND, self.table)
+        x = torch.relu(enc @ self.nerf.density_w0) @ self.nerf.density_w1
+        return torch.exp(x[:, 0])
+
     @torch.no_grad()
     def update_ogrid(self, update_all=None, commit=True):
-        G, dev = synthetic.G, self.device
+        """train.py:75-85: update every cascade's densities, then re-threshold and re-pack the bitfield.
+        ``commit=False`` does all the work into shadow buffers (bench: keeps the marching workload fixed)."""
         if update_all is None:
             update_all = self.step < 256  # utils/types.py:1391-1392
-        G3 = G ** 3
-        grid = self.density_grid if commit else self.density_grid.clone()
-        grid *= 0.95  # :1162 (all cells alive in the synthetic scene)
-        if update_all:
-            idx = torch.arange(G3, dtype=torch.int32, device=dev)
-        else:
-            M = max(1, G3 // 2)
-            first = torch.randint(0, G3, (max(1, M // 2),), device=dev, generator=self.noise_gen)
-            occ = self.occ_mask.nonzero().squeeze(-1)
-            if occ.numel() == 0:
-                occ = torch.arange(G3, device=dev)
-            second = occ[torch.randint(0, occ.numel(), (max(1, M // 2),), device=dev, generator=self.noise_gen)]
-            idx = torch.cat([first, second]).to(torch.int32)
-        coords = morton3d_invert(idx).to(torch.float32) / (G - 1) * 2 - 1  # :1193-1194
-        half = synthetic.BOUND / G
-        coords = coords * (synthetic.BOUND - half)
-        coords = coords + (torch.rand(coords.shape, device=dev, generator=self.noise_gen) * 2 - 1) * half  # :1199-1206
-        dens = []
-        for part in coords.split(self.total_samples):
-            enc = encoders.hashgrid_forward(self.levels, part.contiguous(), synthetic.BOUND, self.table)
-            x = torch.relu(enc @ self.nerf.density_w0) @ self.nerf.density_w1
-            dens.append(torch.exp(x[:, 0]))
-        dens = torch.cat(dens)
-        grid.scatter_reduce_(0, idx.to(torch.int64), dens, reduce="amax")  # atomic max
-        thr = torch.minimum(torch.tensor(synthetic.DENSITY_THRESHOLD, device=dev), grid.mean())  # :1229-1230
-        occ_mask, occupancy = packbits(thr, grid)
-        if commit:  # in place: a captured CUDA graph keeps reading the same buffers
-            self.occ_mask.copy_(occ_mask)
-            self.occupancy.copy_(occupancy)
+        g = self.grid
+        shadow = None if commit else torch.empty_like(g.density)
+        for cas in range(g.K):
+            ogrid.update_ogrid_density(g, self._density_fn, cas, update_all, synthetic.BOUND, self.total_samples,
+                                       out_density=shadow)
+        if self.world_size > 1:  # every rank sampled its own cells: take the max (SURVEY 8e)
+            dp.allreduce_density_grid(g.density if commit else shadow, self.pg)
+        _, occ_mask, occupancy = ogrid.threshold_ogrid(g, synthetic.DIAGONAL_N_STEPS, synthetic.BOUND,
+                                                       density=None if commit else shadow, commit=commit)
         return occ_mask, occupancy

@@ -270,6 +270,29 @@ def test_hashgrid_forward_backward_vs_oracle(oracle, dim, T, N_max):
     assert np.array_equal(n(g) != 0, ref_g != 0)                # exactly the same rows are touched
 
 
+def test_hashgrid_backward_ray_ordered_runs(oracle):
+    """Samples in ray order (neighbouring rows share grid cells on the coarse levels) with zero-gradient
+    rows sprinkled in: exercises the run aggregation of the scatter kernel."""
+    from jaxngp_b200 import encoders as E
+    from oracle import hashgrid_np as H
+    lt = E.make_level_table(16, 2 ** 19, 2, 16, 2048, 3)
+    lv = H.level_table(16, 2 ** 19, 2, 16, 2048, 3)
+    rng = np.random.Generator(np.random.PCG64(77))
+    n_rays, per_ray = 300, 37
+    o = rng.uniform(-0.9, 0.9, (n_rays, 1, 3))
+    d = rng.normal(size=(n_rays, 1, 3))
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    tt = (np.arange(per_ray) * (2 * np.sqrt(3) / 1024))[None, :, None]
+    pts = np.clip(o + tt * d, -1, 1).reshape(-1, 3).astype(np.float32)
+    d_enc = rng.normal(size=(pts.shape[0], 32)).astype(np.float32)
+    d_enc[rng.random(pts.shape[0]) < 0.15] = 0.0          # masked samples
+    d_enc[5000:5100, ::2] = 0.0                            # partially zero rows stay active
+    g = E.hashgrid_backward(lt, t(pts), 1.0, t(d_enc))
+    ref_g = oracle.hashgrid_backward(lv, pts, 1.0, d_enc, 2)
+    assert np.abs(n(g) - ref_g).max() <= 1e-4 * np.abs(ref_g).max()
+    assert np.array_equal(n(g) != 0, ref_g != 0)
+
+
 def test_hashgrid_module_autograd_and_fp16(oracle):
     from jaxngp_b200 import encoders as E
     from oracle import hashgrid_np as H
@@ -345,3 +368,72 @@ def test_hashgrid_tcnn_path(oracle):
     assert np.quantile(err, 0.8) < 2e-2, np.quantile(err, [0.5, 0.8, 0.95])
     with pytest.raises(NotImplementedError):
         J.hashgrid_encode(desc, t(np.asarray(lt.offsets, np.uint32)), coords[:2], params)
+
+
+# ------------------------------------------------------------------ density-grid update (a8)
+def test_ogrid_update_vs_oracle():
+    from jaxngp_b200 import ogrid as OG
+    from oracle import ogrid_np as ON
+    G, bound = 32, 4.0
+    rng = np.random.Generator(np.random.PCG64(8))
+    for cas in (0, 2):
+        M = 5000
+        idx = rng.integers(0, G ** 3, M, dtype=np.uint32)
+        u = rng.random((M, 3), dtype=np.float32)
+        got = n(OG.sample_positions(t(idx), t(u), G, cas, bound))
+        exp = ON.sample_positions(idx, u, G, cas, bound)
+        assert np.allclose(got, exp, rtol=0, atol=1e-6)
+        mip = min(bound, 2.0 ** cas)
+        assert np.abs(got).max() <= mip  # jittered points stay inside the cascade
+    # decay + max with duplicates and dead (-1) cells
+    den = rng.random(G ** 3, dtype=np.float32) * 3
+    den[rng.integers(0, G ** 3, 2000)] = -1.0
+    idx = rng.integers(0, G ** 3, 20000, dtype=np.uint32)
+    idx = idx[den[idx] >= 0]  # only alive cells are ever selected (utils/types.py:1154-1156)
+    new = (rng.random(idx.shape[0], dtype=np.float32) * 4).astype(np.float32)
+    got = n(OG.decay_and_max(t(den), t(idx), t(new)))
+    exp = ON.decay_and_max(den, idx, new)
+    assert np.array_equal(got, exp)  # multiplication and max are exact: bit-equal
+    # in place
+    den_t = t(den)
+    OG.decay_and_max(den_t, t(idx), t(new), out=den_t)
+    assert np.array_equal(n(den_t), exp)
+    # threshold = min(thr_max, mean over alive cells)
+    for thr_max in (0.5, 100.0):
+        got_thr = float(OG.threshold(t(exp), thr_max))
+        assert np.isclose(got_thr, float(ON.threshold(exp, thr_max)), rtol=1e-6)
+
+
+def test_ogrid_full_update_matches_oracle_bitfield(oracle):
+    """update_ogrid_density + threshold_ogrid with supplied draws and an analytic density function:
+    density grid bit-equal, bitfield bit-equal."""
+    from jaxngp_b200 import ogrid as OG, synthetic as S
+    from oracle import ogrid_np as ON
+    G = 64
+    grid = OG.OccupancyDensityGrid(1, G, device=DEV)
+    rng = np.random.Generator(np.random.PCG64(3))
+    grid.density.copy_(t(rng.random(G ** 3, dtype=np.float32)))
+    den0 = n(grid.density).copy()
+    M = G ** 3 // 2
+    draws_np = dict(first=rng.integers(0, G ** 3, M // 2, dtype=np.uint32), second=rng.integers(0, G ** 3, M // 2, dtype=np.uint32),
+                    jitter=rng.random((M, 3), dtype=np.float32))
+    draws = {k: t(v) for k, v in draws_np.items()}
+
+    def density_fn(xyz):
+        inside = (xyz ** 2).sum(-1) < 0.45 ** 2
+        return torch.where(inside, 64.0, 0.0) + 0.001
+
+    OG.update_ogrid_density(grid, density_fn, 0, False, 1.0, 1 << 16, draws=draws)
+    idx_np = np.concatenate([draws_np["first"], draws_np["second"]])
+    coords = ON.sample_positions(idx_np, draws_np["jitter"], G, 0, 1.0)
+    new = (np.where((coords.astype(np.float32) ** 2).sum(-1) < np.float32(0.45 ** 2), 64.0, 0.0) + 0.001).astype(np.float32)
+    exp = ON.decay_and_max(den0, idx_np, new)
+    got = n(grid.density)
+    # points within an ulp of the sphere surface may fall on the other side: allow a handful of cells
+    assert (got != exp).sum() <= 3
+    thr, mask, bits = OG.threshold_ogrid(grid, 1024, 1.0)
+    thr_exp = ON.threshold(got, OG.density_threshold_from_min_step_size(1024, 1.0))
+    assert np.isclose(float(thr), float(thr_exp), rtol=1e-6)
+    omask, obits = oracle.packbits(float(thr), got)
+    assert np.array_equal(n(mask), omask) and np.array_equal(n(bits), obits)
+    assert np.array_equal(n(grid.occupancy), obits)
