@@ -161,6 +161,15 @@ void ngp_ogrid_sample_positions(cudaStream_t, void **, const char *, size_t);
 void ngp_ogrid_decay_max(cudaStream_t, void **, const char *, size_t);
 void ngp_ogrid_threshold(cudaStream_t, void **, const char *, size_t);
 
+/* Fully fused NeRF MLP of make_nerf_ngp (models/nerfs.py:27-128,216-238,422-454) on the tensor cores.
+ * weights = flat f32[9408] = [density W0 32x64 | density W1 64x16 | rgb W0 32x64 | rgb W1 64x64 | rgb W2 64x3],
+ * each row-major [in][out] like the flax Dense kernels.
+ * forward : in enc f32[n,32], dirs f32[n,3] (unit), weights;  out drgbs f32[n,4]  (density_only: out f32[n], dirs unused)
+ * backward: in enc, dirs, weights, d_drgbs f32[n,4];          out d_enc f32[n,32], d_weights f32[9408] */
+typedef struct { uint32_t n_samples, density_only; } NgpNerfMlpDescriptor;
+void ngp_nerf_mlp_forward(cudaStream_t, void **, const char *, size_t);
+void ngp_nerf_mlp_backward(cudaStream_t, void **, const char *, size_t);
+
 /* Adam step of app/nerf/_utils.py:19-77 over a flat f32 buffer [hash table | MLP weights]; elements
  * at index >= decay_begin also receive the reference's (additive) decayed-weights term.
  * in : step u32[1] (device-resident count of completed steps), params f32[n] (updated in place),

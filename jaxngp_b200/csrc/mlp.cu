@@ -1,0 +1,541 @@
+// mlp.cu -- fully fused NeRF MLP of make_nerf_ngp (models/nerfs.py:27-128,216-238,422-454), forward and
+// backward, on the tensor cores (TF32 mma.sync m16n8k8, f32 accumulate -- the precision XLA gives the
+// reference's f32 Dense layers on Ampere+ GPUs).
+//
+//   enc[32] -> W0[32x64] -> ReLU -> W1[64x16] = x ; density = exp(x[0])        (trunc_exp, nerfs.py:222-238)
+//   [x(16) | SH4(dir)(16)] -> W2[32x64] -> ReLU -> W3[64x64] -> ReLU -> W4[64x3] -> sigmoid = rgb
+//
+// Forward: a warp carries 16 samples through all five layers in registers.  The accumulator fragment of
+// one layer IS the A fragment of the next (columns 2t,2t+1 of every 8-block feed k = t, t+4), which only
+// needs the weight rows permuted the same way when B fragments are read from shared memory -- no
+// shuffles, no shared-memory round trip for activations.  Weights (9408 values) sit in shared memory.
+//
+// Backward: one CTA owns 128 samples.  Phase 1 (per warp, 16 samples): recompute the forward, keep the
+// activations of the 128 samples in shared memory, and walk the layers back producing one delta matrix
+// at a time.  Phase 2 (whole CTA, after each delta is written): dW += act^T * delta with the CTA's
+// 128 samples as the reduction dimension; every warp owns a fixed set of dW tiles that stay in its
+// registers for the whole kernel (76 tiles over 8 warps = 40 registers/thread) and are flushed to the
+// global gradient with one atomicAdd per element per CTA at the end.  Activations never touch HBM:
+// traffic is enc (128 B) + dirs (12 B) + d_drgbs (16 B) in, d_enc (128 B) out per sample.
+#include "common.cuh"
+
+namespace ngp {
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kBlockSamples = kWarps * 16;  // 128
+
+// shared-memory weight layout: row stride = N + 4 (mod 32 == 4 -> forward B-fragment loads are conflict free)
+constexpr int S_W0 = 68, S_W1 = 20, S_W2 = 68, S_W3 = 68, S_W4 = 12;
+constexpr int O_W0 = 0, O_W1 = O_W0 + 32 * S_W0, O_W2 = O_W1 + 64 * S_W1, O_W3 = O_W2 + 32 * S_W2,
+              O_W4 = O_W3 + 64 * S_W3, kWeightFloats = O_W4 + 64 * S_W4;  // 10752
+// global flat weight layout [W0 | W1 | W2 | W3 | W4], row-major [in][out] (flax Dense kernels)
+constexpr int G_W0 = 0, G_W1 = G_W0 + 32 * 64, G_W2 = G_W1 + 64 * 16, G_W3 = G_W2 + 32 * 64, G_W4 = G_W3 + 64 * 64,
+              kGlobalWeights = G_W4 + 64 * 3;  // 9408
+// activation buffers of the backward kernel: row stride = K + 8 (mod 32 == 8 -> fragment stores/loads conflict free)
+constexpr int S_A64 = 72, S_A32 = 40, S_D = 72;
+constexpr int O_H0 = 0, O_HIN = O_H0 + kBlockSamples * S_A64, O_H1 = O_HIN + kBlockSamples * S_A32,
+              O_H2 = O_H1 + kBlockSamples * S_A64, O_D = O_H2 + kBlockSamples * S_A64,
+              kActFloats = O_D + kBlockSamples * S_D;
+
+__device__ __forceinline__ uint32_t tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// accumulator fragment (rows g, g+8; cols 2t, 2t+1) -> A fragment under the k-permutation t <-> 2t, t+4 <-> 2t+1
+__device__ __forceinline__ void c_to_a(const float (&c)[4], uint32_t (&a)[4]) {
+    a[0] = tf32(c[0]);
+    a[1] = tf32(c[2]);
+    a[2] = tf32(c[1]);
+    a[3] = tf32(c[3]);
+}
+
+// out[16 x 8*NT] = in[16 x 8*KT] * W, W in shared memory [8*KT][STRIDE] (tf32 bits)
+template <int KT, int NT, int STRIDE>
+__device__ __forceinline__ void layer_forward(const uint32_t (&a)[KT][4], const uint32_t *__restrict__ W,
+                                              float (&acc)[NT][4], uint32_t g, uint32_t t) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+        const uint32_t *w0 = W + (8 * kt + 2 * t) * STRIDE + g;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[nt], a[kt], w0[8 * nt], w0[STRIDE + 8 * nt]);
+    }
+}
+
+// d_in[16 x 8*NT_IN] = d_out[16 x 8*KT_OUT] * W^T, same shared-memory W [8*NT_IN.. rows][STRIDE]
+template <int KT_OUT, int NT_IN, int STRIDE>
+__device__ __forceinline__ void layer_backward(const uint32_t (&a)[KT_OUT][4], const uint32_t *__restrict__ W,
+                                               float (&acc)[NT_IN][4], uint32_t g, uint32_t t) {
+#pragma unroll
+    for (int nt = 0; nt < NT_IN; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT_IN; ++nt) {
+        const uint32_t *w0 = W + (8 * nt + g) * STRIDE + 2 * t;
+#pragma unroll
+        for (int kt = 0; kt < KT_OUT; ++kt) {
+            const uint2 b = *reinterpret_cast<const uint2 *>(w0 + 8 * kt);
+            mma_tf32(acc[nt], a[kt], b.x, b.y);
+        }
+    }
+}
+
+// store an accumulator tile set into a [16 rows of this warp][stride] shared buffer
+template <int NT, int STRIDE>
+__device__ __forceinline__ void store_frag(float *__restrict__ buf, const float (&acc)[NT][4], int col0, uint32_t g,
+                                           uint32_t t) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        *reinterpret_cast<float2 *>(buf + g * STRIDE + col0 + 8 * nt + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<float2 *>(buf + (g + 8) * STRIDE + col0 + 8 * nt + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
+    }
+}
+
+// SH degree 4, the four coefficients this lane feeds into the second half of hin: indices 2t, 2t+1, 8+2t, 9+2t
+// (same basis, order and signs as models/encoders.py:365-406)
+__device__ __forceinline__ void sh4_lane(float x, float y, float z, uint32_t t, float (&o)[4]) {
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    const float s0 = 0.28209479177387814f, s1 = -0.48860251190291987f * y, s2 = 0.48860251190291987f * z,
+                s3 = -0.48860251190291987f * x, s4 = 1.0925484305920792f * xy, s5 = -1.0925484305920792f * yz,
+                s6 = 0.94617469575755997f * z2 - 0.31539156525251999f, s7 = -1.0925484305920792f * xz,
+                s8 = 0.54627421529603959f * x2 - 0.54627421529603959f * y2,
+                s9 = 0.59004358992664352f * y * (-3.0f * x2 + y2), s10 = 2.8906114426405538f * xy * z,
+                s11 = 0.45704579946446572f * y * (1.0f - 5.0f * z2), s12 = 0.3731763325901154f * z * (5.0f * z2 - 3.0f),
+                s13 = 0.45704579946446572f * x * (1.0f - 5.0f * z2), s14 = 1.4453057213202769f * z * (x2 - y2),
+                s15 = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+    o[0] = t == 0 ? s0 : t == 1 ? s2 : t == 2 ? s4 : s6;
+    o[1] = t == 0 ? s1 : t == 1 ? s3 : t == 2 ? s5 : s7;
+    o[2] = t == 0 ? s8 : t == 1 ? s10 : t == 2 ? s12 : s14;
+    o[3] = t == 0 ? s9 : t == 1 ? s11 : t == 2 ? s13 : s15;
+}
+
+__device__ __forceinline__ void load_weights(uint32_t *__restrict__ sw, const float *__restrict__ w) {
+    for (int i = threadIdx.x; i < 32 * 64; i += kThreads) sw[O_W0 + (i / 64) * S_W0 + i % 64] = tf32(__ldg(w + G_W0 + i));
+    for (int i = threadIdx.x; i < 64 * 16; i += kThreads) sw[O_W1 + (i / 16) * S_W1 + i % 16] = tf32(__ldg(w + G_W1 + i));
+    for (int i = threadIdx.x; i < 32 * 64; i += kThreads) sw[O_W2 + (i / 64) * S_W2 + i % 64] = tf32(__ldg(w + G_W2 + i));
+    for (int i = threadIdx.x; i < 64 * 64; i += kThreads) sw[O_W3 + (i / 64) * S_W3 + i % 64] = tf32(__ldg(w + G_W3 + i));
+    for (int i = threadIdx.x; i < 64 * 8; i += kThreads) {  // W4 padded from 3 to 8 output columns with zeros
+        const int r = i / 8, c = i % 8;
+        sw[O_W4 + r * S_W4 + c] = c < 3 ? tf32(__ldg(w + G_W4 + r * 3 + c)) : 0u;
+    }
+}
+
+struct FwdState {  // what the backward needs from the recomputed forward, in fragment layout
+    float x0[2];     // x[:, 0] of rows g, g+8 (valid on lanes t == 0)
+    float rgb[2][2]; // sigmoid outputs: cols 2t, 2t+1 of rows g, g+8 (t == 0: r, g; t == 1: b, pad)
+};
+
+// Forward for this warp's 16 rows starting at `row0` (global sample index).  If kKeep, activations are also
+// written to the warp's rows of the shared activation buffers.
+template <bool kKeep, bool kDensityOnly>
+__device__ __forceinline__ void warp_forward(const uint32_t *__restrict__ sw, float *__restrict__ act, uint32_t warp,
+                                             uint32_t row0, uint32_t n, const float *__restrict__ enc,
+                                             const float *__restrict__ dirs, uint32_t g, uint32_t t, FwdState &st,
+                                             uint32_t (&a_h2)[8][4], float (&out_rgb)[1][4]) {
+    const uint32_t r_lo = row0 + g, r_hi = row0 + g + 8;
+    const bool ok_lo = r_lo < n, ok_hi = r_hi < n;
+    // enc A fragments: cols 8kt+2t, 8kt+2t+1 of rows g, g+8 (float2 loads, every 32 B sector fully used)
+    uint32_t a_in[4][4];
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+        const float2 lo = ok_lo ? __ldg(reinterpret_cast<const float2 *>(enc + (size_t)r_lo * 32 + 8 * kt + 2 * t)) : make_float2(0.f, 0.f);
+        const float2 hi = ok_hi ? __ldg(reinterpret_cast<const float2 *>(enc + (size_t)r_hi * 32 + 8 * kt + 2 * t)) : make_float2(0.f, 0.f);
+        a_in[kt][0] = tf32(lo.x);
+        a_in[kt][1] = tf32(hi.x);
+        a_in[kt][2] = tf32(lo.y);
+        a_in[kt][3] = tf32(hi.y);
+    }
+    float *my_rows_64 = nullptr, *my_rows_32 = nullptr;
+    (void)my_rows_64;
+    (void)my_rows_32;
+    // layer 0: 32 -> 64, ReLU
+    uint32_t a_h0[8][4];
+    {
+        float acc[8][4];
+        layer_forward<4, 8, S_W0>(a_in, sw + O_W0, acc, g, t);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[nt][i] = fmaxf(acc[nt][i], 0.f);
+            c_to_a(acc[nt], a_h0[nt]);
+        }
+        if (kKeep) store_frag<8, S_A64>(act + O_H0 + warp * 16 * S_A64, acc, 0, g, t);
+    }
+    // layer 1: 64 -> 16 (no activation); density = exp(x[0])
+    uint32_t a_hin[4][4];
+    {
+        float acc[2][4];
+        layer_forward<8, 2, S_W1>(a_h0, sw + O_W1, acc, g, t);
+        st.x0[0] = acc[0][0];
+        st.x0[1] = acc[0][2];
+        c_to_a(acc[0], a_hin[0]);
+        c_to_a(acc[1], a_hin[1]);
+        if (kKeep) store_frag<2, S_A32>(act + O_HIN + warp * 16 * S_A32, acc, 0, g, t);
+    }
+    if (kDensityOnly) return;
+    // direction encoding: SH degree 4 into columns 16..31 of hin
+    {
+        float sh_lo[4], sh_hi[4];
+        const float dx0 = ok_lo ? __ldg(dirs + (size_t)r_lo * 3 + 0) : 0.f, dy0 = ok_lo ? __ldg(dirs + (size_t)r_lo * 3 + 1) : 0.f,
+                    dz0 = ok_lo ? __ldg(dirs + (size_t)r_lo * 3 + 2) : 1.f;
+        const float dx1 = ok_hi ? __ldg(dirs + (size_t)r_hi * 3 + 0) : 0.f, dy1 = ok_hi ? __ldg(dirs + (size_t)r_hi * 3 + 1) : 0.f,
+                    dz1 = ok_hi ? __ldg(dirs + (size_t)r_hi * 3 + 2) : 1.f;
+        sh4_lane(dx0, dy0, dz0, t, sh_lo);
+        sh4_lane(dx1, dy1, dz1, t, sh_hi);
+        a_hin[2][0] = tf32(sh_lo[0]); a_hin[2][1] = tf32(sh_hi[0]); a_hin[2][2] = tf32(sh_lo[1]); a_hin[2][3] = tf32(sh_hi[1]);
+        a_hin[3][0] = tf32(sh_lo[2]); a_hin[3][1] = tf32(sh_hi[2]); a_hin[3][2] = tf32(sh_lo[3]); a_hin[3][3] = tf32(sh_hi[3]);
+        if (kKeep) {
+            float *buf = act + O_HIN + warp * 16 * S_A32;
+            *reinterpret_cast<float2 *>(buf + g * S_A32 + 16 + 2 * t) = make_float2(sh_lo[0], sh_lo[1]);
+            *reinterpret_cast<float2 *>(buf + g * S_A32 + 24 + 2 * t) = make_float2(sh_lo[2], sh_lo[3]);
+            *reinterpret_cast<float2 *>(buf + (g + 8) * S_A32 + 16 + 2 * t) = make_float2(sh_hi[0], sh_hi[1]);
+            *reinterpret_cast<float2 *>(buf + (g + 8) * S_A32 + 24 + 2 * t) = make_float2(sh_hi[2], sh_hi[3]);
+        }
+    }
+    // layer 2: 32 -> 64, ReLU
+    uint32_t a_h1[8][4];
+    {
+        float acc[8][4];
+        layer_forward<4, 8, S_W2>(a_hin, sw + O_W2, acc, g, t);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[nt][i] = fmaxf(acc[nt][i], 0.f);
+            c_to_a(acc[nt], a_h1[nt]);
+        }
+        if (kKeep) store_frag<8, S_A64>(act + O_H1 + warp * 16 * S_A64, acc, 0, g, t);
+    }
+    // layer 3: 64 -> 64, ReLU
+    {
+        float acc[8][4];
+        layer_forward<8, 8, S_W3>(a_h1, sw + O_W3, acc, g, t);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[nt][i] = fmaxf(acc[nt][i], 0.f);
+            c_to_a(acc[nt], a_h2[nt]);
+        }
+        if (kKeep) store_frag<8, S_A64>(act + O_H2 + warp * 16 * S_A64, acc, 0, g, t);
+    }
+    // layer 4: 64 -> 3 (padded to 8), sigmoid
+    layer_forward<8, 1, S_W4>(a_h2, sw + O_W4, out_rgb, g, t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out_rgb[0][i] = 1.f / (1.f + expf(-out_rgb[0][i]));
+    st.rgb[0][0] = out_rgb[0][0];
+    st.rgb[0][1] = out_rgb[0][1];
+    st.rgb[1][0] = out_rgb[0][2];
+    st.rgb[1][1] = out_rgb[0][3];
+}
+
+// ---------------------------------------------------------------- forward kernel
+template <bool kDensityOnly>
+__global__ void __launch_bounds__(kThreads) nerf_mlp_forward_kernel(uint32_t n, const float *__restrict__ enc,
+                                                                    const float *__restrict__ dirs,
+                                                                    const float *__restrict__ weights,
+                                                                    float *__restrict__ out) {
+    extern __shared__ __align__(16) uint32_t smem_u32[];
+    uint32_t *sw = smem_u32;
+    load_weights(sw, weights);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3u;
+    const uint32_t n_tiles = (n + 15u) / 16u;
+    for (uint32_t tile = blockIdx.x * kWarps + warp; tile < n_tiles; tile += gridDim.x * kWarps) {
+        const uint32_t row0 = tile * 16u;
+        FwdState st;
+        uint32_t a_h2[8][4];
+        float rgb[1][4];
+        warp_forward<false, kDensityOnly>(sw, nullptr, warp, row0, n, enc, dirs, g, t, st, a_h2, rgb);
+        if (kDensityOnly) {
+            if (t == 0) {
+                if (row0 + g < n) out[row0 + g] = expf(st.x0[0]);
+                if (row0 + g + 8 < n) out[row0 + g + 8] = expf(st.x0[1]);
+            }
+        } else {
+            // lane t == 0 of each row group assembles (density, r, g, b): b comes from lane t == 1
+            const float b_lo = __shfl_sync(0xffffffffu, st.rgb[0][0], (lane & ~3u) + 1);
+            const float b_hi = __shfl_sync(0xffffffffu, st.rgb[1][0], (lane & ~3u) + 1);
+            if (t == 0) {
+                if (row0 + g < n)
+                    reinterpret_cast<float4 *>(out)[row0 + g] = make_float4(expf(st.x0[0]), st.rgb[0][0], st.rgb[0][1], b_lo);
+                if (row0 + g + 8 < n)
+                    reinterpret_cast<float4 *>(out)[row0 + g + 8] = make_float4(expf(st.x0[1]), st.rgb[1][0], st.rgb[1][1], b_hi);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- backward kernel
+// dW tile accumulation over the CTA's 128 samples: acc[mt] += act[:, 16mt' .. ]^T * D[:, 8nt ..]
+template <int MT, int S_ACT>
+__device__ __forceinline__ void dw_accumulate(float (&acc)[MT][4], const float *__restrict__ act, int feat0,
+                                              const float *__restrict__ D, int col0, uint32_t g, uint32_t t) {
+#pragma unroll 4
+    for (int ks = 0; ks < kBlockSamples / 8; ++ks) {
+        const int s = 8 * ks + t;
+        const uint32_t b0 = tf32(D[s * S_D + col0 + g]), b1 = tf32(D[(s + 4) * S_D + col0 + g]);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            uint32_t a[4];
+            const float *p = act + s * S_ACT + feat0 + 16 * mt + g;
+            a[0] = tf32(p[0]);
+            a[1] = tf32(p[8]);
+            a[2] = tf32(p[4 * S_ACT]);
+            a[3] = tf32(p[4 * S_ACT + 8]);
+            mma_tf32(acc[mt], a, b0, b1);
+        }
+    }
+}
+
+// same with the activation operand (enc) read from global memory, rows base .. base+127
+template <int MT>
+__device__ __forceinline__ void dw_accumulate_global(float (&acc)[MT][4], const float *__restrict__ enc, uint32_t base,
+                                                     uint32_t n, const float *__restrict__ D, int col0, uint32_t g, uint32_t t) {
+#pragma unroll 4
+    for (int ks = 0; ks < kBlockSamples / 8; ++ks) {
+        const int s = 8 * ks + t;
+        const uint32_t b0 = tf32(D[s * S_D + col0 + g]), b1 = tf32(D[(s + 4) * S_D + col0 + g]);
+        const bool ok0 = base + s < n, ok1 = base + s + 4 < n;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            uint32_t a[4];
+            const float *p = enc + (size_t)(base + s) * 32 + 16 * mt + g;
+            a[0] = tf32(ok0 ? __ldg(p) : 0.f);
+            a[1] = tf32(ok0 ? __ldg(p + 8) : 0.f);
+            a[2] = tf32(ok1 ? __ldg(p + 4 * 32) : 0.f);
+            a[3] = tf32(ok1 ? __ldg(p + 4 * 32 + 8) : 0.f);
+            mma_tf32(acc[mt], a, b0, b1);
+        }
+    }
+}
+
+// flush one 16x8 dW tile: c0 = (row g, col 2t), c1 = (g, 2t+1), c2 = (g+8, 2t), c3 = (g+8, 2t+1)
+__device__ __forceinline__ void flush_tile(float *__restrict__ dW, int n_cols, int row0, int col0, const float (&c)[4],
+                                           uint32_t g, uint32_t t) {
+    const int c0 = col0 + 2 * t;
+    if (c0 < n_cols) {
+        atomicAdd(dW + (row0 + g) * n_cols + c0, c[0]);
+        atomicAdd(dW + (row0 + g + 8) * n_cols + c0, c[2]);
+    }
+    if (c0 + 1 < n_cols) {
+        atomicAdd(dW + (row0 + g) * n_cols + c0 + 1, c[1]);
+        atomicAdd(dW + (row0 + g + 8) * n_cols + c0 + 1, c[3]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_kernel(uint32_t n, const float *__restrict__ enc,
+                                                                        const float *__restrict__ dirs,
+                                                                        const float *__restrict__ weights,
+                                                                        const float *__restrict__ d_drgbs,
+                                                                        float *__restrict__ d_enc,
+                                                                        float *__restrict__ d_weights) {
+    extern __shared__ __align__(16) uint32_t smem_u32[];
+    uint32_t *sw = smem_u32;
+    float *act = reinterpret_cast<float *>(smem_u32 + kWeightFloats);
+    load_weights(sw, weights);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3u;
+
+    // dW tiles owned by this warp for the whole kernel
+    float dW0[2][4] = {}, dW1[1][4] = {}, dW2[2][4] = {}, dW3[4][4] = {}, dW4[1][4] = {};
+    float *D = act + O_D;
+    float *D_mine = D + warp * 16 * S_D;
+
+    const uint32_t n_blocks = (n + kBlockSamples - 1) / kBlockSamples;
+    for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const uint32_t base = blk * kBlockSamples, row0 = base + warp * 16;
+        const uint32_t r_lo = row0 + g, r_hi = row0 + g + 8;
+        // ---- forward recompute (activations of the CTA's 128 samples -> shared memory)
+        FwdState st;
+        uint32_t a_tmp[8][4];
+        float rgb[1][4];
+        warp_forward<true, false>(sw, act, warp, row0, n, enc, dirs, g, t, st, a_tmp, rgb);
+        const float4 dd_lo = r_lo < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 dd_hi = r_hi < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_hi) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+        // ---- layer 4 delta: d_a3 = d_rgb * rgb * (1 - rgb), cols (2t, 2t+1) of the padded 8
+        float d3[1][4];
+        {
+            const float dr_lo0 = t == 0 ? dd_lo.y : t == 1 ? dd_lo.w : 0.f, dr_lo1 = t == 0 ? dd_lo.z : 0.f;
+            const float dr_hi0 = t == 0 ? dd_hi.y : t == 1 ? dd_hi.w : 0.f, dr_hi1 = t == 0 ? dd_hi.z : 0.f;
+            d3[0][0] = dr_lo0 * st.rgb[0][0] * (1.f - st.rgb[0][0]);
+            d3[0][1] = dr_lo1 * st.rgb[0][1] * (1.f - st.rgb[0][1]);
+            d3[0][2] = dr_hi0 * st.rgb[1][0] * (1.f - st.rgb[1][0]);
+            d3[0][3] = dr_hi1 * st.rgb[1][1] * (1.f - st.rgb[1][1]);
+        }
+        store_frag<1, S_D>(D_mine, d3, 0, g, t);
+        __syncthreads();  // D(d_a3) and all activations of the block are visible
+        if (warp < 4) dw_accumulate<1, S_A64>(dW4, act + O_H2, 16 * warp, D, 0, g, t);
+        // d_h2 = d_a3 * W4^T, masked by ReLU
+        uint32_t a_d[8][4];
+        float dacc[8][4];
+        {
+            uint32_t a3[1][4];
+            c_to_a(d3[0], a3[0]);
+            layer_backward<1, 8, S_W4>(a3, sw + O_W4, dacc, g, t);
+            const float *h = act + O_H2 + warp * 16 * S_A64;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float2 lo = *reinterpret_cast<const float2 *>(h + g * S_A64 + 8 * nt + 2 * t);
+                const float2 hi = *reinterpret_cast<const float2 *>(h + (g + 8) * S_A64 + 8 * nt + 2 * t);
+                dacc[nt][0] = lo.x > 0.f ? dacc[nt][0] : 0.f;
+                dacc[nt][1] = lo.y > 0.f ? dacc[nt][1] : 0.f;
+                dacc[nt][2] = hi.x > 0.f ? dacc[nt][2] : 0.f;
+                dacc[nt][3] = hi.y > 0.f ? dacc[nt][3] : 0.f;
+                c_to_a(dacc[nt], a_d[nt]);
+            }
+        }
+        __syncthreads();  // everyone finished reading D(d_a3)
+        store_frag<8, S_D>(D_mine, dacc, 0, g, t);  // D = d_a2
+        __syncthreads();
+        dw_accumulate<4, S_A64>(dW3, act + O_H1, 0, D, 8 * warp, g, t);
+        // d_h1 = d_a2 * W3^T, masked
+        {
+            layer_backward<8, 8, S_W3>(a_d, sw + O_W3, dacc, g, t);
+            const float *h = act + O_H1 + warp * 16 * S_A64;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float2 lo = *reinterpret_cast<const float2 *>(h + g * S_A64 + 8 * nt + 2 * t);
+                const float2 hi = *reinterpret_cast<const float2 *>(h + (g + 8) * S_A64 + 8 * nt + 2 * t);
+                dacc[nt][0] = lo.x > 0.f ? dacc[nt][0] : 0.f;
+                dacc[nt][1] = lo.y > 0.f ? dacc[nt][1] : 0.f;
+                dacc[nt][2] = hi.x > 0.f ? dacc[nt][2] : 0.f;
+                dacc[nt][3] = hi.y > 0.f ? dacc[nt][3] : 0.f;
+                c_to_a(dacc[nt], a_d[nt]);
+            }
+        }
+        __syncthreads();
+        store_frag<8, S_D>(D_mine, dacc, 0, g, t);  // D = d_a1
+        __syncthreads();
+        dw_accumulate<2, S_A32>(dW2, act + O_HIN, 0, D, 8 * warp, g, t);
+        // d_x = (d_a1 * W2^T)[:, :16] + d_density * exp(clip(x0, -15, 15)) on column 0 (nerfs.py:231-234)
+        float dx[2][4];
+        uint32_t a_dx[2][4];
+        {
+            layer_backward<8, 2, S_W2>(a_d, sw + O_W2, dx, g, t);
+            if (t == 0) {
+                dx[0][0] += dd_lo.x * expf(fminf(fmaxf(st.x0[0], -15.f), 15.f));
+                dx[0][2] += dd_hi.x * expf(fminf(fmaxf(st.x0[1], -15.f), 15.f));
+            }
+            c_to_a(dx[0], a_dx[0]);
+            c_to_a(dx[1], a_dx[1]);
+        }
+        __syncthreads();
+        store_frag<2, S_D>(D_mine, dx, 0, g, t);  // D = d_x (16 columns)
+        __syncthreads();
+        dw_accumulate<1, S_A64>(dW1, act + O_H0, 16 * (warp >> 1), D, 8 * (warp & 1), g, t);
+        // d_h0 = d_x * W1^T, masked
+        {
+            layer_backward<2, 8, S_W1>(a_dx, sw + O_W1, dacc, g, t);
+            const float *h = act + O_H0 + warp * 16 * S_A64;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const float2 lo = *reinterpret_cast<const float2 *>(h + g * S_A64 + 8 * nt + 2 * t);
+                const float2 hi = *reinterpret_cast<const float2 *>(h + (g + 8) * S_A64 + 8 * nt + 2 * t);
+                dacc[nt][0] = lo.x > 0.f ? dacc[nt][0] : 0.f;
+                dacc[nt][1] = lo.y > 0.f ? dacc[nt][1] : 0.f;
+                dacc[nt][2] = hi.x > 0.f ? dacc[nt][2] : 0.f;
+                dacc[nt][3] = hi.y > 0.f ? dacc[nt][3] : 0.f;
+                c_to_a(dacc[nt], a_d[nt]);
+            }
+        }
+        __syncthreads();
+        store_frag<8, S_D>(D_mine, dacc, 0, g, t);  // D = d_a0
+        __syncthreads();
+        dw_accumulate_global<2>(dW0, enc, base, n, D, 8 * warp, g, t);
+        // d_enc = d_a0 * W0^T -> global
+        {
+            float de[4][4];
+            layer_backward<8, 4, S_W0>(a_d, sw + O_W0, de, g, t);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                if (r_lo < n) *reinterpret_cast<float2 *>(d_enc + (size_t)r_lo * 32 + 8 * nt + 2 * t) = make_float2(de[nt][0], de[nt][1]);
+                if (r_hi < n) *reinterpret_cast<float2 *>(d_enc + (size_t)r_hi * 32 + 8 * nt + 2 * t) = make_float2(de[nt][2], de[nt][3]);
+            }
+        }
+        __syncthreads();  // before the next block overwrites the activation buffers and D
+    }
+
+    // ---- flush this CTA's share of the weight gradient
+    flush_tile(d_weights + G_W0, 64, 0, 8 * warp, dW0[0], g, t);
+    flush_tile(d_weights + G_W0, 64, 16, 8 * warp, dW0[1], g, t);
+    flush_tile(d_weights + G_W1, 16, 16 * (warp >> 1), 8 * (warp & 1), dW1[0], g, t);
+    flush_tile(d_weights + G_W2, 64, 0, 8 * warp, dW2[0], g, t);
+    flush_tile(d_weights + G_W2, 64, 16, 8 * warp, dW2[1], g, t);
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) flush_tile(d_weights + G_W3, 64, 16 * mt, 8 * warp, dW3[mt], g, t);
+    if (warp < 4) flush_tile(d_weights + G_W4, 3, 16 * warp, 0, dW4[0], g, t);
+}
+
+constexpr size_t kFwdSmem = kWeightFloats * sizeof(uint32_t);
+constexpr size_t kBwdSmem = (kWeightFloats + kActFloats) * sizeof(uint32_t);
+
+}  // namespace
+}  // namespace ngp
+
+extern "C" {
+
+void ngp_nerf_mlp_forward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *d = descriptor<NgpNerfMlpDescriptor>(opaque, opaque_len, "nerf_mlp_forward");
+    if (!d || d->n_samples == 0) return;
+    BufferCursor b{buffers};
+    const float *enc = b.next<const float>();
+    const float *dirs = b.next<const float>();
+    const float *weights = b.next<const float>();
+    float *out = b.next<float>();
+    static bool configured = false;  // benign race: the attribute call is idempotent
+    if (!configured) {
+        cudaFuncSetAttribute(nerf_mlp_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+        cudaFuncSetAttribute(nerf_mlp_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem);
+        configured = true;
+    }
+    const unsigned tiles = div_up(d->n_samples, 16);
+    const unsigned blocks = min(div_up(tiles, kWarps), 148u * 4u);
+    if (d->density_only)
+        nerf_mlp_forward_kernel<true><<<blocks, kThreads, kFwdSmem, stream>>>(d->n_samples, enc, dirs, weights, out);
+    else
+        nerf_mlp_forward_kernel<false><<<blocks, kThreads, kFwdSmem, stream>>>(d->n_samples, enc, dirs, weights, out);
+    check_launch("nerf_mlp_forward");
+}
+
+void ngp_nerf_mlp_backward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *d = descriptor<NgpNerfMlpDescriptor>(opaque, opaque_len, "nerf_mlp_backward");
+    if (!d) return;
+    BufferCursor b{buffers};
+    const float *enc = b.next<const float>();
+    const float *dirs = b.next<const float>();
+    const float *weights = b.next<const float>();
+    const float *d_drgbs = b.next<const float>();
+    float *d_enc = b.next<float>();
+    float *d_weights = b.next<float>();
+    NGP_CUDA_OK(cudaMemsetAsync(d_weights, 0, kGlobalWeights * sizeof(float), stream), "nerf_mlp_backward");
+    if (d->n_samples == 0) return;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(nerf_mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
+        configured = true;
+    }
+    const unsigned blocks = min(div_up(d->n_samples, kBlockSamples), 148u);
+    nerf_mlp_backward_kernel<<<blocks, kThreads, kBwdSmem, stream>>>(d->n_samples, enc, dirs, weights, d_drgbs, d_enc, d_weights);
+    check_launch("nerf_mlp_backward");
+}
+
+}  // extern "C"

@@ -94,3 +94,7 @@ def make_ogrid_update_descriptor(n_cells, n_updates, decay):
 
 def make_ogrid_threshold_descriptor(n_cells, thr_max):
     return struct.pack("<If", _u32(n_cells, "n_cells"), float(thr_max))
+
+
+def make_nerf_mlp_descriptor(n_samples, density_only=False):
+    return struct.pack("<2I", _u32(n_samples, "n_samples"), int(bool(density_only)))

@@ -3,15 +3,15 @@
     hash-grid(32) -> Dense 64 -> ReLU -> Dense 16 (no bias) ; density = trunc_exp(x[0])
     [x(16) | SH deg 4 (16)] -> Dense 64 -> ReLU -> Dense 64 -> ReLU -> Dense 3 -> sigmoid
 
-The hash-grid encoder runs on this package's CUDA kernels.  The dense layers here are the plain
-library-GEMM arm (torch matmul, TF32 tensor cores); SURVEY 8(f1) ranks the fused tensor-core MLP as
-the next component after the section-8 rows.
+The hash-grid encoder and the dense layers run on this package's CUDA kernels (csrc/hashgrid.cu,
+csrc/mlp.cu: fully fused TF32 tensor-core MLP); a plain torch-matmul arm is kept as a
+cross-check (``fused=False``).
 """
 import math
 
 import torch
 
-from . import encoders
+from . import _lib, descriptors, encoders
 
 
 def sh4(d: torch.Tensor) -> torch.Tensor:
@@ -63,31 +63,96 @@ def glorot_uniform_(w: torch.Tensor, generator=None):
     return w.uniform_(-lim, lim, generator=generator)
 
 
+MLP_SHAPES = (("density_w0", 32, 64), ("density_w1", 64, 16), ("rgb_w0", 32, 64), ("rgb_w1", 64, 64), ("rgb_w2", 64, 3))
+MLP_NUMEL = sum(i * o for _, i, o in MLP_SHAPES)  # 9408
+
+
+def mlp_forward(enc: torch.Tensor, dirs, weights: torch.Tensor) -> torch.Tensor:
+    """Fused tensor-core MLP forward (csrc/mlp.cu).  ``dirs=None``: densities [n] only (nerfs.py:70-72)."""
+    n = enc.shape[0]
+    density_only = dirs is None
+    out = torch.empty((n,) if density_only else (n, 4), dtype=torch.float32, device=enc.device)
+    if n:
+        _lib.call("ngp_nerf_mlp_forward", [enc, enc if density_only else dirs, weights, out],
+                  descriptors.make_nerf_mlp_descriptor(n, density_only))
+    return out
+
+
+def mlp_backward(enc, dirs, weights, d_drgbs, d_weights=None):
+    """Fused backward: returns (d_enc [n, 32], d_weights [9408]); recomputes the forward on chip."""
+    n = enc.shape[0]
+    d_enc = torch.empty(n, 32, dtype=torch.float32, device=enc.device)
+    if d_weights is None:
+        d_weights = torch.empty(MLP_NUMEL, dtype=torch.float32, device=enc.device)
+    _lib.call("ngp_nerf_mlp_backward", [enc, dirs, weights, d_drgbs, d_enc, d_weights],
+              descriptors.make_nerf_mlp_descriptor(n))
+    return d_enc, d_weights
+
+
+class _FusedMLP(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, enc, dirs, weights):
+        enc, dirs, weights = enc.contiguous(), dirs.contiguous(), weights.contiguous()
+        ctx.save_for_backward(enc, dirs, weights)
+        return mlp_forward(enc, dirs, weights)
+
+    @staticmethod
+    def backward(ctx, d_drgbs):
+        enc, dirs, weights = ctx.saved_tensors
+        d_enc, d_w = mlp_backward(enc, dirs, weights, d_drgbs.contiguous())
+        return d_enc, None, d_w
+
+
 class NeRF(torch.nn.Module):
     """``nerf(xyz, dir, appearance_embeddings) -> (drgbs[..., 4], tv)``; ``dir=None`` returns densities
-    only (models/nerfs.py:40-86).  Weights are stored [in, out] like flax Dense kernels."""
+    only (models/nerfs.py:40-86).  The five Dense kernels live in one flat parameter ``mlp_flat``
+    ([in, out] row-major each, flax layout); ``density_w0`` ... ``rgb_w2`` are views of it.
+    ``fused=True`` (default) runs the dense layers in the fused tensor-core kernels of csrc/mlp.cu,
+    ``fused=False`` through plain torch matmuls (the library-GEMM arm, used as a cross-check)."""
 
     def __init__(self, bound: float, inference: bool = False, tv_scale: float = 0.0, device=None, generator=None,
-                 T: int = 2 ** 19):
+                 T: int = 2 ** 19, fused: bool = True):
         super().__init__()
         self.bound = float(bound)
+        self.fused = fused
         Enc = encoders.TCNNHashGridEncoder if inference else encoders.HashGridEncoder  # nerfs.py:431-438
         self.position_encoder = Enc(L=16, T=T, F=2, N_min=2 ** 4, N_max=int(2 ** 11 * bound), tv_scale=tv_scale,
                                     device=device, generator=generator)
+        flat = torch.empty(MLP_NUMEL, dtype=torch.float32, device=device)
+        off = 0
+        for _, i, o in MLP_SHAPES:  # glorot-uniform, no bias (nerfs.py:98,115-119)
+            glorot_uniform_(flat[off:off + i * o].view(i, o), generator)
+            off += i * o
+        self.mlp_flat = torch.nn.Parameter(flat)
 
-        def dense(i, o):
-            return torch.nn.Parameter(glorot_uniform_(torch.empty(i, o, dtype=torch.float32, device=device), generator))
+    def _view(self, name):
+        off = 0
+        for nm, i, o in MLP_SHAPES:
+            if nm == name:
+                return self.mlp_flat[off:off + i * o].view(i, o)
+            off += i * o
+        raise KeyError(name)
 
-        self.density_w0, self.density_w1 = dense(32, 64), dense(64, 16)
-        self.rgb_w0, self.rgb_w1, self.rgb_w2 = dense(32, 64), dense(64, 64), dense(64, 3)
+    density_w0 = property(lambda self: self._view("density_w0"))
+    density_w1 = property(lambda self: self._view("density_w1"))
+    rgb_w0 = property(lambda self: self._view("rgb_w0"))
+    rgb_w1 = property(lambda self: self._view("rgb_w1"))
+    rgb_w2 = property(lambda self: self._view("rgb_w2"))
 
     def mlp_parameters(self):
-        return [self.density_w0, self.density_w1, self.rgb_w0, self.rgb_w1, self.rgb_w2]
+        return [self.mlp_flat]
 
     def forward(self, xyz, dir=None, appearance_embeddings=None):
         shape = xyz.shape[:-1]
         xyz = xyz.reshape(-1, 3)
         pos_enc, tv = self.position_encoder(xyz, self.bound)
+        if self.fused:
+            if dir is None:
+                if torch.is_grad_enabled() and (pos_enc.requires_grad or self.mlp_flat.requires_grad):
+                    raise NotImplementedError("the density-only branch is inference-only (utils/types.py:1208-1217)")
+                return mlp_forward(pos_enc.contiguous(), None, self.mlp_flat.detach()).reshape(*shape, 1), tv
+            drgbs = _FusedMLP.apply(pos_enc, dir.reshape(-1, 3), self.mlp_flat)
+            return drgbs.reshape(*shape, 4), tv
         x = torch.relu(pos_enc @ self.density_w0) @ self.density_w1
         density = trunc_exp(x[:, :1])
         if dir is None:

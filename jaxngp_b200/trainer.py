@@ -80,7 +80,7 @@ class Scene:
 
 class Trainer:
     def __init__(self, device="cuda:0", n_rays=1 << 18, total_samples=1 << 18, lr=1e-2, seed=1000000007, rank=0,
-                 world_size=1, process_group=None, scene=None, T=1 << 19, use_graph=True):
+                 world_size=1, process_group=None, scene=None, T=1 << 19, use_graph=True, fused_mlp=True):
         self.device = torch.device(device)
         self.n_rays, self.total_samples = n_rays, total_samples
         self.rank, self.world_size, self.pg = rank, world_size, process_group
@@ -88,6 +88,7 @@ class Trainer:
         gen = torch.Generator(device=self.device).manual_seed(seed)  # same init on every rank
         self.nerf = nerf_mod.NeRF(bound=synthetic.BOUND, inference=False, device=self.device, generator=gen, T=T)
         self.levels = self.nerf.position_encoder.levels
+        self.fused_mlp = fused_mlp
         self._flatten_parameters()
         self.scene = scene if scene is not None else Scene(self.device)
         # occupancy grid state (utils/types.py:93-144): all-ones bitfield at step 0
@@ -116,27 +117,21 @@ class Trainer:
     # -- flat parameter / gradient / moment buffers ---------------------------------------------
     def _flatten_parameters(self):
         enc = self.nerf.position_encoder
-        mlp = self.nerf.mlp_parameters()
         self.table_numel = enc.latents.numel()
-        assert self.table_numel % 4 == 0
-        total = self.table_numel + sum(p.numel() for p in mlp)
-        total_padded = total + (-total) % 4
-        self.flat_params = torch.zeros(total_padded, dtype=torch.float32, device=self.device)
+        assert self.table_numel % 4 == 0 and nerf_mod.MLP_NUMEL % 4 == 0
+        total = self.table_numel + nerf_mod.MLP_NUMEL
+        self.flat_params = torch.zeros(total, dtype=torch.float32, device=self.device)
         self.flat_grads = torch.zeros_like(self.flat_params)
         self.adam_m = torch.zeros_like(self.flat_params)
         self.adam_v = torch.zeros_like(self.flat_params)
-        off = 0
-        views = []
-        for p in [enc.latents] + mlp:
-            n = p.numel()
-            self.flat_params[off:off + n].copy_(p.detach().reshape(-1))
-            p.data = self.flat_params[off:off + n].view_as(p)
-            views.append((off, n))
-            off += n
+        self.flat_params[: self.table_numel].copy_(enc.latents.detach().reshape(-1))
+        self.flat_params[self.table_numel:].copy_(self.nerf.mlp_flat.detach())
+        enc.latents.data = self.flat_params[: self.table_numel].view_as(enc.latents)
+        self.nerf.mlp_flat.data = self.flat_params[self.table_numel:]
         self.table = enc.latents.data
+        self.mlp_flat = self.nerf.mlp_flat.data
         self.table_grad = self.flat_grads[: self.table_numel].view_as(self.table)
-        self.mlp_params = mlp
-        self.mlp_grad_views = [self.flat_grads[o:o + n].view_as(p) for (o, n), p in zip(views[1:], mlp)]
+        self.mlp_grad = self.flat_grads[self.table_numel:]
 
     # -- one training step ------------------------------------------------------------------------
     def _step_body(self, perm, noises=None, bg=None, apply=True):
@@ -151,23 +146,34 @@ class Trainer:
         mb, ray_is_valid, rays_n, rays_start, _, xyzs, dirs, dss, z_vals = march_rays(
             self.total_samples, synthetic.DIAGONAL_N_STEPS, synthetic.K, synthetic.G, synthetic.BOUND,
             synthetic.STEPSIZE_PORTION, o, d, t_starts, t_ends, noises, self.grid.occupancy)
-        # hash-grid gather outside autograd: its backward writes straight into the flat gradient buffer
-        enc = encoders.hashgrid_forward(self.levels, xyzs, synthetic.BOUND, self.table).requires_grad_(True)
+        # gather, MLP and compositing without autograd: each backward kernel writes straight into the flat
+        # gradient buffer [table grad | MLP grads]
         n = self.nerf
-        x = torch.relu(enc @ n.density_w0) @ n.density_w1
-        density = nerf_mod.trunc_exp(x[:, :1])
-        h = torch.cat([x, nerf_mod.sh4(dirs)], dim=-1)
-        rgb = torch.sigmoid(torch.relu(torch.relu(h @ n.rgb_w0) @ n.rgb_w1) @ n.rgb_w2)
-        drgbs = torch.cat([density, rgb], dim=-1)
-        effective, final_rgbds, _ = integrate_rays(synthetic.NEAR, rays_start, rays_n, bg, dss, z_vals, drgbs)
+        enc = encoders.hashgrid_forward(self.levels, xyzs, synthetic.BOUND, self.table)
+        if self.fused_mlp:
+            drgbs = nerf_mod.mlp_forward(enc, dirs, self.mlp_flat)
+            drgbs_leaf = drgbs
+        else:
+            enc.requires_grad_(True)
+            x = torch.relu(enc @ n.density_w0) @ n.density_w1
+            density = nerf_mod.trunc_exp(x[:, :1])
+            h = torch.cat([x, nerf_mod.sh4(dirs)], dim=-1)
+            rgb = torch.sigmoid(torch.relu(torch.relu(h @ n.rgb_w0) @ n.rgb_w1) @ n.rgb_w2)
+            drgbs = torch.cat([density, rgb], dim=-1)
+            drgbs_leaf = drgbs.detach()
+        drgbs_leaf = drgbs_leaf.requires_grad_(True)
+        effective, final_rgbds, _ = integrate_rays(synthetic.NEAR, rays_start, rays_n, bg, dss, z_vals, drgbs_leaf)
         gt = sc.rgbas_u8[perm].to(torch.float32) / 255  # _utils.py:165
         gt_rgb = gt[:, :3] * gt[:, 3:] + bg * (1 - gt[:, 3:])  # utils/data.py:443-464
         n_valid = ray_is_valid.sum()
         loss = torch.where(ray_is_valid, huber(final_rgbds[:, :3], gt_rgb).mean(-1), 0.0).sum() / n_valid  # :151-156
-        grads = torch.autograd.grad(loss, [enc] + self.mlp_params)
-        encoders.hashgrid_backward(self.levels, xyzs, synthetic.BOUND, grads[0].contiguous(), out=self.table_grad)
-        for view, g in zip(self.mlp_grad_views, grads[1:]):
-            view.copy_(g)
+        (d_drgbs,) = torch.autograd.grad(loss, [drgbs_leaf])
+        if self.fused_mlp:
+            d_enc, _ = nerf_mod.mlp_backward(enc, dirs, self.mlp_flat, d_drgbs.contiguous(), d_weights=self.mlp_grad)
+        else:
+            d_enc, d_w = torch.autograd.grad(drgbs, [enc, n.mlp_flat], d_drgbs)
+            self.mlp_grad.copy_(d_w)
+        encoders.hashgrid_backward(self.levels, xyzs, synthetic.BOUND, d_enc.contiguous(), out=self.table_grad)
         out = dict(loss=loss.detach(), n_valid_rays=n_valid, measured_batch_size_before_compaction=mb,
                    measured_batch_size=effective)
         if apply and self.world_size == 1:
@@ -215,6 +221,8 @@ class Trainer:
     # -- density grid update (utils/types.py:1149-1239) --------------------------------------------
     def _density_fn(self, xyz):
         enc = encoders.hashgrid_forward(self.levels, xyz.contiguous(), synthetic.BOUND, self.table)
+        if self.fused_mlp:
+            return nerf_mod.mlp_forward(enc, None, self.mlp_flat)
         x = torch.relu(enc @ self.nerf.density_w0) @ self.nerf.density_w1
         return torch.exp(x[:, 0])
 

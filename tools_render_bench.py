@@ -1,0 +1,38 @@
+"""C3: 800x800 inference rendering through the reference's slot-refill loop (renderers.render_image_inference)
+with a briefly trained model.  Prints rays/s and fps.  Usage: python tools_render_bench.py [train_steps]"""
+import json
+import sys
+import time
+
+import torch
+
+from jaxngp_b200 import renderers, synthetic
+from jaxngp_b200.trainer import Scene, Trainer
+
+dev = "cuda:0"
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+scene = Scene(dev)
+tr = Trainer(device=dev, scene=scene)
+gen = torch.Generator(device=dev).manual_seed(0)
+for it in range(steps):
+    perm = torch.randint(0, scene.n_pixels, (tr.n_rays,), device=dev, generator=gen, dtype=torch.int32)
+    out = tr.train_step(perm)
+    if (it + 1) % 16 == 0:
+        tr.update_ogrid()
+torch.cuda.synchronize()
+loss = float(out["loss"])
+occ = float(tr.occ_mask.float().mean())
+cam = scene.cam
+res = []
+for view in (0, 7, 33):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rgb, depth = renderers.render_image_inference(tr.nerf, cam, scene.transforms[view], tr.occupancy)
+    torch.cuda.synchronize()
+    res.append(time.perf_counter() - t0)
+gt = scene.rgbas_u8[33 * 640000:34 * 640000].float() / 255
+gt_rgb = (gt[:, :3] * gt[:, 3:] + (1 - gt[:, 3:])).reshape(800, 800, 3)
+mse = float(((rgb.float() / 255 - gt_rgb) ** 2).mean())
+psnr = -10 * torch.log10(torch.tensor(mse)).item()
+print(json.dumps({"train_steps": steps, "final_loss": loss, "occupancy": occ, "frame_s": res, "fps": 1 / min(res),
+                  "rays_per_s": 640000 / min(res), "psnr_view33": psnr}))
