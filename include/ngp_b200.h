@@ -170,6 +170,19 @@ typedef struct { uint32_t n_samples, density_only; } NgpNerfMlpDescriptor;
 void ngp_nerf_mlp_forward(cudaStream_t, void **, const char *, size_t);
 void ngp_nerf_mlp_backward(cudaStream_t, void **, const char *, size_t);
 
+/* Training glue around the four ops (XLA fuses these elementwise chains for the reference):
+ * make_training_rays: app/nerf/_utils.py:93-115 + utils/types.py:398-439 (undistorted PERSPECTIVE camera)
+ *                     + models/renderers/cuda.py:57-97
+ *   in : perm i32[n] (index into views*H*W), transforms f32[V,12] (R row-major, t)
+ *   out: rays_o f32[n,3], rays_d f32[n,3], t_starts f32[n], t_ends f32[n]
+ * huber_loss_grad   : app/nerf/_utils.py:151-165 + utils/data.py:443-464
+ *   in : final_rgbds f32[n,4], ray_is_valid bool[n], perm i32[n], rgbas u8[P,4], bgs f32[n,3]
+ *   out: dL_dfinal_rgbds f32[n,4], loss f32[1], n_valid_rays u32[1] */
+typedef struct { uint32_t n_rays, width, height, n_views; float fx, fy, cx, cy, bound; } NgpTrainingRaysDescriptor;
+typedef struct { uint32_t n_rays; float delta; } NgpHuberLossDescriptor;
+void ngp_make_training_rays(cudaStream_t, void **, const char *, size_t);
+void ngp_huber_loss_grad(cudaStream_t, void **, const char *, size_t);
+
 /* Adam step of app/nerf/_utils.py:19-77 over a flat f32 buffer [hash table | MLP weights]; elements
  * at index >= decay_begin also receive the reference's (additive) decayed-weights term.
  * in : step u32[1] (device-resident count of completed steps), params f32[n] (updated in place),

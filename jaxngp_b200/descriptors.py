@@ -98,3 +98,12 @@ def make_ogrid_threshold_descriptor(n_cells, thr_max):
 
 def make_nerf_mlp_descriptor(n_samples, density_only=False):
     return struct.pack("<2I", _u32(n_samples, "n_samples"), int(bool(density_only)))
+
+
+def make_training_rays_descriptor(n_rays, width, height, n_views, fx, fy, cx, cy, bound):
+    return struct.pack("<4I5f", _u32(n_rays, "n_rays"), _u32(width, "width"), _u32(height, "height"),
+                       _u32(n_views, "n_views"), float(fx), float(fy), float(cx), float(cy), float(bound))
+
+
+def make_huber_loss_descriptor(n_rays, delta):
+    return struct.pack("<If", _u32(n_rays, "n_rays"), float(delta))

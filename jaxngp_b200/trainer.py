@@ -12,8 +12,9 @@ Adam-moment buffers, so data parallelism is a single ``all_reduce`` and the opti
 """
 import torch
 
-from . import _lib, descriptors, dp, encoders, nerf as nerf_mod, ogrid, renderers, synthetic
+from . import _lib, descriptors, dp, encoders, nerf as nerf_mod, ogrid, renderers, synthetic, trainops
 from .volrendjax import integrate_rays, march_rays
+from .volrendjax.integrating import _integrate_bwd, _integrate_fwd
 
 
 def huber(pred, target, delta=0.1):
@@ -80,7 +81,7 @@ class Scene:
 
 class Trainer:
     def __init__(self, device="cuda:0", n_rays=1 << 18, total_samples=1 << 18, lr=1e-2, seed=1000000007, rank=0,
-                 world_size=1, process_group=None, scene=None, T=1 << 19, use_graph=True, fused_mlp=True):
+                 world_size=1, process_group=None, scene=None, T=1 << 19, use_graph=True, fused_mlp=True, fused_glue=None):
         self.device = torch.device(device)
         self.n_rays, self.total_samples = n_rays, total_samples
         self.rank, self.world_size, self.pg = rank, world_size, process_group
@@ -89,6 +90,7 @@ class Trainer:
         self.nerf = nerf_mod.NeRF(bound=synthetic.BOUND, inference=False, device=self.device, generator=gen, T=T)
         self.levels = self.nerf.position_encoder.levels
         self.fused_mlp = fused_mlp
+        self.fused_glue = fused_mlp if fused_glue is None else fused_glue
         self._flatten_parameters()
         self.scene = scene if scene is not None else Scene(self.device)
         # occupancy grid state (utils/types.py:93-144): all-ones bitfield at step 0
@@ -135,6 +137,33 @@ class Trainer:
 
     # -- one training step ------------------------------------------------------------------------
     def _step_body(self, perm, noises=None, bg=None, apply=True):
+        if not self.fused_glue:
+            return self._step_body_torch(perm, noises, bg, apply)
+        sc, dev = self.scene, self.device
+        if noises is None:
+            noises = torch.rand(self.n_rays, device=dev)  # cuda.py:118-122
+        if bg is None:
+            bg = torch.rand(self.n_rays, 3, device=dev)  # random_bg, _utils.py:134-136
+        o, d, t_starts, t_ends = trainops.make_training_rays(perm, sc.transforms, sc.cam, synthetic.BOUND)
+        nxt, exc, ray_is_valid, rays_n, rays_start, _, xyzs, dirs, dss, z_vals = march_rays(
+            self.total_samples, synthetic.DIAGONAL_N_STEPS, synthetic.K, synthetic.G, synthetic.BOUND,
+            synthetic.STEPSIZE_PORTION, o, d, t_starts, t_ends, noises, self.grid.occupancy, raw=True)
+        enc = encoders.hashgrid_forward(self.levels, xyzs, synthetic.BOUND, self.table)
+        drgbs = nerf_mod.mlp_forward(enc, dirs, self.mlp_flat)
+        effective, final_rgbds, final_opac = _integrate_fwd(rays_start, rays_n, bg, dss, z_vals, drgbs)
+        d_final, loss, n_valid = trainops.huber_loss_grad(final_rgbds, ray_is_valid, perm, sc.rgbas_u8, bg)
+        _, _, d_drgbs = _integrate_bwd(synthetic.NEAR, rays_start, rays_n, bg, dss, z_vals, drgbs, final_rgbds,
+                                       final_opac, d_final)
+        d_enc, _ = nerf_mod.mlp_backward(enc, dirs, self.mlp_flat, d_drgbs, d_weights=self.mlp_grad)
+        encoders.hashgrid_backward(self.levels, xyzs, synthetic.BOUND, d_enc, out=self.table_grad)
+        out = dict(loss=loss[0], n_valid_rays=n_valid[0], measured_batch_size_before_compaction=(nxt - exc)[0],
+                   measured_batch_size=effective[0])  # marching/__init__.py:91
+        if apply and self.world_size == 1:
+            self._optimizer_step()
+        return out
+
+    def _step_body_torch(self, perm, noises=None, bg=None, apply=True):
+        """Same step with the glue (ray generation, loss) in torch ops and autograd: the cross-check arm."""
         sc, dev = self.scene, self.device
         perm = perm.to(torch.int64)
         o, d = sc.rays(perm)

@@ -1,0 +1,30 @@
+"""Fused training glue (csrc/trainops.cu): ray generation and the Huber loss with its gradient."""
+import torch
+
+from . import _lib, descriptors
+
+
+def make_training_rays(perm: torch.Tensor, transforms: torch.Tensor, cam: dict, bound: float):
+    """perm int32[n] -> (rays_o [n,3], rays_d [n,3], t_starts [n], t_ends [n]); app/nerf/_utils.py:93-115 +
+    models/renderers/cuda.py:57-97 for an undistorted perspective camera."""
+    n, dev = perm.shape[0], perm.device
+    o = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    d = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    ts = torch.empty(n, dtype=torch.float32, device=dev)
+    te = torch.empty(n, dtype=torch.float32, device=dev)
+    if n:
+        _lib.call("ngp_make_training_rays", [perm, transforms, o, d, ts, te],
+                  descriptors.make_training_rays_descriptor(n, cam["width"], cam["height"], transforms.shape[0],
+                                                            cam["fx"], cam["fy"], cam["cx"], cam["cy"], bound))
+    return o, d, ts, te
+
+
+def huber_loss_grad(final_rgbds, ray_is_valid, perm, rgbas_u8, bgs, delta=0.1):
+    """Returns (dL_dfinal_rgbds [n,4], loss [1], n_valid_rays int32[1]); app/nerf/_utils.py:151-165."""
+    n, dev = final_rgbds.shape[0], final_rgbds.device
+    dL = torch.empty(n, 4, dtype=torch.float32, device=dev)
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    n_valid = torch.empty(1, dtype=torch.int32, device=dev)
+    _lib.call("ngp_huber_loss_grad", [final_rgbds, ray_is_valid, perm, rgbas_u8, bgs, dL, loss, n_valid],
+              descriptors.make_huber_loss_descriptor(n, delta))
+    return dL, loss, n_valid

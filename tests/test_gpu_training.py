@@ -22,6 +22,19 @@ def _params_np(tr):
     return d
 
 
+def test_fused_ray_generation_matches_host_restatement(small_scene):
+    from jaxngp_b200 import synthetic as S, trainops
+    rng = np.random.Generator(np.random.PCG64(4))
+    perm = rng.integers(0, small_scene.n_pixels, 50000).astype(np.int32)
+    o, d, ts, te = trainops.make_training_rays(torch.from_numpy(perm).to(DEV), small_scene.transforms, small_scene.cam, 1.0)
+    hw = small_scene.width * small_scene.height
+    ro, rd = S.pixel_rays(small_scene.transforms.cpu().numpy(), perm // hw, perm % hw, small_scene.cam)
+    rts, rte = S.near_far(ro, rd)
+    assert np.array_equal(o.cpu().numpy(), ro)
+    assert np.allclose(d.cpu().numpy(), rd, atol=2e-7, rtol=0)
+    assert np.allclose(ts.cpu().numpy(), rts, rtol=1e-5, atol=1e-6) and np.allclose(te.cpu().numpy(), rte, rtol=1e-5, atol=1e-6)
+
+
 @pytest.mark.parametrize("fused_mlp", [True, False])
 def test_train_step_gradients_match_oracle(small_scene, fused_mlp):
     from jaxngp_b200 import synthetic as S
