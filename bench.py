@@ -117,7 +117,9 @@ def run_ours(args):
         sampler.start()  # started early: nvidia-smi needs a moment before its first sample
     tr = Trainer(device=dev, n_rays=N_RAYS, total_samples=TOTAL_SAMPLES, rank=rank, world_size=world,
                  use_graph=not args.no_graph)
-    tr.occupancy.copy_(tr.scene.bitfield_gt)  # converged occupancy of the analytic scene (see DESIGN.md "bench state")
+    # converged occupancy of the analytic scene (see DESIGN.md "bench state"): bitfield and its unpacked mask
+    tr.grid.occupancy.copy_(tr.scene.bitfield_gt)
+    tr.grid.occ_mask.copy_(torch.from_numpy(np.unpackbits(tr.scene.bitfield_gt.cpu().numpy(), bitorder="little").astype(bool)).to(dev))
     perms_host = torch.from_numpy(host_perms(W + K, rank)).pin_memory()
     perms_dev = perms_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -3,7 +3,8 @@
 // Replaces deps/volume-rendering-jax/lib/impl/integrating.cu:24-322,325-507.
 //
 // The reference walks each ray with one thread (scalar, uncoalesced loads, a latency chain of
-// n_samples global loads).  Here a warp walks a ray: each lane loads one sample with full-width
+// n_samples global loads).  Here a warp walks a ray (rays dealt round-robin to warps, next chunk's
+// samples prefetched while the current one is composited): each lane loads one sample with full-width
 // coalesced accesses (float4 for drgbs) and evaluates its alpha in parallel; only the
 // transmittance recurrence T <- T * (1 - alpha) is replayed in sample order through shuffles, with
 // the same two rounded operations per sample as the reference, so the early-stop decision
@@ -16,33 +17,49 @@ namespace {
 
 constexpr float kTThreshold = 1e-4f;  // integrating.cu:12
 constexpr int kBlock = 128;
-constexpr int kRaysPerWarp = 32;  // a warp owns 32 consecutive rays: empty ones are finished lane-parallel, the rest walked in turn
 
-struct Chunk {
-    float alpha, one_minus, Tb;  // this lane's sample: alpha, 1-alpha, transmittance before it
-    bool active;                 // sample is composited (T before it > threshold)
-};
-
-// Replays T_{k+1} = T_k * (1 - alpha_k) over the (up to 32) samples held by the lanes, in order,
-// stopping like `for (; T > T_THRESHOLD && idx < n; ++idx)` (integrating.cu:61).
-__device__ __forceinline__ void transmittance_chain(float one_minus, uint32_t count, uint32_t lane, float &T,
-                                                    float &Tb, bool &active, uint32_t &processed) {
-    active = false;
-    Tb = 0.f;
-#pragma unroll 8
+// Replays T_{k+1} = T_k * (1 - alpha_k) over the (up to 32) samples held by the lanes, in sample order, with
+// exactly the reference's two rounded operations per sample, and applies its stopping rule
+// `for (; T > T_THRESHOLD && idx < n; ++idx)` (integrating.cu:61): sample k is composited iff every
+// transmittance before it, including its own T_before, exceeded the threshold.  The 32 products are
+// computed unconditionally (lanes >= count contribute the exact factor 1), so the only dependent chain is
+// 32 FMULs; the shuffles feeding it are independent and pipeline.
+// Returns the number of composited samples; T becomes the transmittance after the last composited one.
+__device__ __forceinline__ uint32_t transmittance_chain(float one_minus, uint32_t count, uint32_t lane, float &T,
+                                                        float &Tb, bool &active) {
+    float run = T, mine = T;
+#pragma unroll
     for (uint32_t k = 0; k < 32; ++k) {
-        float a = __shfl_sync(0xffffffffu, one_minus, k);
-        if (k < count && T > kTThreshold) {
-            if (lane == k) {
-                Tb = T;
-                active = true;
-            }
-            T = __fmul_rn(T, a);
-            ++processed;
-        }
+        const float a = __shfl_sync(0xffffffffu, one_minus, k);
+        if (lane == k) mine = run;  // transmittance before sample k
+        run = __fmul_rn(run, a);
     }
+    Tb = mine;
+    // first sample whose T_before is already at or below the threshold stops the ray
+    const uint32_t stop = __ballot_sync(0xffffffffu, !(mine > kTThreshold) || lane >= count);
+    const uint32_t processed = stop ? (uint32_t)__ffs(stop) - 1u : 32u;
+    active = lane < processed;
+    // transmittance after the last composited sample = T_before of the first one that was not
+    T = processed < 32u ? __shfl_sync(0xffffffffu, mine, processed & 31u) : run;
+    return processed;
 }
 
+struct SampleRegs {
+    float4 v;
+    float z, dt;
+};
+
+__device__ __forceinline__ SampleRegs load_sample(const float4 *__restrict__ drgbs, const float *__restrict__ z_vals,
+                                                  const float *__restrict__ dss, uint32_t s, bool ok) {
+    SampleRegs r;
+    r.v = ok ? __ldg(drgbs + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+    r.z = ok ? __ldg(z_vals + s) : 0.f;
+    r.dt = ok ? __ldg(dss + s) : 0.f;
+    return r;
+}
+
+// One warp per ray, rays dealt round-robin to warps: the rays that own samples sit at the front of the batch
+// (march_rays hands out the budget in ray order), so striding spreads them over all SMs.
 __global__ void __launch_bounds__(kBlock) integrate_rays_kernel(
     uint32_t n_rays, const uint32_t *__restrict__ rays_sample_startidx, const uint32_t *__restrict__ rays_n_samples,
     const float *__restrict__ bgs, const float *__restrict__ dss, const float *__restrict__ z_vals,
@@ -51,48 +68,46 @@ __global__ void __launch_bounds__(kBlock) integrate_rays_kernel(
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = gridDim.x * (kBlock / 32);
     const uint32_t warp_global = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
-    const uint32_t n_groups = (n_rays + kRaysPerWarp - 1) / kRaysPerWarp;
     uint32_t composited = 0;
 
-    for (uint32_t grp = warp_global; grp < n_groups; grp += warps_total) {
-        const uint32_t my_ray = grp * kRaysPerWarp + lane;
-        uint32_t my_start = 0, my_n = 0;
-        if (my_ray < n_rays) {
-            my_start = __ldg(rays_sample_startidx + my_ray);
-            my_n = __ldg(rays_n_samples + my_ray);
-            if (my_n == 0) {  // nothing to composite: T = 1, opacity 0, colour = background (integrating.cu:91-96)
-                final_opacities[my_ray] = 0.f;
-                final_rgbds[my_ray] = make_float4(__ldg(bgs + 3 * (size_t)my_ray + 0), __ldg(bgs + 3 * (size_t)my_ray + 1),
-                                                  __ldg(bgs + 3 * (size_t)my_ray + 2), 0.f);
-            }
+    // rays without samples: T = 1, opacity 0, colour = background (integrating.cu:91-96); thread per ray
+    for (uint32_t ray = blockIdx.x * kBlock + threadIdx.x; ray < n_rays; ray += gridDim.x * kBlock) {
+        if (__ldg(rays_n_samples + ray) == 0) {
+            final_opacities[ray] = 0.f;
+            final_rgbds[ray] = make_float4(__ldg(bgs + 3 * (size_t)ray + 0), __ldg(bgs + 3 * (size_t)ray + 1),
+                                           __ldg(bgs + 3 * (size_t)ray + 2), 0.f);
         }
-        uint32_t todo = __ballot_sync(0xffffffffu, my_n != 0);
-        while (todo) {  // the warp walks the non-empty rays of its group one at a time
+    }
+    for (uint32_t base = 0; base < n_rays; base += warps_total * 32u) {
+        // lane l looks at ray (base + l * warps_total + warp_global): 32 candidate rays per warp per round
+        const uint32_t cand = base + lane * warps_total + warp_global;
+        const uint32_t cand_n = cand < n_rays ? __ldg(rays_n_samples + cand) : 0u;
+        uint32_t todo = __ballot_sync(0xffffffffu, cand_n != 0u);
+        while (todo) {
             const uint32_t q = __ffs(todo) - 1;
             todo &= todo - 1;
-            const uint32_t ray = grp * kRaysPerWarp + q;
-            const uint32_t start = __shfl_sync(0xffffffffu, my_start, q);
-            const uint32_t n = __shfl_sync(0xffffffffu, my_n, q);
+            const uint32_t ray = base + q * warps_total + warp_global;
+            const uint32_t n = __shfl_sync(0xffffffffu, cand_n, q);
+            const uint32_t start = __ldg(rays_sample_startidx + ray);
             float T = 1.f, r = 0.f, g = 0.f, b = 0.f, depth = 0.f;
+            SampleRegs cur = load_sample(drgbs, z_vals, dss, start + lane, lane < n);
             for (uint32_t c = 0; c < n && T > kTThreshold; c += 32) {
                 const uint32_t count = min(32u, n - c);
-                float one_minus = 1.f, alpha = 0.f, z = 0.f;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const SampleRegs nxt = load_sample(drgbs, z_vals, dss, start + c + 32u + lane, c + 32u + lane < n);  // prefetch
+                float one_minus = 1.f, alpha = 0.f;
                 if (lane < count) {
-                    const uint32_t s = start + c + lane;
-                    v = __ldg(drgbs + s);
-                    z = __ldg(z_vals + s);
-                    alpha = 1.f - __expf(-v.x * __ldg(dss + s));  // integrating.cu:64
+                    alpha = 1.f - __expf(-cur.v.x * cur.dt);  // integrating.cu:64
                     one_minus = 1.f - alpha;
                 }
                 float Tb;
                 bool active;
-                transmittance_chain(one_minus, count, lane, T, Tb, active, composited);
+                composited += transmittance_chain(one_minus, count, lane, T, Tb, active);
                 const float w = active ? Tb * alpha : 0.f;
-                r += w * v.y;
-                g += w * v.z;
-                b += w * v.w;
-                depth += w * z;
+                r += w * cur.v.y;
+                g += w * cur.v.z;
+                b += w * cur.v.w;
+                depth += w * cur.z;
+                cur = nxt;
             }
             r = warp_sum(r);
             g = warp_sum(g);
@@ -113,7 +128,7 @@ __global__ void __launch_bounds__(kBlock) integrate_rays_kernel(
             }
         }
     }
-    // `composited` is identical on all lanes (the chain is replicated); one atomic per warp
+    // `composited` is identical on all lanes; one atomic per warp
     if (lane == 0 && composited) atomicAdd(measured_batch_size, composited);
 }
 
@@ -135,74 +150,68 @@ __global__ void __launch_bounds__(kBlock) integrate_rays_backward_kernel(
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warps_total = gridDim.x * (kBlock / 32);
     const uint32_t warp_global = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
-    const uint32_t n_groups = (n_rays + kRaysPerWarp - 1) / kRaysPerWarp;
 
-    for (uint32_t grp = warp_global; grp < n_groups; grp += warps_total) {
-        const uint32_t my_ray = grp * kRaysPerWarp + lane;
-        uint32_t my_start = 0, my_n = 0;
-        if (my_ray < n_rays) {
-            my_start = __ldg(rays_sample_startidx + my_ray);
-            my_n = __ldg(rays_n_samples + my_ray);
-            if (my_n == 0) {  // T stays 1: the whole colour gradient flows to the background (integrating.cu:235-239)
-                const float4 dfin = __ldg(dL_dfinal_rgbds + my_ray);
-                dL_dbgs[3 * (size_t)my_ray + 0] = dfin.x;
-                dL_dbgs[3 * (size_t)my_ray + 1] = dfin.y;
-                dL_dbgs[3 * (size_t)my_ray + 2] = dfin.z;
-            }
+    // rays without samples: T stays 1, the whole colour gradient flows to the background (integrating.cu:235-239)
+    for (uint32_t ray = blockIdx.x * kBlock + threadIdx.x; ray < n_rays; ray += gridDim.x * kBlock) {
+        if (__ldg(rays_n_samples + ray) == 0) {
+            const float4 dfin = __ldg(dL_dfinal_rgbds + ray);
+            dL_dbgs[3 * (size_t)ray + 0] = dfin.x;
+            dL_dbgs[3 * (size_t)ray + 1] = dfin.y;
+            dL_dbgs[3 * (size_t)ray + 2] = dfin.z;
         }
-        uint32_t todo = __ballot_sync(0xffffffffu, my_n != 0);
+    }
+    for (uint32_t base = 0; base < n_rays; base += warps_total * 32u) {
+        const uint32_t cand = base + lane * warps_total + warp_global;
+        const uint32_t cand_n = cand < n_rays ? __ldg(rays_n_samples + cand) : 0u;
+        uint32_t todo = __ballot_sync(0xffffffffu, cand_n != 0u);
         while (todo) {
             const uint32_t q = __ffs(todo) - 1;
             todo &= todo - 1;
-            const uint32_t ray = grp * kRaysPerWarp + q;
-            const uint32_t start = __shfl_sync(0xffffffffu, my_start, q);
-            const uint32_t n = __shfl_sync(0xffffffffu, my_n, q);
+            const uint32_t ray = base + q * warps_total + warp_global;
+            const uint32_t n = __shfl_sync(0xffffffffu, cand_n, q);
+            const uint32_t start = __ldg(rays_sample_startidx + ray);
             const float4 dfin = __ldg(dL_dfinal_rgbds + ray);
-            float T = 1.f;
-            {
-                const float4 fin = __ldg(final_rgbds + ray);
-                const float opac = __ldg(final_opacities + ray);
-                const bool terminated = opac >= 1.f - kTThreshold;  // integrating.cu:158
-                const float bgw = terminated ? 0.f : 1.f - opac;
-                const float bg0 = __ldg(bgs + 3 * (size_t)ray + 0) * bgw, bg1 = __ldg(bgs + 3 * (size_t)ray + 1) * bgw,
-                            bg2 = __ldg(bgs + 3 * (size_t)ray + 2) * bgw;
-                float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;  // running composited colour / depth
-                uint32_t dummy = 0;
-                for (uint32_t c = 0; c < n && T > kTThreshold; c += 32) {
-                    const uint32_t count = min(32u, n - c);
-                    float one_minus = 1.f, alpha = 0.f, z = 0.f, dt = 0.f;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const uint32_t s = start + c + lane;
-                    if (lane < count) {
-                        v = __ldg(drgbs + s);
-                        z = __ldg(z_vals + s);
-                        dt = __ldg(dss + s);
-                        alpha = 1.f - __expf(-v.x * dt);  // integrating.cu:181
-                        one_minus = 1.f - alpha;
-                    }
-                    float Tb;
-                    bool active;
-                    transmittance_chain(one_minus, count, lane, T, Tb, active, dummy);
-                    const float w = active ? Tb * alpha : 0.f;
-                    const float Ta = Tb * one_minus;  // transmittance after this sample, integrating.cu:193
-                    const float ir = cr + warp_incl_scan(w * v.y, lane);
-                    const float ig = cg + warp_incl_scan(w * v.z, lane);
-                    const float ib = cb + warp_incl_scan(w * v.w, lane);
-                    const float id = cd + warp_incl_scan(w * z, lane);
-                    cr = __shfl_sync(0xffffffffu, ir, 31);
-                    cg = __shfl_sync(0xffffffffu, ig, 31);
-                    cb = __shfl_sync(0xffffffffu, ib, 31);
-                    cd = __shfl_sync(0xffffffffu, id, 31);
-                    if (active) {
-                        dL_dz_vals[s] = w * dfin.w;  // integrating.cu:196
-                        float acc = dfin.x * (Ta * v.y - (fin.x - ir) - bg0) + dfin.y * (Ta * v.z - (fin.y - ig) - bg1) +
-                                    dfin.z * (Ta * v.w - (fin.z - ib) - bg2) + dfin.w * (Ta * z - (fin.w - id));
-                        const float dsig = dt * acc;                                            // :199-215
-                        const float reg = (v.x > 4e-5f && z < near_distance) ? 1e-4f : 0.f;     // :221
-                        const float scal = fminf(z * z, 1.f);                                   // :225
-                        dL_ddrgbs[s] = make_float4(scal * dsig + reg, w * dfin.x, w * dfin.y, w * dfin.z);
-                    }
+            const float4 fin = __ldg(final_rgbds + ray);
+            const float opac = __ldg(final_opacities + ray);
+            const bool terminated = opac >= 1.f - kTThreshold;  // integrating.cu:158
+            const float bgw = terminated ? 0.f : 1.f - opac;
+            const float bg0 = __ldg(bgs + 3 * (size_t)ray + 0) * bgw, bg1 = __ldg(bgs + 3 * (size_t)ray + 1) * bgw,
+                        bg2 = __ldg(bgs + 3 * (size_t)ray + 2) * bgw;
+            float T = 1.f, cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;  // running composited colour / depth
+            SampleRegs cur = load_sample(drgbs, z_vals, dss, start + lane, lane < n);
+            for (uint32_t c = 0; c < n && T > kTThreshold; c += 32) {
+                const uint32_t count = min(32u, n - c);
+                const uint32_t s = start + c + lane;
+                const SampleRegs nxt = load_sample(drgbs, z_vals, dss, s + 32u, c + 32u + lane < n);  // prefetch
+                float one_minus = 1.f, alpha = 0.f;
+                if (lane < count) {
+                    alpha = 1.f - __expf(-cur.v.x * cur.dt);  // integrating.cu:181
+                    one_minus = 1.f - alpha;
                 }
+                float Tb;
+                bool active;
+                transmittance_chain(one_minus, count, lane, T, Tb, active);
+                const float w = active ? Tb * alpha : 0.f;
+                const float Ta = Tb * one_minus;  // transmittance after this sample, integrating.cu:193
+                const float ir = cr + warp_incl_scan(w * cur.v.y, lane);
+                const float ig = cg + warp_incl_scan(w * cur.v.z, lane);
+                const float ib = cb + warp_incl_scan(w * cur.v.w, lane);
+                const float id = cd + warp_incl_scan(w * cur.z, lane);
+                cr = __shfl_sync(0xffffffffu, ir, 31);
+                cg = __shfl_sync(0xffffffffu, ig, 31);
+                cb = __shfl_sync(0xffffffffu, ib, 31);
+                cd = __shfl_sync(0xffffffffu, id, 31);
+                if (active) {
+                    const float z = cur.z;
+                    dL_dz_vals[s] = w * dfin.w;  // integrating.cu:196
+                    const float acc = dfin.x * (Ta * cur.v.y - (fin.x - ir) - bg0) + dfin.y * (Ta * cur.v.z - (fin.y - ig) - bg1) +
+                                      dfin.z * (Ta * cur.v.w - (fin.z - ib) - bg2) + dfin.w * (Ta * z - (fin.w - id));
+                    const float dsig = cur.dt * acc;                                          // :199-215
+                    const float reg = (cur.v.x > 4e-5f && z < near_distance) ? 1e-4f : 0.f;   // :221
+                    const float scal = fminf(z * z, 1.f);                                     // :225
+                    dL_ddrgbs[s] = make_float4(scal * dsig + reg, w * dfin.x, w * dfin.y, w * dfin.z);
+                }
+                cur = nxt;
             }
             if (lane == 0 && T > kTThreshold) {  // integrating.cu:235-239
                 dL_dbgs[3 * (size_t)ray + 0] = T * dfin.x;
@@ -288,8 +297,7 @@ void ngp_integrate_rays(cudaStream_t stream, void **buffers, const char *opaque,
     float *final_opacities = b.next<float>();
     NGP_CUDA_OK(cudaMemsetAsync(mbs, 0, sizeof(uint32_t), stream), "integrate_rays");
     if (desc->n_rays == 0) return;
-    const unsigned groups = div_up(desc->n_rays, kRaysPerWarp);
-    const unsigned blocks = min(div_up(groups, kBlock / 32), 148u * 16u);
+    const unsigned blocks = min(div_up(desc->n_rays, kBlock), 148u * 8u);
     integrate_rays_kernel<<<blocks, kBlock, 0, stream>>>(desc->n_rays, start, ns, bgs, dss, z_vals, drgbs, mbs,
                                                          final_rgbds, final_opacities);
     check_launch("integrate_rays");
@@ -318,8 +326,7 @@ void ngp_integrate_rays_backward(cudaStream_t stream, void **buffers, const char
     NGP_CUDA_OK(cudaMemsetAsync(dL_dz, 0, (size_t)desc->total_samples * sizeof(float), stream), "integrate_rays_backward");
     NGP_CUDA_OK(cudaMemsetAsync(dL_dd, 0, (size_t)desc->total_samples * 4 * sizeof(float), stream), "integrate_rays_backward");
     if (desc->n_rays == 0) return;
-    const unsigned groups = div_up(desc->n_rays, kRaysPerWarp);
-    const unsigned blocks = min(div_up(groups, kBlock / 32), 148u * 16u);
+    const unsigned blocks = min(div_up(desc->n_rays, kBlock), 148u * 8u);
     integrate_rays_backward_kernel<<<blocks, kBlock, 0, stream>>>(desc->n_rays, desc->near_distance, start, ns, bgs,
                                                                   dss, z_vals, drgbs, final_rgbds, final_opacities,
                                                                   dL_dfinal, dL_dbgs, dL_dz, dL_dd);

@@ -134,6 +134,7 @@ __device__ __forceinline__ Step march_step(const Grid &g, const Ray &r, float t)
 // Same visited set, same samples, bit for bit; ~30x shorter critical path per ray.
 constexpr int kRaysPerTile = 8;   // warps per CTA, one ray each
 constexpr int kMarchBlock = kRaysPerTile * 32;
+constexpr uint32_t kDrainBatch = 64;  // tiles claimed per ticket once the budget is known to be full
 constexpr uint64_t kFlagAgg = 1ull << 62, kFlagIncl = 2ull << 62, kValueMask = (1ull << 62) - 1;
 
 struct MarchScratch {
@@ -293,10 +294,10 @@ __global__ void __launch_bounds__(kMarchBlock) march_rays_kernel(
     uint8_t *__restrict__ ray_is_valid, uint32_t *__restrict__ rays_n_samples,
     uint32_t *__restrict__ rays_sample_startidx, uint32_t *__restrict__ idcs, float *__restrict__ xyzs,
     float *__restrict__ dirs, float *__restrict__ dss, float *__restrict__ z_vals) {
-    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_tile, s_drain_end;
     __shared__ uint32_t s_count[kRaysPerTile];
     __shared__ unsigned long long s_prefix;
-    __shared__ int s_abandon;
+    __shared__ int s_abandon, s_drain;
 
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const Grid g = make_grid(p.diagonal_n_steps, p.K, p.G, p.bound, p.stepsize_portion, bitfield);
@@ -308,11 +309,34 @@ __global__ void __launch_bounds__(kMarchBlock) march_rays_kernel(
         __syncthreads();
         if (threadIdx.x == 0) {
             s_tile = atomicAdd(&ws->ticket, 1u);
+            s_drain_end = s_tile + 1u;
             s_abandon = 0;
+            s_drain = behind_cut(ws, s_tile) ? 1 : 0;  // decided once per CTA: the branch below must be uniform
         }
         __syncthreads();
-        const uint32_t tile = s_tile;
+        uint32_t tile = s_tile;
         if (tile >= num_tiles) return;
+        if (s_drain) {
+            // Drain: every remaining tile lies behind the cut (tickets only grow), so its rays early-out
+            // (marching.cu:135).  Claim tiles 64 at a time and clear their per-ray outputs with full-width stores.
+            for (;;) {
+                const uint32_t first_ray = tile * kRaysPerTile;
+                const uint32_t end_ray = min(p.n_rays, (s_drain_end) * kRaysPerTile);
+                for (uint32_t r = first_ray + threadIdx.x; r < end_ray; r += kMarchBlock) {
+                    ray_is_valid[r] = 0;
+                    rays_n_samples[r] = 0u;
+                    rays_sample_startidx[r] = 0u;
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    s_tile = atomicAdd(&ws->ticket, kDrainBatch);
+                    s_drain_end = s_tile + kDrainBatch;
+                }
+                __syncthreads();
+                tile = s_tile;
+                if (tile >= num_tiles) return;
+            }
+        }
         const uint32_t i = tile * kRaysPerTile + warp;
         const bool in_range = i < p.n_rays;
 
@@ -348,29 +372,37 @@ __global__ void __launch_bounds__(kMarchBlock) march_rays_kernel(
             tile_total += c;
         }
 
-        // ---- decoupled look-back for the tile's exclusive prefix (thread 0)
-        if (threadIdx.x == 0) {
+        // ---- decoupled look-back for the tile's exclusive prefix: warp 0 inspects 32 predecessors per round
+        if (warp == 0) {
             volatile unsigned long long *status = ws->status;
             unsigned long long prefix = 0;
             bool give_up = s_abandon != 0;
             if (!give_up) {
-                if (tile == 0) {
-                    status[0] = kFlagIncl | tile_total;
-                } else {
-                    status[tile] = kFlagAgg | tile_total;
-                    __threadfence();
-                    for (int64_t j = (int64_t)tile - 1; j >= 0; --j) {
-                        unsigned long long st;
-                        while ((st = status[j]) == 0) {
-                            if (behind_cut(ws, tile)) { give_up = true; break; }
-                        }
-                        if (give_up) break;
-                        prefix += st & kValueMask;
-                        if (st & kFlagIncl) break;
-                    }
-                    if (!give_up) status[tile] = kFlagIncl | (prefix + tile_total);
+                if (lane == 0) status[tile] = (tile == 0 ? kFlagIncl : kFlagAgg) | tile_total;
+                __threadfence();
+                int64_t hi = (int64_t)tile - 1;  // newest predecessor not yet accounted for
+                while (hi >= 0) {
+                    const int64_t j = hi - (int64_t)lane;
+                    unsigned long long st = 0;
+                    bool ready;
+                    do {  // wait until all 32 (existing) predecessors of this round have published something
+                        st = j >= 0 ? status[j] : kFlagIncl;
+                        ready = __all_sync(0xffffffffu, st != 0);
+                        if (!ready && behind_cut(ws, tile)) { give_up = true; break; }
+                    } while (!ready);
+                    if (give_up) break;
+                    // nearest predecessor holding an inclusive prefix ends the walk
+                    const uint32_t incl_mask = __ballot_sync(0xffffffffu, (st & kFlagIncl) != 0 && j >= 0);
+                    const uint32_t stop_lane = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 32u;
+                    unsigned long long v = (j >= 0 && lane <= stop_lane) ? (st & kValueMask) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    prefix += v;
+                    if (incl_mask) break;
+                    hi -= 32;
                 }
-                if (!give_up) {
+                if (!give_up && lane == 0) {
+                    if (tile != 0) status[tile] = kFlagIncl | (prefix + tile_total);
                     __threadfence();
                     if (prefix + tile_total >= p.total_samples) atomicMax(&ws->cut_inv, 0xFFFFFFFFu - tile);
                     if (tile == num_tiles - 1 && prefix + tile_total < p.total_samples) {
@@ -379,8 +411,10 @@ __global__ void __launch_bounds__(kMarchBlock) march_rays_kernel(
                     }
                 }
             }
-            if (give_up) s_abandon = 1;
-            s_prefix = prefix;
+            if (lane == 0) {
+                if (give_up) s_abandon = 1;
+                s_prefix = prefix;
+            }
         }
         __syncthreads();
         if (!in_range) continue;
