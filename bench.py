@@ -229,26 +229,45 @@ def count_launches(tr, perm):
 
 
 def dominant_kernel_roofline(tr, perm, flush):
-    """Hash-grid gradient scatter + forward gather, the step's two dominant kernels of this repo, timed
-    alone on the step's own sample positions.  Algorithmic bytes per point (SURVEY 8d): fwd 1164 B;
-    bwd 1164 B + one zero-fill of the gradient table per launch."""
+    """Times every kernel of the step alone, on the step's own tensors, with CUDA events on the launching
+    stream and an L2 flush before each launch, then reports the roofline of the slowest one.
+    Algorithmic bytes per unit are SURVEY 8(d)'s figures."""
     import torch
-    from jaxngp_b200 import encoders, renderers, synthetic
+    from jaxngp_b200 import _lib, encoders, nerf as nerf_mod, synthetic, trainops
     from jaxngp_b200.volrendjax import march_rays
+    from jaxngp_b200.volrendjax.integrating import _integrate_bwd, _integrate_fwd
     hbm, src = peaks()
-    o, d = tr.scene.rays(perm.to(torch.int64))
-    ts, te = renderers.make_near_far_from_bound(synthetic.BOUND, o, d)
-    out = march_rays(TOTAL_SAMPLES, synthetic.DIAGONAL_N_STEPS, synthetic.K, synthetic.G, synthetic.BOUND, 0.0, o, d, ts,
-                     te, torch.rand(N_RAYS, device=o.device), tr.occupancy)
-    xyzs = out[5]
+    dev = perm.device
+    sc = tr.scene
+    noises, bg = torch.rand(N_RAYS, device=dev), torch.rand(N_RAYS, 3, device=dev)
+    o, d, ts, te = trainops.make_training_rays(perm, sc.transforms, sc.cam, synthetic.BOUND)
+    march = lambda: march_rays(TOTAL_SAMPLES, synthetic.DIAGONAL_N_STEPS, synthetic.K, synthetic.G, synthetic.BOUND, 0.0,
+                               o, d, ts, te, noises, tr.occupancy, raw=True)
+    nxt, exc, valid, rn, rs, idcs, xyzs, dirs, dss, zs = march()
     n = xyzs.shape[0]
-    d_enc = torch.randn(n, 32, device=xyzs.device)
+    used = int((nxt - exc)[0])
+    n_hit = int((rn > 0).sum())
+    enc = encoders.hashgrid_forward(tr.levels, xyzs, 1.0, tr.table)
+    drgbs = nerf_mod.mlp_forward(enc, dirs, tr.mlp_flat)
+    eff, fin, opac = _integrate_fwd(rs, rn, bg, dss, zs, drgbs)
+    d_fin, _, _ = trainops.huber_loss_grad(fin, valid, perm, sc.rgbas_u8, bg)
+    _, _, d_drgbs = _integrate_bwd(synthetic.NEAR, rs, rn, bg, dss, zs, drgbs, fin, opac, d_fin)
+    d_enc, _ = nerf_mod.mlp_backward(enc, dirs, tr.mlp_flat, d_drgbs)
+    P = tr.flat_params.numel()
+    kernels = (
+        # name, launch, algorithmic bytes per launch, note
+        ("march_rays", march, N_RAYS * 45 + used * 36 + (synthetic.K * synthetic.G ** 3) // 8, "36 B/ray in, 9 B/ray + 36 B/sample out, bitfield"),
+        ("hashgrid_a1_forward", lambda: encoders.hashgrid_forward(tr.levels, xyzs, 1.0, tr.table), n * 1164, "1164 B/point"),
+        ("nerf_mlp_forward", lambda: nerf_mod.mlp_forward(enc, dirs, tr.mlp_flat), n * (128 + 12 + 16), "enc 128 + dir 12 in, 16 out per sample; 18.8 kFLOP/sample"),
+        ("integrate_rays", lambda: _integrate_fwd(rs, rn, bg, dss, zs, drgbs), used * 24 + N_RAYS * 40, "24 B/sample + 40 B/ray"),
+        ("huber_loss_grad", lambda: trainops.huber_loss_grad(fin, valid, perm, sc.rgbas_u8, bg), N_RAYS * (16 + 1 + 4 + 4 + 12 + 16), "53 B/ray"),
+        ("integrate_rays_backward", lambda: _integrate_bwd(synthetic.NEAR, rs, rn, bg, dss, zs, drgbs, fin, opac, d_fin), used * 44 + N_RAYS * 68 + n * 20, "44 B/sample + 68 B/ray + zero-fill 20 B/slot"),
+        ("nerf_mlp_backward", lambda: nerf_mod.mlp_backward(enc, dirs, tr.mlp_flat, d_drgbs), n * (128 + 12 + 16 + 128), "284 B/sample; 56 kFLOP/sample"),
+        ("hashgrid_a1_backward", lambda: encoders.hashgrid_backward(tr.levels, xyzs, 1.0, d_enc, out=tr.table_grad), n * 1164 + tr.table_numel * 4, "1164 B/point + table zero-fill"),
+        ("adam_step", lambda: _lib.call("ngp_adam_step", [tr.step_dev, tr.flat_params, tr.flat_grads, tr.adam_m, tr.adam_v], tr.adam_desc), P * 28, "28 B/param"),
+    )
     res = {}
-    for name, fn, nbytes in (
-        ("hashgrid_a1_backward", lambda: encoders.hashgrid_backward(tr.levels, xyzs, 1.0, d_enc, out=tr.table_grad),
-         n * 1164 + tr.table_numel * 4),
-        ("hashgrid_a1_forward", lambda: encoders.hashgrid_forward(tr.levels, xyzs, 1.0, tr.table), n * 1164),
-    ):
+    for name, fn, nbytes, note in kernels:
         times = []
         for _ in range(3 + 10):
             flush.fill_(1)
@@ -259,11 +278,22 @@ def dominant_kernel_roofline(tr, perm, flush):
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
         t_ms = float(np.mean(times[3:]))
-        res[name] = {"ms": t_ms, "algorithmic_bytes": nbytes, "achieved": nbytes / (t_ms * 1e-3) / 1e9}
-    top = "hashgrid_a1_backward"
-    return {"kernel": top, "bound": "hbm", "achieved": res[top]["achieved"], "peak": hbm, "unit": "GB/s",
-            "frac": res[top]["achieved"] / hbm, "peak_source": src, "traffic": None, "points": n,
-            "note": "table (48.8 MB) is L2-resident: the limiter is L2 atomic/sector throughput, see DESIGN.md section 5",
+        res[name] = {"ms": round(t_ms, 4), "algorithmic_bytes": int(nbytes), "achieved_gbs": round(nbytes / (t_ms * 1e-3) / 1e9, 1),
+                     "frac_of_hbm": round(nbytes / (t_ms * 1e-3) / 1e9 / hbm, 3), "per_unit": note}
+    res["nerf_mlp_forward"]["achieved_tflops"] = round(n * 18816 / (res["nerf_mlp_forward"]["ms"] * 1e-3) / 1e12, 2)
+    res["nerf_mlp_backward"]["achieved_tflops"] = round(n * 56448 / (res["nerf_mlp_backward"]["ms"] * 1e-3) / 1e12, 2)
+    top = max(res, key=lambda k: res[k]["ms"])
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/), if present
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic_r01.json"))).get(top)
+    except Exception:
+        pass
+    return {"kernel": top, "bound": "hbm", "achieved": res[top]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+            "frac": res[top]["frac_of_hbm"], "peak_source": src, "traffic": traffic, "sample_slots": n, "samples": used,
+            "rays_with_samples": n_hit,
+            "note": "each kernel timed alone with an L2 flush before every launch (isolated times sum to more than the "
+                    "graph-replayed step, whose kernels find their inputs in L2); limiter per kernel in DESIGN.md section 5",
             "kernels": res}
 
 
