@@ -135,9 +135,13 @@ typedef struct {
     float scales[NGP_HG_MAX_LEVELS];
     uint32_t res[NGP_HG_MAX_LEVELS];
     uint32_t offsets[NGP_HG_MAX_LEVELS + 1];
+    /* forward only: if non-zero, points come in groups of `rows_per_group` (the [n_rays, march_steps_cap]
+     * layout of march_rays_inference) and a 4th input buffer group_counts u32[n_points / rows_per_group]
+     * says how many leading rows of each group are real samples; the other rows are neither read nor written. */
+    uint32_t rows_per_group;
 } NgpHashGridA1Descriptor;
 
-/* in : pos f32[n,dim], table (f32|f16)[rows,F]          out: enc f32[n,L*F] */
+/* in : pos f32[n,dim], table (f32|f16)[rows,F] [, group_counts]   out: enc f32[n,L*F] */
 void ngp_hashgrid_a1_forward(cudaStream_t, void **, const char *, size_t);
 /* in : pos f32[n,dim], d_enc f32[n,L*F]                 out: d_table f32[rows,F] (zero-filled, then scatter-added) */
 void ngp_hashgrid_a1_backward(cudaStream_t, void **, const char *, size_t);
@@ -164,9 +168,14 @@ void ngp_ogrid_threshold(cudaStream_t, void **, const char *, size_t);
 /* Fully fused NeRF MLP of make_nerf_ngp (models/nerfs.py:27-128,216-238,422-454) on the tensor cores.
  * weights = flat f32[9408] = [density W0 32x64 | density W1 64x16 | rgb W0 32x64 | rgb W1 64x64 | rgb W2 64x3],
  * each row-major [in][out] like the flax Dense kernels.
- * forward : in enc f32[n,32], dirs f32[n,3] (unit), weights;  out drgbs f32[n,4]  (density_only: out f32[n], dirs unused)
+ * forward : in enc f32[n,32], dirs f32[n,3] (unit), weights [, group_counts];  out drgbs f32[n,4]  (density_only: out f32[n], dirs unused)
  * backward: in enc, dirs, weights, d_drgbs f32[n,4];          out d_enc f32[n,32], d_weights f32[9408] */
-typedef struct { uint32_t n_samples, density_only; } NgpNerfMlpDescriptor;
+typedef struct {
+    uint32_t n_samples, density_only;
+    /* forward only: grouped layout of march_rays_inference.  If rows_per_group != 0: dirs is f32[n_groups,3]
+     * (one direction per ray) and a 5th input buffer group_counts u32[n_groups] masks the rows as above. */
+    uint32_t rows_per_group;
+} NgpNerfMlpDescriptor;
 void ngp_nerf_mlp_forward(cudaStream_t, void **, const char *, size_t);
 void ngp_nerf_mlp_backward(cudaStream_t, void **, const char *, size_t);
 

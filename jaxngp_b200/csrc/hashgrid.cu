@@ -109,6 +109,7 @@ template <int DIM, int F, typename TT>
 __global__ void __launch_bounds__(kBlock) hashgrid_a1_forward_kernel(const __grid_constant__ NgpHashGridA1Descriptor d,
                                                                       const float *__restrict__ pos,
                                                                       const TT *__restrict__ table,
+                                                                      const uint32_t *__restrict__ group_counts,
                                                                       float *__restrict__ enc) {
     __shared__ LevelMeta s_meta[NGP_HG_MAX_LEVELS];
     if (threadIdx.x < d.L) s_meta[threadIdx.x] = a1_level(d, threadIdx.x);
@@ -116,6 +117,8 @@ __global__ void __launch_bounds__(kBlock) hashgrid_a1_forward_kernel(const __gri
     const uint64_t tid = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
     const uint32_t point = (uint32_t)(tid / d.L), level = (uint32_t)(tid % d.L);
     if (point >= d.n_points) return;
+    // grouped (inference) layout: rows past the group's sample count are padding, skip them
+    if (d.rows_per_group && point % d.rows_per_group >= __ldg(group_counts + point / d.rows_per_group)) return;
     const LevelMeta m = s_meta[level];
 
     uint32_t base[DIM];
@@ -441,10 +444,11 @@ void ngp_hashgrid_a1_forward(cudaStream_t stream, void **buffers, const char *op
     BufferCursor b{buffers};
     const float *pos = b.next<const float>();
     const void *table = b.next<const void>();
+    const uint32_t *group_counts = d->rows_per_group ? b.next<const uint32_t>() : nullptr;
     float *enc = b.next<float>();
     const unsigned blocks = div_up((unsigned long long)d->n_points * d->L, kBlock);
 #define NGP_FWD(DIM, F, TT) \
-    hashgrid_a1_forward_kernel<DIM, F, TT><<<blocks, kBlock, 0, stream>>>(*d, pos, static_cast<const TT *>(table), enc)
+    hashgrid_a1_forward_kernel<DIM, F, TT><<<blocks, kBlock, 0, stream>>>(*d, pos, static_cast<const TT *>(table), group_counts, enc)
     if (d->table_dtype == 0) {
         if (d->dim == 3 && d->F == 2) NGP_FWD(3, 2, float);
         else if (d->dim == 3) NGP_FWD(3, 4, float);

@@ -146,9 +146,12 @@ template <bool kKeep, bool kDensityOnly>
 __device__ __forceinline__ void warp_forward(const uint32_t *__restrict__ sw, float *__restrict__ act, uint32_t warp,
                                              uint32_t row0, uint32_t n, const float *__restrict__ enc,
                                              const float *__restrict__ dirs, uint32_t g, uint32_t t, FwdState &st,
-                                             uint32_t (&a_h2)[8][4], float (&out_rgb)[1][4]) {
+                                             uint32_t (&a_h2)[8][4], float (&out_rgb)[1][4],
+                                             uint32_t rows_per_group = 0, bool ok_lo_in = true, bool ok_hi_in = true) {
     const uint32_t r_lo = row0 + g, r_hi = row0 + g + 8;
-    const bool ok_lo = r_lo < n, ok_hi = r_hi < n;
+    const bool ok_lo = r_lo < n && ok_lo_in, ok_hi = r_hi < n && ok_hi_in;
+    // grouped layout: one direction per group of rows (ray), else one per row
+    const uint32_t d_lo = rows_per_group ? r_lo / rows_per_group : r_lo, d_hi = rows_per_group ? r_hi / rows_per_group : r_hi;
     // enc A fragments: cols 8kt+2t, 8kt+2t+1 of rows g, g+8 (float2 loads, every 32 B sector fully used)
     uint32_t a_in[4][4];
 #pragma unroll
@@ -191,10 +194,10 @@ __device__ __forceinline__ void warp_forward(const uint32_t *__restrict__ sw, fl
     // direction encoding: SH degree 4 into columns 16..31 of hin
     {
         float sh_lo[4], sh_hi[4];
-        const float dx0 = ok_lo ? __ldg(dirs + (size_t)r_lo * 3 + 0) : 0.f, dy0 = ok_lo ? __ldg(dirs + (size_t)r_lo * 3 + 1) : 0.f,
-                    dz0 = ok_lo ? __ldg(dirs + (size_t)r_lo * 3 + 2) : 1.f;
-        const float dx1 = ok_hi ? __ldg(dirs + (size_t)r_hi * 3 + 0) : 0.f, dy1 = ok_hi ? __ldg(dirs + (size_t)r_hi * 3 + 1) : 0.f,
-                    dz1 = ok_hi ? __ldg(dirs + (size_t)r_hi * 3 + 2) : 1.f;
+        const float dx0 = ok_lo ? __ldg(dirs + (size_t)d_lo * 3 + 0) : 0.f, dy0 = ok_lo ? __ldg(dirs + (size_t)d_lo * 3 + 1) : 0.f,
+                    dz0 = ok_lo ? __ldg(dirs + (size_t)d_lo * 3 + 2) : 1.f;
+        const float dx1 = ok_hi ? __ldg(dirs + (size_t)d_hi * 3 + 0) : 0.f, dy1 = ok_hi ? __ldg(dirs + (size_t)d_hi * 3 + 1) : 0.f,
+                    dz1 = ok_hi ? __ldg(dirs + (size_t)d_hi * 3 + 2) : 1.f;
         sh4_lane(dx0, dy0, dz0, t, sh_lo);
         sh4_lane(dx1, dy1, dz1, t, sh_hi);
         a_hin[2][0] = tf32(sh_lo[0]); a_hin[2][1] = tf32(sh_hi[0]); a_hin[2][2] = tf32(sh_lo[1]); a_hin[2][3] = tf32(sh_hi[1]);
@@ -244,9 +247,11 @@ __device__ __forceinline__ void warp_forward(const uint32_t *__restrict__ sw, fl
 
 // ---------------------------------------------------------------- forward kernel
 template <bool kDensityOnly>
-__global__ void __launch_bounds__(kThreads) nerf_mlp_forward_kernel(uint32_t n, const float *__restrict__ enc,
+__global__ void __launch_bounds__(kThreads) nerf_mlp_forward_kernel(uint32_t n, uint32_t rows_per_group,
+                                                                    const float *__restrict__ enc,
                                                                     const float *__restrict__ dirs,
                                                                     const float *__restrict__ weights,
+                                                                    const uint32_t *__restrict__ group_counts,
                                                                     float *__restrict__ out) {
     extern __shared__ __align__(16) uint32_t smem_u32[];
     uint32_t *sw = smem_u32;
@@ -256,23 +261,30 @@ __global__ void __launch_bounds__(kThreads) nerf_mlp_forward_kernel(uint32_t n, 
     const uint32_t n_tiles = (n + 15u) / 16u;
     for (uint32_t tile = blockIdx.x * kWarps + warp; tile < n_tiles; tile += gridDim.x * kWarps) {
         const uint32_t row0 = tile * 16u;
+        bool live_lo = row0 + g < n, live_hi = row0 + g + 8 < n;
+        if (rows_per_group) {  // padding rows of the grouped layout are neither read nor written
+            const uint32_t r_lo = row0 + g, r_hi = row0 + g + 8;
+            live_lo = live_lo && r_lo % rows_per_group < __ldg(group_counts + r_lo / rows_per_group);
+            live_hi = live_hi && r_hi % rows_per_group < __ldg(group_counts + r_hi / rows_per_group);
+            if (!__any_sync(0xffffffffu, live_lo || live_hi)) continue;
+        }
         FwdState st;
         uint32_t a_h2[8][4];
         float rgb[1][4];
-        warp_forward<false, kDensityOnly>(sw, nullptr, warp, row0, n, enc, dirs, g, t, st, a_h2, rgb);
+        warp_forward<false, kDensityOnly>(sw, nullptr, warp, row0, n, enc, dirs, g, t, st, a_h2, rgb, rows_per_group, live_lo, live_hi);
         if (kDensityOnly) {
             if (t == 0) {
-                if (row0 + g < n) out[row0 + g] = expf(st.x0[0]);
-                if (row0 + g + 8 < n) out[row0 + g + 8] = expf(st.x0[1]);
+                if (live_lo) out[row0 + g] = expf(st.x0[0]);
+                if (live_hi) out[row0 + g + 8] = expf(st.x0[1]);
             }
         } else {
             // lane t == 0 of each row group assembles (density, r, g, b): b comes from lane t == 1
             const float b_lo = __shfl_sync(0xffffffffu, st.rgb[0][0], (lane & ~3u) + 1);
             const float b_hi = __shfl_sync(0xffffffffu, st.rgb[1][0], (lane & ~3u) + 1);
             if (t == 0) {
-                if (row0 + g < n)
+                if (live_lo)
                     reinterpret_cast<float4 *>(out)[row0 + g] = make_float4(expf(st.x0[0]), st.rgb[0][0], st.rgb[0][1], b_lo);
-                if (row0 + g + 8 < n)
+                if (live_hi)
                     reinterpret_cast<float4 *>(out)[row0 + g + 8] = make_float4(expf(st.x0[1]), st.rgb[1][0], st.rgb[1][1], b_hi);
             }
         }
@@ -498,6 +510,7 @@ void ngp_nerf_mlp_forward(cudaStream_t stream, void **buffers, const char *opaqu
     const float *enc = b.next<const float>();
     const float *dirs = b.next<const float>();
     const float *weights = b.next<const float>();
+    const uint32_t *group_counts = d->rows_per_group ? b.next<const uint32_t>() : nullptr;
     float *out = b.next<float>();
     static bool configured = false;  // benign race: the attribute call is idempotent
     if (!configured) {
@@ -508,9 +521,9 @@ void ngp_nerf_mlp_forward(cudaStream_t stream, void **buffers, const char *opaqu
     const unsigned tiles = div_up(d->n_samples, 16);
     const unsigned blocks = min(div_up(tiles, kWarps), 148u * 4u);
     if (d->density_only)
-        nerf_mlp_forward_kernel<true><<<blocks, kThreads, kFwdSmem, stream>>>(d->n_samples, enc, dirs, weights, out);
+        nerf_mlp_forward_kernel<true><<<blocks, kThreads, kFwdSmem, stream>>>(d->n_samples, d->rows_per_group, enc, dirs, weights, group_counts, out);
     else
-        nerf_mlp_forward_kernel<false><<<blocks, kThreads, kFwdSmem, stream>>>(d->n_samples, enc, dirs, weights, out);
+        nerf_mlp_forward_kernel<false><<<blocks, kThreads, kFwdSmem, stream>>>(d->n_samples, d->rows_per_group, enc, dirs, weights, group_counts, out);
     check_launch("nerf_mlp_forward");
 }
 

@@ -59,7 +59,8 @@ def make_hashgrid_descriptor(n_coords, L, F, N_min, per_level_scale):
                        float(per_level_scale))
 
 
-def make_hashgrid_a1_descriptor(n_points, dim, L, F, wrap_T, table_dtype, bound, hashed, scales, res, offsets):
+def make_hashgrid_a1_descriptor(n_points, dim, L, F, wrap_T, table_dtype, bound, hashed, scales, res, offsets,
+                                rows_per_group=0):
     """NgpHashGridA1Descriptor (include/ngp_b200.h): level table of models/encoders.py:89-103."""
     if not 0 < L <= HG_MAX_LEVELS:
         raise ValueError(f"L must be in (0, {HG_MAX_LEVELS}], got {L}")
@@ -68,12 +69,12 @@ def make_hashgrid_a1_descriptor(n_points, dim, L, F, wrap_T, table_dtype, bound,
         mask |= (1 << l) if h else 0
     pad = HG_MAX_LEVELS - L
     return struct.pack(
-        f"<6IfI{HG_MAX_LEVELS}f{HG_MAX_LEVELS}I{HG_MAX_LEVELS + 1}I",
+        f"<6IfI{HG_MAX_LEVELS}f{HG_MAX_LEVELS}I{HG_MAX_LEVELS + 1}II",
         _u32(n_points, "n_points"), _u32(dim, "dim"), _u32(L, "L"), _u32(F, "F"), _u32(wrap_T, "wrap_T"),
         _u32(table_dtype, "table_dtype"), float(bound), mask,
         *([float(s) for s in scales] + [0.0] * pad),
         *([int(r) for r in res] + [0] * pad),
-        *([int(o) for o in offsets] + [0] * pad))
+        *([int(o) for o in offsets] + [0] * pad), _u32(rows_per_group, "rows_per_group"))
 
 
 def make_adam_descriptor(n, decay_begin, lr_init, lr_end, decay_rate, transition_steps, transition_begin, staircase,
@@ -96,8 +97,8 @@ def make_ogrid_threshold_descriptor(n_cells, thr_max):
     return struct.pack("<If", _u32(n_cells, "n_cells"), float(thr_max))
 
 
-def make_nerf_mlp_descriptor(n_samples, density_only=False):
-    return struct.pack("<2I", _u32(n_samples, "n_samples"), int(bool(density_only)))
+def make_nerf_mlp_descriptor(n_samples, density_only=False, rows_per_group=0):
+    return struct.pack("<3I", _u32(n_samples, "n_samples"), int(bool(density_only)), _u32(rows_per_group, "rows_per_group"))
 
 
 def make_training_rays_descriptor(n_rays, width, height, n_views, fx, fy, cx, cy, bound):

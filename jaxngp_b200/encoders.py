@@ -61,19 +61,28 @@ def make_level_table(L: int, T: int, F: int, N_min: int, N_max: int, dim: int, a
     return LevelTable(L, T, F, dim, b, tuple(scales), tuple(res), tuple(hashed), tuple(offsets))
 
 
-def _a1_descriptor(lt: LevelTable, n_points: int, bound: float, wrap: str, table_dtype: torch.dtype) -> bytes:
+def _a1_descriptor(lt: LevelTable, n_points: int, bound: float, wrap: str, table_dtype: torch.dtype,
+                   rows_per_group: int = 0) -> bytes:
     return descriptors.make_hashgrid_a1_descriptor(
         n_points=n_points, dim=lt.dim, L=lt.L, F=lt.F, wrap_T=lt.T if wrap == "jaxngp" else 0,
         table_dtype={torch.float32: 0, torch.float16: 1}[table_dtype], bound=bound, hashed=lt.hashed,
-        scales=lt.scales, res=lt.res, offsets=lt.offsets)
+        scales=lt.scales, res=lt.res, offsets=lt.offsets, rows_per_group=rows_per_group)
 
 
-def hashgrid_forward(lt: LevelTable, pos: torch.Tensor, bound: float, table: torch.Tensor, wrap: str = "jaxngp"):
-    """enc[n, L*F] = HashGridEncoder gather (models/encoders.py:216-233); no autograd."""
+def hashgrid_forward(lt: LevelTable, pos: torch.Tensor, bound: float, table: torch.Tensor, wrap: str = "jaxngp",
+                     group_counts: torch.Tensor = None, rows_per_group: int = 0):
+    """enc[n, L*F] = HashGridEncoder gather (models/encoders.py:216-233); no autograd.  With
+    ``group_counts`` (int32 [n / rows_per_group]) only the first ``group_counts[g]`` rows of each group of
+    ``rows_per_group`` rows are encoded (the [n_rays, cap] sample layout of march_rays_inference); the
+    padding rows are left unwritten."""
     n = pos.shape[0]
     enc = torch.empty(n, lt.L * lt.F, dtype=torch.float32, device=pos.device)
     if n:
-        _lib.call("ngp_hashgrid_a1_forward", [pos, table, enc], _a1_descriptor(lt, n, bound, wrap, table.dtype))
+        if group_counts is None:
+            _lib.call("ngp_hashgrid_a1_forward", [pos, table, enc], _a1_descriptor(lt, n, bound, wrap, table.dtype))
+        else:
+            _lib.call("ngp_hashgrid_a1_forward", [pos, table, group_counts, enc],
+                      _a1_descriptor(lt, n, bound, wrap, table.dtype, rows_per_group))
     return enc
 
 

@@ -67,14 +67,21 @@ MLP_SHAPES = (("density_w0", 32, 64), ("density_w1", 64, 16), ("rgb_w0", 32, 64)
 MLP_NUMEL = sum(i * o for _, i, o in MLP_SHAPES)  # 9408
 
 
-def mlp_forward(enc: torch.Tensor, dirs, weights: torch.Tensor) -> torch.Tensor:
-    """Fused tensor-core MLP forward (csrc/mlp.cu).  ``dirs=None``: densities [n] only (nerfs.py:70-72)."""
+def mlp_forward(enc: torch.Tensor, dirs, weights: torch.Tensor, group_counts: torch.Tensor = None,
+                rows_per_group: int = 0) -> torch.Tensor:
+    """Fused tensor-core MLP forward (csrc/mlp.cu).  ``dirs=None``: densities [n] only (nerfs.py:70-72).
+    Grouped layout (``group_counts`` int32 [n / rows_per_group]): ``dirs`` holds ONE direction per group and
+    only the first ``group_counts[g]`` rows of each group are evaluated; padding rows are left unwritten."""
     n = enc.shape[0]
     density_only = dirs is None
     out = torch.empty((n,) if density_only else (n, 4), dtype=torch.float32, device=enc.device)
     if n:
-        _lib.call("ngp_nerf_mlp_forward", [enc, enc if density_only else dirs, weights, out],
-                  descriptors.make_nerf_mlp_descriptor(n, density_only))
+        if group_counts is None:
+            _lib.call("ngp_nerf_mlp_forward", [enc, enc if density_only else dirs, weights, out],
+                      descriptors.make_nerf_mlp_descriptor(n, density_only))
+        else:
+            _lib.call("ngp_nerf_mlp_forward", [enc, enc if density_only else dirs, weights, group_counts, out],
+                      descriptors.make_nerf_mlp_descriptor(n, density_only, rows_per_group))
     return out
 
 
@@ -141,6 +148,18 @@ class NeRF(torch.nn.Module):
 
     def mlp_parameters(self):
         return [self.mlp_flat]
+
+    @torch.no_grad()
+    def forward_grouped(self, xyzs, ray_dirs, n_samples):
+        """Inference fast path for the [n_rays, cap, 3] sample layout of march_rays_inference: one direction
+        per ray, only the first ``n_samples[i]`` samples of ray i are evaluated (the rest of the output is
+        unspecified, integrate_rays_inference never reads it).  Same numbers as ``forward`` on the live rows."""
+        n, cap = xyzs.shape[0], xyzs.shape[1]
+        enc_mod = self.position_encoder
+        enc = encoders.hashgrid_forward(enc_mod.levels, xyzs.reshape(-1, 3), self.bound, enc_mod.latents.detach(),
+                                        enc_mod.wrap, group_counts=n_samples, rows_per_group=cap)
+        drgbs = mlp_forward(enc, ray_dirs.contiguous(), self.mlp_flat.detach(), group_counts=n_samples, rows_per_group=cap)
+        return drgbs.reshape(n, cap, 4)
 
     def forward(self, xyz, dir=None, appearance_embeddings=None):
         shape = xyz.shape[:-1]

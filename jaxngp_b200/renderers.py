@@ -53,7 +53,7 @@ def render_rays_train(nerf, o_world, d_world, bg, total_samples, occupancy_bitfi
 
 @torch.no_grad()
 def render_image_inference(nerf, cam, transform_cw, occupancy_bitfield, *, bg=(1.0, 1.0, 1.0), diagonal_n_steps=1024,
-                           K=1, G=128, bound=1.0, stepsize_portion=0.0, march_steps_cap=8, n_rays=8192):
+                           K=1, G=128, bound=1.0, stepsize_portion=0.0, march_steps_cap=8, n_rays=8192, grouped=True):
     """cuda.py:244-373: the reference's host loop, op for op.  Returns (rgb u8 [H, W, 3], depth f32 [H, W])."""
     o, d = make_rays_worldspace(cam, transform_cw)
     n_pixels = o.shape[0]
@@ -77,8 +77,11 @@ def render_image_inference(nerf, cam, transform_cw, occupancy_bitfield, *, bg=(1
                 occupancy_bitfield=occupancy_bitfield, next_ray_index_in=next_ray_index, terminated=terminated,
                 indices=indices)
             idx64 = (indices.to(torch.int64) & 0xFFFFFFFF).clamp(max=n_pixels - 1)
-            dirs = d[idx64][:, None, :].expand(-1, march_steps_cap, -1)
-            drgbs, _ = nerf(xyzs, dirs, None)
+            if grouped and hasattr(nerf, "forward_grouped"):
+                drgbs = nerf.forward_grouped(xyzs, d[idx64], n_samples)  # skips the padding rows of every slot
+            else:
+                dirs = d[idx64][:, None, :].expand(-1, march_steps_cap, -1)  # cuda.py:222-228
+                drgbs, _ = nerf(xyzs, dirs, None)
             cnt, terminated, rays_rgbd, rays_T = integrate_rays_inference(
                 rays_bg=rays_bg, rays_rgbd=rays_rgbd, rays_T=rays_T, n_samples=n_samples, indices=indices, dss=dss,
                 z_vals=z_vals, drgbs=drgbs.contiguous())
@@ -86,3 +89,115 @@ def render_image_inference(nerf, cam, transform_cw, occupancy_bitfield, *, bg=(1
         n_rendered += int(torch.stack(counts).sum())  # one host sync per batch of iterations
     rgb = (rays_rgbd[:, :3].clamp(0, 1) * 255 + 0.5).to(torch.uint8).reshape(cam["height"], cam["width"], 3)
     return rgb, rays_rgbd[:, 3].reshape(cam["height"], cam["width"])
+
+
+class InferenceRenderer:
+    """``render_image_inference`` (models/renderers/cuda.py:244-373) with the per-iteration work of the
+    slot-refill loop (march_rays_inference -> NeRF -> integrate_rays_inference -> scatter back,
+    cuda.py:180-241) captured ONCE in a CUDA graph over preallocated state, so a frame costs one ray
+    generation launch plus one graph replay per loop iteration and one host read per batch of iterations
+    (the reference's own `n_rendered_rays` check, cuda.py:326,361).  Same ops, same numbers: the image is
+    bit-identical to ``render_image_inference``."""
+
+    def __init__(self, nerf, cam, occupancy_bitfield, *, bg=(1.0, 1.0, 1.0), diagonal_n_steps=1024, K=1, G=128,
+                 bound=1.0, stepsize_portion=0.0, march_steps_cap=16, n_rays=131072, pixel_indices=None):
+        from . import _lib, descriptors, trainops  # noqa: F401
+        self.nerf, self.cam, self.bits = nerf, cam, occupancy_bitfield
+        dev = occupancy_bitfield.device
+        self.dev, self.bound, self.cap = dev, bound, march_steps_cap
+        if pixel_indices is None:
+            pixel_indices = torch.arange(cam["width"] * cam["height"], dtype=torch.int32, device=dev)
+        self.pixels = pixel_indices.to(torch.int32).contiguous()  # the rays this renderer owns (tile sharding)
+        N = self.N = self.pixels.shape[0]
+        n = self.n = min(n_rays, N)
+        f32, i32 = torch.float32, torch.int32
+        self.o, self.d = torch.empty(N, 3, dtype=f32, device=dev), torch.empty(N, 3, dtype=f32, device=dev)
+        self.t_starts, self.t_ends = torch.empty(N + 1, dtype=f32, device=dev), torch.empty(N, dtype=f32, device=dev)
+        self.rays_rgbd, self.rays_T = torch.empty(N + 1, 4, dtype=f32, device=dev), torch.empty(N + 1, dtype=f32, device=dev)
+        self.rays_bg = torch.tensor(bg, dtype=f32, device=dev).expand(N, 3).contiguous()
+        self.terminated = torch.empty(n, dtype=torch.bool, device=dev)
+        self.indices = torch.empty(n, dtype=i32, device=dev)
+        self.next_in, self.next_out = torch.empty(1, dtype=i32, device=dev), torch.empty(1, dtype=i32, device=dev)
+        self.n_samples = torch.empty(n, dtype=i32, device=dev)
+        self.t_out = torch.empty(n, dtype=f32, device=dev)
+        self.xyzs = torch.empty(n, self.cap, 3, dtype=f32, device=dev)
+        self.dss, self.z_vals = torch.empty(n, self.cap, dtype=f32, device=dev), torch.empty(n, self.cap, dtype=f32, device=dev)
+        self.term_cnt = torch.empty(1, dtype=i32, device=dev)
+        self.rgbd_out, self.T_out = torch.empty(n, 4, dtype=f32, device=dev), torch.empty(n, dtype=f32, device=dev)
+        self.n_done = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.samples_done = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.pose = torch.empty(1, 12, dtype=f32, device=dev)
+        self._march_desc = descriptors.make_marching_inference_descriptor(N, n, diagonal_n_steps, K, G, self.cap, bound,
+                                                                          stepsize_portion)
+        self._integ_desc = descriptors.make_integrating_inference_descriptor(N, n, self.cap)
+        self._rays_desc = descriptors.make_training_rays_descriptor(N, cam["width"], cam["height"], 1, cam["fx"], cam["fy"],
+                                                                    cam["cx"], cam["cy"], bound)
+        self._graph = None
+
+    def _iteration(self):
+        from . import _lib
+        _lib.call("ngp_march_rays_inference",
+                  [self.o, self.d, self.t_starts, self.t_ends, self.bits, self.next_in, self.terminated, self.indices,
+                   self.next_out, self.indices, self.n_samples, self.t_out, self.xyzs, self.dss, self.z_vals],
+                  self._march_desc)
+        self.next_in.copy_(self.next_out)
+        idx = (self.indices.to(torch.int64) & 0xFFFFFFFF).clamp(max=self.N)  # row N = scratch row (dropped writes)
+        self.t_starts.index_copy_(0, idx, self.t_out)  # marching/__init__.py:156
+        drgbs = self.nerf.forward_grouped(self.xyzs, self.d[idx.clamp(max=self.N - 1)], self.n_samples)
+        _lib.call("ngp_integrate_rays_inference",
+                  [self.rays_bg, self.rays_rgbd, self.rays_T, self.n_samples, self.indices, self.dss, self.z_vals, drgbs,
+                   self.term_cnt, self.terminated, self.rgbd_out, self.T_out], self._integ_desc)
+        self.rays_rgbd.index_copy_(0, idx, self.rgbd_out)  # integrating/__init__.py:108-109
+        self.rays_T.index_copy_(0, idx, self.T_out)
+        self.n_done += self.term_cnt
+        self.samples_done += self.n_samples.sum()
+
+    @torch.no_grad()
+    def render(self, transform_cw):
+        """Returns (rgb u8 [N, 3], depth f32 [N]) for the renderer's pixels."""
+        from . import _lib
+        self.pose.copy_(transform_cw.reshape(1, 12))
+        _lib.call("ngp_make_training_rays", [self.pixels, self.pose, self.o, self.d, self.t_starts, self.t_ends],
+                  self._rays_desc)
+        return self.render_current_rays()
+
+    @torch.no_grad()
+    def render_rays(self, o, d, t_starts, t_ends):
+        """Same, for caller-supplied rays (parity tests feed the rays of ``make_rays_worldspace``)."""
+        self.o.copy_(o)
+        self.d.copy_(d)
+        self.t_starts[: self.N].copy_(t_starts)
+        self.t_ends.copy_(t_ends)
+        return self.render_current_rays()
+
+    @torch.no_grad()
+    def render_current_rays(self):
+        self.rays_rgbd.zero_()
+        self.rays_T.fill_(1.0)
+        self.terminated.fill_(True)
+        self.indices.zero_()
+        self.next_in.zero_()
+        self.n_done.zero_()
+        self.samples_done.zero_()
+        if self._graph is None:
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            state = [t.clone() for t in (self.t_starts, self.rays_rgbd, self.rays_T, self.terminated, self.indices, self.next_in)]
+            with torch.cuda.stream(side):
+                self._iteration()  # warm-up on the capture stream
+                self._graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._graph, stream=side):
+                    self._iteration()
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+            for t, s in zip((self.t_starts, self.rays_rgbd, self.rays_T, self.terminated, self.indices, self.next_in), state):
+                t.copy_(s)  # undo the two warm-up iterations
+            self.n_done.zero_()
+            self.samples_done.zero_()
+        n_rendered = 0
+        while n_rendered < self.N:  # cuda.py:326-361
+            iters = 2 ** (int(math.log2(max(1, (self.N - n_rendered) // self.n))) + 1)
+            for _ in range(iters):
+                self._graph.replay()
+            n_rendered = int(self.n_done)  # one host read per batch of iterations
+        rgb = (self.rays_rgbd[: self.N, :3].clamp(0, 1) * 255 + 0.5).to(torch.uint8)
+        return rgb, self.rays_rgbd[: self.N, 3]
