@@ -57,7 +57,7 @@ def test_descriptor_wire_format():
     with pytest.raises(RuntimeError):
         D.make_packbits_descriptor(0)  # ffi.cc:57-59
     a1 = D.make_hashgrid_a1_descriptor(10, 3, 16, 2, 1 << 19, 0, 1.0, [0] * 5 + [1] * 11, [1.0] * 16, [2] * 16, list(range(17)))
-    assert len(a1) == 32 + 4 * (32 + 32 + 33)
+    assert len(a1) == 32 + 4 * (32 + 32 + 33) + 4  # + rows_per_group
 
 
 def test_level_table_matches_reference_defaults():
