@@ -25,6 +25,8 @@ namespace {
 
 constexpr float kTwoSqrt3 = 3.4641015529632568359f;  // 2 * (float)SQRT3, volrend.h:18
 
+__device__ __forceinline__ uint32_t div_up_dev(uint32_t a, uint32_t b) { return (a + b - 1u) / b; }
+
 struct Grid {
     uint32_t K, G, G3;
     float Gf, inv_G, bound, portion, ds_lo, ds_hi;
@@ -199,6 +201,49 @@ __device__ __forceinline__ EvalPoint eval_point(const Grid &g, const Ray &r, flo
     return s;
 }
 
+// The chain t_{k+1} = fl(t_k + ds(t_k)) from `t_base`: lane j gets t_j, `t_next_base` = t_32 (warp-uniform).
+// Constant ds (stepsize_portion == 0, the NeRF-synthetic configuration): while t stays inside one binade
+// every t_k is a multiple of u = ulp(t_base) and fl(t_k + ds) = t_k + d with the SAME d = fl(t_base + ds) -
+// t_base (ds rounded to the u grid), unless ds sits exactly on a rounding tie of that grid (then the
+// result depends on the parity of t_k).  So when t_base + 32 d is still in t_base's binade and there is no
+// tie, t_j = t_base + j d exactly -- one FMA per lane whose exact result is representable -- bit-equal to
+// the 31 dependent additions.  Otherwise (3 binade crossings per ray, ties, t_base == 0) the additions are
+// replayed one by one.
+__device__ __forceinline__ float chain_points(const Grid &g, float t_base, uint32_t lane, bool const_ds, float ds0,
+                                              float &t_next_base) {
+    if (const_ds) {
+        const float t1 = __fadd_rn(t_base, ds0);
+        const float d = __fadd_rn(t1, -t_base);            // exact (Sterbenz-like: both on the u grid, same binade checked below)
+        const float err = __fadd_rn(ds0, -d);              // exact rounding error of t_base + ds0
+        const float t32 = __fmaf_rn(32.f, d, t_base);
+        const uint32_t e0 = __float_as_uint(t_base) >> 23, e32 = __float_as_uint(t32) >> 23;  // sign 0: biased exponents
+        const float half_u = __uint_as_float(((e0 > 24u ? e0 : 24u) - 24u) << 23);             // ulp(t_base) / 2
+        const bool fast = t_base > 0.f && e0 == e32 && e0 > 24u && fabsf(err) != half_u && d > 0.f;
+        if (fast) {
+            t_next_base = t32;
+            return __fmaf_rn((float)lane, d, t_base);
+        }
+        float t = t_base;
+#pragma unroll
+        for (int i = 0; i < 31; ++i) {
+            const float tn = __fadd_rn(t, ds0);
+            if (i < (int)lane) t = tn;
+        }
+        const float t_last = __shfl_sync(0xffffffffu, t, 31);
+        t_next_base = __fadd_rn(t_last, ds0);
+        return t;
+    }
+    float t = t_base;
+#pragma unroll 4
+    for (int i = 0; i < 31; ++i) {
+        const float tn = __fadd_rn(t, calc_ds(g, t));
+        if (i < (int)lane) t = tn;
+    }
+    const float t_last = __shfl_sync(0xffffffffu, t, 31);
+    t_next_base = __fadd_rn(t_last, calc_ds(g, t_last));
+    return t;
+}
+
 struct SampleSink {
     uint32_t *idcs;
     float *xyzs, *dirs, *dss, *z_vals;
@@ -220,22 +265,8 @@ __device__ __forceinline__ uint32_t march_ray_warp(const Grid &g, const Ray &r, 
     float pend_t = 0.f;
     while (n < limit) {
         // chain: lane j holds t_base advanced j times
-        float t = t_base;
-        if (const_ds) {
-#pragma unroll
-            for (int i = 0; i < 31; ++i) {
-                const float tn = __fadd_rn(t, ds0);
-                if (i < (int)lane) t = tn;
-            }
-        } else {
-#pragma unroll 4
-            for (int i = 0; i < 31; ++i) {
-                const float tn = __fadd_rn(t, calc_ds(g, t));
-                if (i < (int)lane) t = tn;
-            }
-        }
-        const float t_last = __shfl_sync(0xffffffffu, t, 31);
-        const float t_next_base = __fadd_rn(t_last, calc_ds(g, t_last));
+        float t_next_base;
+        const float t = chain_points(g, t_base, lane, const_ds, ds0, t_next_base);
         const bool in = t < t_end;
         const uint32_t V = __ballot_sync(0xffffffffu, in);
         if (V == 0u) break;
@@ -472,106 +503,175 @@ __global__ void __launch_bounds__(256) march_rays_tail_kernel(
 }
 
 // ---------------------------------------------------------------- inference march
-constexpr int kInferBlock = 128;
+//
+// Two launches.  (1) rank kernel: fresh rays are handed to terminated slots in SLOT ORDER (the
+// reference uses atomicAdd arrival order, marching.cu:300): every 1024-slot block scans its flags
+// and writes each slot's rank inside the block plus the block total.  (2) march kernel: one WARP
+// per slot.  Like the training march it evaluates 32 consecutive points of the fixed parameter
+// chain at once and replays the reference's visit rule over the results (bit-equal sample
+// positions, counts and resume parameter t), instead of one thread walking a dependent chain of
+// bitfield loads per slot: with 10^5 slots in flight the kernel is issue-bound, not latency-bound.
+constexpr int kRankBlock = 256, kRankSlots = 1024;  // 4 flags per thread
+constexpr int kInferWarps = 8;
 
-__global__ void __launch_bounds__(kInferBlock) march_rays_inference_kernel(
+__global__ void __launch_bounds__(kRankBlock) march_rays_inference_rank_kernel(
+    uint32_t n_rays, const uint8_t *__restrict__ terminated, uint32_t *__restrict__ block_total,
+    uint32_t *__restrict__ rank_in_block) {
+    __shared__ uint32_t s_warp[kRankBlock / 32];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t first = blockIdx.x * kRankSlots + threadIdx.x * 4u;
+    uint32_t f[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f[k] = (first + k < n_rays && terminated[first + k]) ? 1u : 0u;
+    const uint32_t mine = f[0] + f[1] + f[2] + f[3];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kRankBlock / 32; ++w) {
+        if (w < (int)warp) base += s_warp[w];
+        total += s_warp[w];
+    }
+    uint32_t r = base + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (first + k < n_rays) rank_in_block[first + k] = r;
+        r += f[k];
+    }
+    if (threadIdx.x == 0) block_total[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kInferWarps * 32) march_rays_inference_kernel(
     NgpMarchingInferenceDescriptor p, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
     const float *__restrict__ t_starts, const float *__restrict__ t_ends, const uint8_t *__restrict__ bitfield,
     const uint32_t *__restrict__ next_ray_index_in, const uint8_t *__restrict__ terminated,
-    const uint32_t *__restrict__ indices_in, uint32_t *__restrict__ next_ray_index,
-    uint32_t *__restrict__ indices_out, uint32_t *__restrict__ n_samples, float *__restrict__ t_starts_out,
-    float *__restrict__ xyzs, float *__restrict__ dss, float *__restrict__ z_vals) {
-    __shared__ uint32_t s_partial[kInferBlock / 32];
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-
-    // Rank of this slot among the terminated slots, in slot order: fresh rays are handed out
-    // deterministically (the reference uses atomicAdd arrival order, marching.cu:300).
-    // Slots before this block are counted directly from the flags (n_rays is a few thousand).
-    uint32_t before = 0;
-    const uint32_t block_begin = blockIdx.x * blockDim.x;
-    for (uint32_t j = threadIdx.x; j < block_begin; j += blockDim.x) before += terminated[j] ? 1u : 0u;
-    before = warp_sum_u32(before);
-    if (lane == 0) s_partial[warp] = before;
-    __syncthreads();
-    uint32_t base = 0;
-#pragma unroll
-    for (int w = 0; w < kInferBlock / 32; ++w) base += s_partial[w];
-    __syncthreads();
-    const bool mine = i < p.n_rays && terminated[i];
-    const uint32_t ballot = __ballot_sync(0xffffffffu, mine);
-    if (lane == 0) s_partial[warp] = __popc(ballot);
-    __syncthreads();
-    uint32_t rank = base + __popc(ballot & ((1u << lane) - 1u));
-    uint32_t block_total = 0;
-#pragma unroll
-    for (int w = 0; w < kInferBlock / 32; ++w) {
-        if (w < (int)warp) rank += s_partial[w];
-        block_total += s_partial[w];
-    }
-    const uint32_t counter_in = __ldg(next_ray_index_in);
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *next_ray_index = counter_in + base + block_total;
+    const uint32_t *indices_in, const uint32_t *__restrict__ block_total,
+    const uint32_t *__restrict__ rank_in_block, uint32_t *__restrict__ next_ray_index, uint32_t *indices_out,
+    uint32_t *__restrict__ n_samples, float *__restrict__ t_starts_out, float *__restrict__ xyzs,
+    float *__restrict__ dss, float *__restrict__ z_vals) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t i = blockIdx.x * kInferWarps + (threadIdx.x >> 5);  // slot of this warp
     if (i >= p.n_rays) return;
+    const uint32_t counter_in = __ldg(next_ray_index_in);
+    const bool mine = terminated[i] != 0;
+    uint32_t ray_idx;
+    if (mine || i == p.n_rays - 1) {  // terminated slots before this slot's 1024-block
+        const uint32_t nb = mine ? i / kRankSlots : 0u, nb_all = div_up_dev(p.n_rays, kRankSlots);
+        uint32_t before = 0, all = 0;
+        for (uint32_t j = lane; j < nb_all; j += 32) {
+            const uint32_t c = (j < nb || i == p.n_rays - 1) ? __ldg(block_total + j) : 0u;
+            if (j < nb) before += c;
+            all += c;
+        }
+        before = warp_sum_u32(before);
+        if (i == p.n_rays - 1) {
+            all = warp_sum_u32(all);
+            if (lane == 0) *next_ray_index = counter_in + all;
+        }
+        ray_idx = mine ? counter_in + before + __ldg(rank_in_block + i) : indices_in[i];
+    } else {
+        ray_idx = indices_in[i];
+    }
+    if (lane == 0) indices_out[i] = ray_idx;
 
     const uint32_t cap = p.march_steps_cap;
     float *__restrict__ o_xyzs = xyzs + (size_t)i * cap * 3;
     float *__restrict__ o_dss = dss + (size_t)i * cap;
     float *__restrict__ o_z = z_vals + (size_t)i * cap;
 
-    const uint32_t ray_idx = mine ? counter_in + rank : __ldg(indices_in + i);
-    indices_out[i] = ray_idx;
     uint32_t steps = 0;
-    float t = 0.f;
+    float t_cur = 0.f, t_end = 0.f;
     bool live = ray_idx < p.n_total_rays;
-    float t_end = 0.f;
     if (live) {
-        t = __ldg(t_starts + ray_idx);
+        t_cur = __ldg(t_starts + ray_idx);
         t_end = __ldg(t_ends + ray_idx);
-        live = !(t_end < t);  // marching.cu:317 (strict)
+        live = !(t_end < t_cur);  // marching.cu:317 (strict)
     }
     if (live) {
         const Grid g = make_grid(p.diagonal_n_steps, p.K, p.G, p.bound, p.stepsize_portion, bitfield);
         const Ray ray = load_ray(rays_o, rays_d, ray_idx);
-        while (steps < cap && t < t_end) {
-            Step s = march_step<true>(g, ray, t);
-            if (s.occupied) {
-                o_xyzs[steps * 3 + 0] = s.px;
-                o_xyzs[steps * 3 + 1] = s.py;
-                o_xyzs[steps * 3 + 2] = s.pz;
-                o_dss[steps] = s.ds;
-                o_z[steps] = t;
-                ++steps;
-            }
-            t = s.t_next;
-        }
-        if (t >= t_end) {  // far-plane sample, marching.cu:367-394
-            Step s = march_step<false>(g, ray, t_end);
-            if (s.occupied) {
-                if (steps > 0 && __fadd_rn(o_dss[steps - 1], o_z[steps - 1]) >= t_end)
-                    o_dss[steps - 1] = __fadd_rn(t_end, -o_z[steps - 1]);
-                if (steps < cap) {
-                    o_xyzs[steps * 3 + 0] = s.px;
-                    o_xyzs[steps * 3 + 1] = s.py;
-                    o_xyzs[steps * 3 + 2] = s.pz;
-                    o_dss[steps] = s.ds;
-                    o_z[steps] = t_end;
-                    ++steps;
-                } else {
-                    t = t_end;
+        const bool const_ds = g.portion == 0.f;
+        const float ds0 = calc_ds(g, 0.f);
+        float last_ds = 0.f, last_z = 0.f;  // most recent sample (for the far-plane clip below)
+        // marching.cu:323-365: `t_cur` is the reference's loop variable t, always a point of the chain
+        while (steps < cap && t_cur < t_end) {
+            float t_next_base;
+            const float t = chain_points(g, t_cur, lane, const_ds, ds0, t_next_base);
+            const EvalPoint s = eval_point(g, ray, t);
+            const uint32_t V = __ballot_sync(0xffffffffu, t < t_end);
+            const uint32_t O = __ballot_sync(0xffffffffu, s.occupied);
+            uint32_t v = 0;  // chain index of the point the reference visits next
+            for (;;) {
+                if (v >= 32u) { t_cur = t_next_base; break; }
+                if (steps >= cap || !((V >> v) & 1u)) { t_cur = __shfl_sync(0xffffffffu, t, v); break; }
+                if ((O >> v) & 1u) {
+                    const uint32_t rest = (O & V) >> v;  // consecutive occupied in-range points starting at v
+                    uint32_t run = (rest == (0xFFFFFFFFu >> v)) ? 32u - v : (uint32_t)__ffs(~rest) - 1u;
+                    run = min(run, cap - steps);
+                    if (lane >= v && lane < v + run) {
+                        const uint32_t w = steps + (lane - v);
+                        o_xyzs[w * 3 + 0] = s.px;
+                        o_xyzs[w * 3 + 1] = s.py;
+                        o_xyzs[w * 3 + 2] = s.pz;
+                        o_dss[w] = s.ds;
+                        o_z[w] = t;
+                    }
+                    steps += run;
+                    v += run;
+                    last_ds = __shfl_sync(0xffffffffu, s.ds, v - 1u);
+                    last_z = __shfl_sync(0xffffffffu, t, v - 1u);
+                } else {  // empty: the next visited point is the first chain point at or past the voxel boundary
+                    const float nt = __shfl_sync(0xffffffffu, s.next_t, v);
+                    const uint32_t above = (v == 31u) ? 0u : (0xFFFFFFFFu << (v + 1u));
+                    const uint32_t m = __ballot_sync(0xffffffffu, t >= nt) & above;
+                    if (m) {
+                        v = __ffs(m) - 1;
+                    } else {  // boundary beyond this chunk: walk the chain like the reference (marching.cu:186-188)
+                        float tc = t_next_base;
+                        while (tc < nt) tc = __fadd_rn(tc, calc_ds(g, tc));
+                        t_cur = tc;
+                        break;
+                    }
                 }
             }
         }
-    } else {
-        t = 0.f;  // the reference leaves the memset zeros for rays it skips
+        if (t_cur >= t_end) {  // far-plane sample, marching.cu:367-394
+            const EvalPoint s = eval_point(g, ray, t_end);  // same value on every lane
+            if (s.occupied) {
+                if (steps > 0 && __fadd_rn(last_ds, last_z) >= t_end) {
+                    if (lane == 0) o_dss[steps - 1] = __fadd_rn(t_end, -last_z);
+                }
+                if (steps < cap) {
+                    if (lane == 0) {
+                        o_xyzs[steps * 3 + 0] = s.px;
+                        o_xyzs[steps * 3 + 1] = s.py;
+                        o_xyzs[steps * 3 + 2] = s.pz;
+                        o_dss[steps] = s.ds;
+                        o_z[steps] = t_end;
+                    }
+                    ++steps;
+                } else {
+                    t_cur = t_end;
+                }
+            }
+        }
     }
-    n_samples[i] = steps;
-    t_starts_out[i] = live ? t : 0.f;
-    for (uint32_t s = steps; s < cap; ++s) {  // zero the unused tail (reference: memsets, marching.cu:565-570)
-        o_xyzs[s * 3 + 0] = 0.f;
-        o_xyzs[s * 3 + 1] = 0.f;
-        o_xyzs[s * 3 + 2] = 0.f;
-        o_dss[s] = 0.f;
-        o_z[s] = 0.f;
+    if (lane == 0) {
+        n_samples[i] = steps;
+        t_starts_out[i] = live ? t_cur : 0.f;  // the reference leaves the memset zeros for rays it skips
+    }
+    // zero the unused tail (reference: memsets, marching.cu:565-570)
+    __syncwarp();
+    for (uint32_t k = steps * 3 + lane; k < cap * 3; k += 32) o_xyzs[k] = 0.f;
+    for (uint32_t k = steps + lane; k < cap; k += 32) {
+        o_dss[k] = 0.f;
+        o_z[k] = 0.f;
     }
 }
 
@@ -662,9 +762,16 @@ void ngp_march_rays_inference(cudaStream_t stream, void **buffers, const char *o
                     "march_rays_inference");
         return;
     }
-    march_rays_inference_kernel<<<div_up(desc->n_rays, kInferBlock), kInferBlock, 0, stream>>>(
-        *desc, rays_o, rays_d, t_starts, t_ends, bitfield, next_in, terminated, indices_in, next_out, indices_out,
-        n_samples, t_starts_out, xyzs, dss, z_vals);
+    const unsigned rank_blocks = div_up(desc->n_rays, kRankSlots);
+    auto *ws = static_cast<uint32_t *>(workspace(stream, ((size_t)rank_blocks + desc->n_rays) * sizeof(uint32_t)));
+    if (!ws) return;
+    uint32_t *block_total = ws, *rank_in_block = ws + rank_blocks;
+    march_rays_inference_rank_kernel<<<rank_blocks, kRankBlock, 0, stream>>>(desc->n_rays, terminated, block_total,
+                                                                             rank_in_block);
+    if (!check_launch("march_rays_inference(rank)")) return;
+    march_rays_inference_kernel<<<div_up(desc->n_rays, kInferWarps), kInferWarps * 32, 0, stream>>>(
+        *desc, rays_o, rays_d, t_starts, t_ends, bitfield, next_in, terminated, indices_in, block_total, rank_in_block,
+        next_out, indices_out, n_samples, t_starts_out, xyzs, dss, z_vals);
     check_launch("march_rays_inference");
 }
 

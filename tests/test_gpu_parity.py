@@ -244,6 +244,54 @@ def test_inference_loop_matches_oracle_and_reference(oracle, ref):
         assert np.array_equal(gn[np.argsort(gi, kind="stable")], rn_[np.argsort(ri, kind="stable")])
 
 
+@pytest.mark.parametrize("case,cap,n_slots", [("scene", 8, 5000), ("scene", 16, 3000), ("cascades", 5, 2500),
+                                              ("cascades", 40, 1500), ("dense", 1, 1100), ("dense", 33, 700), ("miss", 8, 300)])
+def test_march_rays_inference_slot_states_bit_exact(oracle, ref, case, cap, n_slots):
+    """march_rays_inference alone, three consecutive calls over arbitrary slot states (some slots terminated,
+    some resuming mid-ray, slot count spanning several 1024-slot rank blocks, more slots than rays left):
+    every output bit-equal to the oracle; per-ray payloads bit-equal to the reference kernel.  'dense'
+    (all-ones grid) exercises the far-plane rule (marching.cu:367-394), 'cascades' K=3 with exponential steps."""
+    from jaxngp_b200 import volrendjax as V
+    st, arr = inputs.march_case(case)
+    st = dict(diagonal_n_steps=st["diagonal_n_steps"], K=st["K"], G=st["G"], march_steps_cap=cap, bound=st["bound"],
+              stepsize_portion=st["stepsize_portion"])
+    N = arr["rays_o"].shape[0]
+    rng = np.random.Generator(np.random.PCG64(cap * 1000 + n_slots))
+    term = np.ones(n_slots, np.bool_)
+    idx = np.zeros(n_slots, np.uint32)
+    nri = np.zeros(1, np.uint32)
+    ts_o = arr["t_starts"].copy()
+    ts_g = t(ts_o)
+    fixed = {k: arr[k] for k in ("rays_o", "rays_d", "t_ends")}
+    fixed_g = {k: t(v) for k, v in fixed.items()}
+    bits_g = t(arr["occupancy_bitfield"])
+    idx_g, nri_g = t(idx), t(nri)
+    for call in range(3):
+        o = oracle.march_rays_inference(**st, **fixed, t_starts=ts_o, occupancy_bitfield=arr["occupancy_bitfield"],
+                                        next_ray_index_in=nri, terminated=term, indices=idx)
+        g = V.march_rays_inference(**st, **fixed_g, t_starts=ts_g, occupancy_bitfield=bits_g, next_ray_index_in=nri_g,
+                                   terminated=t(term), indices=idx_g)
+        names = ("next_ray_index", "indices", "n_samples", "t_starts", "xyzs", "dss", "z_vals")
+        for name, a, b in zip(names, g[:7], o[:7]):
+            a, b = n(a), np.asarray(b)
+            assert np.array_equal(a.view(np.uint32).ravel(), b.view(np.uint32).ravel()), (call, name)
+        if call == 0:  # reference kernel: arrival-order admission, so compare per admitted ray
+            r = ref.march_rays_inference(**st, **fixed_g, t_starts=t(arr["t_starts"]), occupancy_bitfield=bits_g,
+                                         next_ray_index_in=t(np.zeros(1, np.uint32)), terminated=t(term), indices=t(idx))
+            gi, ri = n(g[1]).astype(np.int64), n(r[1]).astype(np.int64)
+            assert np.array_equal(np.sort(gi), np.sort(ri))
+            go, ro = np.argsort(gi, kind="stable"), np.argsort(ri, kind="stable")
+            for k in (2, 4, 5, 6):
+                a, b = n(g[k])[go], n(r[k])[ro]
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), k
+            live = np.sort(gi)[np.sort(gi) < N]
+            assert np.array_equal(n(g[3]).view(np.uint32)[live], n(r[3]).view(np.uint32)[live])
+        nri, idx, ns, ts_o = o[0], o[1], o[2], o[3]
+        nri_g, idx_g, ts_g = g[0], g[1], g[3]
+        # next state: slots that ran out of samples terminate, plus a random third (early stop by transmittance)
+        term = (ns < cap) | (rng.random(n_slots) < 0.33)
+
+
 # ------------------------------------------------------------------ hash-grid encoder
 @pytest.mark.parametrize("dim,T,N_max", [(3, 2 ** 19, 2048), (3, 2 ** 14, 512), (2, 2 ** 19, 2 ** 19), (2, 2 ** 12, 4096)])
 def test_hashgrid_forward_backward_vs_oracle(oracle, dim, T, N_max):
