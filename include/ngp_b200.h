@@ -87,6 +87,14 @@ void ngp_march_rays(cudaStream_t, void **, const char *, size_t);
  * terminated slots in slot order. */
 void ngp_march_rays_inference(cudaStream_t, void **, const char *, size_t);
 
+/* Renderer fast path (no reference counterpart): advances every ray of a frame through the
+ * empty space in front of its first occupied point, following the reference loop's visit rule exactly
+ * (marching.cu:323-365), so that march_rays_inference started from t_out emits bit-identical samples.
+ * descriptor: NgpMarchingInferenceDescriptor (n_rays and march_steps_cap unused)
+ * in : rays_o f32[N,3], rays_d f32[N,3], t_starts f32[N], t_ends f32[N], bitfield u8[..]
+ * out: t_out f32[N] (may alias t_starts) */
+void ngp_march_rays_skip_empty(cudaStream_t, void **, const char *, size_t);
+
 /* replace volrendjax::morton3d / morton3d_invert (volrend.h:143-154, marching.cu:606-665)
  * morton3d: in xyzs u32[len,3], out idcs u32[len];  invert: in idcs u32[len], out xyzs u32[len,3] */
 void ngp_morton3d(cudaStream_t, void **, const char *, size_t);
@@ -178,6 +186,15 @@ typedef struct {
 } NgpNerfMlpDescriptor;
 void ngp_nerf_mlp_forward(cudaStream_t, void **, const char *, size_t);
 void ngp_nerf_mlp_backward(cudaStream_t, void **, const char *, size_t);
+
+/* HashGridEncoder fused in front of the MLP forward: the [n,32] encoding feeds the first layer's
+ * tensor-core fragments directly.  Bit-identical to hashgrid_a1_forward followed by nerf_mlp_forward.
+ * Needs dim=3, L=16, F=2, power-of-two wrap_T, table aligned to two rows; otherwise NGP_ERR_ARGUMENT (status -2).
+ * in : pos f32[n,3], table (f32|f16)[rows,2], dirs f32[n,3] (grouped: f32[n_groups,3]; density_only: unused),
+ *      weights f32[9408] [, group_counts u32[n_groups] if grid.rows_per_group != 0]
+ * out: drgbs f32[n,4] (density_only: f32[n]) [, enc f32[n,32] if write_enc] */
+typedef struct { NgpHashGridA1Descriptor grid; uint32_t density_only, write_enc; } NgpNerfFusedDescriptor;
+void ngp_nerf_fused_forward(cudaStream_t, void **, const char *, size_t);
 
 /* Training glue around the four ops (XLA fuses these elementwise chains for the reference):
  * make_training_rays: app/nerf/_utils.py:93-115 + utils/types.py:398-439 (undistorted PERSPECTIVE camera)

@@ -19,93 +19,20 @@
 // Backward: level-major warps with run aggregation (see the kernel), `red.global.add.v2.f32` (one
 // 8-byte L2 reduction per corner instead of two scalar atomics), after a zero-fill of the table grad.
 #include "common.cuh"
+#include "hashgrid.cuh"
 
 namespace ngp {
 namespace {
 
 constexpr int kBlock = 256;
-constexpr uint32_t kPrime1 = 2654435761u, kPrime2 = 805459861u;  // encoders.py:169
+using hg::LevelMeta;
+using hg::RowIO;
+using hg::a1_level;
+using hg::grid_row;
+using hg::kPrime1;
+using hg::kPrime2;
 
-struct LevelMeta {
-    float scale;
-    uint32_t res, offset, wrap, hashed;
-};
-
-template <int DIM>
-__device__ __forceinline__ uint32_t grid_row(const uint32_t (&v)[DIM], const LevelMeta &m) {
-    uint32_t idx;
-    if (m.hashed) {  // encoders.py:157-177
-        idx = v[0] ^ (v[1] * kPrime1);
-        if (DIM == 3) idx ^= v[2] * kPrime2;
-    } else {  // encoders.py:134-155 (uint32 wrap-around arithmetic)
-        idx = v[0] + v[1] * m.res;
-        if (DIM == 3) idx += v[2] * m.res * m.res;
-    }
-    // `mod wrap` (encoders.py:187); power-of-two wraps are a mask, others rarely exceed the range
-    if ((m.wrap & (m.wrap - 1u)) == 0u) idx &= m.wrap - 1u;
-    else if (idx >= m.wrap) idx %= m.wrap;
-    return idx + m.offset;
-}
-
-template <typename TT, int F>
-struct RowIO;
-template <>
-struct RowIO<float, 2> {
-    static __device__ __forceinline__ void load(const float *t, uint32_t row, float (&f)[2]) {
-        float2 v = __ldg(reinterpret_cast<const float2 *>(t) + row);
-        f[0] = v.x; f[1] = v.y;
-    }
-};
-template <>
-struct RowIO<float, 4> {
-    static __device__ __forceinline__ void load(const float *t, uint32_t row, float (&f)[4]) {
-        float4 v = __ldg(reinterpret_cast<const float4 *>(t) + row);
-        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
-    }
-};
-template <>
-struct RowIO<__half, 2> {
-    static __device__ __forceinline__ void load(const __half *t, uint32_t row, float (&f)[2]) {
-        __half2 h = __ldg(reinterpret_cast<const __half2 *>(t) + row);
-        float2 v = __half22float2(h);
-        f[0] = v.x; f[1] = v.y;
-    }
-};
-template <>
-struct RowIO<__half, 4> {
-    static __device__ __forceinline__ void load(const __half *t, uint32_t row, float (&f)[4]) {
-        uint2 raw = __ldg(reinterpret_cast<const uint2 *>(t) + row);
-        float2 a = __half22float2(*reinterpret_cast<__half2 *>(&raw.x));
-        float2 b = __half22float2(*reinterpret_cast<__half2 *>(&raw.y));
-        f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
-    }
-};
-
-__device__ __forceinline__ LevelMeta a1_level(const NgpHashGridA1Descriptor &d, uint32_t level) {
-    LevelMeta m;
-    m.scale = d.scales[level];
-    m.res = d.res[level];
-    m.offset = d.offsets[level];
-    m.wrap = d.wrap_T ? d.wrap_T : d.offsets[level + 1] - d.offsets[level];
-    m.hashed = (d.hashed_mask >> level) & 1u;
-    return m;
-}
-
-// cell base and fractional offsets of a point at one level (encoders.py:87,116-123,204,216-218)
-template <int DIM>
-__device__ __forceinline__ void a1_cell(const float *__restrict__ pos, uint32_t point, float bound, float scale,
-                                        uint32_t (&base)[DIM], float (&fr)[DIM]) {
-#pragma unroll
-    for (int k = 0; k < DIM; ++k) {
-        float p01 = __fdiv_rn(__fadd_rn(__ldg(pos + (size_t)point * DIM + k), bound), __fmul_rn(2.f, bound));
-        float ps = __fadd_rn(__fmul_rn(p01, scale), .5f);  // mul then add, as the XLA-CPU reference path
-        float fl = floorf(ps);
-        base[k] = (uint32_t)(int)fl;
-        fr[k] = ps - fl;
-    }
-}
-
-template <int DIM, int F, typename TT>
+template <int DIM, int F, typename TT, bool kPaired, bool kPow2>
 __global__ void __launch_bounds__(kBlock) hashgrid_a1_forward_kernel(const __grid_constant__ NgpHashGridA1Descriptor d,
                                                                       const float *__restrict__ pos,
                                                                       const TT *__restrict__ table,
@@ -115,43 +42,24 @@ __global__ void __launch_bounds__(kBlock) hashgrid_a1_forward_kernel(const __gri
     if (threadIdx.x < d.L) s_meta[threadIdx.x] = a1_level(d, threadIdx.x);
     __syncthreads();
     const uint64_t tid = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
-    const uint32_t point = (uint32_t)(tid / d.L), level = (uint32_t)(tid % d.L);
+    uint32_t point, level;
+    if ((d.L & (d.L - 1u)) == 0u) {  // L = 16: shift and mask instead of a 64-bit division
+        point = (uint32_t)(tid >> (31 - __clz(d.L)));
+        level = (uint32_t)tid & (d.L - 1u);
+    } else {
+        point = (uint32_t)(tid / d.L);
+        level = (uint32_t)(tid % d.L);
+    }
     if (point >= d.n_points) return;
     // grouped (inference) layout: rows past the group's sample count are padding, skip them
     if (d.rows_per_group && point % d.rows_per_group >= __ldg(group_counts + point / d.rows_per_group)) return;
     const LevelMeta m = s_meta[level];
-
-    uint32_t base[DIM];
-    float fr[DIM];
-    a1_cell<DIM>(pos, point, d.bound, m.scale, base, fr);
-
-    constexpr int NC = 1 << DIM;
-    uint32_t rows[NC];
-    float w[NC];
+    float x[DIM];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        uint32_t v[DIM];
-        float wc = 1.f;
-#pragma unroll
-        for (int k = 0; k < DIM; ++k) {
-            const uint32_t bit = (c >> (DIM - 1 - k)) & 1;  // last axis fastest, encoders.py:16-33
-            v[k] = base[k] + bit;
-            wc *= bit ? fr[k] : 1.f - fr[k];  // encoders.py:204-213 (clip is a no-op for frac in [0,1))
-        }
-        rows[c] = grid_row<DIM>(v, m);
-        w[c] = wc;
-    }
-    float vals[NC][F];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) RowIO<TT, F>::load(table, rows[c], vals[c]);
-    float acc[F];
-#pragma unroll
-    for (int f = 0; f < F; ++f) acc[f] = 0.f;
-#pragma unroll
-    for (int c = 0; c < NC; ++c)
-#pragma unroll
-        for (int f = 0; f < F; ++f) acc[f] = fmaf(w[c], vals[c][f], acc[f]);
-
+    for (int k = 0; k < DIM; ++k) x[k] = __ldg(pos + (size_t)point * DIM + k);
+    float p01[DIM], acc[F];
+    hg::unit_pos<DIM>(x, d.bound, p01);
+    hg::encode_point_level<DIM, F, TT, kPaired, kPow2>(table, m, p01, acc);
     float *out = enc + ((size_t)point * d.L + level) * F;  // [n, L*F], level-major / feature-minor (:233)
     if (F == 2) *reinterpret_cast<float2 *>(out) = make_float2(acc[0], acc[1]);
     else *reinterpret_cast<float4 *>(out) = make_float4(acc[0], acc[1], acc[F - 2], acc[F - 1]);
@@ -164,7 +72,7 @@ __global__ void __launch_bounds__(kBlock) hashgrid_a1_forward_kernel(const __gri
 // reduction and only the run's first lane issues the 8 reductions.  L2 reductions are issued per
 // active lane (~1.3 cycles each), so this removes ~55 % of them on ray-ordered samples; on
 // incoherent points the run detection costs three shuffles and a vote per level.
-template <int DIM, int F>
+template <int DIM, int F, bool kPaired>
 __global__ void __launch_bounds__(kBlock) hashgrid_a1_backward_kernel(const __grid_constant__ NgpHashGridA1Descriptor d,
                                                                        const float *__restrict__ pos,
                                                                        const float *__restrict__ d_enc,
@@ -248,14 +156,32 @@ __global__ void __launch_bounds__(kBlock) hashgrid_a1_backward_kernel(const __gr
                     }
             }
             if (head) {
+                // corners c and c + NC/2 differ by +1 along x; when their rows are neighbours (2k, 2k+1) both
+                // gradients go out in ONE 16-byte reduction (F = 2; needs d_table 16-byte aligned, kPaired)
 #pragma unroll
-                for (int c = 0; c < NC; ++c) {
-                    uint32_t vert[DIM];
+                for (int c = 0; c < NC / 2; ++c) {
+                    uint32_t va[DIM], vb[DIM];
 #pragma unroll
-                    for (int k = 0; k < DIM; ++k) vert[k] = base[k] + ((c >> (DIM - 1 - k)) & 1);
-                    float *dst = d_table + (size_t)grid_row<DIM>(vert, m) * F;
-                    if (F == 2) red_add_v2(dst, v[c][0], v[c][1]);
-                    else red_add_v4(dst, v[c][0], v[c][1], v[c][F - 2], v[c][F - 1]);
+                    for (int k = 0; k < DIM; ++k) {
+                        va[k] = base[k] + ((c >> (DIM - 1 - k)) & 1);
+                        vb[k] = base[k] + (((c + NC / 2) >> (DIM - 1 - k)) & 1);
+                    }
+                    const uint32_t ra = grid_row<DIM>(va, m), rb = grid_row<DIM>(vb, m);
+                    if (F == 2) {
+                        if (kPaired && (ra ^ rb) == 1u) {
+                            const bool a_hi = ra & 1u;
+                            red_add_v4(d_table + (size_t)(ra & ~1u) * 2, a_hi ? v[c + NC / 2][0] : v[c][0],
+                                       a_hi ? v[c + NC / 2][1] : v[c][1], a_hi ? v[c][0] : v[c + NC / 2][0],
+                                       a_hi ? v[c][1] : v[c + NC / 2][1]);
+                        } else {
+                            red_add_v2(d_table + (size_t)ra * 2, v[c][0], v[c][1]);
+                            red_add_v2(d_table + (size_t)rb * 2, v[c + NC / 2][0], v[c + NC / 2][1]);
+                        }
+                    } else {
+                        red_add_v4(d_table + (size_t)ra * F, v[c][0], v[c][1], v[c][F - 2], v[c][F - 1]);
+                        red_add_v4(d_table + (size_t)rb * F, v[c + NC / 2][0], v[c + NC / 2][1], v[c + NC / 2][F - 2],
+                                   v[c + NC / 2][F - 1]);
+                    }
                 }
             }
         }
@@ -447,8 +373,17 @@ void ngp_hashgrid_a1_forward(cudaStream_t stream, void **buffers, const char *op
     const uint32_t *group_counts = d->rows_per_group ? b.next<const uint32_t>() : nullptr;
     float *enc = b.next<float>();
     const unsigned blocks = div_up((unsigned long long)d->n_points * d->L, kBlock);
-#define NGP_FWD(DIM, F, TT) \
-    hashgrid_a1_forward_kernel<DIM, F, TT><<<blocks, kBlock, 0, stream>>>(*d, pos, static_cast<const TT *>(table), group_counts, enc)
+    // one aligned load for both corners of an x-pair needs the table base aligned to two rows
+    const bool paired = (reinterpret_cast<uintptr_t>(table) % (2 * d->F * (d->table_dtype == 0 ? 4 : 2))) == 0;
+    const bool pow2 = d->wrap_T != 0 && (d->wrap_T & (d->wrap_T - 1u)) == 0;
+#define NGP_FWD_(DIM, F, TT, P, W) \
+    hashgrid_a1_forward_kernel<DIM, F, TT, P, W><<<blocks, kBlock, 0, stream>>>(*d, pos, static_cast<const TT *>(table), group_counts, enc)
+#define NGP_FWD(DIM, F, TT)                              \
+    do {                                                 \
+        if (paired && pow2) NGP_FWD_(DIM, F, TT, true, true);   \
+        else if (paired) NGP_FWD_(DIM, F, TT, true, false);     \
+        else NGP_FWD_(DIM, F, TT, false, false);                \
+    } while (0)
     if (d->table_dtype == 0) {
         if (d->dim == 3 && d->F == 2) NGP_FWD(3, 2, float);
         else if (d->dim == 3) NGP_FWD(3, 4, float);
@@ -461,6 +396,7 @@ void ngp_hashgrid_a1_forward(cudaStream_t stream, void **buffers, const char *op
         else NGP_FWD(2, 4, __half);
     }
 #undef NGP_FWD
+#undef NGP_FWD_
     check_launch("hashgrid_a1_forward");
 }
 
@@ -477,10 +413,15 @@ void ngp_hashgrid_a1_backward(cudaStream_t stream, void **buffers, const char *o
                 "hashgrid_a1_backward");
     if (d->n_points == 0) return;
     const unsigned blocks = div_up(d->n_points, kBlock);  // one CTA per 256 points, all levels
-    if (d->dim == 3 && d->F == 2) hashgrid_a1_backward_kernel<3, 2><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
-    else if (d->dim == 3) hashgrid_a1_backward_kernel<3, 4><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
-    else if (d->F == 2) hashgrid_a1_backward_kernel<2, 2><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
-    else hashgrid_a1_backward_kernel<2, 4><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
+    const bool paired = reinterpret_cast<uintptr_t>(d_table) % 16 == 0;
+    if (d->dim == 3 && d->F == 2) {
+        if (paired) hashgrid_a1_backward_kernel<3, 2, true><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
+        else hashgrid_a1_backward_kernel<3, 2, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
+    } else if (d->dim == 3) hashgrid_a1_backward_kernel<3, 4, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
+    else if (d->F == 2) {
+        if (paired) hashgrid_a1_backward_kernel<2, 2, true><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
+        else hashgrid_a1_backward_kernel<2, 2, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
+    } else hashgrid_a1_backward_kernel<2, 4, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
     check_launch("hashgrid_a1_backward");
 }
 

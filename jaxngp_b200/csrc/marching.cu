@@ -675,6 +675,38 @@ __global__ void __launch_bounds__(kInferWarps * 32) march_rays_inference_kernel(
     }
 }
 
+// ---------------------------------------------------------------- empty-space pre-advance (inference)
+// The state a ray carries between march_rays_inference calls is its parameter t alone
+// (marching/__init__.py:156), and until the reference's loop (marching.cu:323-365) meets its first
+// occupied point it only moves t along the visit sequence without emitting anything.  This kernel runs
+// that prefix for every ray of a frame once, one THREAD per ray (the visit sequence touches ~1 chain
+// point in 5, so a thread hopping voxel to voxel does a fraction of the warp-cooperative march's work):
+// t_out = the first visited point that is occupied, or the last visited point < t_end if there is none.  Feeding
+// t_out to march_rays_inference as t_starts yields bit-identical samples and final t.
+__global__ void __launch_bounds__(128) march_rays_skip_empty_kernel(
+    NgpMarchingInferenceDescriptor p, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+    const float *t_starts, const float *__restrict__ t_ends, const uint8_t *__restrict__ bitfield, float *t_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_total_rays) return;
+    float t = t_starts[i];
+    const float t_end = __ldg(t_ends + i);
+    if (!(t_end < t)) {  // marching.cu:317
+        const Grid g = make_grid(p.diagonal_n_steps, p.K, p.G, p.bound, p.stepsize_portion, bitfield);
+        const Ray ray = load_ray(rays_o, rays_d, i);
+        float t_prev = t;
+        while (t < t_end) {
+            const Step s = march_step<true>(g, ray, t);
+            if (s.occupied) break;
+            t_prev = t;
+            t = s.t_next;
+        }
+        // nothing occupied before t_end: hand back the LAST visited point still inside the ray, so the march
+        // re-visits it, steps past t_end to the same final t and applies the far-plane rule (marching.cu:367-394)
+        if (!(t < t_end)) t = t_prev;
+    }
+    t_out[i] = t;
+}
+
 }  // namespace
 }  // namespace ngp
 
@@ -773,6 +805,28 @@ void ngp_march_rays_inference(cudaStream_t stream, void **buffers, const char *o
         *desc, rays_o, rays_d, t_starts, t_ends, bitfield, next_in, terminated, indices_in, block_total, rank_in_block,
         next_out, indices_out, n_samples, t_starts_out, xyzs, dss, z_vals);
     check_launch("march_rays_inference");
+}
+
+void ngp_march_rays_skip_empty(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *desc = descriptor<NgpMarchingInferenceDescriptor>(opaque, opaque_len, "march_rays_skip_empty");
+    if (!desc) return;
+    if (desc->K == 0 || desc->G == 0 || desc->G > 1024) {
+        set_error(NGP_ERR_ARGUMENT, "march_rays_skip_empty: expected K > 0 and 0 < G <= 1024, got K=%u G=%u", desc->K, desc->G);
+        return;
+    }
+    if (desc->n_total_rays == 0) return;
+    BufferCursor b{buffers};
+    const float *rays_o = b.next<const float>();
+    const float *rays_d = b.next<const float>();
+    const float *t_starts = b.next<const float>();
+    const float *t_ends = b.next<const float>();
+    const uint8_t *bitfield = b.next<const uint8_t>();
+    float *t_out = b.next<float>();
+    march_rays_skip_empty_kernel<<<div_up(desc->n_total_rays, 128), 128, 0, stream>>>(*desc, rays_o, rays_d, t_starts, t_ends,
+                                                                                      bitfield, t_out);
+    check_launch("march_rays_skip_empty");
 }
 
 }  // extern "C"

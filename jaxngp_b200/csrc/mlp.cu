@@ -18,6 +18,7 @@
 // global gradient with one atomicAdd per element per CTA at the end.  Activations never touch HBM:
 // traffic is enc (128 B) + dirs (12 B) + d_drgbs (16 B) in, d_enc (128 B) out per sample.
 #include "common.cuh"
+#include "hashgrid.cuh"
 
 namespace ngp {
 namespace {
@@ -140,20 +141,9 @@ struct FwdState {  // what the backward needs from the recomputed forward, in fr
     float rgb[2][2]; // sigmoid outputs: cols 2t, 2t+1 of rows g, g+8 (t == 0: r, g; t == 1: b, pad)
 };
 
-// Forward for this warp's 16 rows starting at `row0` (global sample index).  If kKeep, activations are also
-// written to the warp's rows of the shared activation buffers.
-template <bool kKeep, bool kDensityOnly>
-__device__ __forceinline__ void warp_forward(const uint32_t *__restrict__ sw, float *__restrict__ act, uint32_t warp,
-                                             uint32_t row0, uint32_t n, const float *__restrict__ enc,
-                                             const float *__restrict__ dirs, uint32_t g, uint32_t t, FwdState &st,
-                                             uint32_t (&a_h2)[8][4], float (&out_rgb)[1][4],
-                                             uint32_t rows_per_group = 0, bool ok_lo_in = true, bool ok_hi_in = true) {
-    const uint32_t r_lo = row0 + g, r_hi = row0 + g + 8;
-    const bool ok_lo = r_lo < n && ok_lo_in, ok_hi = r_hi < n && ok_hi_in;
-    // grouped layout: one direction per group of rows (ray), else one per row
-    const uint32_t d_lo = rows_per_group ? r_lo / rows_per_group : r_lo, d_hi = rows_per_group ? r_hi / rows_per_group : r_hi;
-    // enc A fragments: cols 8kt+2t, 8kt+2t+1 of rows g, g+8 (float2 loads, every 32 B sector fully used)
-    uint32_t a_in[4][4];
+// enc A fragments of a 16-row tile: cols 8kt+2t, 8kt+2t+1 of rows g, g+8 (float2 loads, every 32 B sector fully used)
+__device__ __forceinline__ void load_enc_fragments(const float *__restrict__ enc, uint32_t r_lo, uint32_t r_hi, bool ok_lo,
+                                                   bool ok_hi, uint32_t t, uint32_t (&a_in)[4][4]) {
 #pragma unroll
     for (int kt = 0; kt < 4; ++kt) {
         const float2 lo = ok_lo ? __ldg(reinterpret_cast<const float2 *>(enc + (size_t)r_lo * 32 + 8 * kt + 2 * t)) : make_float2(0.f, 0.f);
@@ -163,6 +153,20 @@ __device__ __forceinline__ void warp_forward(const uint32_t *__restrict__ sw, fl
         a_in[kt][2] = tf32(lo.y);
         a_in[kt][3] = tf32(hi.y);
     }
+}
+
+// Forward for this warp's 16 rows starting at `row0` (global sample index) from the enc fragments `a_in`.
+// If kKeep, activations are also written to the warp's rows of the shared activation buffers.
+template <bool kKeep, bool kDensityOnly>
+__device__ __forceinline__ void warp_forward_from(const uint32_t *__restrict__ sw, float *__restrict__ act, uint32_t warp,
+                                                  uint32_t row0, uint32_t n, const uint32_t (&a_in)[4][4],
+                                                  const float *__restrict__ dirs, uint32_t g, uint32_t t, FwdState &st,
+                                                  uint32_t (&a_h2)[8][4], float (&out_rgb)[1][4],
+                                                  uint32_t rows_per_group = 0, bool ok_lo_in = true, bool ok_hi_in = true) {
+    const uint32_t r_lo = row0 + g, r_hi = row0 + g + 8;
+    const bool ok_lo = r_lo < n && ok_lo_in, ok_hi = r_hi < n && ok_hi_in;
+    // grouped layout: one direction per group of rows (ray), else one per row
+    const uint32_t d_lo = rows_per_group ? r_lo / rows_per_group : r_lo, d_hi = rows_per_group ? r_hi / rows_per_group : r_hi;
     float *my_rows_64 = nullptr, *my_rows_32 = nullptr;
     (void)my_rows_64;
     (void)my_rows_32;
@@ -245,6 +249,19 @@ __device__ __forceinline__ void warp_forward(const uint32_t *__restrict__ sw, fl
     st.rgb[1][1] = out_rgb[0][3];
 }
 
+template <bool kKeep, bool kDensityOnly>
+__device__ __forceinline__ void warp_forward(const uint32_t *__restrict__ sw, float *__restrict__ act, uint32_t warp,
+                                             uint32_t row0, uint32_t n, const float *__restrict__ enc,
+                                             const float *__restrict__ dirs, uint32_t g, uint32_t t, FwdState &st,
+                                             uint32_t (&a_h2)[8][4], float (&out_rgb)[1][4],
+                                             uint32_t rows_per_group = 0, bool ok_lo_in = true, bool ok_hi_in = true) {
+    const uint32_t r_lo = row0 + g, r_hi = row0 + g + 8;
+    uint32_t a_in[4][4];
+    load_enc_fragments(enc, r_lo, r_hi, r_lo < n && ok_lo_in, r_hi < n && ok_hi_in, t, a_in);
+    warp_forward_from<kKeep, kDensityOnly>(sw, act, warp, row0, n, a_in, dirs, g, t, st, a_h2, out_rgb, rows_per_group,
+                                           ok_lo_in, ok_hi_in);
+}
+
 // ---------------------------------------------------------------- forward kernel
 template <bool kDensityOnly>
 __global__ void __launch_bounds__(kThreads) nerf_mlp_forward_kernel(uint32_t n, uint32_t rows_per_group,
@@ -286,6 +303,87 @@ __global__ void __launch_bounds__(kThreads) nerf_mlp_forward_kernel(uint32_t n, 
                     reinterpret_cast<float4 *>(out)[row0 + g] = make_float4(expf(st.x0[0]), st.rgb[0][0], st.rgb[0][1], b_lo);
                 if (live_hi)
                     reinterpret_cast<float4 *>(out)[row0 + g + 8] = make_float4(expf(st.x0[1]), st.rgb[1][0], st.rgb[1][1], b_hi);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- encoder fused in front of the MLP (forward)
+// The hash-grid gather feeds the MLP's first A fragments directly: lane (g, t) of a warp owns rows g, g+8 of the
+// warp's 16-sample tile and needs feature columns 8kt+2t, 8kt+2t+1 = BOTH features of level 4kt+t, kt = 0..3, so it
+// gathers 2 points x 4 levels x 8 corners itself (branch-free predicated loads, 16 rows in flight at a time) and the
+// [n, 32] encoding never goes through HBM (inference), or is written once for the backward pass (training,
+// kWriteEnc) without being read back.  While one warp waits on its gathers (L1/L2-bound) others run their
+// tensor-core layers (issue-bound): the two halves of the forward overlap inside one SM.
+// Same arithmetic as hashgrid_a1_forward + nerf_mlp_forward => same bits.
+template <typename TT, bool kDensityOnly, bool kWriteEnc>
+__global__ void __launch_bounds__(kThreads) nerf_fused_forward_kernel(const __grid_constant__ NgpNerfFusedDescriptor d,
+                                                                      const float *__restrict__ pos,
+                                                                      const TT *__restrict__ table,
+                                                                      const float *__restrict__ dirs,
+                                                                      const float *__restrict__ weights,
+                                                                      const uint32_t *__restrict__ group_counts,
+                                                                      float *__restrict__ out, float *__restrict__ enc_out) {
+    extern __shared__ __align__(16) uint32_t smem_u32[];
+    uint32_t *sw = smem_u32;
+    hg::LevelMeta *s_meta = reinterpret_cast<hg::LevelMeta *>(smem_u32 + kWeightFloats);
+    load_weights(sw, weights);
+    if (threadIdx.x < 16) s_meta[threadIdx.x] = hg::a1_level(d.grid, threadIdx.x);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3u;
+    const uint32_t n = d.grid.n_points, rows_per_group = d.grid.rows_per_group;
+    const float bound = d.grid.bound;
+    const uint32_t n_tiles = (n + 15u) / 16u;
+    for (uint32_t tile = blockIdx.x * kWarps + warp; tile < n_tiles; tile += gridDim.x * kWarps) {
+        const uint32_t row0 = tile * 16u, r_lo = row0 + g, r_hi = row0 + g + 8;
+        bool live_lo = r_lo < n, live_hi = r_hi < n;
+        if (rows_per_group) {  // padding rows of the grouped layout are neither read nor written
+            live_lo = live_lo && r_lo % rows_per_group < __ldg(group_counts + r_lo / rows_per_group);
+            live_hi = live_hi && r_hi % rows_per_group < __ldg(group_counts + r_hi / rows_per_group);
+            if (!__any_sync(0xffffffffu, live_lo || live_hi)) continue;
+        }
+        float x_lo[3] = {0.f, 0.f, 0.f}, x_hi[3] = {0.f, 0.f, 0.f};
+        if (live_lo) {
+            x_lo[0] = __ldg(pos + (size_t)r_lo * 3 + 0); x_lo[1] = __ldg(pos + (size_t)r_lo * 3 + 1); x_lo[2] = __ldg(pos + (size_t)r_lo * 3 + 2);
+        }
+        if (live_hi) {
+            x_hi[0] = __ldg(pos + (size_t)r_hi * 3 + 0); x_hi[1] = __ldg(pos + (size_t)r_hi * 3 + 1); x_hi[2] = __ldg(pos + (size_t)r_hi * 3 + 2);
+        }
+        float p_lo[3], p_hi[3];
+        hg::unit_pos<3>(x_lo, bound, p_lo);
+        hg::unit_pos<3>(x_hi, bound, p_hi);
+        uint32_t a_in[4][4];
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+            const hg::LevelMeta m = s_meta[4 * kt + t];
+            float lo[2], hi[2];
+            hg::encode_point_level_pred<TT>(table, m, p_lo, live_lo, lo);
+            hg::encode_point_level_pred<TT>(table, m, p_hi, live_hi, hi);
+            a_in[kt][0] = tf32(lo[0]);
+            a_in[kt][1] = tf32(hi[0]);
+            a_in[kt][2] = tf32(lo[1]);
+            a_in[kt][3] = tf32(hi[1]);
+            if (kWriteEnc) {
+                if (live_lo) *reinterpret_cast<float2 *>(enc_out + (size_t)r_lo * 32 + 8 * kt + 2 * t) = make_float2(lo[0], lo[1]);
+                if (live_hi) *reinterpret_cast<float2 *>(enc_out + (size_t)r_hi * 32 + 8 * kt + 2 * t) = make_float2(hi[0], hi[1]);
+            }
+        }
+        FwdState st;
+        uint32_t a_h2[8][4];
+        float rgb[1][4];
+        warp_forward_from<false, kDensityOnly>(sw, nullptr, warp, row0, n, a_in, dirs, g, t, st, a_h2, rgb, rows_per_group,
+                                               live_lo, live_hi);
+        if (kDensityOnly) {
+            if (t == 0) {
+                if (live_lo) out[r_lo] = expf(st.x0[0]);
+                if (live_hi) out[r_hi] = expf(st.x0[1]);
+            }
+        } else {
+            const float b_lo = __shfl_sync(0xffffffffu, st.rgb[0][0], (lane & ~3u) + 1);
+            const float b_hi = __shfl_sync(0xffffffffu, st.rgb[1][0], (lane & ~3u) + 1);
+            if (t == 0) {
+                if (live_lo) reinterpret_cast<float4 *>(out)[r_lo] = make_float4(expf(st.x0[0]), st.rgb[0][0], st.rgb[0][1], b_lo);
+                if (live_hi) reinterpret_cast<float4 *>(out)[r_hi] = make_float4(expf(st.x0[1]), st.rgb[1][0], st.rgb[1][1], b_hi);
             }
         }
     }
@@ -494,6 +592,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_kernel(uint32_t
 }
 
 constexpr size_t kFwdSmem = kWeightFloats * sizeof(uint32_t);
+constexpr size_t kFusedSmem = kFwdSmem + 16 * sizeof(hg::LevelMeta);
 constexpr size_t kBwdSmem = (kWeightFloats + kActFloats) * sizeof(uint32_t);
 
 }  // namespace
@@ -549,6 +648,54 @@ void ngp_nerf_mlp_backward(cudaStream_t stream, void **buffers, const char *opaq
     const unsigned blocks = min(div_up(d->n_samples, kBlockSamples), 148u);
     nerf_mlp_backward_kernel<<<blocks, kThreads, kBwdSmem, stream>>>(d->n_samples, enc, dirs, weights, d_drgbs, d_enc, d_weights);
     check_launch("nerf_mlp_backward");
+}
+
+void ngp_nerf_fused_forward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *d = descriptor<NgpNerfFusedDescriptor>(opaque, opaque_len, "nerf_fused_forward");
+    if (!d) return;
+    const NgpHashGridA1Descriptor &gd = d->grid;
+    BufferCursor b{buffers};
+    const float *pos = b.next<const float>();
+    const void *table = b.next<const void>();
+    const float *dirs = b.next<const float>();
+    const float *weights = b.next<const float>();
+    const uint32_t *group_counts = gd.rows_per_group ? b.next<const uint32_t>() : nullptr;
+    float *out = b.next<float>();
+    float *enc_out = d->write_enc ? b.next<float>() : nullptr;
+    const size_t pair_bytes = gd.table_dtype == 0 ? 16 : 8;
+    if (gd.dim != 3 || gd.L != 16 || gd.F != 2 || gd.table_dtype > 1 || gd.wrap_T == 0 || (gd.wrap_T & (gd.wrap_T - 1u)) != 0 ||
+        reinterpret_cast<uintptr_t>(table) % pair_bytes != 0) {
+        set_error(NGP_ERR_ARGUMENT,
+                  "nerf_fused_forward: needs dim=3 L=16 F=2, power-of-two wrap_T and a table aligned to two rows "
+                  "(got dim=%u L=%u F=%u wrap_T=%u); use hashgrid_a1_forward + nerf_mlp_forward", gd.dim, gd.L, gd.F, gd.wrap_T);
+        return;
+    }
+    if (gd.n_points == 0) return;
+    const unsigned tiles = div_up(gd.n_points, 16);
+    // persistent grid: 3 CTAs of 8 warps are resident per SM (80 registers, 43 KB shared memory); more CTAs than that
+    // only repeat the weight staging
+    const unsigned blocks = min(div_up(tiles, kWarps), 148u * 3u);
+#define NGP_FUSED(TT, DO, WE)                                                                                          \
+    do {                                                                                                               \
+        static bool configured = false; /* benign race: idempotent */                                                  \
+        if (!configured) {                                                                                             \
+            cudaFuncSetAttribute(nerf_fused_forward_kernel<TT, DO, WE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem); \
+            configured = true;                                                                                         \
+        }                                                                                                              \
+        nerf_fused_forward_kernel<TT, DO, WE><<<blocks, kThreads, kFusedSmem, stream>>>(                                \
+            *d, pos, static_cast<const TT *>(table), dirs, weights, group_counts, out, enc_out);                       \
+    } while (0)
+    if (gd.table_dtype == 0) {
+        if (d->density_only) { if (d->write_enc) NGP_FUSED(float, true, true); else NGP_FUSED(float, true, false); }
+        else { if (d->write_enc) NGP_FUSED(float, false, true); else NGP_FUSED(float, false, false); }
+    } else {
+        if (d->density_only) { if (d->write_enc) NGP_FUSED(__half, true, true); else NGP_FUSED(__half, true, false); }
+        else { if (d->write_enc) NGP_FUSED(__half, false, true); else NGP_FUSED(__half, false, false); }
+    }
+#undef NGP_FUSED
+    check_launch("nerf_fused_forward");
 }
 
 }  // extern "C"

@@ -85,6 +85,35 @@ def mlp_forward(enc: torch.Tensor, dirs, weights: torch.Tensor, group_counts: to
     return out
 
 
+def fused_supported(lt, table: torch.Tensor, wrap: str = "jaxngp") -> bool:
+    """Shapes ngp_nerf_fused_forward covers (include/ngp_b200.h); anything else runs encoder and MLP as two ops."""
+    pair_bytes = 16 if table.dtype == torch.float32 else 8
+    return (lt.dim == 3 and lt.L == 16 and lt.F == 2 and wrap == "jaxngp" and lt.T & (lt.T - 1) == 0
+            and table.dtype in (torch.float32, torch.float16) and table.data_ptr() % pair_bytes == 0)
+
+
+def fused_forward(lt, pos: torch.Tensor, bound: float, table: torch.Tensor, dirs, weights: torch.Tensor, *,
+                  wrap: str = "jaxngp", group_counts: torch.Tensor = None, rows_per_group: int = 0, want_enc: bool = False):
+    """Hash-grid encoder fused in front of the MLP forward (csrc/mlp.cu ``nerf_fused_forward_kernel``): bit-identical
+    to ``encoders.hashgrid_forward`` + ``mlp_forward``, without the [n, 32] round trip through HBM.
+    Returns ``drgbs`` (``dirs=None``: densities [n]); with ``want_enc`` also the encoding (kept for the backward)."""
+    n = pos.shape[0]
+    density_only = dirs is None
+    out = torch.empty((n,) if density_only else (n, 4), dtype=torch.float32, device=pos.device)
+    enc = torch.empty(n, 32, dtype=torch.float32, device=pos.device) if want_enc else None
+    if n:
+        desc = encoders._a1_descriptor(lt, n, bound, wrap, table.dtype, rows_per_group) + \
+            descriptors.struct.pack("<2I", int(density_only), int(want_enc))
+        bufs = [pos, table, pos if density_only else dirs, weights]
+        if group_counts is not None:
+            bufs.append(group_counts)
+        bufs.append(out)
+        if want_enc:
+            bufs.append(enc)
+        _lib.call("ngp_nerf_fused_forward", bufs, desc)
+    return (out, enc) if want_enc else out
+
+
 def mlp_backward(enc, dirs, weights, d_drgbs, d_weights=None):
     """Fused backward: returns (d_enc [n, 32], d_weights [9408]); recomputes the forward on chip."""
     n = enc.shape[0]
@@ -156,6 +185,10 @@ class NeRF(torch.nn.Module):
         unspecified, integrate_rays_inference never reads it).  Same numbers as ``forward`` on the live rows."""
         n, cap = xyzs.shape[0], xyzs.shape[1]
         enc_mod = self.position_encoder
+        if self.fused and fused_supported(enc_mod.levels, enc_mod.latents, enc_mod.wrap):
+            return fused_forward(enc_mod.levels, xyzs.reshape(-1, 3), self.bound, enc_mod.latents.detach(),
+                                 ray_dirs.contiguous(), self.mlp_flat.detach(), wrap=enc_mod.wrap, group_counts=n_samples,
+                                 rows_per_group=cap).reshape(n, cap, 4)
         enc = encoders.hashgrid_forward(enc_mod.levels, xyzs.reshape(-1, 3), self.bound, enc_mod.latents.detach(),
                                         enc_mod.wrap, group_counts=n_samples, rows_per_group=cap)
         drgbs = mlp_forward(enc, ray_dirs.contiguous(), self.mlp_flat.detach(), group_counts=n_samples, rows_per_group=cap)

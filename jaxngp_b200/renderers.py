@@ -100,11 +100,12 @@ class InferenceRenderer:
     bit-identical to ``render_image_inference``."""
 
     def __init__(self, nerf, cam, occupancy_bitfield, *, bg=(1.0, 1.0, 1.0), diagonal_n_steps=1024, K=1, G=128,
-                 bound=1.0, stepsize_portion=0.0, march_steps_cap=16, n_rays=131072, pixel_indices=None):
+                 bound=1.0, stepsize_portion=0.0, march_steps_cap=16, n_rays=131072, pixel_indices=None, skip_empty=True):
         from . import _lib, descriptors, trainops  # noqa: F401
         self.nerf, self.cam, self.bits = nerf, cam, occupancy_bitfield
         dev = occupancy_bitfield.device
         self.dev, self.bound, self.cap = dev, bound, march_steps_cap
+        self.skip_empty = skip_empty
         if pixel_indices is None:
             pixel_indices = torch.arange(cam["width"] * cam["height"], dtype=torch.int32, device=dev)
         self.pixels = pixel_indices.to(torch.int32).contiguous()  # the rays this renderer owns (tile sharding)
@@ -172,6 +173,10 @@ class InferenceRenderer:
 
     @torch.no_grad()
     def render_current_rays(self):
+        from . import _lib
+        if self.skip_empty:  # walk every ray to its first occupied point once, thread per ray (same samples, bit for bit)
+            _lib.call("ngp_march_rays_skip_empty", [self.o, self.d, self.t_starts, self.t_ends, self.bits, self.t_starts],
+                      self._march_desc)
         self.rays_rgbd.zero_()
         self.rays_T.fill_(1.0)
         self.terminated.fill_(True)

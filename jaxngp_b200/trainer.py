@@ -81,7 +81,7 @@ class Scene:
 
 class Trainer:
     def __init__(self, device="cuda:0", n_rays=1 << 18, total_samples=1 << 18, lr=1e-2, seed=1000000007, rank=0,
-                 world_size=1, process_group=None, scene=None, T=1 << 19, use_graph=True, fused_mlp=True, fused_glue=None):
+                 world_size=1, process_group=None, scene=None, T=1 << 19, use_graph=True, fused_mlp=True, fused_glue=None, fused_encoder=None):
         self.device = torch.device(device)
         self.n_rays, self.total_samples = n_rays, total_samples
         self.rank, self.world_size, self.pg = rank, world_size, process_group
@@ -92,6 +92,7 @@ class Trainer:
         self.fused_mlp = fused_mlp
         self.fused_glue = fused_mlp if fused_glue is None else fused_glue
         self._flatten_parameters()
+        self.fused_encoder = (fused_mlp and nerf_mod.fused_supported(self.levels, self.table)) if fused_encoder is None else fused_encoder
         self.scene = scene if scene is not None else Scene(self.device)
         # occupancy grid state (utils/types.py:93-144): all-ones bitfield at step 0
         self.grid = ogrid.OccupancyDensityGrid(synthetic.K, synthetic.G, device=self.device)
@@ -148,8 +149,11 @@ class Trainer:
         nxt, exc, ray_is_valid, rays_n, rays_start, _, xyzs, dirs, dss, z_vals = march_rays(
             self.total_samples, synthetic.DIAGONAL_N_STEPS, synthetic.K, synthetic.G, synthetic.BOUND,
             synthetic.STEPSIZE_PORTION, o, d, t_starts, t_ends, noises, self.grid.occupancy, raw=True)
-        enc = encoders.hashgrid_forward(self.levels, xyzs, synthetic.BOUND, self.table)
-        drgbs = nerf_mod.mlp_forward(enc, dirs, self.mlp_flat)
+        if self.fused_encoder:  # encoder gather feeding the MLP's first tensor-core fragments (enc written once, for the backward)
+            drgbs, enc = nerf_mod.fused_forward(self.levels, xyzs, synthetic.BOUND, self.table, dirs, self.mlp_flat, want_enc=True)
+        else:
+            enc = encoders.hashgrid_forward(self.levels, xyzs, synthetic.BOUND, self.table)
+            drgbs = nerf_mod.mlp_forward(enc, dirs, self.mlp_flat)
         effective, final_rgbds, final_opac = _integrate_fwd(rays_start, rays_n, bg, dss, z_vals, drgbs)
         d_final, loss, n_valid = trainops.huber_loss_grad(final_rgbds, ray_is_valid, perm, sc.rgbas_u8, bg)
         _, _, d_drgbs = _integrate_bwd(synthetic.NEAR, rays_start, rays_n, bg, dss, z_vals, drgbs, final_rgbds,
@@ -249,6 +253,8 @@ class Trainer:
 
     # -- density grid update (utils/types.py:1149-1239) --------------------------------------------
     def _density_fn(self, xyz):
+        if self.fused_encoder:
+            return nerf_mod.fused_forward(self.levels, xyz.contiguous(), synthetic.BOUND, self.table, None, self.mlp_flat)
         enc = encoders.hashgrid_forward(self.levels, xyz.contiguous(), synthetic.BOUND, self.table)
         if self.fused_mlp:
             return nerf_mod.mlp_forward(enc, None, self.mlp_flat)

@@ -292,6 +292,33 @@ def test_march_rays_inference_slot_states_bit_exact(oracle, ref, case, cap, n_sl
         term = (ns < cap) | (rng.random(n_slots) < 0.33)
 
 
+@pytest.mark.parametrize("case", ["scene", "cascades", "dense", "miss"])
+def test_march_rays_skip_empty_preserves_inference_march(case):
+    """ngp_march_rays_skip_empty (renderer fast path) moves t_starts to the first occupied visited point; the
+    samples march_rays_inference then emits, and the t it hands back, must not change by a single bit."""
+    from jaxngp_b200 import _lib, descriptors, volrendjax as V
+    st, arr = inputs.march_case(case)
+    st = dict(diagonal_n_steps=st["diagonal_n_steps"], K=st["K"], G=st["G"], march_steps_cap=12, bound=st["bound"],
+              stepsize_portion=st["stepsize_portion"])
+    N = arr["rays_o"].shape[0]
+    o, d, ts, te, bits = (t(arr[k]) for k in ("rays_o", "rays_d", "t_starts", "t_ends", "occupancy_bitfield"))
+    ts2 = torch.empty_like(ts)
+    desc = descriptors.make_marching_inference_descriptor(N, N, st["diagonal_n_steps"], st["K"], st["G"], 12, st["bound"],
+                                                          st["stepsize_portion"])
+    _lib.call("ngp_march_rays_skip_empty", [o, d, ts, te, bits, ts2], desc)
+    assert (ts2 >= ts).all()
+    if case != "dense":
+        assert (ts2 > ts).any() or case == "miss"
+    term, idx, nri = t(np.ones(N, np.bool_)), t(np.zeros(N, np.uint32)), t(np.zeros(1, np.uint32))
+    a = V.march_rays_inference(**st, rays_o=o, rays_d=d, t_starts=ts, t_ends=te, occupancy_bitfield=bits,
+                               next_ray_index_in=nri, terminated=term, indices=idx)
+    b = V.march_rays_inference(**st, rays_o=o, rays_d=d, t_starts=ts2, t_ends=te, occupancy_bitfield=bits,
+                               next_ray_index_in=nri, terminated=term, indices=idx)
+    for k, (x, y) in enumerate(zip(a[:7], b[:7])):
+        assert torch.equal(x.view(torch.int32) if x.dtype == torch.float32 else x,
+                           y.view(torch.int32) if y.dtype == torch.float32 else y), k
+
+
 # ------------------------------------------------------------------ hash-grid encoder
 @pytest.mark.parametrize("dim,T,N_max", [(3, 2 ** 19, 2048), (3, 2 ** 14, 512), (2, 2 ** 19, 2 ** 19), (2, 2 ** 12, 4096)])
 def test_hashgrid_forward_backward_vs_oracle(oracle, dim, T, N_max):

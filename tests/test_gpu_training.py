@@ -152,6 +152,42 @@ def test_fused_mlp_matches_fp32_reference():
     torch.backends.cuda.matmul.allow_tf32 = True
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_fused_encoder_mlp_forward_is_bit_identical_to_the_two_ops(dtype):
+    """ngp_nerf_fused_forward (encoder gather feeding the MLP fragments) against hashgrid_a1_forward +
+    nerf_mlp_forward: same arithmetic in the same order, so every output bit must agree -- plain, density-only
+    (density-grid update) and grouped (march_rays_inference layout with padding rows) variants."""
+    from jaxngp_b200 import encoders as E, nerf as nerf_mod
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    lt = E.make_level_table(16, 2 ** 19, 2, 16, 2048, 3)
+    table = ((torch.rand(lt.rows, 2, device=DEV, generator=gen) - 0.5) * 2).to(dtype)
+    w = (torch.rand(nerf_mod.MLP_NUMEL, device=DEV, generator=gen) - 0.5) * 0.6
+    n = 50021  # not a multiple of 16: the last tile is partial
+    pos = torch.rand(n, 3, device=DEV, generator=gen) * 2 - 1
+    pos[:64] = torch.tensor([1.0, -1.0, 0.999999], device=DEV)  # cube faces: Q1 spill rows on the dense levels
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV, generator=gen), dim=-1)
+    assert nerf_mod.fused_supported(lt, table)
+    enc = E.hashgrid_forward(lt, pos, 1.0, table)
+    ref = nerf_mod.mlp_forward(enc, dirs, w)
+    got, got_enc = nerf_mod.fused_forward(lt, pos, 1.0, table, dirs, w, want_enc=True)
+    assert torch.equal(got_enc, enc) and torch.equal(got, ref)
+    assert torch.equal(nerf_mod.fused_forward(lt, pos, 1.0, table, dirs, w), ref)
+    assert torch.equal(nerf_mod.fused_forward(lt, pos, 1.0, table, None, w), nerf_mod.mlp_forward(enc, None, w))
+    # grouped: 3000 rays x 12 slots, random fill counts (0 .. 12)
+    n_rays, cap = 3000, 12
+    counts = torch.randint(0, cap + 1, (n_rays,), device=DEV, generator=gen, dtype=torch.int32)
+    gpos = torch.rand(n_rays * cap, 3, device=DEV, generator=gen) * 2 - 1
+    gdirs = torch.nn.functional.normalize(torch.randn(n_rays, 3, device=DEV, generator=gen), dim=-1)
+    genc = E.hashgrid_forward(lt, gpos, 1.0, table, group_counts=counts, rows_per_group=cap)
+    gref = nerf_mod.mlp_forward(genc, gdirs, w, group_counts=counts, rows_per_group=cap).reshape(n_rays, cap, 4)
+    ggot = nerf_mod.fused_forward(lt, gpos, 1.0, table, gdirs, w, group_counts=counts, rows_per_group=cap).reshape(n_rays, cap, 4)
+    live = torch.arange(cap, device=DEV)[None, :] < counts[:, None]
+    assert torch.equal(ggot[live], gref[live])
+    # and the ungrouped evaluation of the same rows
+    full = nerf_mod.mlp_forward(E.hashgrid_forward(lt, gpos, 1.0, table), gdirs[:, None, :].expand(-1, cap, -1).reshape(-1, 3).contiguous(), w)
+    assert torch.equal(ggot[live], full.reshape(n_rays, cap, 4)[live])
+
+
 def test_graph_renderer_is_bit_identical_to_reference_loop(small_scene):
     """InferenceRenderer (one CUDA graph per loop iteration, grouped encoder/MLP) against
     render_image_inference (the reference's host loop, op for op) on the same rays."""
