@@ -179,6 +179,13 @@ def run_ours(args):
     # stream, L2 flushed between iterations
     roof = dominant_kernel_roofline(tr, perms_dev[W], flush) if rank == 0 else None
 
+    render = hashenc = None
+    if not args.no_extras:
+        del flush
+        tr.release_graph()
+        render = render_bench(dev, rank, world, scene=tr.scene)
+        if rank == 0:
+            hashenc = hashenc_bench(dev)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -201,7 +208,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": N_RAYS * 4, "d2h_bytes_per_step": 4, "loss": loss},
         "gpu_launches": tr_counts["ours"] * K,
         "launches_per_step": tr_counts,
-        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "render": render, "hashenc": hashenc,
     }
     if args.with_ref_gpu:
         line["ref_gpu"] = run_subprocess_json(["--impl", "reference-gpu", "--steps", str(min(K, 10)), "--warmup", "3"])
@@ -257,8 +264,8 @@ def dominant_kernel_roofline(tr, perm, flush):
     kernels = (
         # name, launch, algorithmic bytes per launch, note
         ("march_rays", march, N_RAYS * 45 + used * 36 + (synthetic.K * synthetic.G ** 3) // 8, "36 B/ray in, 9 B/ray + 36 B/sample out, bitfield"),
-        ("hashgrid_a1_forward", lambda: encoders.hashgrid_forward(tr.levels, xyzs, 1.0, tr.table), n * 1164, "1164 B/point"),
-        ("nerf_mlp_forward", lambda: nerf_mod.mlp_forward(enc, dirs, tr.mlp_flat), n * (128 + 12 + 16), "enc 128 + dir 12 in, 16 out per sample; 18.8 kFLOP/sample"),
+        ("nerf_fused_forward", lambda: nerf_mod.fused_forward(tr.levels, xyzs, 1.0, tr.table, dirs, tr.mlp_flat, want_enc=True),
+         n * (1164 + 12 + 16), "encoder 1164 B/point (xyz, 128 corner rows, enc kept for the backward) + dir 12 + drgb 16; 18.8 kFLOP/sample"),
         ("integrate_rays", lambda: _integrate_fwd(rs, rn, bg, dss, zs, drgbs), used * 24 + N_RAYS * 40, "24 B/sample + 40 B/ray"),
         ("huber_loss_grad", lambda: trainops.huber_loss_grad(fin, valid, perm, sc.rgbas_u8, bg), N_RAYS * (16 + 1 + 4 + 4 + 12 + 16), "53 B/ray"),
         ("integrate_rays_backward", lambda: _integrate_bwd(synthetic.NEAR, rs, rn, bg, dss, zs, drgbs, fin, opac, d_fin), used * 44 + N_RAYS * 68 + n * 20, "44 B/sample + 68 B/ray + zero-fill 20 B/slot"),
@@ -280,7 +287,7 @@ def dominant_kernel_roofline(tr, perm, flush):
         t_ms = float(np.mean(times[3:]))
         res[name] = {"ms": round(t_ms, 4), "algorithmic_bytes": int(nbytes), "achieved_gbs": round(nbytes / (t_ms * 1e-3) / 1e9, 1),
                      "frac_of_hbm": round(nbytes / (t_ms * 1e-3) / 1e9 / hbm, 3), "per_unit": note}
-    res["nerf_mlp_forward"]["achieved_tflops"] = round(n * 18816 / (res["nerf_mlp_forward"]["ms"] * 1e-3) / 1e12, 2)
+    res["nerf_fused_forward"]["achieved_tflops"] = round(n * 18816 / (res["nerf_fused_forward"]["ms"] * 1e-3) / 1e12, 2)
     res["nerf_mlp_backward"]["achieved_tflops"] = round(n * 56448 / (res["nerf_mlp_backward"]["ms"] * 1e-3) / 1e12, 2)
     top = max(res, key=lambda k: res[k]["ms"])
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/), if present
@@ -295,6 +302,118 @@ def dominant_kernel_roofline(tr, perm, flush):
             "note": "each kernel timed alone with an L2 flush before every launch (isolated times sum to more than the "
                     "graph-replayed step, whose kernels find their inputs in L2); limiter per kernel in DESIGN.md section 5",
             "kernels": res}
+
+
+# ------------------------------------------------------------------------------------------- extras (C3, C4)
+def render_bench(dev, rank, world, scene=None, frames=10, train_steps=300, n_slots=131072, cap=16):
+    """BASELINE configs[2] (C3): 800x800 frames through march_rays_inference / integrate_rays_inference
+    (InferenceRenderer: the reference's slot-refill loop, one CUDA graph per iteration), image rows dealt to the
+    ranks in interleaved 32-row bands, one all-gather of the u8 image per frame.  The model is trained here for
+    `train_steps` steps first (identical replicas: same seeds on every rank)."""
+    import torch
+    import torch.distributed as dist
+    from jaxngp_b200 import dp, renderers
+    from jaxngp_b200.trainer import Scene, Trainer
+    scene = scene if scene is not None else Scene(dev)
+    tr = Trainer(device=dev, scene=scene)  # world_size=1: every rank trains the same replica
+    gen = torch.Generator(device=dev).manual_seed(0)
+    for it in range(train_steps):
+        perm = torch.randint(0, scene.n_pixels, (tr.n_rays,), device=dev, generator=gen, dtype=torch.int32)
+        tr.train_step(perm)
+        if (it + 1) % 16 == 0:
+            tr.update_ogrid()
+    H, Wd = scene.cam["height"], scene.cam["width"]
+    rows = dp.tile_rows(H, rank, world).to(dev)
+    pixels = (rows[:, None] * Wd + torch.arange(Wd, device=dev)[None, :]).reshape(-1).to(torch.int32)
+    R = renderers.InferenceRenderer(tr.nerf, scene.cam, tr.occupancy, n_rays=min(n_slots, pixels.numel()), march_steps_cap=cap,
+                                    pixel_indices=pixels)
+    views = [(7 * k + 3) % scene.n_views for k in range(frames + 2)]
+
+    def frame(v):
+        rgb, _ = R.render(scene.transforms[v])
+        return dp.gather_image(rows, rgb.reshape(rows.numel(), Wd, 3), H) if world > 1 else rgb
+
+    for v in views[:2]:
+        frame(v)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    samples = 0
+    e0.record()
+    for v in views[2:]:
+        img = frame(v)
+        samples += int(R.samples_done)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    smp = torch.tensor([samples], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(smp)
+    # quality of the frame just rendered against the analytic ground truth of that view (white background)
+    v = views[-1]
+    gt = scene.rgbas_u8[v * H * Wd:(v + 1) * H * Wd].float() / 255
+    gt_rgb = gt[:, :3] * gt[:, 3:] + (1 - gt[:, 3:])
+    full = img.reshape(-1, 3).float() / 255 if world > 1 else None
+    if full is None:
+        full = torch.zeros(H * Wd, 3, device=dev)
+        full[pixels.long()] = img.reshape(-1, 3).float() / 255
+    psnr = float(-10 * torch.log10(((full - gt_rgb) ** 2).mean()))
+    ms_frame = float(ms) / frames
+    return {"metric": "800x800 inference render rays/s", "rays_per_s": 640000 / (ms_frame * 1e-3), "fps": 1e3 / ms_frame,
+            "ms_per_frame": ms_frame, "frames": frames, "n_gpus": world, "samples_per_frame": int(smp) / frames,
+            "slots_per_gpu": R.n, "march_steps_cap": cap, "model": f"trained {train_steps} steps in this run (C2 step)",
+            "psnr_last_frame": psnr, "sharding": "interleaved 32-row bands, all-gather of the u8 image per frame"}
+
+
+def hashenc_bench(dev, n=1 << 22, log2_T=(19, 20, 21, 22, 23, 24), iters=10):
+    """BASELINE configs[3] (C4): HashGridEncoder forward + backward on 2^22 uniform points, L=16 F=2, T swept across
+    the L2/HBM boundary.  GB/s = SURVEY 8(d)'s algorithmic bytes (1164 B/point each way + the gradient-table
+    zero-fill) / CUDA-event time.  Also measures an L2-resident copy as the L2 denominator 8(d) asks for."""
+    import torch
+    from jaxngp_b200 import encoders as E
+    hbm, src = peaks()
+    g = torch.Generator(device=dev)
+    pos = torch.rand(n, 3, device=dev, generator=g.manual_seed(42)) * 2 - 1
+    d_enc = torch.randn(n, 32, device=dev, generator=g.manual_seed(44))
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    a, b = torch.empty(8 << 20, device=dev), torch.empty(8 << 20, device=dev)  # 32 MB + 32 MB: L2 resident
+    l2_ms = timed(lambda: b.copy_(a))
+    sweep = []
+    for lt2 in log2_T:
+        lt = E.make_level_table(16, 2 ** lt2, 2, 16, 2048, 3)
+        table = (torch.rand(lt.rows, 2, device=dev, generator=g.manual_seed(43)) * 2 - 1) * 1e-4
+        grad = torch.empty_like(table)
+        f_ms = timed(lambda: E.hashgrid_forward(lt, pos, 1.0, table))
+        b_ms = timed(lambda: E.hashgrid_backward(lt, pos, 1.0, d_enc, out=grad))
+        fb = n * 1164, n * 1164 + table.numel() * 4
+        sweep.append({"log2_T": lt2, "table_mb": round(table.numel() * 4 / 2 ** 20, 1), "fwd_ms": round(f_ms, 3),
+                      "bwd_ms": round(b_ms, 3), "fwd_gbs": round(fb[0] / f_ms / 1e6, 1), "bwd_gbs": round(fb[1] / b_ms / 1e6, 1),
+                      "fwd_bwd_gbs": round((fb[0] + fb[1]) / (f_ms + b_ms) / 1e6, 1),
+                      "frac_of_hbm": round((fb[0] + fb[1]) / (f_ms + b_ms) / 1e6 / hbm, 3)})
+        del table, grad
+    return {"metric": "hash-enc fwd+bwd GB/s (algorithmic bytes, 2^22 points, L=16 F=2, f32 table)", "points": n,
+            "hbm_peak_gbs": hbm, "peak_source": src, "l2_resident_copy_gbs": round(2 * a.numel() * 4 / l2_ms / 1e6, 1),
+            "l2_note": "64 MB working set copied in place of HBM traffic (torch copy kernel, read+write bytes): the L2 "
+                       "denominator SURVEY 8(d) asks for; the gather itself is bound by L1 tag lookups (DESIGN.md 5)",
+            "inputs": "points within L2-exceeding arrays (pos 50 MB, enc/d_enc 537 MB): no flush needed", "sweep": sweep}
+
 
 
 # ------------------------------------------------------------------------------------------- CPU arms
@@ -491,6 +610,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C3 render and C4 hash-encoder measurements")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu launch lists)")
     ap.add_argument("--profile", type=int, default=0, help="run N steps between cudaProfilerStart/Stop and exit")
     ap.add_argument("--with-ref-gpu", action="store_true", help="also time the reference's CUDA ops arm in a subprocess")

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(kThreads) nerf_mlp_forward_kernel(uint32_t n, 
 // tensor-core layers (issue-bound): the two halves of the forward overlap inside one SM.
 // Same arithmetic as hashgrid_a1_forward + nerf_mlp_forward => same bits.
 template <typename TT, bool kDensityOnly, bool kWriteEnc>
-__global__ void __launch_bounds__(kThreads) nerf_fused_forward_kernel(const __grid_constant__ NgpNerfFusedDescriptor d,
+__global__ void __launch_bounds__(kThreads, 3) nerf_fused_forward_kernel(const __grid_constant__ NgpNerfFusedDescriptor d,
                                                                       const float *__restrict__ pos,
                                                                       const TT *__restrict__ table,
                                                                       const float *__restrict__ dirs,

@@ -251,6 +251,11 @@ class Trainer:
             self._optimizer_step()
         return self._static_out
 
+    def release_graph(self):
+        """Drop the captured step graph (and its private memory pool)."""
+        self._graph = None
+        self._static_out = None
+
     # -- density grid update (utils/types.py:1149-1239) --------------------------------------------
     def _density_fn(self, xyz):
         if self.fused_encoder:
