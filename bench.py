@@ -137,10 +137,9 @@ def run_ours(args):
         launches0 = _lib.launch_count
         e0.record()
         for k in range(n_steps):
-            if e2e:  # H2D of this step's inputs from pinned memory
-                out = tr.train_step(perms_host[first + k])
-            else:
-                out = tr.train_step(perms_dev[first + k])
+            src = perms_host if e2e else perms_dev  # e2e: H2D of every step's inputs from pinned memory
+            nxt = src[first + k + 1] if k + 1 < n_steps else None  # next batch: its march overlaps this step's optimizer
+            out = tr.train_step(src[first + k], nxt)
             samples += out["measured_batch_size_before_compaction"]
             if (k + 1) % OGRID_EVERY == 0:
                 tr.update_ogrid(update_all=False, commit=False)
@@ -200,7 +199,7 @@ def run_ours(args):
                                "2^18 rays = 2^18 sample slots per step per GPU, 128^3 density grid, diagonal_n_steps=1024, "
                                "hash grid L=16 T=2^19 F=2, random-init weights, analytic occupancy",
                    "n_rays_per_gpu": N_RAYS, "total_samples_per_gpu": TOTAL_SAMPLES, "ogrid_update_every": OGRID_EVERY,
-                   "parallelism": f"ray-sharded dp{world}, one NCCL all-reduce of the flat gradient per step",
+                   "parallelism": f"ray-sharded dp{world}; flat gradient reduce-scatter -> Adam on 1/{world} of the parameters -> parameter all-gather (NCCL)",
                    "l2": "per-step working set (table+grads+moments+activations ~0.5 GB) exceeds the 126 MB L2; no flush",
                    "cuda_graph": not args.no_graph},
         "samples_per_step": samples / K,
@@ -260,7 +259,7 @@ def dominant_kernel_roofline(tr, perm, flush):
     d_fin, _, _ = trainops.huber_loss_grad(fin, valid, perm, sc.rgbas_u8, bg)
     _, _, d_drgbs = _integrate_bwd(synthetic.NEAR, rs, rn, bg, dss, zs, drgbs, fin, opac, d_fin)
     d_enc, _ = nerf_mod.mlp_backward(enc, dirs, tr.mlp_flat, d_drgbs)
-    P = tr.flat_params.numel()
+    P = tr.shard_hi - tr.shard_lo  # this rank's optimizer shard (all parameters on one GPU)
     kernels = (
         # name, launch, algorithmic bytes per launch, note
         ("march_rays", march, N_RAYS * 45 + used * 36 + (synthetic.K * synthetic.G ** 3) // 8, "36 B/ray in, 9 B/ray + 36 B/sample out, bitfield"),
@@ -271,7 +270,7 @@ def dominant_kernel_roofline(tr, perm, flush):
         ("integrate_rays_backward", lambda: _integrate_bwd(synthetic.NEAR, rs, rn, bg, dss, zs, drgbs, fin, opac, d_fin), used * 44 + N_RAYS * 68 + n * 20, "44 B/sample + 68 B/ray + zero-fill 20 B/slot"),
         ("nerf_mlp_backward", lambda: nerf_mod.mlp_backward(enc, dirs, tr.mlp_flat, d_drgbs), n * (128 + 12 + 16 + 128), "284 B/sample; 56 kFLOP/sample"),
         ("hashgrid_a1_backward", lambda: encoders.hashgrid_backward(tr.levels, xyzs, 1.0, d_enc, out=tr.table_grad), n * 1164 + tr.table_numel * 4, "1164 B/point + table zero-fill"),
-        ("adam_step", lambda: _lib.call("ngp_adam_step", [tr.step_dev, tr.flat_params, tr.flat_grads, tr.adam_m, tr.adam_v], tr.adam_desc), P * 28, "28 B/param"),
+        ("adam_step", lambda: _lib.call("ngp_adam_step", [tr.step_dev, tr.flat_params[tr.shard_lo:tr.shard_hi], tr.flat_grads[tr.shard_lo:tr.shard_hi], tr.adam_m, tr.adam_v], tr.adam_desc), P * 28, "28 B/param"),
     )
     res = {}
     for name, fn, nbytes, note in kernels:

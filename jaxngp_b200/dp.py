@@ -1,8 +1,11 @@
 """Ray-sharded data parallelism: what each rank owns and the one exchange per step.
 
 Training: every rank draws its own ray batch (disjoint index streams), runs the whole step locally and
-all-reduces ONE flat gradient buffer [hash-table grad | MLP grads]; the optimizer divides by the world
-size (NgpAdamDescriptor.grad_scale), so replicas stay bit-identical without a parameter broadcast.
+exchanges ONE flat gradient buffer [hash-table grad | MLP grads] per step.  The all-reduce is split into its two
+halves around the optimizer (ZeRO-1 style): reduce-scatter the gradient, run Adam on this rank's 1/N of the
+parameters and moments (the optimizer is HBM-bound at 28 B/parameter, so its time shrinks with N), all-gather
+the updated parameters.  Same bytes on NVLink as one all-reduce; the optimizer divides by the world size
+(NgpAdamDescriptor.grad_scale) and replicas stay bit-identical.
 Inference: image rows are dealt to ranks in interleaved tiles; the only collective is the final gather.
 """
 import torch
@@ -14,6 +17,39 @@ def allreduce_flat_gradients(flat_grads: torch.Tensor, group=None) -> torch.Tens
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
     return flat_grads
+
+
+def shard_bounds(n_padded: int, rank: int, world_size: int):
+    """[begin, end) of the flat parameter buffer owned by `rank` (n_padded is a multiple of 4 * world_size)."""
+    per = n_padded // world_size
+    return rank * per, (rank + 1) * per
+
+
+def reduce_scatter_flat_gradients(flat_grads: torch.Tensor, rank: int, world_size: int, group=None) -> torch.Tensor:
+    """SUM reduce-scatter: returns this rank's shard of the summed gradient (a view into ``flat_grads``).
+    Half of an all-reduce; the other half is ``all_gather_flat_parameters`` after the sharded optimizer step."""
+    lo, hi = shard_bounds(flat_grads.numel(), rank, world_size)
+    shard = flat_grads[lo:hi]
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return shard
+    if dist.get_backend(group) == "nccl":
+        dist.reduce_scatter_tensor(shard, flat_grads, op=dist.ReduceOp.SUM, group=group)  # in place on the rank's slice
+    else:  # gloo (CPU tests) has no reduce-scatter: same result through an all-reduce
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return shard
+
+
+def all_gather_flat_parameters(flat_params: torch.Tensor, rank: int, world_size: int, group=None) -> torch.Tensor:
+    """Every rank updated its own shard of ``flat_params``: gather the shards in place."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        lo, hi = shard_bounds(flat_params.numel(), rank, world_size)
+        if dist.get_backend(group) == "nccl":
+            dist.all_gather_into_tensor(flat_params, flat_params[lo:hi], group=group)
+        else:
+            parts = [torch.empty(hi - lo, dtype=flat_params.dtype, device=flat_params.device) for _ in range(world_size)]
+            dist.all_gather(parts, flat_params[lo:hi].clone(), group=group)
+            flat_params.copy_(torch.cat(parts))
+    return flat_params
 
 
 def allreduce_density_grid(grid: torch.Tensor, group=None) -> torch.Tensor:

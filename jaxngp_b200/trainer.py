@@ -100,14 +100,17 @@ class Trainer:
         self.step = 0
         torch.cuda.manual_seed(seed + 1 + rank)  # per-rank perturbation / background streams (graph-safe default generator)
         self.noise_gen = None
+        # weight decay applies to the MLP weights only (_utils.py:45-77): index >= table_numel, shard relative
+        decay_begin = min(max(self.table_numel - self.shard_lo, 0), self.shard_hi - self.shard_lo)
         self.adam_desc = descriptors.make_adam_descriptor(
-            n=self.flat_params.numel(), decay_begin=self.table_numel, lr_init=lr, lr_end=lr / 100, decay_rate=1 / 3,
+            n=self.shard_hi - self.shard_lo, decay_begin=decay_begin, lr_init=lr, lr_end=lr / 100, decay_rate=1 / 3,
             transition_steps=10_000, transition_begin=10_000, staircase=True, b1=0.9, b2=0.99, eps=1e-15,
             eps_root=1e-15, weight_decay=1e-6, grad_scale=1.0 / world_size)
         self.use_graph = use_graph
-        self._graph = None
+        self._graph = self._march_graph = None
         self._static_perm = torch.zeros(n_rays, dtype=torch.int32, device=self.device)
-        self._static_out = None
+        self._static_out = self._static_marched = None
+        self._prefetched = None
 
     @property
     def occupancy(self):
@@ -122,33 +125,41 @@ class Trainer:
         enc = self.nerf.position_encoder
         self.table_numel = enc.latents.numel()
         assert self.table_numel % 4 == 0 and nerf_mod.MLP_NUMEL % 4 == 0
-        total = self.table_numel + nerf_mod.MLP_NUMEL
+        self.n_params = self.table_numel + nerf_mod.MLP_NUMEL
+        total = -(-self.n_params // 32) * 32  # padded so that every rank's shard (world <= 8) is float4-aligned
         self.flat_params = torch.zeros(total, dtype=torch.float32, device=self.device)
         self.flat_grads = torch.zeros_like(self.flat_params)
-        self.adam_m = torch.zeros_like(self.flat_params)
-        self.adam_v = torch.zeros_like(self.flat_params)
+        # optimizer state: this rank's shard only (ZeRO-1, dp.py); the whole buffer on one GPU
+        self.shard_lo, self.shard_hi = dp.shard_bounds(total, self.rank, self.world_size)
+        self.adam_m = torch.zeros(self.shard_hi - self.shard_lo, dtype=torch.float32, device=self.device)
+        self.adam_v = torch.zeros_like(self.adam_m)
         self.flat_params[: self.table_numel].copy_(enc.latents.detach().reshape(-1))
-        self.flat_params[self.table_numel:].copy_(self.nerf.mlp_flat.detach())
+        self.flat_params[self.table_numel:self.n_params].copy_(self.nerf.mlp_flat.detach())
         enc.latents.data = self.flat_params[: self.table_numel].view_as(enc.latents)
-        self.nerf.mlp_flat.data = self.flat_params[self.table_numel:]
+        self.nerf.mlp_flat.data = self.flat_params[self.table_numel:self.n_params]
         self.table = enc.latents.data
         self.mlp_flat = self.nerf.mlp_flat.data
         self.table_grad = self.flat_grads[: self.table_numel].view_as(self.table)
-        self.mlp_grad = self.flat_grads[self.table_numel:]
+        self.mlp_grad = self.flat_grads[self.table_numel:self.n_params]
 
     # -- one training step ------------------------------------------------------------------------
-    def _step_body(self, perm, noises=None, bg=None, apply=True):
-        if not self.fused_glue:
-            return self._step_body_torch(perm, noises, bg, apply)
-        sc, dev = self.scene, self.device
+    def _march_body(self, perm, noises=None):
+        """Ray generation + march_rays: the part of the step that does not depend on the parameters (it reads the
+        rays and the occupancy bitfield only), so the next step's can overlap this step's gradient exchange and
+        optimizer (train_step)."""
+        sc = self.scene
         if noises is None:
-            noises = torch.rand(self.n_rays, device=dev)  # cuda.py:118-122
-        if bg is None:
-            bg = torch.rand(self.n_rays, 3, device=dev)  # random_bg, _utils.py:134-136
+            noises = torch.rand(self.n_rays, device=self.device)  # cuda.py:118-122
         o, d, t_starts, t_ends = trainops.make_training_rays(perm, sc.transforms, sc.cam, synthetic.BOUND)
-        nxt, exc, ray_is_valid, rays_n, rays_start, _, xyzs, dirs, dss, z_vals = march_rays(
-            self.total_samples, synthetic.DIAGONAL_N_STEPS, synthetic.K, synthetic.G, synthetic.BOUND,
-            synthetic.STEPSIZE_PORTION, o, d, t_starts, t_ends, noises, self.grid.occupancy, raw=True)
+        return march_rays(self.total_samples, synthetic.DIAGONAL_N_STEPS, synthetic.K, synthetic.G, synthetic.BOUND,
+                          synthetic.STEPSIZE_PORTION, o, d, t_starts, t_ends, noises, self.grid.occupancy, raw=True)
+
+    def _compute_body(self, perm, marched, bg=None):
+        """Encoder + MLP forward, integrate, loss, and the whole backward into the flat gradient buffer."""
+        sc = self.scene
+        if bg is None:
+            bg = torch.rand(self.n_rays, 3, device=self.device)  # random_bg, _utils.py:134-136
+        nxt, exc, ray_is_valid, rays_n, rays_start, _, xyzs, dirs, dss, z_vals = marched
         if self.fused_encoder:  # encoder gather feeding the MLP's first tensor-core fragments (enc written once, for the backward)
             drgbs, enc = nerf_mod.fused_forward(self.levels, xyzs, synthetic.BOUND, self.table, dirs, self.mlp_flat, want_enc=True)
         else:
@@ -160,8 +171,13 @@ class Trainer:
                                        final_opac, d_final)
         d_enc, _ = nerf_mod.mlp_backward(enc, dirs, self.mlp_flat, d_drgbs, d_weights=self.mlp_grad)
         encoders.hashgrid_backward(self.levels, xyzs, synthetic.BOUND, d_enc, out=self.table_grad)
-        out = dict(loss=loss[0], n_valid_rays=n_valid[0], measured_batch_size_before_compaction=(nxt - exc)[0],
-                   measured_batch_size=effective[0])  # marching/__init__.py:91
+        return dict(loss=loss[0], n_valid_rays=n_valid[0], measured_batch_size_before_compaction=(nxt - exc)[0],
+                    measured_batch_size=effective[0])  # marching/__init__.py:91
+
+    def _step_body(self, perm, noises=None, bg=None, apply=True):
+        if not self.fused_glue:
+            return self._step_body_torch(perm, noises, bg, apply)
+        out = self._compute_body(perm, self._march_body(perm, noises), bg)
         if apply and self.world_size == 1:
             self._optimizer_step()
         return out
@@ -214,47 +230,72 @@ class Trainer:
         return out
 
     def _optimizer_step(self):
-        """[all-reduce of the flat gradient] + Adam.  With more than one rank this part stays outside the
-        CUDA graph: the collective is issued eagerly on the current stream between the captured
-        compute graph and the optimizer launch."""
-        if self.world_size > 1:  # one collective per step over [table grad | MLP grads]
-            dp.allreduce_flat_gradients(self.flat_grads, self.pg)
-        _lib.call("ngp_adam_step", [self.step_dev, self.flat_params, self.flat_grads, self.adam_m, self.adam_v],
-                  self.adam_desc)
+        """Gradient exchange + Adam.  With more than one rank this part stays outside the CUDA graph: the
+        collectives are issued eagerly on the current stream after the captured compute graph."""
+        lo, hi = self.shard_lo, self.shard_hi
+        # reduce-scatter [table grad | MLP grads] -> Adam on this rank's shard -> all-gather the parameters
+        g = dp.reduce_scatter_flat_gradients(self.flat_grads, self.rank, self.world_size, self.pg)
+        _lib.call("ngp_adam_step", [self.step_dev, self.flat_params[lo:hi], g, self.adam_m, self.adam_v], self.adam_desc)
+        dp.all_gather_flat_parameters(self.flat_params, self.rank, self.world_size, self.pg)
         self.step_dev += 1
 
-    def train_step(self, perm):
-        """perm: int32 [n_rays] indices into the scene's pixels (device tensor).  Returns device-side
-        metrics (no host synchronisation)."""
+    def train_step(self, perm, next_perm=None):
+        """perm: int32 [n_rays] indices into the scene's pixels (device or pinned host tensor).  Returns
+        device-side metrics (no host synchronisation).
+
+        ``next_perm`` (optional) is the batch of the FOLLOWING call: its ray generation and march are enqueued on a
+        side stream as soon as this step's backward has finished and run concurrently with this step's gradient
+        exchange and optimizer, which they do not depend on (same numbers as running them afterwards; a committed
+        density-grid update in between drops the prefetch)."""
         self.step += 1
-        if not self.use_graph:
+        if not self.use_graph or not self.fused_glue:
             out = self._step_body(perm)
             if self.world_size > 1:
                 self._optimizer_step()
             return out
-        self._static_perm.copy_(perm, non_blocking=True)
+        main = torch.cuda.current_stream(self.device)
         if self._graph is None:
-            side = torch.cuda.Stream(device=self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side):
-                for _ in range(2):  # warm-up on the capture stream (scratch blocks, cuBLAS handles)
-                    self._step_body(self._static_perm)
-                    if self.world_size > 1:
-                        self._optimizer_step()
+            self._side = torch.cuda.Stream(device=self.device)
+            self._static_perm.copy_(perm, non_blocking=True)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                for _ in range(2):  # warm-up on the capture stream (scratch blocks)
+                    self._compute_body(self._static_perm, self._march_body(self._static_perm))
+                    self._optimizer_step()
+                self._march_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._march_graph, stream=self._side):
+                    self._static_marched = self._march_body(self._static_perm)
                 self._graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph, stream=side):
-                    self._static_out = self._step_body(self._static_perm)
-            torch.cuda.current_stream(self.device).wait_stream(side)
+                with torch.cuda.graph(self._graph, stream=self._side):
+                    self._static_out = self._compute_body(self._static_perm, self._static_marched)
+            main.wait_stream(self._side)
             self.step += 2
+            self._ev_march, self._ev_compute = torch.cuda.Event(), torch.cuda.Event()
+            self._prefetched = None
+        key = (perm.data_ptr(), perm.numel())
+        if self._prefetched is not None:
+            main.wait_event(self._ev_march)  # marched on the side stream during the previous optimizer step
+        if self._prefetched != key:
+            self._static_perm.copy_(perm, non_blocking=True)
+            self._march_graph.replay()
+        self._prefetched = None
         self._graph.replay()
-        if self.world_size > 1:
-            self._optimizer_step()
+        if next_perm is not None:
+            self._ev_compute.record(main)
+            self._side.wait_event(self._ev_compute)  # the backward still reads this step's samples
+            with torch.cuda.stream(self._side):
+                self._static_perm.copy_(next_perm, non_blocking=True)
+                self._march_graph.replay()
+                self._ev_march.record(self._side)
+            self._prefetched = (next_perm.data_ptr(), next_perm.numel())
+        self._optimizer_step()
         return self._static_out
 
     def release_graph(self):
         """Drop the captured step graph (and its private memory pool)."""
-        self._graph = None
-        self._static_out = None
+        self._graph = self._march_graph = None
+        self._static_out = self._static_marched = None
+        self._prefetched = None
 
     # -- density grid update (utils/types.py:1149-1239) --------------------------------------------
     def _density_fn(self, xyz):
@@ -272,6 +313,9 @@ class Trainer:
         ``commit=False`` does all the work into shadow buffers (bench: keeps the marching workload fixed)."""
         if update_all is None:
             update_all = self.step < 256  # utils/types.py:1391-1392
+        if commit and self._prefetched is not None:  # a prefetched march saw the old bitfield: redo it
+            torch.cuda.current_stream(self.device).wait_event(self._ev_march)
+            self._prefetched = None
         g = self.grid
         shadow = None if commit else torch.empty_like(g.density)
         for cas in range(g.K):

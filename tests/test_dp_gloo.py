@@ -22,6 +22,15 @@ def _worker(rank, world, port, q):
     import bench
     flat = torch.full((1000,), float(rank + 1))
     dp.allreduce_flat_gradients(flat)
+    # ZeRO-1 exchange: reduce-scatter the gradient, update the own shard, all-gather the parameters
+    n = 64
+    grads = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    params = torch.zeros(n)
+    lo, hi = dp.shard_bounds(n, rank, world)
+    shard = dp.reduce_scatter_flat_gradients(grads, rank, world)
+    params[lo:hi] = -shard  # "optimizer" on the shard
+    dp.all_gather_flat_parameters(params, rank, world)
+    assert torch.equal(params, -3.0 * torch.arange(n, dtype=torch.float32)), params
     grid = torch.arange(16, dtype=torch.float32) * (1 if rank == 0 else -1) + rank
     dp.allreduce_density_grid(grid)
     H, Wd = 100, 7
