@@ -95,6 +95,21 @@ void ngp_march_rays_inference(cudaStream_t, void **, const char *, size_t);
  * out: t_out f32[N] (may alias t_starts) */
 void ngp_march_rays_skip_empty(cudaStream_t, void **, const char *, size_t);
 
+/* Renderer fast paths: the two inference ops with the scatters the reference's Python wrappers do afterwards
+ * (marching/__init__.py:156, integrating/__init__.py:108-109) folded into the kernels; same descriptors.
+ * march_rays_inference_inplace
+ *   in/out: t_starts f32[N] (advanced in place), next_ray_index u32[1], indices u32[n]
+ *   in    : rays_o, rays_d, t_ends, bitfield, terminated bool[n]
+ *   out   : n_samples u32[n], xyzs f32[n,cap,3], dss f32[n,cap], z_vals f32[n,cap], ray_dirs f32[n,3]
+ *   buffers: rays_o, rays_d, t_starts, t_ends, bitfield, next_ray_index, terminated, indices,
+ *            n_samples, xyzs, dss, z_vals, ray_dirs
+ * integrate_rays_inference_inplace
+ *   in/out: rays_rgbd f32[N,4], rays_T f32[N], counters u64[2] (+= terminated rays, += samples marched)
+ *   in    : rays_bg, n_samples, indices, dss, z_vals, drgbs        out: terminated bool[n]
+ *   buffers: rays_bg, rays_rgbd, rays_T, n_samples, indices, dss, z_vals, drgbs, terminated, counters */
+void ngp_march_rays_inference_inplace(cudaStream_t, void **, const char *, size_t);
+void ngp_integrate_rays_inference_inplace(cudaStream_t, void **, const char *, size_t);
+
 /* replace volrendjax::morton3d / morton3d_invert (volrend.h:143-154, marching.cu:606-665)
  * morton3d: in xyzs u32[len,3], out idcs u32[len];  invert: in idcs u32[len], out xyzs u32[len,3] */
 void ngp_morton3d(cudaStream_t, void **, const char *, size_t);
@@ -195,6 +210,11 @@ void ngp_nerf_mlp_backward(cudaStream_t, void **, const char *, size_t);
  * out: drgbs f32[n,4] (density_only: f32[n]) [, enc f32[n,32] if write_enc] */
 typedef struct { NgpHashGridA1Descriptor grid; uint32_t density_only, write_enc; } NgpNerfFusedDescriptor;
 void ngp_nerf_fused_forward(cudaStream_t, void **, const char *, size_t);
+
+/* Diagnostic: known-answer test of the tcgen05 (kind::tf32) operand formats of csrc/umma.cuh -- forward, dgrad and
+ * wgrad GEMM shapes on swizzled shared-memory panels with TMEM accumulators.  No descriptor (opaque_len = 0).
+ * in : A f32[128,32], W f32[32,64], G f32[128,64]     out: A.W f32[128,64], G.W^T f32[128,32], G^T.A f32[64,32] */
+void ngp_umma_selftest(cudaStream_t, void **, const char *, size_t);
 
 /* Training glue around the four ops (XLA fuses these elementwise chains for the reference):
  * make_training_rays: app/nerf/_utils.py:93-115 + utils/types.py:398-439 (undistorted PERSPECTIVE camera)

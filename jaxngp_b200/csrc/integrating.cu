@@ -222,25 +222,31 @@ __global__ void __launch_bounds__(kBlock) integrate_rays_backward_kernel(
     }
 }
 
+// kInPlace (renderer fast path, ngp_integrate_rays_inference_inplace): results go straight to row `ray` of the frame
+// state (the reference scatters them afterwards, integrating/__init__.py:108-109; every ray belongs to one slot) and
+// the terminated-ray and sample counts are ACCUMULATED into 64-bit counters instead of being returned per call.
+template <bool kInPlace>
 __global__ void __launch_bounds__(kBlock) integrate_rays_inference_kernel(
-    NgpIntegratingInferenceDescriptor p, const float *__restrict__ rays_bg, const float4 *__restrict__ rays_rgbd,
-    const float *__restrict__ rays_T, const uint32_t *__restrict__ n_samples, const uint32_t *__restrict__ indices,
+    NgpIntegratingInferenceDescriptor p, const float *__restrict__ rays_bg, const float4 *rays_rgbd,
+    const float *rays_T, const uint32_t *__restrict__ n_samples, const uint32_t *__restrict__ indices,
     const float *__restrict__ dss, const float *__restrict__ z_vals, const float4 *__restrict__ drgbs,
-    uint32_t *__restrict__ terminate_cnt, uint8_t *__restrict__ terminated, float4 *__restrict__ rays_rgbd_out,
-    float *__restrict__ rays_T_out) {
+    uint32_t *__restrict__ terminate_cnt, uint8_t *__restrict__ terminated, float4 *rays_rgbd_out,
+    float *rays_T_out, unsigned long long *__restrict__ counters) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     bool term = false;
+    uint32_t my_samples = 0;
     if (i < p.n_rays) {
         float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
         float T_out = 0.f;
         const uint32_t ns = __ldg(n_samples + i), ray = __ldg(indices + i);
+        my_samples = ns;
         if (ray < p.n_total_rays) {
             const uint32_t cap = p.march_steps_cap;
             const float *__restrict__ rds = dss + (size_t)i * cap;
             const float *__restrict__ rz = z_vals + (size_t)i * cap;
             const float4 *__restrict__ rc = drgbs + (size_t)i * cap;
-            float T = __ldg(rays_T + ray);
-            float4 acc = __ldg(rays_rgbd + ray);
+            float T = rays_T[ray];
+            float4 acc = rays_rgbd[ray];
             for (uint32_t s = 0; T > kTThreshold && s < ns; ++s) {  // integrating.cu:278-291
                 const float4 v = __ldg(rc + s);
                 const float alpha = 1.f - __expf(-v.x * __ldg(rds + s));
@@ -268,11 +274,24 @@ __global__ void __launch_bounds__(kBlock) integrate_rays_inference_kernel(
             }
         }
         terminated[i] = term ? 1 : 0;
-        rays_rgbd_out[i] = out;
-        rays_T_out[i] = T_out;
+        if (!kInPlace) {
+            rays_rgbd_out[i] = out;
+            rays_T_out[i] = T_out;
+        } else if (ray < p.n_total_rays) {
+            rays_rgbd_out[ray] = out;
+            rays_T_out[ray] = T_out;
+        }
     }
     const uint32_t votes = __popc(__ballot_sync(0xffffffffu, term));
-    if ((threadIdx.x & 31u) == 0 && votes) atomicAdd(terminate_cnt, votes);
+    if (!kInPlace) {
+        if ((threadIdx.x & 31u) == 0 && votes) atomicAdd(terminate_cnt, votes);
+    } else {
+        const uint32_t smp = warp_sum_u32(my_samples);
+        if ((threadIdx.x & 31u) == 0) {
+            if (votes) atomicAdd(counters + 0, (unsigned long long)votes);
+            if (smp) atomicAdd(counters + 1, (unsigned long long)smp);
+        }
+    }
 }
 
 }  // namespace
@@ -353,9 +372,30 @@ void ngp_integrate_rays_inference(cudaStream_t stream, void **buffers, const cha
     float *T_out = b.next<float>();
     NGP_CUDA_OK(cudaMemsetAsync(terminate_cnt, 0, sizeof(uint32_t), stream), "integrate_rays_inference");
     if (desc->n_rays == 0) return;
-    integrate_rays_inference_kernel<<<div_up(desc->n_rays, kBlock), kBlock, 0, stream>>>(
-        *desc, rays_bg, rays_rgbd, rays_T, ns, indices, dss, z_vals, drgbs, terminate_cnt, terminated, rgbd_out, T_out);
+    integrate_rays_inference_kernel<false><<<div_up(desc->n_rays, kBlock), kBlock, 0, stream>>>(
+        *desc, rays_bg, rays_rgbd, rays_T, ns, indices, dss, z_vals, drgbs, terminate_cnt, terminated, rgbd_out, T_out, nullptr);
     check_launch("integrate_rays_inference");
+}
+
+void ngp_integrate_rays_inference_inplace(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *desc = descriptor<NgpIntegratingInferenceDescriptor>(opaque, opaque_len, "integrate_rays_inference_inplace");
+    if (!desc || desc->n_rays == 0) return;
+    BufferCursor b{buffers};
+    const float *rays_bg = b.next<const float>();
+    float4 *rays_rgbd = b.next<float4>();
+    float *rays_T = b.next<float>();
+    const uint32_t *ns = b.next<const uint32_t>();
+    const uint32_t *indices = b.next<const uint32_t>();
+    const float *dss = b.next<const float>();
+    const float *z_vals = b.next<const float>();
+    const float4 *drgbs = b.next<const float4>();
+    uint8_t *terminated = b.next<uint8_t>();
+    auto *counters = b.next<unsigned long long>();
+    integrate_rays_inference_kernel<true><<<div_up(desc->n_rays, kBlock), kBlock, 0, stream>>>(
+        *desc, rays_bg, rays_rgbd, rays_T, ns, indices, dss, z_vals, drgbs, nullptr, terminated, rays_rgbd, rays_T, counters);
+    check_launch("integrate_rays_inference_inplace");
 }
 
 }  // extern "C"

@@ -516,7 +516,9 @@ constexpr int kInferWarps = 8;
 
 __global__ void __launch_bounds__(kRankBlock) march_rays_inference_rank_kernel(
     uint32_t n_rays, const uint8_t *__restrict__ terminated, uint32_t *__restrict__ block_total,
-    uint32_t *__restrict__ rank_in_block) {
+    uint32_t *__restrict__ rank_in_block, const uint32_t *__restrict__ counter_src, uint32_t *__restrict__ counter_snapshot) {
+    // in-place variant: the march kernel overwrites the ray counter it also reads, so it reads this copy instead
+    if (counter_snapshot && blockIdx.x == 0 && threadIdx.x == 0) *counter_snapshot = *counter_src;
     __shared__ uint32_t s_warp[kRankBlock / 32];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t first = blockIdx.x * kRankSlots + threadIdx.x * 4u;
@@ -547,14 +549,18 @@ __global__ void __launch_bounds__(kRankBlock) march_rays_inference_rank_kernel(
     if (threadIdx.x == 0) block_total[blockIdx.x] = total;
 }
 
+// kInPlace (renderer fast path, ngp_march_rays_inference_inplace): the scatter the reference does after the op
+// (t_starts.at[indices].set(t_starts_out), marching/__init__.py:156) happens here -- every ray belongs to exactly one
+// slot -- and the slot's ray direction is copied out for the MLP (cuda.py:222-228 gathers it with rays_d[indices]).
+template <bool kInPlace>
 __global__ void __launch_bounds__(kInferWarps * 32) march_rays_inference_kernel(
     NgpMarchingInferenceDescriptor p, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
-    const float *__restrict__ t_starts, const float *__restrict__ t_ends, const uint8_t *__restrict__ bitfield,
+    const float *t_starts, const float *__restrict__ t_ends, const uint8_t *__restrict__ bitfield,
     const uint32_t *__restrict__ next_ray_index_in, const uint8_t *__restrict__ terminated,
     const uint32_t *indices_in, const uint32_t *__restrict__ block_total,
     const uint32_t *__restrict__ rank_in_block, uint32_t *__restrict__ next_ray_index, uint32_t *indices_out,
-    uint32_t *__restrict__ n_samples, float *__restrict__ t_starts_out, float *__restrict__ xyzs,
-    float *__restrict__ dss, float *__restrict__ z_vals) {
+    uint32_t *__restrict__ n_samples, float *t_starts_out, float *__restrict__ xyzs,
+    float *__restrict__ dss, float *__restrict__ z_vals, float *__restrict__ ray_dirs) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t i = blockIdx.x * kInferWarps + (threadIdx.x >> 5);  // slot of this warp
     if (i >= p.n_rays) return;
@@ -589,7 +595,7 @@ __global__ void __launch_bounds__(kInferWarps * 32) march_rays_inference_kernel(
     float t_cur = 0.f, t_end = 0.f;
     bool live = ray_idx < p.n_total_rays;
     if (live) {
-        t_cur = __ldg(t_starts + ray_idx);
+        t_cur = t_starts[ray_idx];  // plain load: the in-place variant writes this element back below
         t_end = __ldg(t_ends + ray_idx);
         live = !(t_end < t_cur);  // marching.cu:317 (strict)
     }
@@ -664,8 +670,11 @@ __global__ void __launch_bounds__(kInferWarps * 32) march_rays_inference_kernel(
     }
     if (lane == 0) {
         n_samples[i] = steps;
-        t_starts_out[i] = live ? t_cur : 0.f;  // the reference leaves the memset zeros for rays it skips
+        const float t_store = live ? t_cur : 0.f;  // the reference leaves the memset zeros for rays it skips
+        if (!kInPlace) t_starts_out[i] = t_store;
+        else if (ray_idx < p.n_total_rays) t_starts_out[ray_idx] = t_store;  // out-of-range indices are dropped
     }
+    if (kInPlace && lane < 3) ray_dirs[3 * (size_t)i + lane] = ray_idx < p.n_total_rays ? __ldg(rays_d + 3 * (size_t)ray_idx + lane) : 0.f;
     // zero the unused tail (reference: memsets, marching.cu:565-570)
     __syncwarp();
     for (uint32_t k = steps * 3 + lane; k < cap * 3; k += 32) o_xyzs[k] = 0.f;
@@ -763,48 +772,63 @@ void ngp_march_rays(cudaStream_t stream, void **buffers, const char *opaque, siz
     }
 }
 
-void ngp_march_rays_inference(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+static void launch_march_rays_inference(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len, bool in_place) {
     using namespace ngp;
     clear_error();
-    auto *desc = descriptor<NgpMarchingInferenceDescriptor>(opaque, opaque_len, "march_rays_inference");
+    const char *op = in_place ? "march_rays_inference_inplace" : "march_rays_inference";
+    auto *desc = descriptor<NgpMarchingInferenceDescriptor>(opaque, opaque_len, op);
     if (!desc) return;
     if (desc->K == 0 || desc->G == 0 || desc->G > 1024) {
-        set_error(NGP_ERR_ARGUMENT, "march_rays_inference: expected K > 0 and 0 < G <= 1024, got K=%u G=%u",
-                  desc->K, desc->G);
+        set_error(NGP_ERR_ARGUMENT, "%s: expected K > 0 and 0 < G <= 1024, got K=%u G=%u", op, desc->K, desc->G);
         return;
     }
     BufferCursor b{buffers};
     const float *rays_o = b.next<const float>();
     const float *rays_d = b.next<const float>();
-    const float *t_starts = b.next<const float>();
+    float *t_starts = b.next<float>();
     const float *t_ends = b.next<const float>();
     const uint8_t *bitfield = b.next<const uint8_t>();
-    const uint32_t *next_in = b.next<const uint32_t>();
+    uint32_t *next_in = b.next<uint32_t>();
     const uint8_t *terminated = b.next<const uint8_t>();
-    const uint32_t *indices_in = b.next<const uint32_t>();
-    uint32_t *next_out = b.next<uint32_t>();
-    uint32_t *indices_out = b.next<uint32_t>();
+    uint32_t *indices_in = b.next<uint32_t>();
+    uint32_t *next_out = in_place ? next_in : b.next<uint32_t>();
+    uint32_t *indices_out = in_place ? indices_in : b.next<uint32_t>();
     uint32_t *n_samples = b.next<uint32_t>();
-    float *t_starts_out = b.next<float>();
+    float *t_starts_out = in_place ? t_starts : b.next<float>();
     float *xyzs = b.next<float>();
     float *dss = b.next<float>();
     float *z_vals = b.next<float>();
+    float *ray_dirs = in_place ? b.next<float>() : nullptr;
     if (desc->n_rays == 0) {
-        NGP_CUDA_OK(cudaMemcpyAsync(next_out, next_in, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream),
-                    "march_rays_inference");
+        if (!in_place)
+            NGP_CUDA_OK(cudaMemcpyAsync(next_out, next_in, sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream), op);
         return;
     }
     const unsigned rank_blocks = div_up(desc->n_rays, kRankSlots);
-    auto *ws = static_cast<uint32_t *>(workspace(stream, ((size_t)rank_blocks + desc->n_rays) * sizeof(uint32_t)));
+    auto *ws = static_cast<uint32_t *>(workspace(stream, ((size_t)rank_blocks + desc->n_rays + 1) * sizeof(uint32_t)));
     if (!ws) return;
-    uint32_t *block_total = ws, *rank_in_block = ws + rank_blocks;
-    march_rays_inference_rank_kernel<<<rank_blocks, kRankBlock, 0, stream>>>(desc->n_rays, terminated, block_total,
-                                                                             rank_in_block);
-    if (!check_launch("march_rays_inference(rank)")) return;
-    march_rays_inference_kernel<<<div_up(desc->n_rays, kInferWarps), kInferWarps * 32, 0, stream>>>(
-        *desc, rays_o, rays_d, t_starts, t_ends, bitfield, next_in, terminated, indices_in, block_total, rank_in_block,
-        next_out, indices_out, n_samples, t_starts_out, xyzs, dss, z_vals);
-    check_launch("march_rays_inference");
+    uint32_t *block_total = ws, *rank_in_block = ws + rank_blocks, *snapshot = ws + rank_blocks + desc->n_rays;
+    march_rays_inference_rank_kernel<<<rank_blocks, kRankBlock, 0, stream>>>(desc->n_rays, terminated, block_total, rank_in_block,
+                                                                             next_in, in_place ? snapshot : nullptr);
+    if (!check_launch(op)) return;
+    const unsigned grid = div_up(desc->n_rays, kInferWarps);
+    if (in_place)
+        march_rays_inference_kernel<true><<<grid, kInferWarps * 32, 0, stream>>>(
+            *desc, rays_o, rays_d, t_starts, t_ends, bitfield, snapshot, terminated, indices_in, block_total, rank_in_block,
+            next_out, indices_out, n_samples, t_starts_out, xyzs, dss, z_vals, ray_dirs);
+    else
+        march_rays_inference_kernel<false><<<grid, kInferWarps * 32, 0, stream>>>(
+            *desc, rays_o, rays_d, t_starts, t_ends, bitfield, next_in, terminated, indices_in, block_total, rank_in_block,
+            next_out, indices_out, n_samples, t_starts_out, xyzs, dss, z_vals, nullptr);
+    check_launch(op);
+}
+
+void ngp_march_rays_inference(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    launch_march_rays_inference(stream, buffers, opaque, opaque_len, false);
+}
+
+void ngp_march_rays_inference_inplace(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    launch_march_rays_inference(stream, buffers, opaque, opaque_len, true);
 }
 
 void ngp_march_rays_skip_empty(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {

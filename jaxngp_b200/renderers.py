@@ -118,15 +118,12 @@ class InferenceRenderer:
         self.rays_bg = torch.tensor(bg, dtype=f32, device=dev).expand(N, 3).contiguous()
         self.terminated = torch.empty(n, dtype=torch.bool, device=dev)
         self.indices = torch.empty(n, dtype=i32, device=dev)
-        self.next_in, self.next_out = torch.empty(1, dtype=i32, device=dev), torch.empty(1, dtype=i32, device=dev)
+        self.next_in = torch.empty(1, dtype=i32, device=dev)
+        self.ray_dirs = torch.empty(n, 3, dtype=f32, device=dev)
         self.n_samples = torch.empty(n, dtype=i32, device=dev)
-        self.t_out = torch.empty(n, dtype=f32, device=dev)
         self.xyzs = torch.empty(n, self.cap, 3, dtype=f32, device=dev)
         self.dss, self.z_vals = torch.empty(n, self.cap, dtype=f32, device=dev), torch.empty(n, self.cap, dtype=f32, device=dev)
-        self.term_cnt = torch.empty(1, dtype=i32, device=dev)
-        self.rgbd_out, self.T_out = torch.empty(n, 4, dtype=f32, device=dev), torch.empty(n, dtype=f32, device=dev)
-        self.n_done = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.samples_done = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.counters = torch.zeros(2, dtype=torch.int64, device=dev)  # rays terminated, samples marched (this frame)
         self.pose = torch.empty(1, 12, dtype=f32, device=dev)
         self._march_desc = descriptors.make_marching_inference_descriptor(N, n, diagonal_n_steps, K, G, self.cap, bound,
                                                                           stepsize_portion)
@@ -136,22 +133,16 @@ class InferenceRenderer:
         self._graph = None
 
     def _iteration(self):
+        """One pass of the slot-refill loop (cuda.py:180-241): three custom calls, no torch glue -- the scatters back
+        into the frame state are folded into the kernels (``*_inplace`` entry points, include/ngp_b200.h)."""
         from . import _lib
-        _lib.call("ngp_march_rays_inference",
+        _lib.call("ngp_march_rays_inference_inplace",
                   [self.o, self.d, self.t_starts, self.t_ends, self.bits, self.next_in, self.terminated, self.indices,
-                   self.next_out, self.indices, self.n_samples, self.t_out, self.xyzs, self.dss, self.z_vals],
-                  self._march_desc)
-        self.next_in.copy_(self.next_out)
-        idx = (self.indices.to(torch.int64) & 0xFFFFFFFF).clamp(max=self.N)  # row N = scratch row (dropped writes)
-        self.t_starts.index_copy_(0, idx, self.t_out)  # marching/__init__.py:156
-        drgbs = self.nerf.forward_grouped(self.xyzs, self.d[idx.clamp(max=self.N - 1)], self.n_samples)
-        _lib.call("ngp_integrate_rays_inference",
+                   self.n_samples, self.xyzs, self.dss, self.z_vals, self.ray_dirs], self._march_desc)
+        drgbs = self.nerf.forward_grouped(self.xyzs, self.ray_dirs, self.n_samples)
+        _lib.call("ngp_integrate_rays_inference_inplace",
                   [self.rays_bg, self.rays_rgbd, self.rays_T, self.n_samples, self.indices, self.dss, self.z_vals, drgbs,
-                   self.term_cnt, self.terminated, self.rgbd_out, self.T_out], self._integ_desc)
-        self.rays_rgbd.index_copy_(0, idx, self.rgbd_out)  # integrating/__init__.py:108-109
-        self.rays_T.index_copy_(0, idx, self.T_out)
-        self.n_done += self.term_cnt
-        self.samples_done += self.n_samples.sum()
+                   self.terminated, self.counters], self._integ_desc)
 
     @torch.no_grad()
     def render(self, transform_cw):
@@ -182,8 +173,7 @@ class InferenceRenderer:
         self.terminated.fill_(True)
         self.indices.zero_()
         self.next_in.zero_()
-        self.n_done.zero_()
-        self.samples_done.zero_()
+        self.counters.zero_()
         if self._graph is None:
             side = torch.cuda.Stream(device=self.dev)
             side.wait_stream(torch.cuda.current_stream(self.dev))
@@ -196,13 +186,17 @@ class InferenceRenderer:
             torch.cuda.current_stream(self.dev).wait_stream(side)
             for t, s in zip((self.t_starts, self.rays_rgbd, self.rays_T, self.terminated, self.indices, self.next_in), state):
                 t.copy_(s)  # undo the two warm-up iterations
-            self.n_done.zero_()
-            self.samples_done.zero_()
+            self.counters.zero_()
         n_rendered = 0
         while n_rendered < self.N:  # cuda.py:326-361
             iters = 2 ** (int(math.log2(max(1, (self.N - n_rendered) // self.n))) + 1)
             for _ in range(iters):
                 self._graph.replay()
-            n_rendered = int(self.n_done)  # one host read per batch of iterations
+            n_rendered = int(self.counters[0])  # one host read per batch of iterations
         rgb = (self.rays_rgbd[: self.N, :3].clamp(0, 1) * 255 + 0.5).to(torch.uint8)
         return rgb, self.rays_rgbd[: self.N, 3]
+
+    @property
+    def samples_done(self):
+        """Samples marched for the last frame (device scalar)."""
+        return self.counters[1]
