@@ -119,7 +119,8 @@ __device__ __forceinline__ Step march_step(const Grid &g, const Ray &r, float t)
         float ay = axis_delta(gy, r.dy, r.iy, s.py, g.inv_G, mip_bound);
         float az = axis_delta(gz, r.dz, r.iz, s.pz, g.inv_G, mip_bound);
         float next_t = __fadd_rn(t, fmaxf(0.f, fminf(ax, fminf(ay, az))));
-        while (s.t_next < next_t) s.t_next = __fadd_rn(s.t_next, calc_ds(g, s.t_next));
+        // (bounded: a non-finite boundary distance would spin forever here, as it does in the reference)
+        for (uint32_t guard = 0; s.t_next < next_t && guard < (1u << 20); ++guard) s.t_next = __fadd_rn(s.t_next, calc_ds(g, s.t_next));
     }
     return s;
 }
@@ -640,7 +641,7 @@ __global__ void __launch_bounds__(kInferWarps * 32) march_rays_inference_kernel(
                         v = __ffs(m) - 1;
                     } else {  // boundary beyond this chunk: walk the chain like the reference (marching.cu:186-188)
                         float tc = t_next_base;
-                        while (tc < nt) tc = __fadd_rn(tc, calc_ds(g, tc));
+                        for (uint32_t guard = 0; tc < nt && guard < (1u << 20); ++guard) tc = __fadd_rn(tc, calc_ds(g, tc));
                         t_cur = tc;
                         break;
                     }

@@ -51,6 +51,13 @@ def render_rays_train(nerf, o_world, d_world, bg, total_samples, occupancy_bitfi
     return metrics, final_rgbds, tv
 
 
+def _max_loop_passes(n_pixels, n_slots, diagonal_n_steps, bound, cap):
+    """Upper bound on slot-refill passes: every ray needs at most ceil(per-ray step cap / cap) + 1 passes in a slot and
+    the slots work through ceil(n_pixels / n_slots) rounds of rays; doubled for the power-of-two batching."""
+    per_ray = math.ceil(diagonal_n_steps * max(bound, 1.0) * 4 / cap) + 2
+    return 4 * per_ray * (math.ceil(n_pixels / max(n_slots, 1)) + 1)
+
+
 @torch.no_grad()
 def render_image_inference(nerf, cam, transform_cw, occupancy_bitfield, *, bg=(1.0, 1.0, 1.0), diagonal_n_steps=1024,
                            K=1, G=128, bound=1.0, stepsize_portion=0.0, march_steps_cap=8, n_rays=8192, grouped=True):
@@ -67,8 +74,13 @@ def render_image_inference(nerf, cam, transform_cw, occupancy_bitfield, *, bg=(1
     indices = torch.zeros(n_rays, dtype=torch.int32, device=dev)
     next_ray_index = torch.zeros(1, dtype=torch.int32, device=dev)
     n_rendered = 0
+    passes, max_passes = 0, _max_loop_passes(n_pixels, n_rays, diagonal_n_steps, bound, march_steps_cap)
     while n_rendered < n_pixels:  # cuda.py:326
         iters = 2 ** (int(math.log2(max(1, (n_pixels - n_rendered) // n_rays))) + 1)  # cuda.py:327-328
+        passes += iters
+        if passes > max_passes:
+            raise RuntimeError(f"render_image_inference: {n_rendered}/{n_pixels} rays finished after {passes} passes "
+                               f"(bound {max_passes}): the slot-refill loop is not making progress")
         counts = []
         for _ in range(iters):
             next_ray_index, indices, n_samples, t_starts, xyzs, dss, z_vals = march_rays_inference(
@@ -131,6 +143,7 @@ class InferenceRenderer:
         self._rays_desc = descriptors.make_training_rays_descriptor(N, cam["width"], cam["height"], 1, cam["fx"], cam["fy"],
                                                                     cam["cx"], cam["cy"], bound)
         self._graph = None
+        self._max_passes = _max_loop_passes(N, n, diagonal_n_steps, bound, self.cap)
 
     def _iteration(self):
         """One pass of the slot-refill loop (cuda.py:180-241): three custom calls, no torch glue -- the scatters back
@@ -188,8 +201,13 @@ class InferenceRenderer:
                 t.copy_(s)  # undo the two warm-up iterations
             self.counters.zero_()
         n_rendered = 0
+        passes = 0
         while n_rendered < self.N:  # cuda.py:326-361
             iters = 2 ** (int(math.log2(max(1, (self.N - n_rendered) // self.n))) + 1)
+            passes += iters
+            if passes > self._max_passes:
+                raise RuntimeError(f"InferenceRenderer: {n_rendered}/{self.N} rays finished after {passes} passes (bound "
+                                   f"{self._max_passes}, counters {self.counters.tolist()}): the loop is not making progress")
             for _ in range(iters):
                 self._graph.replay()
             n_rendered = int(self.counters[0])  # one host read per batch of iterations
