@@ -292,7 +292,8 @@ def dominant_kernel_roofline(tr, perm, flush):
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/), if present
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic_r01.json"))).get(top)
+        import glob
+        traffic = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "dram_traffic_r*.json")))[-1])).get(top)
     except Exception:
         pass
     return {"kernel": top, "bound": "hbm", "achieved": res[top]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
