@@ -201,6 +201,8 @@ typedef struct {
 } NgpNerfMlpDescriptor;
 void ngp_nerf_mlp_forward(cudaStream_t, void **, const char *, size_t);
 void ngp_nerf_mlp_backward(cudaStream_t, void **, const char *, size_t);
+/* Same contract, weight gradients on mma.sync instead of tcgen05/TMEM (the cross-check arm of the tests). */
+void ngp_nerf_mlp_backward_mma(cudaStream_t, void **, const char *, size_t);
 
 /* HashGridEncoder fused in front of the MLP forward: the [n,32] encoding feeds the first layer's
  * tensor-core fragments directly.  Bit-identical to hashgrid_a1_forward followed by nerf_mlp_forward.

@@ -19,6 +19,7 @@
 // traffic is enc (128 B) + dirs (12 B) + d_drgbs (16 B) in, d_enc (128 B) out per sample.
 #include "common.cuh"
 #include "hashgrid.cuh"
+#include "umma.cuh"
 
 namespace ngp {
 namespace {
@@ -39,6 +40,33 @@ constexpr int S_A64 = 72, S_A32 = 40, S_D = 72;
 constexpr int O_H0 = 0, O_HIN = O_H0 + kBlockSamples * S_A64, O_H1 = O_HIN + kBlockSamples * S_A32,
               O_H2 = O_H1 + kBlockSamples * S_A64, O_D = O_H2 + kBlockSamples * S_A64,
               kActFloats = O_D + kBlockSamples * S_D;
+
+// ---- tcgen05 wgrad path of the backward kernel: activations / deltas of the CTA's 128 samples as MN-major tf32
+// panels (umma.cuh: rows = sample, 32 features per 128-byte row, SWIZZLE_128B_BASE32B), byte offsets from a
+// 1024-byte aligned base.  PB_S holds the two narrow deltas (d_a3: 3 of 32 columns, d_x: 16 of 32), zero elsewhere.
+constexpr uint32_t kPanel = kBlockSamples * 128u;  // 16 KB: 128 samples x 32 features
+constexpr uint32_t PB_ENC = 0, PB_H0 = PB_ENC + kPanel, PB_HIN = PB_H0 + 2 * kPanel, PB_H1 = PB_HIN + kPanel,
+                   PB_H2 = PB_H1 + 2 * kPanel, PB_S = PB_H2 + 2 * kPanel, PB_DA = PB_S + kPanel,
+                   kPanelBytes = PB_DA + 2 * kPanel;  // 180224
+// TMEM columns of the weight-gradient accumulators (f32, M = 64 rows each, live for the whole kernel)
+constexpr uint32_t T_W3 = 0, T_W0 = 64, T_W2 = 96, T_W1 = 128, T_W4 = 160, kTmemCols = 256;
+
+// byte offset of this lane's float2 (row 16*warp + g, columns col .. col+1 with col = 8*block + 2t) in a panel set;
+// row g + 8 is 1024 bytes further (same swizzle phase)
+__device__ __forceinline__ uint32_t panel_frag_offset(uint32_t warp, uint32_t g, uint32_t t, int col8) {
+    return (uint32_t)(col8 >> 5) * kPanel + (16u * warp + g) * 128u + (((((uint32_t)col8 >> 3) & 3u) ^ (g & 3u)) << 5) + t * 8u;
+}
+// store A-fragment-ordered tf32 bits (c_to_a layout: [0] = (g, 2t), [1] = (g+8, 2t), [2] = (g, 2t+1), [3] = (g+8, 2t+1))
+template <int NT>
+__device__ __forceinline__ void store_frag_panel(uint8_t *__restrict__ panel, const uint32_t (&a)[NT][4], int col0,
+                                                 uint32_t warp, uint32_t g, uint32_t t) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const uint32_t off = panel_frag_offset(warp, g, t, col0 + 8 * nt);
+        *reinterpret_cast<uint2 *>(panel + off) = make_uint2(a[nt][0], a[nt][2]);
+        *reinterpret_cast<uint2 *>(panel + off + 1024u) = make_uint2(a[nt][1], a[nt][3]);
+    }
+}
 
 __device__ __forceinline__ uint32_t tf32(float x) {
     uint32_t r;
@@ -85,12 +113,13 @@ __device__ __forceinline__ void layer_backward(const uint32_t (&a)[KT_OUT][4], c
     for (int nt = 0; nt < NT_IN; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+    // kt outer, nt inner: consecutive MMAs go to different accumulators (no back-to-back dependency)
+    const uint32_t *w0 = W + g * STRIDE + 2 * t;
 #pragma unroll
-    for (int nt = 0; nt < NT_IN; ++nt) {
-        const uint32_t *w0 = W + (8 * nt + g) * STRIDE + 2 * t;
+    for (int kt = 0; kt < KT_OUT; ++kt) {
 #pragma unroll
-        for (int kt = 0; kt < KT_OUT; ++kt) {
-            const uint2 b = *reinterpret_cast<const uint2 *>(w0 + 8 * kt);
+        for (int nt = 0; nt < NT_IN; ++nt) {
+            const uint2 b = *reinterpret_cast<const uint2 *>(w0 + 8 * nt * STRIDE + 8 * kt);
             mma_tf32(acc[nt], a[kt], b.x, b.y);
         }
     }
@@ -156,8 +185,9 @@ __device__ __forceinline__ void load_enc_fragments(const float *__restrict__ enc
 }
 
 // Forward for this warp's 16 rows starting at `row0` (global sample index) from the enc fragments `a_in`.
-// If kKeep, activations are also written to the warp's rows of the shared activation buffers.
-template <bool kKeep, bool kDensityOnly>
+// kKeep == 1: activations are also written to the warp's rows of the padded shared activation buffers (act, f32);
+// kKeep == 2: ... as tf32 bits into the MN-major panels of the tcgen05 wgrad path (act = panel base).
+template <int kKeep, bool kDensityOnly>
 __device__ __forceinline__ void warp_forward_from(const uint32_t *__restrict__ sw, float *__restrict__ act, uint32_t warp,
                                                   uint32_t row0, uint32_t n, const uint32_t (&a_in)[4][4],
                                                   const float *__restrict__ dirs, uint32_t g, uint32_t t, FwdState &st,
@@ -181,7 +211,8 @@ __device__ __forceinline__ void warp_forward_from(const uint32_t *__restrict__ s
             for (int i = 0; i < 4; ++i) acc[nt][i] = fmaxf(acc[nt][i], 0.f);
             c_to_a(acc[nt], a_h0[nt]);
         }
-        if (kKeep) store_frag<8, S_A64>(act + O_H0 + warp * 16 * S_A64, acc, 0, g, t);
+        if (kKeep == 1) store_frag<8, S_A64>(act + O_H0 + warp * 16 * S_A64, acc, 0, g, t);
+        if (kKeep == 2) store_frag_panel<8>(reinterpret_cast<uint8_t *>(act) + PB_H0, a_h0, 0, warp, g, t);
     }
     // layer 1: 64 -> 16 (no activation); density = exp(x[0])
     uint32_t a_hin[4][4];
@@ -192,7 +223,7 @@ __device__ __forceinline__ void warp_forward_from(const uint32_t *__restrict__ s
         st.x0[1] = acc[0][2];
         c_to_a(acc[0], a_hin[0]);
         c_to_a(acc[1], a_hin[1]);
-        if (kKeep) store_frag<2, S_A32>(act + O_HIN + warp * 16 * S_A32, acc, 0, g, t);
+        if (kKeep == 1) store_frag<2, S_A32>(act + O_HIN + warp * 16 * S_A32, acc, 0, g, t);
     }
     if (kDensityOnly) return;
     // direction encoding: SH degree 4 into columns 16..31 of hin
@@ -206,7 +237,8 @@ __device__ __forceinline__ void warp_forward_from(const uint32_t *__restrict__ s
         sh4_lane(dx1, dy1, dz1, t, sh_hi);
         a_hin[2][0] = tf32(sh_lo[0]); a_hin[2][1] = tf32(sh_hi[0]); a_hin[2][2] = tf32(sh_lo[1]); a_hin[2][3] = tf32(sh_hi[1]);
         a_hin[3][0] = tf32(sh_lo[2]); a_hin[3][1] = tf32(sh_hi[2]); a_hin[3][2] = tf32(sh_lo[3]); a_hin[3][3] = tf32(sh_hi[3]);
-        if (kKeep) {
+        if (kKeep == 2) store_frag_panel<4>(reinterpret_cast<uint8_t *>(act) + PB_HIN, a_hin, 0, warp, g, t);
+        if (kKeep == 1) {
             float *buf = act + O_HIN + warp * 16 * S_A32;
             *reinterpret_cast<float2 *>(buf + g * S_A32 + 16 + 2 * t) = make_float2(sh_lo[0], sh_lo[1]);
             *reinterpret_cast<float2 *>(buf + g * S_A32 + 24 + 2 * t) = make_float2(sh_lo[2], sh_lo[3]);
@@ -225,7 +257,8 @@ __device__ __forceinline__ void warp_forward_from(const uint32_t *__restrict__ s
             for (int i = 0; i < 4; ++i) acc[nt][i] = fmaxf(acc[nt][i], 0.f);
             c_to_a(acc[nt], a_h1[nt]);
         }
-        if (kKeep) store_frag<8, S_A64>(act + O_H1 + warp * 16 * S_A64, acc, 0, g, t);
+        if (kKeep == 1) store_frag<8, S_A64>(act + O_H1 + warp * 16 * S_A64, acc, 0, g, t);
+        if (kKeep == 2) store_frag_panel<8>(reinterpret_cast<uint8_t *>(act) + PB_H1, a_h1, 0, warp, g, t);
     }
     // layer 3: 64 -> 64, ReLU
     {
@@ -237,7 +270,8 @@ __device__ __forceinline__ void warp_forward_from(const uint32_t *__restrict__ s
             for (int i = 0; i < 4; ++i) acc[nt][i] = fmaxf(acc[nt][i], 0.f);
             c_to_a(acc[nt], a_h2[nt]);
         }
-        if (kKeep) store_frag<8, S_A64>(act + O_H2 + warp * 16 * S_A64, acc, 0, g, t);
+        if (kKeep == 1) store_frag<8, S_A64>(act + O_H2 + warp * 16 * S_A64, acc, 0, g, t);
+        if (kKeep == 2) store_frag_panel<8>(reinterpret_cast<uint8_t *>(act) + PB_H2, a_h2, 0, warp, g, t);
     }
     // layer 4: 64 -> 3 (padded to 8), sigmoid
     layer_forward<8, 1, S_W4>(a_h2, sw + O_W4, out_rgb, g, t);
@@ -249,7 +283,7 @@ __device__ __forceinline__ void warp_forward_from(const uint32_t *__restrict__ s
     st.rgb[1][1] = out_rgb[0][3];
 }
 
-template <bool kKeep, bool kDensityOnly>
+template <int kKeep, bool kDensityOnly>
 __device__ __forceinline__ void warp_forward(const uint32_t *__restrict__ sw, float *__restrict__ act, uint32_t warp,
                                              uint32_t row0, uint32_t n, const float *__restrict__ enc,
                                              const float *__restrict__ dirs, uint32_t g, uint32_t t, FwdState &st,
@@ -591,9 +625,232 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_kernel(uint32_t
     if (warp < 4) flush_tile(d_weights + G_W4, 3, 16 * warp, 0, dW4[0], g, t);
 }
 
+// ---------------------------------------------------------------- backward kernel, weight gradients on tcgen05
+// Same per-warp register chain as above (forward recompute and the delta of every layer on mma.sync, 16 samples
+// per warp), but the weight gradients -- 60 % of the instructions of the kernel above, all of them shared-memory
+// fragment loads feeding small MMAs -- move to the 5th-generation tensor core: every activation / delta of the
+// CTA's 128 samples is written ONCE, as tf32 bits, into an MN-major shared-memory panel (the bits the next layer's
+// A fragment uses anyway), and ONE thread issues dW (+)= act^T . delta as 16 tcgen05.mma (M = 64, K = 8 samples
+// each) per layer.  The five accumulators (192 TMEM columns) stay in tensor memory for the CTA's whole lifetime and
+// are flushed with one atomicAdd per element at the end.  The MMAs run asynchronously under the next layer's
+// register chain; mbarriers (tcgen05.commit) only guard the reuse of a panel:
+//   bar_w4: dW4 has read h2 / the narrow panel  -> d_a1 may overwrite h2, d_x the narrow panel
+//   bar_w3: dW3 has read d_a2                   -> d_a0 may overwrite it
+//   bar_w0: everything of this block is done    -> the next block may overwrite the panels
+template <int NT>
+__device__ __forceinline__ void relu_mask_to_a(const uint8_t *__restrict__ panel, uint32_t warp, uint32_t g, uint32_t t,
+                                               float (&dacc)[NT][4], uint32_t (&a_d)[NT][4]) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const uint32_t off = panel_frag_offset(warp, g, t, 8 * nt);
+        const float2 lo = *reinterpret_cast<const float2 *>(panel + off);
+        const float2 hi = *reinterpret_cast<const float2 *>(panel + off + 1024u);
+        dacc[nt][0] = lo.x > 0.f ? dacc[nt][0] : 0.f;
+        dacc[nt][1] = lo.y > 0.f ? dacc[nt][1] : 0.f;
+        dacc[nt][2] = hi.x > 0.f ? dacc[nt][2] : 0.f;
+        dacc[nt][3] = hi.y > 0.f ? dacc[nt][3] : 0.f;
+        c_to_a(dacc[nt], a_d[nt]);
+    }
+}
+
+// D[64 x N] (+)= A^T . B over the 128 samples: A = 64-feature panel pair, B = N-feature panel(s), both MN-major
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool accumulate) {
+#pragma unroll 4
+    for (uint32_t ks = 0; ks < kBlockSamples / 8; ++ks)
+        umma::mma_tf32(tmem_d, umma::desc_mn_major(a_addr, ks, kPanel), umma::desc_mn_major(b_addr, ks, kPanel), idesc,
+                       accumulate || ks > 0);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_umma_kernel(uint32_t n, const float *__restrict__ enc,
+                                                                             const float *__restrict__ dirs,
+                                                                             const float *__restrict__ weights,
+                                                                             const float *__restrict__ d_drgbs,
+                                                                             float *__restrict__ d_enc,
+                                                                             float *__restrict__ d_weights) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // aligned by an offset from the array (not through an integer round trip) so that the compiler keeps the
+    // shared address space and emits LDS/STS rather than generic loads and stores
+    uint8_t *panels = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint32_t *sw = reinterpret_cast<uint32_t *>(panels + kPanelBytes);
+    __shared__ uint64_t bar_w4, bar_w3, bar_w0;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, g = lane >> 2, t = lane & 3u;
+
+    load_weights(sw, weights);
+    for (uint32_t i = tid; i < kPanel / 16; i += kThreads) reinterpret_cast<uint4 *>(panels + PB_S)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        umma::mbar_init(&bar_w4, 1);
+        umma::mbar_init(&bar_w3, 1);
+        umma::mbar_init(&bar_w0, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, kTmemCols);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t pa = umma::smem_u32(panels);
+    constexpr uint32_t kI32 = umma::make_idesc(64, 32, true, true), kI64 = umma::make_idesc(64, 64, true, true);
+    float *act = reinterpret_cast<float *>(panels);
+
+    const uint32_t n_blocks = (n + kBlockSamples - 1) / kBlockSamples;
+    uint32_t it = 0;
+    for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+        const uint32_t par = it & 1u;
+        const bool acc = it > 0;
+        const uint32_t base = blk * kBlockSamples, row0 = base + warp * 16;
+        const uint32_t r_lo = row0 + g, r_hi = row0 + g + 8;
+        uint32_t a_in[4][4];
+        load_enc_fragments(enc, r_lo, r_hi, r_lo < n, r_hi < n, t, a_in);
+        const float4 dd_lo = r_lo < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 dd_hi = r_hi < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_hi) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (it > 0) umma::mbar_wait(&bar_w0, par ^ 1u);  // the previous block's wgrad MMAs have read every panel
+        store_frag_panel<4>(panels + PB_ENC, a_in, 0, warp, g, t);
+        // ---- forward recompute; h0, hin, h1, h2 of the CTA's 128 samples -> panels
+        FwdState st;
+        uint32_t a_tmp[8][4];
+        float rgb[1][4];
+        warp_forward_from<2, false>(sw, act, warp, row0, n, a_in, dirs, g, t, st, a_tmp, rgb);
+
+        // ---- layer 4 delta: d_a3 = d_rgb * rgb * (1 - rgb), cols (2t, 2t+1) of the padded 8
+        float d3[1][4];
+        uint32_t a3[2][4];
+        {
+            const float dr_lo0 = t == 0 ? dd_lo.y : t == 1 ? dd_lo.w : 0.f, dr_lo1 = t == 0 ? dd_lo.z : 0.f;
+            const float dr_hi0 = t == 0 ? dd_hi.y : t == 1 ? dd_hi.w : 0.f, dr_hi1 = t == 0 ? dd_hi.z : 0.f;
+            d3[0][0] = dr_lo0 * st.rgb[0][0] * (1.f - st.rgb[0][0]);
+            d3[0][1] = dr_lo1 * st.rgb[0][1] * (1.f - st.rgb[0][1]);
+            d3[0][2] = dr_hi0 * st.rgb[1][0] * (1.f - st.rgb[1][0]);
+            d3[0][3] = dr_hi1 * st.rgb[1][1] * (1.f - st.rgb[1][1]);
+            c_to_a(d3[0], a3[0]);
+            a3[1][0] = a3[1][1] = a3[1][2] = a3[1][3] = 0u;  // columns 8..15 held d_x of the previous block
+        }
+        store_frag_panel<2>(panels + PB_S, a3, 0, warp, g, t);
+        umma::fence_smem_to_async();
+        __syncthreads();  // panels of the whole block are visible to the tensor core
+        if (tid == 0) {
+            umma::fence_after_sync();
+            issue_wgrad(tmem + T_W4, pa + PB_H2, pa + PB_S, kI32, acc);  // dW4 = h2^T . d_a3
+            umma::commit(&bar_w4);
+        }
+        // d_a2 = (d_a3 . W4^T) masked by h2 > 0
+        uint32_t a_d[8][4];
+        float dacc[8][4];
+        {
+            uint32_t a3k[1][4];
+            a3k[0][0] = a3[0][0]; a3k[0][1] = a3[0][1]; a3k[0][2] = a3[0][2]; a3k[0][3] = a3[0][3];
+            layer_backward<1, 8, S_W4>(a3k, sw + O_W4, dacc, g, t);
+            relu_mask_to_a<8>(panels + PB_H2, warp, g, t, dacc, a_d);
+        }
+        store_frag_panel<8>(panels + PB_DA, a_d, 0, warp, g, t);
+        umma::fence_smem_to_async();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            issue_wgrad(tmem + T_W3, pa + PB_H1, pa + PB_DA, kI64, acc);  // dW3 = h1^T . d_a2
+            umma::commit(&bar_w3);
+        }
+        // d_a1 = (d_a2 . W3^T) masked by h1 > 0 -> takes over the h2 panels
+        layer_backward<8, 8, S_W3>(a_d, sw + O_W3, dacc, g, t);
+        relu_mask_to_a<8>(panels + PB_H1, warp, g, t, dacc, a_d);
+        umma::mbar_wait(&bar_w4, par);
+        store_frag_panel<8>(panels + PB_H2, a_d, 0, warp, g, t);
+        umma::fence_smem_to_async();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            issue_wgrad(tmem + T_W2, pa + PB_H2, pa + PB_HIN, kI32, acc);  // dW2^T = d_a1^T . hin
+        }
+        // d_x = (d_a1 . W2^T)[:, :16] + d_density * exp(clip(x0, -15, 15)) on column 0 (nerfs.py:231-234)
+        float dx[2][4];
+        uint32_t a_dx[2][4];
+        layer_backward<8, 2, S_W2>(a_d, sw + O_W2, dx, g, t);
+        if (t == 0) {
+            dx[0][0] += dd_lo.x * expf(fminf(fmaxf(st.x0[0], -15.f), 15.f));
+            dx[0][2] += dd_hi.x * expf(fminf(fmaxf(st.x0[1], -15.f), 15.f));
+        }
+        c_to_a(dx[0], a_dx[0]);
+        c_to_a(dx[1], a_dx[1]);
+        store_frag_panel<2>(panels + PB_S, a_dx, 0, warp, g, t);
+        umma::fence_smem_to_async();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            issue_wgrad(tmem + T_W1, pa + PB_H0, pa + PB_S, kI32, acc);  // dW1 = h0^T . d_x
+        }
+        // d_a0 = (d_x . W1^T) masked by h0 > 0 -> takes over the d_a2 panels
+        layer_backward<2, 8, S_W1>(a_dx, sw + O_W1, dacc, g, t);
+        relu_mask_to_a<8>(panels + PB_H0, warp, g, t, dacc, a_d);
+        umma::mbar_wait(&bar_w3, par);
+        store_frag_panel<8>(panels + PB_DA, a_d, 0, warp, g, t);
+        umma::fence_smem_to_async();
+        __syncthreads();
+        if (tid == 0) {
+            umma::fence_after_sync();
+            issue_wgrad(tmem + T_W0, pa + PB_DA, pa + PB_ENC, kI32, acc);  // dW0^T = d_a0^T . enc
+            umma::commit(&bar_w0);
+        }
+        // d_enc = d_a0 . W0^T -> global
+        {
+            float de[4][4];
+            layer_backward<8, 4, S_W0>(a_d, sw + O_W0, de, g, t);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                if (r_lo < n) *reinterpret_cast<float2 *>(d_enc + (size_t)r_lo * 32 + 8 * nt + 2 * t) = make_float2(de[nt][0], de[nt][1]);
+                if (r_hi < n) *reinterpret_cast<float2 *>(d_enc + (size_t)r_hi * 32 + 8 * nt + 2 * t) = make_float2(de[nt][2], de[nt][3]);
+            }
+        }
+    }
+
+    // ---- flush the CTA's weight gradients: row m of an M = 64 accumulator sits in lane (m % 16) + 32 (m / 16)
+    if (it > 0) {
+        umma::mbar_wait(&bar_w0, (it - 1u) & 1u);
+        umma::fence_after_sync();
+        const uint32_t q = warp & 3u, m = 16u * q + lane;
+        const uint32_t taddr = tmem + ((32u * q) << 16);
+        const bool mine = lane < 16u;
+        uint32_t v[32];
+        if (warp < 4) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {  // dW3[m][32h + j]
+                umma::tmem_ld32(taddr + T_W3 + 32 * h, v);
+                umma::tmem_ld_wait();
+                if (mine)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(d_weights + G_W3 + m * 64 + 32 * h + j, __uint_as_float(v[j]));
+            }
+            umma::tmem_ld32(taddr + T_W0, v);  // dW0^T[m = out][j = in]
+            umma::tmem_ld_wait();
+            if (mine)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(d_weights + G_W0 + j * 64 + m, __uint_as_float(v[j]));
+        } else {
+            umma::tmem_ld32(taddr + T_W2, v);  // dW2^T[m = out][j = in]
+            umma::tmem_ld_wait();
+            if (mine)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(d_weights + G_W2 + j * 64 + m, __uint_as_float(v[j]));
+            umma::tmem_ld32(taddr + T_W1, v);  // dW1[m][j < 16]
+            umma::tmem_ld_wait();
+            if (mine)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) atomicAdd(d_weights + G_W1 + m * 16 + j, __uint_as_float(v[j]));
+            umma::tmem_ld32(taddr + T_W4, v);  // dW4[m][j < 3]
+            umma::tmem_ld_wait();
+            if (mine)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) atomicAdd(d_weights + G_W4 + m * 3 + j, __uint_as_float(v[j]));
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+}
+
 constexpr size_t kFwdSmem = kWeightFloats * sizeof(uint32_t);
 constexpr size_t kFusedSmem = kFwdSmem + 16 * sizeof(hg::LevelMeta);
 constexpr size_t kBwdSmem = (kWeightFloats + kActFloats) * sizeof(uint32_t);
+constexpr size_t kBwdUmmaSmem = 1024 + kPanelBytes + kWeightFloats * sizeof(uint32_t);  // 224,256 B
 
 }  // namespace
 }  // namespace ngp
@@ -642,12 +899,36 @@ void ngp_nerf_mlp_backward(cudaStream_t stream, void **buffers, const char *opaq
     if (d->n_samples == 0) return;
     static bool configured = false;
     if (!configured) {
+        cudaFuncSetAttribute(nerf_mlp_backward_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdUmmaSmem);
+        configured = true;
+    }
+    const unsigned blocks = min(div_up(d->n_samples, kBlockSamples), 148u);
+    nerf_mlp_backward_umma_kernel<<<blocks, kThreads, kBwdUmmaSmem, stream>>>(d->n_samples, enc, dirs, weights, d_drgbs, d_enc, d_weights);
+    check_launch("nerf_mlp_backward");
+}
+
+void ngp_nerf_mlp_backward_mma(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *d = descriptor<NgpNerfMlpDescriptor>(opaque, opaque_len, "nerf_mlp_backward_mma");
+    if (!d) return;
+    BufferCursor b{buffers};
+    const float *enc = b.next<const float>();
+    const float *dirs = b.next<const float>();
+    const float *weights = b.next<const float>();
+    const float *d_drgbs = b.next<const float>();
+    float *d_enc = b.next<float>();
+    float *d_weights = b.next<float>();
+    NGP_CUDA_OK(cudaMemsetAsync(d_weights, 0, kGlobalWeights * sizeof(float), stream), "nerf_mlp_backward_mma");
+    if (d->n_samples == 0) return;
+    static bool configured = false;
+    if (!configured) {
         cudaFuncSetAttribute(nerf_mlp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem);
         configured = true;
     }
     const unsigned blocks = min(div_up(d->n_samples, kBlockSamples), 148u);
     nerf_mlp_backward_kernel<<<blocks, kThreads, kBwdSmem, stream>>>(d->n_samples, enc, dirs, weights, d_drgbs, d_enc, d_weights);
-    check_launch("nerf_mlp_backward");
+    check_launch("nerf_mlp_backward_mma");
 }
 
 void ngp_nerf_fused_forward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {

@@ -152,6 +152,26 @@ def test_fused_mlp_matches_fp32_reference():
     torch.backends.cuda.matmul.allow_tf32 = True
 
 
+@pytest.mark.parametrize("n", [100, 128 * 148 * 3 + 77, (1 << 18) + 5])
+def test_mlp_backward_tcgen05_wgrad_matches_mma_sync_arm(n):
+    """The two backward kernels share the per-warp register chain (d_enc: same bits) and differ in where the weight
+    gradients are reduced: tcgen05.mma into TMEM accumulators that live across the CTA's blocks vs mma.sync into
+    registers.  Several blocks per CTA exercise the accumulate flag, the panel reuse barriers and both parities."""
+    from jaxngp_b200 import nerf as nerf_mod
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    model = nerf_mod.NeRF(bound=1.0, device=DEV, generator=gen, T=2 ** 14)
+    w = model.mlp_flat.detach().clone()
+    enc = torch.randn(n, 32, device=DEV, generator=gen) * 0.5
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV, generator=gen), dim=-1)
+    d_out = torch.randn(n, 4, device=DEV, generator=gen)
+    for rep in range(2):  # second call: TMEM re-allocated, accumulators start from zero again
+        g_enc_a, g_w_a = nerf_mod.mlp_backward(enc, dirs, w, d_out, impl="umma")
+        g_enc_b, g_w_b = nerf_mod.mlp_backward(enc, dirs, w, d_out, impl="mma")
+        torch.cuda.synchronize()
+        assert (g_enc_a != g_enc_b).float().mean() <= 1e-5, rep
+        assert (g_w_a - g_w_b).abs().max() <= 2e-4 * g_w_b.abs().max(), (rep, (g_w_a - g_w_b).abs().max(), g_w_b.abs().max())
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
 def test_fused_encoder_mlp_forward_is_bit_identical_to_the_two_ops(dtype):
     """ngp_nerf_fused_forward (encoder gather feeding the MLP fragments) against hashgrid_a1_forward +
