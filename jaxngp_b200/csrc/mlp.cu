@@ -695,15 +695,21 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_umma_kernel(uin
 
     const uint32_t n_blocks = (n + kBlockSamples - 1) / kBlockSamples;
     uint32_t it = 0;
+    // this block's global inputs are fetched one block ahead (under the previous block's last layer)
+    uint32_t a_in[4][4];
+    float4 dd_lo = make_float4(0.f, 0.f, 0.f, 0.f), dd_hi = dd_lo;
+    auto fetch = [&](uint32_t blk) {
+        const uint32_t r_lo = blk * kBlockSamples + warp * 16 + g, r_hi = r_lo + 8;
+        load_enc_fragments(enc, r_lo, r_hi, r_lo < n, r_hi < n, t, a_in);
+        dd_lo = r_lo < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dd_hi = r_hi < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_hi) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    if (blockIdx.x < n_blocks) fetch(blockIdx.x);
     for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
         const uint32_t par = it & 1u;
         const bool acc = it > 0;
         const uint32_t base = blk * kBlockSamples, row0 = base + warp * 16;
         const uint32_t r_lo = row0 + g, r_hi = row0 + g + 8;
-        uint32_t a_in[4][4];
-        load_enc_fragments(enc, r_lo, r_hi, r_lo < n, r_hi < n, t, a_in);
-        const float4 dd_lo = r_lo < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 dd_hi = r_hi < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_hi) : make_float4(0.f, 0.f, 0.f, 0.f);
         if (it > 0) umma::mbar_wait(&bar_w0, par ^ 1u);  // the previous block's wgrad MMAs have read every panel
         store_frag_panel<4>(panels + PB_ENC, a_in, 0, warp, g, t);
         // ---- forward recompute; h0, hin, h1, h2 of the CTA's 128 samples -> panels
@@ -790,6 +796,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_umma_kernel(uin
             issue_wgrad(tmem + T_W0, pa + PB_DA, pa + PB_ENC, kI32, acc);  // dW0^T = d_a0^T . enc
             umma::commit(&bar_w0);
         }
+        if (blk + gridDim.x < n_blocks) fetch(blk + gridDim.x);
         // d_enc = d_a0 . W0^T -> global
         {
             float de[4][4];

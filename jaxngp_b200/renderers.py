@@ -189,8 +189,10 @@ class InferenceRenderer:
         self.counters.zero_()
         if self._graph is None:
             side = torch.cuda.Stream(device=self.dev)
-            side.wait_stream(torch.cuda.current_stream(self.dev))
+            # snapshot BEFORE the side stream is released: its warm-up iteration mutates this state, and a clone
+            # enqueued after wait_stream could run behind it (then the "undo" below would restore the mutated state)
             state = [t.clone() for t in (self.t_starts, self.rays_rgbd, self.rays_T, self.terminated, self.indices, self.next_in)]
+            side.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(side):
                 self._iteration()  # warm-up on the capture stream
                 self._graph = torch.cuda.CUDAGraph()
