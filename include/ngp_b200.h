@@ -212,6 +212,10 @@ void ngp_nerf_mlp_backward_mma(cudaStream_t, void **, const char *, size_t);
  * out: drgbs f32[n,4] (density_only: f32[n]) [, enc f32[n,32] if write_enc] */
 typedef struct { NgpHashGridA1Descriptor grid; uint32_t density_only, write_enc; } NgpNerfFusedDescriptor;
 void ngp_nerf_fused_forward(cudaStream_t, void **, const char *, size_t);
+/* Same contract (density_only = 0 only) with the five dense layers on tcgen05.mma kind::tf32 and TMEM accumulators:
+ * 128-sample tiles, one thread per sample from the gather to the output.  Same tf32 operand rounding as the mma.sync
+ * kernel; results agree to f32 accumulation-order error (rel 1e-5), not bit for bit. */
+void ngp_nerf_fused_forward_umma(cudaStream_t, void **, const char *, size_t);
 
 /* Diagnostic: known-answer test of the tcgen05 (kind::tf32) operand formats of csrc/umma.cuh -- forward, dgrad and
  * wgrad GEMM shapes on swizzled shared-memory panels with TMEM accumulators.  No descriptor (opaque_len = 0).

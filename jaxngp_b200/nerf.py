@@ -93,7 +93,8 @@ def fused_supported(lt, table: torch.Tensor, wrap: str = "jaxngp") -> bool:
 
 
 def fused_forward(lt, pos: torch.Tensor, bound: float, table: torch.Tensor, dirs, weights: torch.Tensor, *,
-                  wrap: str = "jaxngp", group_counts: torch.Tensor = None, rows_per_group: int = 0, want_enc: bool = False):
+                  wrap: str = "jaxngp", group_counts: torch.Tensor = None, rows_per_group: int = 0, want_enc: bool = False,
+                  impl: str = "mma"):
     """Hash-grid encoder fused in front of the MLP forward (csrc/mlp.cu ``nerf_fused_forward_kernel``): bit-identical
     to ``encoders.hashgrid_forward`` + ``mlp_forward``, without the [n, 32] round trip through HBM.
     Returns ``drgbs`` (``dirs=None``: densities [n]); with ``want_enc`` also the encoding (kept for the backward)."""
@@ -110,7 +111,7 @@ def fused_forward(lt, pos: torch.Tensor, bound: float, table: torch.Tensor, dirs
         bufs.append(out)
         if want_enc:
             bufs.append(enc)
-        _lib.call("ngp_nerf_fused_forward", bufs, desc)
+        _lib.call("ngp_nerf_fused_forward_umma" if impl == "umma" and not density_only else "ngp_nerf_fused_forward", bufs, desc)
     return (out, enc) if want_enc else out
 
 
@@ -152,6 +153,9 @@ class NeRF(torch.nn.Module):
         super().__init__()
         self.bound = float(bound)
         self.fused = fused
+        #: kernel behind ``forward_grouped`` (the inference renderer): "umma" = dense layers on tcgen05 / TMEM over
+        #: tiles of live slots only, "mma" = the mma.sync kernel (bit-identical to the ungrouped ``forward``)
+        self.grouped_impl = "umma"
         Enc = encoders.TCNNHashGridEncoder if inference else encoders.HashGridEncoder  # nerfs.py:431-438
         self.position_encoder = Enc(L=16, T=T, F=2, N_min=2 ** 4, N_max=int(2 ** 11 * bound), tv_scale=tv_scale,
                                     device=device, generator=generator)
@@ -189,7 +193,7 @@ class NeRF(torch.nn.Module):
         if self.fused and fused_supported(enc_mod.levels, enc_mod.latents, enc_mod.wrap):
             return fused_forward(enc_mod.levels, xyzs.reshape(-1, 3), self.bound, enc_mod.latents.detach(),
                                  ray_dirs.contiguous(), self.mlp_flat.detach(), wrap=enc_mod.wrap, group_counts=n_samples,
-                                 rows_per_group=cap).reshape(n, cap, 4)
+                                 rows_per_group=cap, impl=self.grouped_impl if cap <= 128 else "mma").reshape(n, cap, 4)
         enc = encoders.hashgrid_forward(enc_mod.levels, xyzs.reshape(-1, 3), self.bound, enc_mod.latents.detach(),
                                         enc_mod.wrap, group_counts=n_samples, rows_per_group=cap)
         drgbs = mlp_forward(enc, ray_dirs.contiguous(), self.mlp_flat.detach(), group_counts=n_samples, rows_per_group=cap)

@@ -208,6 +208,41 @@ def test_fused_encoder_mlp_forward_is_bit_identical_to_the_two_ops(dtype):
     assert torch.equal(ggot[live], full.reshape(n_rays, cap, 4)[live])
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_fused_forward_tcgen05_matches_mma_sync_kernel(dtype):
+    """ngp_nerf_fused_forward_umma (dense layers on tcgen05.mma, accumulators in TMEM, one thread per sample) against
+    the mma.sync kernel: the encoding it keeps for the backward must be the same bits (same gather), the outputs agree
+    to accumulation-order error.  Plain layout with a partial last tile, several tiles per group, and the grouped
+    (march_rays_inference) layout with padding rows and fully padded tiles."""
+    from jaxngp_b200 import encoders as E, nerf as nerf_mod
+    gen = torch.Generator(device=DEV).manual_seed(4)
+    lt = E.make_level_table(16, 2 ** 19, 2, 16, 2048, 3)
+    table = ((torch.rand(lt.rows, 2, device=DEV, generator=gen) - 0.5) * 2).to(dtype)
+    w = (torch.rand(nerf_mod.MLP_NUMEL, device=DEV, generator=gen) - 0.5) * 0.6
+    for n in (1, 127, 128 * 148 * 3 * 2 + 77):
+        pos = torch.rand(n, 3, device=DEV, generator=gen) * 2 - 1
+        dirs = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV, generator=gen), dim=-1)
+        ref, ref_enc = nerf_mod.fused_forward(lt, pos, 1.0, table, dirs, w, want_enc=True)
+        got, got_enc = nerf_mod.fused_forward(lt, pos, 1.0, table, dirs, w, want_enc=True, impl="umma")
+        assert torch.equal(got_enc, ref_enc), n
+        assert torch.allclose(got, ref, rtol=2e-5, atol=2e-6), (n, (got - ref).abs().max())
+        got2 = nerf_mod.fused_forward(lt, pos, 1.0, table, dirs, w, impl="umma")
+        assert torch.equal(got2, got), n
+    n_rays, cap = 40000, 16
+    counts = torch.randint(0, cap + 1, (n_rays,), device=DEV, generator=gen, dtype=torch.int32)
+    counts[1000:3000] = 0  # fully padded tiles
+    gpos = torch.rand(n_rays * cap, 3, device=DEV, generator=gen) * 2 - 1
+    gdirs = torch.nn.functional.normalize(torch.randn(n_rays, 3, device=DEV, generator=gen), dim=-1)
+    live = torch.arange(cap, device=DEV)[None, :] < counts[:, None]
+    for rows in (cap, 12):
+        c = counts.clamp(max=rows)
+        lv = torch.arange(rows, device=DEV)[None, :] < c[:, None]
+        gp = gpos[: n_rays * rows]
+        gref = nerf_mod.fused_forward(lt, gp, 1.0, table, gdirs, w, group_counts=c, rows_per_group=rows).reshape(n_rays, rows, 4)
+        ggot = nerf_mod.fused_forward(lt, gp, 1.0, table, gdirs, w, group_counts=c, rows_per_group=rows, impl="umma").reshape(n_rays, rows, 4)
+        assert torch.allclose(ggot[lv], gref[lv], rtol=2e-5, atol=2e-6), rows
+
+
 def test_graph_renderer_is_bit_identical_to_reference_loop(small_scene):
     """InferenceRenderer (one CUDA graph per loop iteration, grouped encoder/MLP) against
     render_image_inference (the reference's host loop, op for op) on the same rays."""
@@ -217,6 +252,7 @@ def test_graph_renderer_is_bit_identical_to_reference_loop(small_scene):
     with torch.no_grad():  # make the field non-trivial: visible densities inside the occupied region
         model.position_encoder.latents.uniform_(-1.0, 1.0, generator=gen)
     cam, pose, bits = small_scene.cam, small_scene.transforms[1], small_scene.bitfield_gt
+    model.grouped_impl = "mma"  # the bit-identical arm; the tcgen05 arm is compared in test_gpu_fullsize_properties.py
     ref_rgb, ref_depth = renderers.render_image_inference(model, cam, pose, bits, n_rays=1024, march_steps_cap=8, grouped=False)
     o, d = renderers.make_rays_worldspace(cam, pose)
     ts, te = renderers.make_near_far_from_bound(1.0, o, d)
