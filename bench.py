@@ -33,6 +33,16 @@ METRIC = "train samples/s (NeRF-synthetic shape, 2^18 samples/step)"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
 
 
+def tensor_peak_tf32():
+    """Dense tf32 tensor peak for a kernel timed alone: half the MEASURED bf16 burst rate (tf32 runs at half the
+    bf16 rate on this part: 1.1 vs 2.25 PFLOP/s nominal); fallback = B200_PROFILING.md's 1.59 PFLOP/s bf16."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["bf16_tflops"]) / 2, "measured bf16_tflops / 2 (MEASURED_PEAKS.json; tf32 = half the bf16 rate)"
+    except Exception:
+        return 1590.0 / 2, "fallback bf16 1.59 PFLOP/s / 2 (B200_PROFILING.md)"
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -296,12 +306,18 @@ def dominant_kernel_roofline(tr, perm, flush):
         traffic = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "dram_traffic_r*.json")))[-1])).get(top)
     except Exception:
         pass
-    return {"kernel": top, "bound": "hbm", "achieved": res[top]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
-            "frac": res[top]["frac_of_hbm"], "peak_source": src, "traffic": traffic, "sample_slots": n, "samples": used,
-            "rays_with_samples": n_hit,
-            "note": "each kernel timed alone with an L2 flush before every launch (isolated times sum to more than the "
-                    "graph-replayed step, whose kernels find their inputs in L2); limiter per kernel in DESIGN.md section 5",
-            "kernels": res}
+    common = {"kernel": top, "traffic": traffic, "sample_slots": n, "samples": used, "rays_with_samples": n_hit,
+              "note": "each kernel timed alone with an L2 flush before every launch (isolated times sum to more than the "
+                      "graph-replayed step, whose kernels find their inputs in L2); limiter per kernel in DESIGN.md section 5",
+              "kernels": res}
+    if "achieved_tflops" in res[top]:  # the dense contraction (fused MLP): tensor roofline; its HBM fraction is in `kernels`
+        tpeak, tsrc = tensor_peak_tf32()
+        return {"bound": "tensor", "achieved": res[top]["achieved_tflops"], "peak": tpeak, "unit": "TFLOP/s",
+                "frac": round(res[top]["achieved_tflops"] / tpeak, 4), "peak_source": tsrc,
+                "flops_per_unit": "56,448 FLOP per sample slot (forward recompute 18,816 + input gradients + weight gradients), "
+                                  "x 2^18 slots per launch", **common}
+    return {"bound": "hbm", "achieved": res[top]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+            "frac": res[top]["frac_of_hbm"], "peak_source": src, **common}
 
 
 # ------------------------------------------------------------------------------------------- extras (C3, C4)
@@ -402,9 +418,13 @@ def hashenc_bench(dev, n=1 << 22, log2_T=(19, 20, 21, 22, 23, 24), iters=10):
         grad = torch.empty_like(table)
         f_ms = timed(lambda: E.hashgrid_forward(lt, pos, 1.0, table))
         b_ms = timed(lambda: E.hashgrid_backward(lt, pos, 1.0, d_enc, out=grad))
+        table16 = table.half()
+        f16_ms = timed(lambda: E.hashgrid_forward(lt, pos, 1.0, table16))  # fp16 storage variant: 652 B/point
+        del table16
         fb = n * 1164, n * 1164 + table.numel() * 4
         sweep.append({"log2_T": lt2, "table_mb": round(table.numel() * 4 / 2 ** 20, 1), "fwd_ms": round(f_ms, 3),
                       "bwd_ms": round(b_ms, 3), "fwd_gbs": round(fb[0] / f_ms / 1e6, 1), "bwd_gbs": round(fb[1] / b_ms / 1e6, 1),
+                      "fwd_f16_table_ms": round(f16_ms, 3), "fwd_f16_table_gbs": round(n * 652 / f16_ms / 1e6, 1),
                       "fwd_bwd_gbs": round((fb[0] + fb[1]) / (f_ms + b_ms) / 1e6, 1),
                       "frac_of_hbm": round((fb[0] + fb[1]) / (f_ms + b_ms) / 1e6 / hbm, 3)})
         del table, grad

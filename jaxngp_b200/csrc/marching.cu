@@ -210,13 +210,15 @@ __device__ __forceinline__ EvalPoint eval_point(const Grid &g, const Ray &r, flo
 // tie, t_j = t_base + j d exactly -- one FMA per lane whose exact result is representable -- bit-equal to
 // the 31 dependent additions.  Otherwise (3 binade crossings per ray, ties, t_base == 0) the additions are
 // replayed one by one.
+// W = lanes that share the chain (32: the whole warp; 16: half a warp, `mask` = that half's lanes, `lane` < 16)
+template <int W = 32>
 __device__ __forceinline__ float chain_points(const Grid &g, float t_base, uint32_t lane, bool const_ds, float ds0,
-                                              float &t_next_base) {
+                                              float &t_next_base, uint32_t mask = 0xffffffffu) {
     if (const_ds) {
         const float t1 = __fadd_rn(t_base, ds0);
         const float d = __fadd_rn(t1, -t_base);            // exact (Sterbenz-like: both on the u grid, same binade checked below)
         const float err = __fadd_rn(ds0, -d);              // exact rounding error of t_base + ds0
-        const float t32 = __fmaf_rn(32.f, d, t_base);
+        const float t32 = __fmaf_rn((float)W, d, t_base);  // t_W
         const uint32_t e0 = __float_as_uint(t_base) >> 23, e32 = __float_as_uint(t32) >> 23;  // sign 0: biased exponents
         const float half_u = __uint_as_float(((e0 > 24u ? e0 : 24u) - 24u) << 23);             // ulp(t_base) / 2
         const bool fast = t_base > 0.f && e0 == e32 && e0 > 24u && fabsf(err) != half_u && d > 0.f;
@@ -226,21 +228,21 @@ __device__ __forceinline__ float chain_points(const Grid &g, float t_base, uint3
         }
         float t = t_base;
 #pragma unroll
-        for (int i = 0; i < 31; ++i) {
+        for (int i = 0; i < W - 1; ++i) {
             const float tn = __fadd_rn(t, ds0);
             if (i < (int)lane) t = tn;
         }
-        const float t_last = __shfl_sync(0xffffffffu, t, 31);
+        const float t_last = __shfl_sync(mask, t, W - 1, W);
         t_next_base = __fadd_rn(t_last, ds0);
         return t;
     }
     float t = t_base;
 #pragma unroll 4
-    for (int i = 0; i < 31; ++i) {
+    for (int i = 0; i < W - 1; ++i) {
         const float tn = __fadd_rn(t, calc_ds(g, t));
         if (i < (int)lane) t = tn;
     }
-    const float t_last = __shfl_sync(0xffffffffu, t, 31);
+    const float t_last = __shfl_sync(mask, t, W - 1, W);
     t_next_base = __fadd_rn(t_last, calc_ds(g, t_last));
     return t;
 }
@@ -553,7 +555,9 @@ __global__ void __launch_bounds__(kRankBlock) march_rays_inference_rank_kernel(
 // kInPlace (renderer fast path, ngp_march_rays_inference_inplace): the scatter the reference does after the op
 // (t_starts.at[indices].set(t_starts_out), marching/__init__.py:156) happens here -- every ray belongs to exactly one
 // slot -- and the slot's ray direction is copied out for the MLP (cuda.py:222-228 gathers it with rays_d[indices]).
-template <bool kInPlace>
+// W = lanes per slot: a whole warp (32) or half a warp (16: two slots per warp, each half with its own lane mask --
+// at march_steps_cap <= 16 one 16-point chunk of the chain already covers a full pass through occupied space).
+template <bool kInPlace, int W>
 __global__ void __launch_bounds__(kInferWarps * 32) march_rays_inference_kernel(
     NgpMarchingInferenceDescriptor p, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
     const float *t_starts, const float *__restrict__ t_ends, const uint8_t *__restrict__ bitfield,
@@ -562,23 +566,32 @@ __global__ void __launch_bounds__(kInferWarps * 32) march_rays_inference_kernel(
     const uint32_t *__restrict__ rank_in_block, uint32_t *__restrict__ next_ray_index, uint32_t *indices_out,
     uint32_t *__restrict__ n_samples, float *t_starts_out, float *__restrict__ xyzs,
     float *__restrict__ dss, float *__restrict__ z_vals, float *__restrict__ ray_dirs) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t i = blockIdx.x * kInferWarps + (threadIdx.x >> 5);  // slot of this warp
+    constexpr uint32_t kW = W, kWMask = W == 32 ? 0xFFFFFFFFu : 0xFFFFu;
+    const uint32_t lane = threadIdx.x & (kW - 1u);
+    const uint32_t shift = W == 32 ? 0u : (threadIdx.x & 16u);  // position of this slot's lanes in the warp
+    const uint32_t mask = kWMask << shift;
+    const uint32_t i = blockIdx.x * (kInferWarps * 32u / kW) + threadIdx.x / kW;  // slot of this lane group
     if (i >= p.n_rays) return;
+    auto group_sum = [&](uint32_t v) {
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, W);
+        return v;
+    };
+    auto ballot = [&](bool pred) { return (__ballot_sync(mask, pred) >> shift) & kWMask; };
     const uint32_t counter_in = __ldg(next_ray_index_in);
     const bool mine = terminated[i] != 0;
     uint32_t ray_idx;
     if (mine || i == p.n_rays - 1) {  // terminated slots before this slot's 1024-block
         const uint32_t nb = mine ? i / kRankSlots : 0u, nb_all = div_up_dev(p.n_rays, kRankSlots);
         uint32_t before = 0, all = 0;
-        for (uint32_t j = lane; j < nb_all; j += 32) {
+        for (uint32_t j = lane; j < nb_all; j += kW) {
             const uint32_t c = (j < nb || i == p.n_rays - 1) ? __ldg(block_total + j) : 0u;
             if (j < nb) before += c;
             all += c;
         }
-        before = warp_sum_u32(before);
+        before = group_sum(before);
         if (i == p.n_rays - 1) {
-            all = warp_sum_u32(all);
+            all = group_sum(all);
             if (lane == 0) *next_ray_index = counter_in + all;
         }
         ray_idx = mine ? counter_in + before + __ldg(rank_in_block + i) : indices_in[i];
@@ -609,17 +622,17 @@ __global__ void __launch_bounds__(kInferWarps * 32) march_rays_inference_kernel(
         // marching.cu:323-365: `t_cur` is the reference's loop variable t, always a point of the chain
         while (steps < cap && t_cur < t_end) {
             float t_next_base;
-            const float t = chain_points(g, t_cur, lane, const_ds, ds0, t_next_base);
+            const float t = chain_points<W>(g, t_cur, lane, const_ds, ds0, t_next_base, mask);
             const EvalPoint s = eval_point(g, ray, t);
-            const uint32_t V = __ballot_sync(0xffffffffu, t < t_end);
-            const uint32_t O = __ballot_sync(0xffffffffu, s.occupied);
+            const uint32_t V = ballot(t < t_end);
+            const uint32_t O = ballot(s.occupied);
             uint32_t v = 0;  // chain index of the point the reference visits next
             for (;;) {
-                if (v >= 32u) { t_cur = t_next_base; break; }
-                if (steps >= cap || !((V >> v) & 1u)) { t_cur = __shfl_sync(0xffffffffu, t, v); break; }
+                if (v >= kW) { t_cur = t_next_base; break; }
+                if (steps >= cap || !((V >> v) & 1u)) { t_cur = __shfl_sync(mask, t, v, W); break; }
                 if ((O >> v) & 1u) {
                     const uint32_t rest = (O & V) >> v;  // consecutive occupied in-range points starting at v
-                    uint32_t run = (rest == (0xFFFFFFFFu >> v)) ? 32u - v : (uint32_t)__ffs(~rest) - 1u;
+                    uint32_t run = (rest == (kWMask >> v)) ? kW - v : (uint32_t)__ffs(~rest) - 1u;
                     run = min(run, cap - steps);
                     if (lane >= v && lane < v + run) {
                         const uint32_t w = steps + (lane - v);
@@ -631,12 +644,12 @@ __global__ void __launch_bounds__(kInferWarps * 32) march_rays_inference_kernel(
                     }
                     steps += run;
                     v += run;
-                    last_ds = __shfl_sync(0xffffffffu, s.ds, v - 1u);
-                    last_z = __shfl_sync(0xffffffffu, t, v - 1u);
+                    last_ds = __shfl_sync(mask, s.ds, v - 1u, W);
+                    last_z = __shfl_sync(mask, t, v - 1u, W);
                 } else {  // empty: the next visited point is the first chain point at or past the voxel boundary
-                    const float nt = __shfl_sync(0xffffffffu, s.next_t, v);
-                    const uint32_t above = (v == 31u) ? 0u : (0xFFFFFFFFu << (v + 1u));
-                    const uint32_t m = __ballot_sync(0xffffffffu, t >= nt) & above;
+                    const float nt = __shfl_sync(mask, s.next_t, v, W);
+                    const uint32_t above = (v == kW - 1u) ? 0u : ((kWMask << (v + 1u)) & kWMask);
+                    const uint32_t m = ballot(t >= nt) & above;
                     if (m) {
                         v = __ffs(m) - 1;
                     } else {  // boundary beyond this chunk: walk the chain like the reference (marching.cu:186-188)
@@ -677,9 +690,9 @@ __global__ void __launch_bounds__(kInferWarps * 32) march_rays_inference_kernel(
     }
     if (kInPlace && lane < 3) ray_dirs[3 * (size_t)i + lane] = ray_idx < p.n_total_rays ? __ldg(rays_d + 3 * (size_t)ray_idx + lane) : 0.f;
     // zero the unused tail (reference: memsets, marching.cu:565-570)
-    __syncwarp();
-    for (uint32_t k = steps * 3 + lane; k < cap * 3; k += 32) o_xyzs[k] = 0.f;
-    for (uint32_t k = steps + lane; k < cap; k += 32) {
+    __syncwarp(mask);
+    for (uint32_t k = steps * 3 + lane; k < cap * 3; k += kW) o_xyzs[k] = 0.f;
+    for (uint32_t k = steps + lane; k < cap; k += kW) {
         o_dss[k] = 0.f;
         o_z[k] = 0.f;
     }
@@ -812,15 +825,19 @@ static void launch_march_rays_inference(cudaStream_t stream, void **buffers, con
     march_rays_inference_rank_kernel<<<rank_blocks, kRankBlock, 0, stream>>>(desc->n_rays, terminated, block_total, rank_in_block,
                                                                              next_in, in_place ? snapshot : nullptr);
     if (!check_launch(op)) return;
-    const unsigned grid = div_up(desc->n_rays, kInferWarps);
-    if (in_place)
-        march_rays_inference_kernel<true><<<grid, kInferWarps * 32, 0, stream>>>(
-            *desc, rays_o, rays_d, t_starts, t_ends, bitfield, snapshot, terminated, indices_in, block_total, rank_in_block,
-            next_out, indices_out, n_samples, t_starts_out, xyzs, dss, z_vals, ray_dirs);
-    else
-        march_rays_inference_kernel<false><<<grid, kInferWarps * 32, 0, stream>>>(
-            *desc, rays_o, rays_d, t_starts, t_ends, bitfield, next_in, terminated, indices_in, block_total, rank_in_block,
-            next_out, indices_out, n_samples, t_starts_out, xyzs, dss, z_vals, nullptr);
+    // half a warp per slot when one 16-point chunk of the chain covers the cap, else a whole warp
+    const bool half = desc->march_steps_cap <= 16;
+    const unsigned grid = div_up(desc->n_rays, half ? 2 * kInferWarps : kInferWarps);
+#define NGP_MARCH_INF(IP, W, counter, dirs_ptr)                                                                        \
+    march_rays_inference_kernel<IP, W><<<grid, kInferWarps * 32, 0, stream>>>(                                         \
+        *desc, rays_o, rays_d, t_starts, t_ends, bitfield, counter, terminated, indices_in, block_total, rank_in_block, \
+        next_out, indices_out, n_samples, t_starts_out, xyzs, dss, z_vals, dirs_ptr)
+    if (in_place) {
+        if (half) NGP_MARCH_INF(true, 16, snapshot, ray_dirs); else NGP_MARCH_INF(true, 32, snapshot, ray_dirs);
+    } else {
+        if (half) NGP_MARCH_INF(false, 16, next_in, nullptr); else NGP_MARCH_INF(false, 32, next_in, nullptr);
+    }
+#undef NGP_MARCH_INF
     check_launch(op);
 }
 

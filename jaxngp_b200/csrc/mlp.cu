@@ -68,11 +68,9 @@ __device__ __forceinline__ void store_frag_panel(uint8_t *__restrict__ panel, co
     }
 }
 
-__device__ __forceinline__ uint32_t tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// round to tf32: nearest, ties away from zero -- cvt.rna.tf32.f32 for every finite input, in two integer
+// instructions instead of the four the conversion compiles to (it special-cases NaN/Inf, which never occur here)
+__device__ __forceinline__ uint32_t tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
