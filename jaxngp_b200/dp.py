@@ -30,7 +30,8 @@ def reduce_scatter_flat_gradients(flat_grads: torch.Tensor, rank: int, world_siz
     Half of an all-reduce; the other half is ``all_gather_flat_parameters`` after the sharded optimizer step."""
     lo, hi = shard_bounds(flat_grads.numel(), rank, world_size)
     shard = flat_grads[lo:hi]
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    # world_size == 1: a replica trainer inside a multi-rank job (bench.py's render model) exchanges nothing
+    if world_size == 1 or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return shard
     if dist.get_backend(group) == "nccl":
         dist.reduce_scatter_tensor(shard, flat_grads, op=dist.ReduceOp.SUM, group=group)  # in place on the rank's slice
@@ -41,7 +42,7 @@ def reduce_scatter_flat_gradients(flat_grads: torch.Tensor, rank: int, world_siz
 
 def all_gather_flat_parameters(flat_params: torch.Tensor, rank: int, world_size: int, group=None) -> torch.Tensor:
     """Every rank updated its own shard of ``flat_params``: gather the shards in place."""
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if world_size > 1 and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         lo, hi = shard_bounds(flat_params.numel(), rank, world_size)
         if dist.get_backend(group) == "nccl":
             dist.all_gather_into_tensor(flat_params, flat_params[lo:hi], group=group)

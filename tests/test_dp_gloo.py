@@ -31,6 +31,11 @@ def _worker(rank, world, port, q):
     params[lo:hi] = -shard  # "optimizer" on the shard
     dp.all_gather_flat_parameters(params, rank, world)
     assert torch.equal(params, -3.0 * torch.arange(n, dtype=torch.float32)), params
+    # a replica (world_size = 1 trainer inside the 2-rank job, bench.py's render model) exchanges nothing
+    own = torch.arange(n, dtype=torch.float32) * (rank + 1)
+    assert dp.reduce_scatter_flat_gradients(own, 0, 1).numel() == n
+    assert torch.equal(own, torch.arange(n, dtype=torch.float32) * (rank + 1))
+    assert torch.equal(dp.all_gather_flat_parameters(own, 0, 1), torch.arange(n, dtype=torch.float32) * (rank + 1))
     grid = torch.arange(16, dtype=torch.float32) * (1 if rank == 0 else -1) + rank
     dp.allreduce_density_grid(grid)
     H, Wd = 100, 7
