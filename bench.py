@@ -133,6 +133,8 @@ def run_ours(args):
     perms_host = torch.from_numpy(host_perms(W + K, rank)).pin_memory()
     perms_dev = perms_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    host_loss = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_events = [torch.cuda.Event() for _ in range(2)]
 
     def barrier():
         if world > 1:
@@ -153,8 +155,16 @@ def run_ours(args):
             samples += out["measured_batch_size_before_compaction"]
             if (k + 1) % OGRID_EVERY == 0:
                 tr.update_ogrid(update_all=False, commit=False)
-            if e2e:  # D2H read of the step's result
-                loss_host = float(out["loss"])
+            if e2e:  # D2H read of every step's result, one step behind so that the host never stalls the device:
+                # the loss goes to pinned memory asynchronously and is consumed while the next step runs
+                host_loss[k & 1].copy_(out["loss"].reshape(1), non_blocking=True)
+                loss_events[k & 1].record()
+                if k > 0:
+                    loss_events[(k - 1) & 1].synchronize()
+                    loss_host = float(host_loss[(k - 1) & 1])
+        if e2e:
+            loss_events[(n_steps - 1) & 1].synchronize()
+            loss_host = float(host_loss[(n_steps - 1) & 1])
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -214,7 +224,9 @@ def run_ours(args):
                    "cuda_graph": not args.no_graph},
         "samples_per_step": samples / K,
         "e2e": {"value": samples_e2e / (ms_e2e / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e / K,
-                "h2d_bytes_per_step": N_RAYS * 4, "d2h_bytes_per_step": 4, "loss": loss},
+                "h2d_bytes_per_step": N_RAYS * 4, "d2h_bytes_per_step": 4, "loss": loss,
+                "note": "every step: pixel indices copied from pinned host memory, loss copied back to pinned host memory "
+                        "(read by the host one step later, while the next step runs)"},
         "gpu_launches": tr_counts["ours"] * K,
         "launches_per_step": tr_counts,
         "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "render": render, "hashenc": hashenc,
@@ -344,10 +356,11 @@ def render_bench(dev, rank, world, scene=None, frames=10, train_steps=300, n_slo
     R = renderers.InferenceRenderer(tr.nerf, scene.cam, tr.occupancy, n_rays=min(n_slots, pixels.numel()), march_steps_cap=cap,
                                     pixel_indices=pixels)
     views = [(7 * k + 3) % scene.n_views for k in range(frames + 2)]
+    gather = dp.ImageGather(H, Wd, 3, rank, world, dev) if world > 1 else None
 
     def frame(v):
         rgb, _ = R.render(scene.transforms[v])
-        return dp.gather_image(rows, rgb.reshape(rows.numel(), Wd, 3), H) if world > 1 else rgb
+        return gather(rgb.reshape(rows.numel(), Wd, 3)) if world > 1 else rgb
 
     for v in views[:2]:
         frame(v)

@@ -67,6 +67,43 @@ def tile_rows(height: int, rank: int, world_size: int, tile: int = 32):
     return rows[((rows // tile) % world_size) == rank]
 
 
+class ImageGather:
+    """Final gather of a tile-sharded frame ("no collective beyond the final gather").  ``tile_rows`` is a
+    pure function of (height, rank, world), so every rank knows every rank's rows up front: ONE
+    ``all_gather_into_tensor`` of the padded u8 row bands per frame and one precomputed index scatter -- no size
+    exchange, no host synchronisation."""
+
+    def __init__(self, height: int, width: int, channels: int, rank: int, world_size: int, device, dtype=torch.uint8,
+                 tile: int = 32, group=None):
+        self.group, self.world, self.rank = group, world_size, rank
+        rows = [tile_rows(height, r, world_size, tile) for r in range(world_size)]
+        self.max_rows = max(int(r.numel()) for r in rows)
+        self.n_local = int(rows[rank].numel())
+        self.local_rows = rows[rank].to(device)
+        self.send = torch.zeros(self.max_rows, width, channels, dtype=dtype, device=device)
+        self.recv = torch.empty(world_size, self.max_rows, width, channels, dtype=dtype, device=device)
+        # where row k of rank r's band goes in the full image, and which (r, k) pairs are real rows
+        src = torch.cat([torch.arange(r.numel()) + i * self.max_rows for i, r in enumerate(rows)])
+        self.src = src.to(device)
+        self.dst = torch.cat(rows).to(device)
+        self.out = torch.empty(height, width, channels, dtype=dtype, device=device)
+
+    def __call__(self, local_pixels: torch.Tensor) -> torch.Tensor:
+        """local_pixels [n_local_rows, W, C] -> the full image [H, W, C] on every rank."""
+        if self.world == 1 or not (dist.is_available() and dist.is_initialized()):
+            self.out[self.local_rows] = local_pixels
+            return self.out
+        self.send[: self.n_local].copy_(local_pixels)
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        else:
+            parts = [torch.empty_like(self.send) for _ in range(self.world)]
+            dist.all_gather(parts, self.send, group=self.group)
+            self.recv.copy_(torch.stack(parts))
+        self.out[self.dst] = self.recv.reshape(self.world * self.max_rows, *self.recv.shape[2:])[self.src]
+        return self.out
+
+
 def gather_image(local_rows: torch.Tensor, local_pixels: torch.Tensor, height: int, group=None) -> torch.Tensor:
     """All-gather the per-rank row bands into the full image [height, W, C] on every rank."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1

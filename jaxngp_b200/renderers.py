@@ -143,7 +143,8 @@ class InferenceRenderer:
         self._rays_desc = descriptors.make_training_rays_descriptor(N, cam["width"], cam["height"], 1, cam["fx"], cam["fy"],
                                                                     cam["cx"], cam["cy"], bound)
         self._graph = None
-        self._max_passes = _max_loop_passes(N, n, diagonal_n_steps, bound, self.cap)
+        self._host_counters = self._host_events = None
+        self._max_passes = 2 * _max_loop_passes(N, n, diagonal_n_steps, bound, self.cap)
 
     def _iteration(self):
         """One pass of the slot-refill loop (cuda.py:180-241): three custom calls, no torch glue -- the scatters back
@@ -202,9 +203,14 @@ class InferenceRenderer:
             for t, s in zip((self.t_starts, self.rays_rgbd, self.rays_T, self.terminated, self.indices, self.next_in), state):
                 t.copy_(s)  # undo the two warm-up iterations
             self.counters.zero_()
-        n_rendered = 0
-        passes = 0
-        while n_rendered < self.N:  # cuda.py:326-361
+        # cuda.py:326-361 with the host check one batch behind: the counter of batch k is copied to pinned memory and
+        # read while batch k+1 already runs, so the GPU never waits for the host.  The one surplus batch enqueued
+        # when the frame turns out to be complete runs on idle slots only (no ray index < N): no state changes.
+        if self._host_counters is None:
+            self._host_counters = [torch.zeros(2, dtype=torch.int64).pin_memory() for _ in range(2)]
+            self._host_events = [torch.cuda.Event() for _ in range(2)]
+        n_rendered, passes, batch, pending = 0, 0, 0, None
+        while True:
             iters = 2 ** (int(math.log2(max(1, (self.N - n_rendered) // self.n))) + 1)
             passes += iters
             if passes > self._max_passes:
@@ -212,7 +218,16 @@ class InferenceRenderer:
                                    f"{self._max_passes}, counters {self.counters.tolist()}): the loop is not making progress")
             for _ in range(iters):
                 self._graph.replay()
-            n_rendered = int(self.counters[0])  # one host read per batch of iterations
+            slot = batch & 1
+            self._host_counters[slot].copy_(self.counters, non_blocking=True)
+            self._host_events[slot].record()
+            if pending is not None:
+                self._host_events[pending].synchronize()
+                n_rendered = int(self._host_counters[pending][0])
+                if n_rendered >= self.N:
+                    break
+            pending = slot
+            batch += 1
         rgb = (self.rays_rgbd[: self.N, :3].clamp(0, 1) * 255 + 0.5).to(torch.uint8)
         return rgb, self.rays_rgbd[: self.N, 3]
 

@@ -42,6 +42,8 @@ def _worker(rank, world, port, q):
     rows = dp.tile_rows(H, rank, world, tile=8)
     local = (rows[:, None] * Wd + torch.arange(Wd)[None]).to(torch.float32)[..., None]
     img = dp.gather_image(rows, local, H)
+    fast = dp.ImageGather(H, Wd, 1, rank, world, "cpu", dtype=torch.float32, tile=8)(local)
+    assert torch.equal(fast, img)
     perms = bench.host_perms(2, rank)
     q.put((rank, flat.sum().item(), grid.tolist(), img[..., 0].tolist(), rows.tolist(), perms[:, :64].tolist()))
     dist.destroy_process_group()
