@@ -9,8 +9,10 @@
 //              SWIZZLE_128B_BASE32B exists (32-byte chunks, c ^ (r & 3)).  Forward B operands (weights with N = out,
 //              K = in) and both wgrad operands (activations / deltas with K = the sample index).
 // The two swizzles differ, so a tf32 tensor read in both orientations needs two shared-memory copies (16-bit
-// operands use SWIZZLE_128B for both) -- the reason the TF32 backward pass of csrc/mlp.cu stays on mma.sync for
-// now: its activations + deltas + weights in both formats exceed 227 KB at 128-sample tiles.
+// operands use SWIZZLE_128B for both).  That shapes the kernels: the forward (mlp_fwd_umma.cu) only needs K-major
+// activations + MN-major weights; the backward (mlp.cu) keeps its per-warp input-gradient chain on mma.sync and gives
+// the tensor core the weight gradients, whose operands (activations, deltas) are both MN-major -- activations +
+// deltas + weights in BOTH formats would exceed 227 KB at 128-sample tiles.
 #pragma once
 #include <cstdint>
 

@@ -148,18 +148,22 @@ class Trainer:
         rays and the occupancy bitfield only), so the next step's can overlap this step's gradient exchange and
         optimizer (train_step)."""
         sc = self.scene
+        bg = None
         if noises is None:
-            noises = torch.rand(self.n_rays, device=self.device)  # cuda.py:118-122
+            # one generator launch for both random inputs of the step: the march perturbations (cuda.py:118-122) and
+            # the random backgrounds the loss composites onto (_utils.py:134-136), which travel with the marched batch
+            rnd = torch.rand(4 * self.n_rays, device=self.device)
+            noises, bg = rnd[: self.n_rays], rnd[self.n_rays:].view(self.n_rays, 3)
         o, d, t_starts, t_ends = trainops.make_training_rays(perm, sc.transforms, sc.cam, synthetic.BOUND)
         return march_rays(self.total_samples, synthetic.DIAGONAL_N_STEPS, synthetic.K, synthetic.G, synthetic.BOUND,
-                          synthetic.STEPSIZE_PORTION, o, d, t_starts, t_ends, noises, self.grid.occupancy, raw=True)
+                          synthetic.STEPSIZE_PORTION, o, d, t_starts, t_ends, noises, self.grid.occupancy, raw=True) + (bg,)
 
     def _compute_body(self, perm, marched, bg=None):
         """Encoder + MLP forward, integrate, loss, and the whole backward into the flat gradient buffer."""
         sc = self.scene
+        nxt, exc, ray_is_valid, rays_n, rays_start, _, xyzs, dirs, dss, z_vals, marched_bg = marched
         if bg is None:
-            bg = torch.rand(self.n_rays, 3, device=self.device)  # random_bg, _utils.py:134-136
-        nxt, exc, ray_is_valid, rays_n, rays_start, _, xyzs, dirs, dss, z_vals = marched
+            bg = marched_bg if marched_bg is not None else torch.rand(self.n_rays, 3, device=self.device)  # random_bg, _utils.py:134-136
         if self.fused_encoder:  # encoder gather feeding the MLP's first tensor-core fragments (enc written once, for the backward)
             drgbs, enc = nerf_mod.fused_forward(self.levels, xyzs, synthetic.BOUND, self.table, dirs, self.mlp_flat, want_enc=True)
         else:
