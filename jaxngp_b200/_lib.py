@@ -13,7 +13,7 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libngp_b200.so")
+LIB_PATH = os.environ.get("NGP_B200_LIB") or os.path.join(_HERE, "lib", "libngp_b200.so")  # override: A/B builds
 CSRC = os.path.join(_HERE, "csrc")
 
 #: every symbol include/ngp_b200.h declares

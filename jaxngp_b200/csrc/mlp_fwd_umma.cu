@@ -14,7 +14,7 @@
 //            group's mbarrier
 //   epilog : thread r reads TMEM lane r (tcgen05.ld 32x32b), applies ReLU / exp / SH / sigmoid, rounds to tf32 and
 //            writes row r of the next layer's A panel (P_B, or P_A again for [x | SH(dir)])
-// Every MMA is awaited before its epilogue, so two panels (16 KB + 32 KB) and 64 TMEM columns per group suffice.
+// Every MMA is awaited before its epilogue, so ONE 32 KB panel pair and 64 TMEM columns per group suffice.
 // Instruction budget per 16 samples: ~1300 warp instructions against ~2100 for the mma.sync kernel, whose B-fragment
 // shared-memory loads, HMMA issue and fragment conversions the tensor core now does asynchronously.
 #include "common.cuh"
@@ -24,15 +24,20 @@
 namespace ngp {
 namespace {
 
-constexpr int kGroups = 3, kGroupThreads = 128, kThreadsU = kGroups * kGroupThreads;
+#ifndef NGP_UMMA_GROUPS
+#define NGP_UMMA_GROUPS 4
+#endif
+constexpr int kGroups = NGP_UMMA_GROUPS, kGroupThreads = 128, kThreadsU = kGroups * kGroupThreads;
 constexpr uint32_t kTile = 128;
-constexpr uint32_t kPA = kTile * 128u, kPB = 2 * kTile * 128u, kGroupBytes = kPA + kPB;  // 48 KB per group
+// one 32 KB panel pair per group: every MMA is awaited before the epilogue that overwrites its A operand, so the
+// 32-wide inputs (enc, then [x | SH]) live in the first panel of the pair the 64-wide activations use
+constexpr uint32_t kPA = kTile * 128u, kPB = 2 * kTile * 128u, kGroupBytes = kPB;
 // weight panels (MN-major: row = input feature k, 32 output features per 128-byte row; narrow layers zero-padded to 32)
 constexpr uint32_t WB0 = 0, WB1 = WB0 + 2 * 32 * 128, WB2 = WB1 + 64 * 128, WB3 = WB2 + 2 * 32 * 128,
                    WB4 = WB3 + 2 * 64 * 128, kWBytes = WB4 + 64 * 128;  // 49152
 constexpr int G_W0 = 0, G_W1 = G_W0 + 32 * 64, G_W2 = G_W1 + 64 * 16, G_W3 = G_W2 + 32 * 64, G_W4 = G_W3 + 64 * 64;
-constexpr uint32_t kTmemColsPerGroup = 64, kTmemCols = 256;
-constexpr size_t kFwdUmmaSmem = 1024 + kWBytes + kGroups * kGroupBytes;  // 197,632 B
+constexpr uint32_t kTmemColsPerGroup = 64, kTmemCols = kGroups <= 4 ? 256 : 512;
+constexpr size_t kFwdUmmaSmem = 1024 + kWBytes + kGroups * kGroupBytes;
 
 // round to tf32 (nearest, ties away from zero -- cvt.rna.tf32.f32 without its NaN/Inf special case): 2 instructions
 __device__ __forceinline__ uint32_t tf32r(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
@@ -119,8 +124,8 @@ __global__ void __launch_bounds__(kThreadsU, 1) nerf_fused_forward_umma_kernel(c
     __shared__ uint64_t bars[kGroups];
     __shared__ uint32_t tmem_slot;
     __shared__ hg::LevelMeta s_meta[16];
-    const uint32_t tid = threadIdx.x, group = tid / kGroupThreads, r = tid % kGroupThreads, gw = r >> 5, lane = tid & 31u;
-    uint8_t *PA = base + kWBytes + group * kGroupBytes, *PB = PA + kPA;
+    const uint32_t tid = threadIdx.x, group = tid / kGroupThreads, r = tid % kGroupThreads, gw = r >> 5;
+    uint8_t *PB = base + kWBytes + group * kGroupBytes, *PA = PB;
 
     stage_weight(wsm + WB0, weights + G_W0, 32, 64, 64);
     stage_weight(wsm + WB1, weights + G_W1, 64, 16, 32);
