@@ -290,6 +290,9 @@ def dominant_kernel_roofline(tr, perm, flush):
         ("integrate_rays", lambda: _integrate_fwd(rs, rn, bg, dss, zs, drgbs), used * 24 + N_RAYS * 40, "24 B/sample + 40 B/ray"),
         ("huber_loss_grad", lambda: trainops.huber_loss_grad(fin, valid, perm, sc.rgbas_u8, bg), N_RAYS * (16 + 1 + 4 + 4 + 12 + 16), "53 B/ray"),
         ("integrate_rays_backward", lambda: _integrate_bwd(synthetic.NEAR, rs, rn, bg, dss, zs, drgbs, fin, opac, d_fin), used * 44 + N_RAYS * 68 + n * 20, "44 B/sample + 68 B/ray + zero-fill 20 B/slot"),
+        ("integrate_loss_fused (replaces the three above in the step)",
+         lambda: trainops.integrate_loss_fused(synthetic.NEAR, rs, rn, bg, dss, zs, drgbs, valid, perm, sc.rgbas_u8),
+         used * 44 + N_RAYS * 70 + n * 16, "44 B/sample + 70 B/ray + zero-fill 16 B/slot"),
         ("nerf_mlp_backward", lambda: nerf_mod.mlp_backward(enc, dirs, tr.mlp_flat, d_drgbs), n * (128 + 12 + 16 + 128), "284 B/sample; 56 kFLOP/sample"),
         ("hashgrid_a1_backward", lambda: encoders.hashgrid_backward(tr.levels, xyzs, 1.0, d_enc, out=tr.table_grad), n * 1164 + tr.table_numel * 4, "1164 B/point + table zero-fill"),
         ("adam_step", lambda: _lib.call("ngp_adam_step", [tr.step_dev, tr.flat_params[tr.shard_lo:tr.shard_hi], tr.flat_grads[tr.shard_lo:tr.shard_hi], tr.adam_m, tr.adam_v], tr.adam_desc), P * 28, "28 B/param"),

@@ -99,6 +99,28 @@ __device__ __forceinline__ uint32_t warp_sum_u32(uint32_t v) { return __reduce_a
 __device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
+// Huber loss (optax.huber_loss, mean over the three channels) of one ray's colour against its ground-truth pixel
+// composited onto the ray's background (utils/data.py:459-463), and its gradient scaled by inv_n = 1 / n_valid
+// (app/nerf/_utils.py:151-165).  Shared by huber_loss_grad (trainops.cu) and the fused integrate + loss kernel.
+__device__ __forceinline__ float4 huber_ray(float4 pred, uchar4 px, float bg0, float bg1, float bg2, float delta, float inv_n,
+                                            float &per_ray) {
+    const float a = (float)px.w / 255.f;
+    const float gt[3] = {(float)px.x / 255.f, (float)px.y / 255.f, (float)px.z / 255.f};
+    const float pr[3] = {pred.x, pred.y, pred.z}, bg[3] = {bg0, bg1, bg2};
+    float gr[3];
+    per_ray = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float target = gt[c] * a + bg[c] * (1.f - a);
+        const float err = pr[c] - target;
+        const float ae = fabsf(err), q = fminf(ae, delta);
+        per_ray += 0.5f * q * q + delta * (ae - q);
+        gr[c] = fminf(fmaxf(err, -delta), delta) * (1.f / 3.f) * inv_n;
+    }
+    per_ray *= (1.f / 3.f);
+    return make_float4(gr[0], gr[1], gr[2], 0.f);
+}
+
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }

@@ -222,6 +222,152 @@ __global__ void __launch_bounds__(kBlock) integrate_rays_backward_kernel(
     }
 }
 
+__global__ void __launch_bounds__(kBlock) count_valid_rays_kernel(uint32_t n, const uint8_t *__restrict__ valid,
+                                                                   uint32_t *__restrict__ n_valid) {
+    uint32_t c = 0;
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) c += valid[i] ? 1u : 0u;
+    c = warp_sum_u32(c);
+    if ((threadIdx.x & 31u) == 0 && c) atomicAdd(n_valid, c);
+}
+
+// Training fast path (ngp_integrate_loss_fused): integrate_rays, the Huber loss against the ground-truth pixels and
+// integrate_rays_backward for the colour/density gradient in ONE pass per ray -- the warp that composited a ray
+// keeps its result in registers, forms dL/dfinal from it and walks the ray's samples (still in L1/L2) a second time
+// for dL/ddrgbs.  Same arithmetic in the same order as the three ops (final_rgbds, opacities and dL_ddrgbs come out
+// bit-identical); the background / depth gradients nothing consumes in training are not produced.
+__global__ void __launch_bounds__(kBlock) integrate_loss_fused_kernel(
+    NgpIntegrateLossDescriptor p, const uint32_t *__restrict__ rays_sample_startidx, const uint32_t *__restrict__ rays_n_samples,
+    const float *__restrict__ bgs, const float *__restrict__ dss, const float *__restrict__ z_vals,
+    const float4 *__restrict__ drgbs, const uint8_t *__restrict__ valid, const int32_t *__restrict__ perm,
+    const uchar4 *__restrict__ rgbas, const uint32_t *__restrict__ n_valid_ptr, uint32_t *__restrict__ measured_batch_size,
+    float4 *__restrict__ final_rgbds, float *__restrict__ final_opacities, float4 *__restrict__ dL_ddrgbs,
+    float *__restrict__ loss) {
+    const uint32_t n_rays = p.n_rays;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warps_total = gridDim.x * (kBlock / 32);
+    const uint32_t warp_global = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5);
+    const float inv_n = 1.f / (float)__ldg(n_valid_ptr);
+    uint32_t composited = 0;
+    float loss_acc = 0.f;
+
+    // rays without samples: colour = background, no sample gradients; they still count in the loss
+    for (uint32_t ray = blockIdx.x * kBlock + threadIdx.x; ray < n_rays; ray += gridDim.x * kBlock) {
+        if (__ldg(rays_n_samples + ray) == 0) {
+            const float b0 = __ldg(bgs + 3 * (size_t)ray + 0), b1 = __ldg(bgs + 3 * (size_t)ray + 1), b2 = __ldg(bgs + 3 * (size_t)ray + 2);
+            const float4 out = make_float4(b0, b1, b2, 0.f);
+            final_opacities[ray] = 0.f;
+            final_rgbds[ray] = out;
+            if (valid[ray]) {
+                float per_ray;
+                huber_ray(out, __ldg(rgbas + (uint32_t)__ldg(perm + ray)), b0, b1, b2, p.delta, inv_n, per_ray);
+                loss_acc += per_ray;
+            }
+        }
+    }
+    for (uint32_t base = 0; base < n_rays; base += warps_total * 32u) {
+        const uint32_t cand = base + lane * warps_total + warp_global;
+        const uint32_t cand_n = cand < n_rays ? __ldg(rays_n_samples + cand) : 0u;
+        uint32_t todo = __ballot_sync(0xffffffffu, cand_n != 0u);
+        while (todo) {
+            const uint32_t q = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t ray = base + q * warps_total + warp_global;
+            const uint32_t n = __shfl_sync(0xffffffffu, cand_n, q);
+            const uint32_t start = __ldg(rays_sample_startidx + ray);
+            const float b0 = __ldg(bgs + 3 * (size_t)ray + 0), b1 = __ldg(bgs + 3 * (size_t)ray + 1), b2 = __ldg(bgs + 3 * (size_t)ray + 2);
+            // ---- forward (integrate_rays_kernel)
+            float T = 1.f, r = 0.f, g = 0.f, b = 0.f, depth = 0.f;
+            {
+                SampleRegs cur = load_sample(drgbs, z_vals, dss, start + lane, lane < n);
+                for (uint32_t c = 0; c < n && T > kTThreshold; c += 32) {
+                    const uint32_t count = min(32u, n - c);
+                    const SampleRegs nxt = load_sample(drgbs, z_vals, dss, start + c + 32u + lane, c + 32u + lane < n);
+                    float one_minus = 1.f, alpha = 0.f;
+                    if (lane < count) {
+                        alpha = 1.f - __expf(-cur.v.x * cur.dt);
+                        one_minus = 1.f - alpha;
+                    }
+                    float Tb;
+                    bool active;
+                    composited += transmittance_chain(one_minus, count, lane, T, Tb, active);
+                    const float w = active ? Tb * alpha : 0.f;
+                    r += w * cur.v.y;
+                    g += w * cur.v.z;
+                    b += w * cur.v.w;
+                    depth += w * cur.z;
+                    cur = nxt;
+                }
+            }
+            r = warp_sum(r);
+            g = warp_sum(g);
+            b = warp_sum(b);
+            depth = warp_sum(depth);
+            const float opac = 1.f - T;
+            float4 fin;
+            if (T <= kTThreshold) {
+                const float idenom = 1.f / opac;
+                fin = make_float4(r * idenom, g * idenom, b * idenom, depth * idenom);
+            } else {
+                fin = make_float4(r + T * b0, g + T * b1, b + T * b2, depth);
+            }
+            if (lane == 0) {
+                final_opacities[ray] = opac;
+                final_rgbds[ray] = fin;
+            }
+            // ---- loss and its gradient (huber_loss_grad_kernel)
+            float4 dfin = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid[ray]) {
+                float per_ray;
+                dfin = huber_ray(fin, __ldg(rgbas + (uint32_t)__ldg(perm + ray)), b0, b1, b2, p.delta, inv_n, per_ray);
+                if (lane == 0) loss_acc += per_ray;
+            }
+            // ---- backward (integrate_rays_backward_kernel), colour / density gradient only
+            const bool terminated = opac >= 1.f - kTThreshold;
+            const float bgw = terminated ? 0.f : 1.f - opac;
+            const float bg0 = b0 * bgw, bg1 = b1 * bgw, bg2 = b2 * bgw;
+            float cr = 0.f, cg = 0.f, cb = 0.f, cd = 0.f;
+            T = 1.f;
+            SampleRegs cur = load_sample(drgbs, z_vals, dss, start + lane, lane < n);
+            for (uint32_t c = 0; c < n && T > kTThreshold; c += 32) {
+                const uint32_t count = min(32u, n - c);
+                const uint32_t s = start + c + lane;
+                const SampleRegs nxt = load_sample(drgbs, z_vals, dss, s + 32u, c + 32u + lane < n);
+                float one_minus = 1.f, alpha = 0.f;
+                if (lane < count) {
+                    alpha = 1.f - __expf(-cur.v.x * cur.dt);
+                    one_minus = 1.f - alpha;
+                }
+                float Tb;
+                bool active;
+                transmittance_chain(one_minus, count, lane, T, Tb, active);
+                const float w = active ? Tb * alpha : 0.f;
+                const float Ta = Tb * one_minus;
+                const float ir = cr + warp_incl_scan(w * cur.v.y, lane);
+                const float ig = cg + warp_incl_scan(w * cur.v.z, lane);
+                const float ib = cb + warp_incl_scan(w * cur.v.w, lane);
+                const float id = cd + warp_incl_scan(w * cur.z, lane);
+                cr = __shfl_sync(0xffffffffu, ir, 31);
+                cg = __shfl_sync(0xffffffffu, ig, 31);
+                cb = __shfl_sync(0xffffffffu, ib, 31);
+                cd = __shfl_sync(0xffffffffu, id, 31);
+                if (active) {
+                    const float z = cur.z;
+                    const float acc = dfin.x * (Ta * cur.v.y - (fin.x - ir) - bg0) + dfin.y * (Ta * cur.v.z - (fin.y - ig) - bg1) +
+                                      dfin.z * (Ta * cur.v.w - (fin.z - ib) - bg2) + dfin.w * (Ta * z - (fin.w - id));
+                    const float dsig = cur.dt * acc;
+                    const float reg = (cur.v.x > 4e-5f && z < p.near_distance) ? 1e-4f : 0.f;
+                    const float scal = fminf(z * z, 1.f);
+                    dL_ddrgbs[s] = make_float4(scal * dsig + reg, w * dfin.x, w * dfin.y, w * dfin.z);
+                }
+                cur = nxt;
+            }
+        }
+    }
+    if (lane == 0 && composited) atomicAdd(measured_batch_size, composited);
+    loss_acc = warp_sum(loss_acc);
+    if (lane == 0 && loss_acc != 0.f) atomicAdd(loss, loss_acc * inv_n);
+}
+
 // kInPlace (renderer fast path, ngp_integrate_rays_inference_inplace): results go straight to row `ray` of the frame
 // state (the reference scatters them afterwards, integrating/__init__.py:108-109; every ray belongs to one slot) and
 // the terminated-ray and sample counts are ACCUMULATED into 64-bit counters instead of being returned per call.
@@ -396,6 +542,38 @@ void ngp_integrate_rays_inference_inplace(cudaStream_t stream, void **buffers, c
     integrate_rays_inference_kernel<true><<<div_up(desc->n_rays, kBlock), kBlock, 0, stream>>>(
         *desc, rays_bg, rays_rgbd, rays_T, ns, indices, dss, z_vals, drgbs, nullptr, terminated, rays_rgbd, rays_T, counters);
     check_launch("integrate_rays_inference_inplace");
+}
+
+void ngp_integrate_loss_fused(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *desc = descriptor<NgpIntegrateLossDescriptor>(opaque, opaque_len, "integrate_loss_fused");
+    if (!desc) return;
+    BufferCursor b{buffers};
+    const uint32_t *startidx = b.next<const uint32_t>();
+    const uint32_t *ns = b.next<const uint32_t>();
+    const float *bgs = b.next<const float>();
+    const float *dss = b.next<const float>();
+    const float *z_vals = b.next<const float>();
+    const float4 *drgbs = b.next<const float4>();
+    const uint8_t *valid = b.next<const uint8_t>();
+    const int32_t *perm = b.next<const int32_t>();
+    const uchar4 *rgbas = b.next<const uchar4>();
+    uint32_t *mbs = b.next<uint32_t>();
+    float4 *final_rgbds = b.next<float4>();
+    float *final_opacities = b.next<float>();
+    float4 *dL_dd = b.next<float4>();
+    float *loss = b.next<float>();
+    uint32_t *n_valid = b.next<uint32_t>();
+    NGP_CUDA_OK(cudaMemsetAsync(mbs, 0, sizeof(uint32_t), stream), "integrate_loss_fused");
+    NGP_CUDA_OK(cudaMemsetAsync(n_valid, 0, sizeof(uint32_t), stream), "integrate_loss_fused");
+    NGP_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), stream), "integrate_loss_fused");
+    NGP_CUDA_OK(cudaMemsetAsync(dL_dd, 0, (size_t)desc->total_samples * 4 * sizeof(float), stream), "integrate_loss_fused");
+    if (desc->n_rays == 0) return;
+    count_valid_rays_kernel<<<min(div_up(desc->n_rays, kBlock), 148u * 4u), kBlock, 0, stream>>>(desc->n_rays, valid, n_valid);
+    integrate_loss_fused_kernel<<<min(div_up(desc->n_rays, kBlock), 148u * 8u), kBlock, 0, stream>>>(
+        *desc, startidx, ns, bgs, dss, z_vals, drgbs, valid, perm, rgbas, n_valid, mbs, final_rgbds, final_opacities, dL_dd, loss);
+    check_launch("integrate_loss_fused");
 }
 
 }  // extern "C"

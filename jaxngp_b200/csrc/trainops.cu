@@ -77,21 +77,8 @@ __global__ void __launch_bounds__(kBlock) huber_loss_grad_kernel(NgpHuberLossDes
         if (valid[i]) {
             const float4 pred = __ldg(final_rgbds + i);
             const uchar4 px = __ldg(rgbas + (uint32_t)__ldg(perm + i));
-            const float a = (float)px.w / 255.f;
-            const float gt[3] = {(float)px.x / 255.f, (float)px.y / 255.f, (float)px.z / 255.f};
-            const float pr[3] = {pred.x, pred.y, pred.z};
-            float gr[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float bg = __ldg(bgs + 3 * (size_t)i + c);
-                const float target = gt[c] * a + bg * (1.f - a);  // utils/data.py:459-463
-                const float err = pr[c] - target;
-                const float ae = fabsf(err), q = fminf(ae, d.delta);
-                per_ray += 0.5f * q * q + d.delta * (ae - q);  // optax.huber_loss
-                gr[c] = fminf(fmaxf(err, -d.delta), d.delta) * (1.f / 3.f) * inv_n;
-            }
-            per_ray *= (1.f / 3.f);
-            g = make_float4(gr[0], gr[1], gr[2], 0.f);
+            g = huber_ray(pred, px, __ldg(bgs + 3 * (size_t)i + 0), __ldg(bgs + 3 * (size_t)i + 1), __ldg(bgs + 3 * (size_t)i + 2),
+                          d.delta, inv_n, per_ray);
         }
         dL_dfinal[i] = g;
     }

@@ -106,5 +106,9 @@ def make_training_rays_descriptor(n_rays, width, height, n_views, fx, fy, cx, cy
                        _u32(n_views, "n_views"), float(fx), float(fy), float(cx), float(cy), float(bound))
 
 
+def make_integrate_loss_descriptor(n_rays, total_samples, near_distance, delta):
+    return struct.pack("<2I2f", _u32(n_rays, "n_rays"), _u32(total_samples, "total_samples"), float(near_distance), float(delta))
+
+
 def make_huber_loss_descriptor(n_rays, delta):
     return struct.pack("<If", _u32(n_rays, "n_rays"), float(delta))

@@ -91,6 +91,7 @@ class Trainer:
         self.levels = self.nerf.position_encoder.levels
         self.fused_mlp = fused_mlp
         self.fused_glue = fused_mlp if fused_glue is None else fused_glue
+        self.fused_loss = True  # ngp_integrate_loss_fused instead of integrate_rays / huber_loss_grad / integrate_rays_backward
         self._flatten_parameters()
         self.fused_encoder = (fused_mlp and nerf_mod.fused_supported(self.levels, self.table)) if fused_encoder is None else fused_encoder
         self.scene = scene if scene is not None else Scene(self.device)
@@ -169,10 +170,14 @@ class Trainer:
         else:
             enc = encoders.hashgrid_forward(self.levels, xyzs, synthetic.BOUND, self.table)
             drgbs = nerf_mod.mlp_forward(enc, dirs, self.mlp_flat)
-        effective, final_rgbds, final_opac = _integrate_fwd(rays_start, rays_n, bg, dss, z_vals, drgbs)
-        d_final, loss, n_valid = trainops.huber_loss_grad(final_rgbds, ray_is_valid, perm, sc.rgbas_u8, bg)
-        _, _, d_drgbs = _integrate_bwd(synthetic.NEAR, rays_start, rays_n, bg, dss, z_vals, drgbs, final_rgbds,
-                                       final_opac, d_final)
+        if self.fused_loss:  # integrate, loss and integrate backward in one pass per ray (same bits as the three ops)
+            effective, final_rgbds, final_opac, d_drgbs, loss, n_valid = trainops.integrate_loss_fused(
+                synthetic.NEAR, rays_start, rays_n, bg, dss, z_vals, drgbs, ray_is_valid, perm, sc.rgbas_u8)
+        else:
+            effective, final_rgbds, final_opac = _integrate_fwd(rays_start, rays_n, bg, dss, z_vals, drgbs)
+            d_final, loss, n_valid = trainops.huber_loss_grad(final_rgbds, ray_is_valid, perm, sc.rgbas_u8, bg)
+            _, _, d_drgbs = _integrate_bwd(synthetic.NEAR, rays_start, rays_n, bg, dss, z_vals, drgbs, final_rgbds,
+                                           final_opac, d_final)
         d_enc, _ = nerf_mod.mlp_backward(enc, dirs, self.mlp_flat, d_drgbs, d_weights=self.mlp_grad)
         encoders.hashgrid_backward(self.levels, xyzs, synthetic.BOUND, d_enc, out=self.table_grad)
         return dict(loss=loss[0], n_valid_rays=n_valid[0], measured_batch_size_before_compaction=(nxt - exc)[0],

@@ -152,6 +152,34 @@ def test_fused_mlp_matches_fp32_reference():
     torch.backends.cuda.matmul.allow_tf32 = True
 
 
+def test_fused_integrate_loss_matches_the_three_ops(small_scene):
+    """ngp_integrate_loss_fused against integrate_rays -> huber_loss_grad -> integrate_rays_backward on a marched
+    batch (rays with and without samples, early-terminated rays, an overflowing budget): same bits for the composited
+    colours, opacities and sample gradients, same counts, loss to summation-order error."""
+    from jaxngp_b200 import synthetic, trainops
+    from jaxngp_b200.trainer import Trainer
+    from jaxngp_b200.volrendjax.integrating import _integrate_bwd, _integrate_fwd
+    for n_rays, budget in ((1 << 14, 1 << 17), (1 << 14, 1 << 13)):
+        tr = Trainer(device=DEV, n_rays=n_rays, total_samples=budget, scene=small_scene, use_graph=False)
+        tr.grid.occupancy.copy_(small_scene.bitfield_gt)
+        gen = torch.Generator(device=DEV).manual_seed(2)
+        perm = torch.randint(0, small_scene.n_pixels, (n_rays,), device=DEV, generator=gen, dtype=torch.int32)
+        _, _, valid, rn, rs, _, xyzs, dirs, dss, zs, bg = tr._march_body(perm)
+        S = xyzs.shape[0]
+        drgbs = torch.rand(S, 4, device=DEV, generator=gen) * torch.tensor([40.0, 1.0, 1.0, 1.0], device=DEV)
+        drgbs[: S // 3, 0] *= 0.01  # thin media: rays that never saturate
+        eff, fin, opac = _integrate_fwd(rs, rn, bg, dss, zs, drgbs)
+        d_fin, loss, nv = trainops.huber_loss_grad(fin, valid, perm, small_scene.rgbas_u8, bg)
+        _, _, d_ref = _integrate_bwd(synthetic.NEAR, rs, rn, bg, dss, zs, drgbs, fin, opac, d_fin)
+        mbs, fin2, opac2, d2, loss2, nv2 = trainops.integrate_loss_fused(synthetic.NEAR, rs, rn, bg, dss, zs, drgbs, valid, perm,
+                                                                         small_scene.rgbas_u8)
+        assert int(mbs) == int(eff) and int(nv2) == int(nv) and int(nv) > 0
+        assert torch.equal(fin2, fin) and torch.equal(opac2, opac)
+        assert torch.equal(d2, d_ref)
+        assert abs(float(loss2) - float(loss)) <= 1e-5 * abs(float(loss)) + 1e-9
+        assert float(d_ref.abs().max()) > 0
+
+
 @pytest.mark.parametrize("n", [100, 128 * 148 * 3 + 77, (1 << 18) + 5])
 def test_mlp_backward_tcgen05_wgrad_matches_mma_sync_arm(n):
     """The two backward kernels share the per-warp register chain (d_enc: same bits) and differ in where the weight
