@@ -77,6 +77,9 @@ void ngp_pack_density_into_bits(cudaStream_t, void **, const char *, size_t);
  * Sample ranges are handed out in RAY ORDER (deterministic); the reference hands them out in
  * atomic arrival order (marching.cu:205).  See DESIGN.md "march_rays compaction". */
 void ngp_march_rays(cudaStream_t, void **, const char *, size_t);
+/* Launch hint for the calling host thread: persistent CTAs per SM of the following ngp_march_rays launches
+ * (0 = default, 4).  A caller that overlaps the march with other kernels uses 1 so that it runs underneath them. */
+void ngp_b200_set_march_ctas_per_sm(int ctas_per_sm);
 
 /* replaces volrendjax::march_rays_inference (volrend.h:135-140, marching.cu:524-604)
  * in : rays_o f32[N,3], rays_d f32[N,3], t_starts f32[N], t_ends f32[N], bitfield u8[..],

@@ -23,7 +23,8 @@ OPS = (
     "ngp_integrate_rays_inference", "ngp_hashgrid_encode", "ngp_hashgrid_encode_backward",
     "ngp_hashgrid_a1_forward", "ngp_hashgrid_a1_backward", "ngp_adam_step", "ngp_ogrid_sample_positions", "ngp_ogrid_decay_max", "ngp_ogrid_threshold", "ngp_nerf_mlp_forward", "ngp_nerf_mlp_backward", "ngp_nerf_mlp_backward_mma", "ngp_nerf_fused_forward", "ngp_nerf_fused_forward_umma", "ngp_umma_selftest", "ngp_make_training_rays", "ngp_huber_loss_grad", "ngp_integrate_loss_fused",
 )
-STATUS_SYMBOLS = ("ngp_b200_abi_version", "ngp_b200_last_status", "ngp_b200_last_error", "ngp_b200_clear_error")
+STATUS_SYMBOLS = ("ngp_b200_abi_version", "ngp_b200_last_status", "ngp_b200_last_error", "ngp_b200_clear_error",
+                  "ngp_b200_set_march_ctas_per_sm")
 
 _lib = None
 launch_count = 0  # number of custom calls issued through this binding (bench.py reports it)
@@ -59,6 +60,8 @@ def lib():
         _lib.ngp_b200_last_status.restype = C.c_int
         _lib.ngp_b200_last_error.restype = C.c_char_p
         _lib.ngp_b200_clear_error.restype = None
+        _lib.ngp_b200_set_march_ctas_per_sm.restype = None
+        _lib.ngp_b200_set_march_ctas_per_sm.argtypes = [C.c_int]
     return _lib
 
 

@@ -735,7 +735,13 @@ __global__ void __launch_bounds__(128) march_rays_skip_empty_kernel(
 }  // namespace
 }  // namespace ngp
 
+namespace ngp {
+thread_local int g_march_ctas_per_sm = 0;  // 0 = default (4)
+}
+
 extern "C" {
+
+void ngp_b200_set_march_ctas_per_sm(int ctas_per_sm) { ngp::g_march_ctas_per_sm = ctas_per_sm; }
 
 void ngp_march_rays(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
     using namespace ngp;
@@ -773,8 +779,21 @@ void ngp_march_rays(cudaStream_t stream, void **buffers, const char *opaque, siz
         auto *ws = static_cast<MarchScratch *>(workspace(stream, ws_bytes));
         if (!ws) return;
         NGP_CUDA_OK(cudaMemsetAsync(ws, 0, ws_bytes, stream), "march_rays");
-        // persistent grid: 4 CTAs of 8 warps per SM keep ~4.7k rays in flight, in ray order
-        const unsigned grid = min(num_tiles, 148u * 4u);
+        // persistent grid: 4 CTAs of 8 warps per SM keep ~4.7k rays in flight, in ray order; a caller that runs the
+        // march underneath other kernels (trainer.py prefetches the next batch) asks for fewer so that it does not
+        // crowd them out (ngp_b200_set_march_ctas_per_sm)
+        const unsigned per_sm = g_march_ctas_per_sm > 0 ? (unsigned)g_march_ctas_per_sm : 4u;
+        {   // An SM only hosts CTAs of one shared-memory carve-out at a time.  The fused MLP backward needs the
+            // largest one (225 KB), so a march running underneath it must ask for the same configuration or the
+            // backward's CTAs wait until the persistent march CTAs have left their SMs.  Costs the march nothing
+            // measurable: its working set (the 256 KB bitfield) is an L2 hit either way.
+            static bool configured = false;  // benign race: idempotent
+            if (!configured) {
+                cudaFuncSetAttribute(march_rays_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                configured = true;
+            }
+        }
+        const unsigned grid = min(num_tiles, 148u * per_sm);
         march_rays_kernel<<<grid, kMarchBlock, 0, stream>>>(*desc, ws, num_tiles, rays_o, rays_d, t_starts, t_ends,
                                                            noises, bitfield, next_loc, exceeded, valid, rays_n,
                                                            rays_start, idcs, xyzs, dirs, dss, z_vals);

@@ -91,6 +91,7 @@ class Trainer:
         self.levels = self.nerf.position_encoder.levels
         self.fused_mlp = fused_mlp
         self.fused_glue = fused_mlp if fused_glue is None else fused_glue
+        self.prefetch_march_ctas_per_sm = 1
         self.fused_loss = True  # ngp_integrate_loss_fused instead of integrate_rays / huber_loss_grad / integrate_rays_backward
         self._flatten_parameters()
         self.fused_encoder = (fused_mlp and nerf_mod.fused_supported(self.levels, self.table)) if fused_encoder is None else fused_encoder
@@ -109,9 +110,9 @@ class Trainer:
             eps_root=1e-15, weight_decay=1e-6, grad_scale=1.0 / world_size)
         self.use_graph = use_graph
         self._graph = self._march_graph = None
-        self._static_perm = torch.zeros(n_rays, dtype=torch.int32, device=self.device)
-        self._static_out = self._static_marched = None
+        self._static_perm = self._static_out = self._static_marched = None
         self._prefetched = None
+        self._slot = 0
 
     @property
     def occupancy(self):
@@ -252,10 +253,12 @@ class Trainer:
         """perm: int32 [n_rays] indices into the scene's pixels (device or pinned host tensor).  Returns
         device-side metrics (no host synchronisation).
 
-        ``next_perm`` (optional) is the batch of the FOLLOWING call: its ray generation and march are enqueued on a
-        side stream as soon as this step's backward has finished and run concurrently with this step's gradient
-        exchange and optimizer, which they do not depend on (same numbers as running them afterwards; a committed
-        density-grid update in between drops the prefetch)."""
+        ``next_perm`` (optional) is the batch of the FOLLOWING call.  Ray generation and march depend on the batch
+        and the occupancy bitfield only, not on the parameters, so they are enqueued on a side stream right away and
+        run underneath this whole step (forward, backward, gradient exchange, optimizer) instead of on its critical
+        path.  The marched batches are double-buffered (two march graphs, two compute graphs over their own static
+        buffers): the slot the side stream writes was last read by the PREVIOUS step's backward.  Same numbers as
+        marching afterwards; a committed density-grid update in between drops the prefetch."""
         self.step += 1
         if not self.use_graph or not self.fused_glue:
             out = self._step_body(perm)
@@ -264,44 +267,68 @@ class Trainer:
             return out
         main = torch.cuda.current_stream(self.device)
         if self._graph is None:
-            self._side = torch.cuda.Stream(device=self.device)
-            self._static_perm.copy_(perm, non_blocking=True)
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                for _ in range(2):  # warm-up on the capture stream (scratch blocks)
-                    self._compute_body(self._static_perm, self._march_body(self._static_perm))
-                    self._optimizer_step()
-                self._march_graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._march_graph, stream=self._side):
-                    self._static_marched = self._march_body(self._static_perm)
-                self._graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self._graph, stream=self._side):
-                    self._static_out = self._compute_body(self._static_perm, self._static_marched)
-            main.wait_stream(self._side)
-            self.step += 2
-            self._ev_march, self._ev_compute = torch.cuda.Event(), torch.cuda.Event()
-            self._prefetched = None
+            self._capture_graphs(perm, main)
+        cur = self._slot
         key = (perm.data_ptr(), perm.numel())
-        if self._prefetched is not None:
-            main.wait_event(self._ev_march)  # marched on the side stream during the previous optimizer step
-        if self._prefetched != key:
-            self._static_perm.copy_(perm, non_blocking=True)
-            self._march_graph.replay()
+        if self._prefetched == key:
+            main.wait_event(self._ev_march[cur])  # marched on the side stream during the previous step
+        else:
+            if self._prefetched is not None:  # a different batch was prefetched into this slot: let it finish first
+                main.wait_event(self._ev_march[cur])
+            self._static_perm[cur].copy_(perm, non_blocking=True)
+            self._march_graph[cur].replay()
         self._prefetched = None
-        self._graph.replay()
         if next_perm is not None:
-            self._ev_compute.record(main)
-            self._side.wait_event(self._ev_compute)  # the backward still reads this step's samples
+            nxt = 1 - cur
+            self._ev_free.record(main)  # everything that read slot `nxt` (the previous step) precedes this point
+            self._side.wait_event(self._ev_free)
             with torch.cuda.stream(self._side):
-                self._static_perm.copy_(next_perm, non_blocking=True)
-                self._march_graph.replay()
-                self._ev_march.record(self._side)
+                self._static_perm[nxt].copy_(next_perm, non_blocking=True)
+                self._march_graph[nxt].replay()
+                self._ev_march[nxt].record(self._side)
             self._prefetched = (next_perm.data_ptr(), next_perm.numel())
+        self._graph[cur].replay()
         self._optimizer_step()
-        return self._static_out
+        self._slot = 1 - cur
+        return self._static_out[cur]
+
+    def _capture_graphs(self, perm, main):
+        self._side = torch.cuda.Stream(device=self.device)
+        self._static_perm = [torch.zeros(self.n_rays, dtype=torch.int32, device=self.device) for _ in range(2)]
+        self._static_perm[0].copy_(perm, non_blocking=True)
+        self._static_perm[1].copy_(perm, non_blocking=True)
+        self._side.wait_stream(main)
+        self._march_graph, self._graph, self._static_marched, self._static_out = [], [], [], []
+        with torch.cuda.stream(self._side):
+            for _ in range(2):  # warm-up on the capture stream (scratch blocks)
+                self._compute_body(self._static_perm[0], self._march_body(self._static_perm[0]))
+                self._optimizer_step()
+            for slot in range(2):
+                mg = torch.cuda.CUDAGraph()
+                # the captured march runs underneath the step's other kernels: a small persistent grid keeps it from
+                # crowding them out of the SMs (its tiles are taken by ticket, so any grid size does all the work)
+                _lib.lib().ngp_b200_set_march_ctas_per_sm(self.prefetch_march_ctas_per_sm)
+                try:
+                    with torch.cuda.graph(mg, stream=self._side):
+                        marched = self._march_body(self._static_perm[slot])
+                finally:
+                    _lib.lib().ngp_b200_set_march_ctas_per_sm(0)
+                cg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(cg, stream=self._side):
+                    out = self._compute_body(self._static_perm[slot], marched)
+                self._march_graph.append(mg)
+                self._graph.append(cg)
+                self._static_marched.append(marched)
+                self._static_out.append(out)
+        main.wait_stream(self._side)
+        self.step += 2
+        self._ev_march = [torch.cuda.Event(), torch.cuda.Event()]
+        self._ev_free = torch.cuda.Event()
+        self._prefetched = None
+        self._slot = 0
 
     def release_graph(self):
-        """Drop the captured step graph (and its private memory pool)."""
+        """Drop the captured step graphs (and their private memory pools)."""
         self._graph = self._march_graph = None
         self._static_out = self._static_marched = None
         self._prefetched = None
@@ -323,7 +350,7 @@ class Trainer:
         if update_all is None:
             update_all = self.step < 256  # utils/types.py:1391-1392
         if commit and self._prefetched is not None:  # a prefetched march saw the old bitfield: redo it
-            torch.cuda.current_stream(self.device).wait_event(self._ev_march)
+            torch.cuda.current_stream(self.device).wait_event(self._ev_march[self._slot])
             self._prefetched = None
         g = self.grid
         shadow = None if commit else torch.empty_like(g.density)
