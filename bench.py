@@ -336,7 +336,7 @@ def dominant_kernel_roofline(tr, perm, flush):
 
 
 # ------------------------------------------------------------------------------------------- extras (C3, C4)
-def render_bench(dev, rank, world, scene=None, frames=10, train_steps=300, n_slots=131072, cap=16):
+def render_bench(dev, rank, world, scene=None, frames=10, train_steps=300, n_slots=262144, cap=16):
     """BASELINE configs[2] (C3): 800x800 frames through march_rays_inference / integrate_rays_inference
     (InferenceRenderer: the reference's slot-refill loop, one CUDA graph per iteration), image rows dealt to the
     ranks in interleaved 32-row bands, one all-gather of the u8 image per frame.  The model is trained here for

@@ -110,7 +110,7 @@ def test_integrate_rays_c2_bounds_and_gradient_check():
 
 
 def test_frame_c3_fast_renderer_equals_reference_loop():
-    """C3 (800x800, 640,000 rays): the graph renderer (skip-empty pre-pass, in-place ops, fused encoder+MLP, 131072
+    """C3 (800x800, 640,000 rays): the graph renderer (skip-empty pre-pass, in-place ops, fused encoder+MLP, 262144
     slots x 16 steps) against the reference's slot-refill loop at its own defaults (8192 slots x 8 steps, op by op,
     unfused) on the same rays: every pixel of the u8 image identical, every ray rendered exactly once."""
     from jaxngp_b200 import renderers

@@ -13,7 +13,7 @@ from jaxngp_b200.trainer import Scene, Trainer
 
 dev = "cuda:0"
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-n_slots = int(sys.argv[2]) if len(sys.argv) > 2 else 131072
+n_slots = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
 cap = int(sys.argv[3]) if len(sys.argv) > 3 else 16
 scene = Scene(dev)
 tr = Trainer(device=dev, scene=scene)
