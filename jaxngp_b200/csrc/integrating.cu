@@ -565,10 +565,16 @@ void ngp_integrate_loss_fused(cudaStream_t stream, void **buffers, const char *o
     float4 *dL_dd = b.next<float4>();
     float *loss = b.next<float>();
     uint32_t *n_valid = b.next<uint32_t>();
-    NGP_CUDA_OK(cudaMemsetAsync(mbs, 0, sizeof(uint32_t), stream), "integrate_loss_fused");
-    NGP_CUDA_OK(cudaMemsetAsync(n_valid, 0, sizeof(uint32_t), stream), "integrate_loss_fused");
-    NGP_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), stream), "integrate_loss_fused");
     NGP_CUDA_OK(cudaMemsetAsync(dL_dd, 0, (size_t)desc->total_samples * 4 * sizeof(float), stream), "integrate_loss_fused");
+    // the three scalar outputs are zero-filled with one memset node when the caller laid them out back to back
+    // (trainops.integrate_loss_fused does)
+    if (n_valid == mbs + 1 && reinterpret_cast<uint32_t *>(loss) == mbs + 2) {
+        NGP_CUDA_OK(cudaMemsetAsync(mbs, 0, 3 * sizeof(uint32_t), stream), "integrate_loss_fused");
+    } else {
+        NGP_CUDA_OK(cudaMemsetAsync(mbs, 0, sizeof(uint32_t), stream), "integrate_loss_fused");
+        NGP_CUDA_OK(cudaMemsetAsync(n_valid, 0, sizeof(uint32_t), stream), "integrate_loss_fused");
+        NGP_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), stream), "integrate_loss_fused");
+    }
     if (desc->n_rays == 0) return;
     count_valid_rays_kernel<<<min(div_up(desc->n_rays, kBlock), 148u * 4u), kBlock, 0, stream>>>(desc->n_rays, valid, n_valid);
     integrate_loss_fused_kernel<<<min(div_up(desc->n_rays, kBlock), 148u * 8u), kBlock, 0, stream>>>(

@@ -35,12 +35,11 @@ def integrate_loss_fused(near_distance, rays_sample_startidx, rays_n_samples, bg
     """integrate_rays -> Huber loss -> integrate_rays_backward in one launch (csrc/integrating.cu).  Returns
     (measured_batch_size [1], final_rgbds [n,4], final_opacities [n], dL_ddrgbs [S,4], loss [1], n_valid_rays [1])."""
     n, S, dev = bgs.shape[0], drgbs.shape[0], drgbs.device
-    mbs = torch.empty(1, dtype=torch.int32, device=dev)
+    scalars = torch.empty(4, dtype=torch.int32, device=dev)  # [mbs | n_valid | loss]: one zero-fill for the three
+    mbs, n_valid, loss = scalars[0:1], scalars[1:2], scalars[2:3].view(torch.float32)
     fin = torch.empty(n, 4, dtype=torch.float32, device=dev)
     opac = torch.empty(n, dtype=torch.float32, device=dev)
     d_drgbs = torch.empty(S, 4, dtype=torch.float32, device=dev)
-    loss = torch.empty(1, dtype=torch.float32, device=dev)
-    n_valid = torch.empty(1, dtype=torch.int32, device=dev)
     _lib.call("ngp_integrate_loss_fused",
               [rays_sample_startidx, rays_n_samples, bgs, dss, z_vals, drgbs, ray_is_valid, perm, rgbas_u8,
                mbs, fin, opac, d_drgbs, loss, n_valid],
