@@ -1,6 +1,7 @@
 // runtime.cu -- status channel and per-stream scratch pool of libngp_b200.
 #include <mutex>
 #include <unordered_map>
+#include <vector>
 
 #include "common.cuh"
 
@@ -26,6 +27,7 @@ struct KeyHash {
 };
 std::mutex g_mutex;
 std::unordered_map<Key, Block, KeyHash> g_blocks;
+std::vector<void *> g_retired;  // outgrown blocks, kept alive for captured graphs (see workspace())
 }  // namespace
 
 void set_error(int status, const char *fmt, ...) {
@@ -48,9 +50,11 @@ void *workspace(cudaStream_t stream, size_t bytes) {
     std::lock_guard<std::mutex> lock(g_mutex);
     Block &b = g_blocks[Key{device, stream}];
     if (b.bytes < bytes) {
-        // the old block may still be in use by work already enqueued on `stream`: free it in
-        // stream order, allocate the new one synchronously (first use / growth only)
-        if (b.ptr) cudaFreeAsync(b.ptr, stream);
+        // The old block may still be referenced: by work already enqueued on `stream`, and -- for good -- by CUDA
+        // graphs that captured an op which used it (the trainer and the inference renderer replay such graphs for
+        // their whole lifetime).  It is therefore retired, not freed: growth happens a handful of times per process
+        // (sizes are geometric) and the blocks are a few MB.
+        if (b.ptr) g_retired.push_back(b.ptr);
         size_t want = bytes < (1u << 20) ? (1u << 20) : bytes + bytes / 2;
         void *p = nullptr;
         if (cudaMalloc(&p, want) != cudaSuccess) {

@@ -51,6 +51,7 @@ def test_descriptor_wire_format():
     assert len(D.make_integrating_backward_descriptor(1, 2, 0.3)) == 12
     assert len(D.make_integrating_inference_descriptor(1, 2, 3)) == 12
     assert len(D.make_hashgrid_descriptor(1, 16, 2, 16, 1.38)) == 20
+    assert D.make_integrate_loss_descriptor(3, 9, 0.3, 0.1) == struct.pack("<2I2f", 3, 9, 0.3, 0.1)  # NgpIntegrateLossDescriptor
     assert D.make_marching_descriptor(7, 9, 1024, 1, 128, 1.0, 0.5) == struct.pack("<IIIIIff", 7, 9, 1024, 1, 128, 1.0, 0.5)
     with pytest.raises(RuntimeError):
         D.make_marching_descriptor(1, 1, 1, 0, 1, 1.0, 0.0)  # ffi.cc:79-81
