@@ -238,8 +238,10 @@ typedef struct { uint32_t n_rays; float delta; } NgpHuberLossDescriptor;
 void ngp_make_training_rays(cudaStream_t, void **, const char *, size_t);
 void ngp_huber_loss_grad(cudaStream_t, void **, const char *, size_t);
 
-/* integrate_rays + huber_loss_grad + integrate_rays_backward (colour / density gradient only) in one pass per ray:
- * bit-identical final_rgbds, opacities and dL_ddrgbs to the three ops in sequence.
+/* integrate_rays (integrating.cu:24-99) + the Huber loss of train_step (app/nerf/_utils.py:151-165, target pixel
+ * composited onto the random background, utils/data.py:459-463) + integrate_rays_backward (integrating.cu:101-240,
+ * colour / density gradient only) in one pass per ray: bit-identical final_rgbds, opacities and dL_ddrgbs to the
+ * three ops in sequence.
  *   in : rays_sample_startidx u32[n], rays_n_samples u32[n], bgs f32[n,3], dss f32[S], z_vals f32[S], drgbs f32[S,4],
  *        ray_is_valid bool[n], perm i32[n], rgbas u8[P,4]
  *   out: measured_batch_size u32[1], final_rgbds f32[n,4], final_opacities f32[n], dL_ddrgbs f32[S,4], loss f32[1],
