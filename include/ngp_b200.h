@@ -104,6 +104,8 @@ void ngp_march_rays_skip_empty(cudaStream_t, void **, const char *, size_t);
  *   in/out: t_starts f32[N] (advanced in place), next_ray_index u32[1], indices u32[n]
  *   in    : rays_o, rays_d, t_ends, bitfield, terminated bool[n]
  *   out   : n_samples u32[n], xyzs f32[n,cap,3], dss f32[n,cap], z_vals f32[n,cap], ray_dirs f32[n,3]
+ *           (only the first n_samples[i] rows of slot i are defined: unlike march_rays_inference, which zero-fills
+ *            the tail as the reference does, this variant feeds consumers that never read past n_samples)
  *   buffers: rays_o, rays_d, t_starts, t_ends, bitfield, next_ray_index, terminated, indices,
  *            n_samples, xyzs, dss, z_vals, ray_dirs
  * integrate_rays_inference_inplace

@@ -691,12 +691,16 @@ __global__ void __launch_bounds__(kInferWarps * 32, 8) march_rays_inference_kern
         else if (ray_idx < p.n_total_rays) t_starts_out[ray_idx] = t_store;  // out-of-range indices are dropped
     }
     if (kInPlace && lane < 3) ray_dirs[3 * (size_t)i + lane] = ray_idx < p.n_total_rays ? __ldg(rays_d + 3 * (size_t)ray_idx + lane) : 0.f;
-    // zero the unused tail (reference: memsets, marching.cu:565-570)
-    __syncwarp(mask);
-    for (uint32_t k = steps * 3 + lane; k < cap * 3; k += kW) o_xyzs[k] = 0.f;
-    for (uint32_t k = steps + lane; k < cap; k += kW) {
-        o_dss[k] = 0.f;
-        o_z[k] = 0.f;
+    // zero the unused tail (reference: memsets, marching.cu:565-570).  The in-place variant feeds consumers that only
+    // read the first n_samples rows of a slot (grouped encoder/MLP, integrate_rays_inference), so it skips the fill:
+    // 320 bytes per idle slot per pass, most of this kernel's traffic late in a frame.
+    if (!kInPlace) {
+        __syncwarp(mask);
+        for (uint32_t k = steps * 3 + lane; k < cap * 3; k += kW) o_xyzs[k] = 0.f;
+        for (uint32_t k = steps + lane; k < cap; k += kW) {
+            o_dss[k] = 0.f;
+            o_z[k] = 0.f;
+        }
     }
 }
 
