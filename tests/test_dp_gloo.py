@@ -67,3 +67,32 @@ def test_dp_host_logic_world2():
     expect = (np.arange(100)[:, None] * 7 + np.arange(7)[None]).tolist()
     assert img0 == expect and img1 == expect      # every rank ends with the whole image
     assert p0 != p1                                # disjoint ray streams per rank
+
+
+def test_shard_layout_and_image_bands_for_1_2_4_8_ranks():
+    """Host-side partition math of the multi-GPU paths, no process group needed: ZeRO-1 shards of the padded flat
+    buffer are equal, float4-aligned and cover it; the interleaved row bands of ImageGather partition the image and
+    its precomputed scatter puts every band row back where it belongs."""
+    from jaxngp_b200 import dp, nerf as nerf_mod
+    from jaxngp_b200 import encoders as E
+    lt = E.make_level_table(16, 2 ** 19, 2, 16, 2048, 3)
+    n_params = lt.rows * 2 + nerf_mod.MLP_NUMEL
+    total = -(-n_params // 32) * 32  # trainer.py: padded so that every rank's shard (world <= 8) is float4-aligned
+    H, W = 800, 5
+    full = (torch.arange(H)[:, None] * W + torch.arange(W)[None]).to(torch.float32)[..., None]
+    for world in (1, 2, 4, 8):
+        bounds = [dp.shard_bounds(total, r, world) for r in range(world)]
+        assert bounds[0][0] == 0 and bounds[-1][1] == total
+        assert all(b[1] == bounds[i + 1][0] for i, b in enumerate(bounds[:-1]))
+        assert len({hi - lo for lo, hi in bounds}) == 1 and all(lo % 4 == 0 for lo, _ in bounds)
+        gathers = [dp.ImageGather(H, W, 1, r, world, "cpu", dtype=torch.float32) for r in range(world)]
+        rows = torch.cat([g.local_rows for g in gathers])
+        assert sorted(rows.tolist()) == list(range(H))
+        # emulate the all-gather: every rank's padded send buffer, stacked in rank order
+        recv = torch.zeros(world, gathers[0].max_rows, W, 1)
+        for r, g in enumerate(gathers):
+            recv[r, : g.n_local] = full[g.local_rows]
+        g0 = gathers[0]
+        out = torch.empty(H, W, 1)
+        out[g0.dst] = recv.reshape(world * g0.max_rows, W, 1)[g0.src]
+        assert torch.equal(out, full)
