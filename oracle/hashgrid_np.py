@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- independent numpy restatement of the reference's pure-JAX
-HashGridEncoder (models/encoders.py:58-256).  "Parity unpinned": jax is absent from this image so
-the reference module cannot be executed; this file and oracle/ngp_oracle.c are two independent
-restatements of the cited lines, cross-checked against each other in tests/.
+HashGridEncoder (models/encoders.py:58-256).  Pinned: jax is absent from this image, but the reference module
+runs unmodified on numpy stand-ins (oracle/ref_shim.py); its outputs are committed as
+tests/golden/encoder_reference.npz and tests/test_oracle_golden.py checks this file (<= 2e-6) and
+oracle/ngp_oracle.c (exact) against them.
 """
 import math
 

@@ -1,0 +1,62 @@
+"""TEST INFRASTRUCTURE ONLY -- golden vectors for the hash-grid encoder from the reference's OWN code.
+
+Runs ``HashGridEncoder.__call__`` of /root/reference/models/encoders.py (unmodified; executed on numpy through
+oracle/ref_shim.py, since jax/flax are absent here) on the seeded inputs of tests/inputs.py and writes
+tests/golden/encoder_reference.npz: per configuration the query points and the reference's encodings.  The tables are
+not stored (48 MB): tests regenerate them with ``inputs.encoder_table(rows, 2, amp=1.0)`` (PCG64, fixed seed); the
+reference itself checks their shape -- its ``self.param(..., (offsets[-1], F), ...)`` request must match the rows the
+oracle's level table predicts, which pins the table geometry (6,098,120 rows at C2, 5,592,320 at C1) as well.
+
+    python oracle/make_golden_encoder.py        # needs /root/reference; run in the build container only
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CONFIGS = (  # (dim, T, N_max): C2 / C4 shape, C1 (imagefit) shape, a small table that hashes from level 3 on
+    (3, 2 ** 19, 2048),
+    (2, 2 ** 19, 2 ** 19),
+    (3, 2 ** 14, 512),
+)
+N_POINTS = 256
+PARAM = "latent codes stored on grid vertices"  # models/encoders.py:106
+
+
+def edge_points(dim):
+    return np.array([[-1.0] * dim, [1.0] * dim, [0.0] * dim, [0.999999] * dim, [0.96] * dim, [-0.5] * dim,
+                     [0.933334] * dim], np.float32)
+
+
+def main():
+    from oracle import hashgrid_np as H
+    from oracle import ref_shim
+    from tests import inputs
+    ref = ref_shim.install()
+    out = {}
+    for dim, T, N_max in CONFIGS:
+        lv = H.level_table(16, T, 2, 16, N_max, dim)
+        rows = int(lv["offsets"][-1])
+        pts = inputs.encoder_points(N_POINTS, dim)
+        pts[:7] = edge_points(dim)
+        table = inputs.encoder_table(rows, 2, amp=1.0)
+        enc_mod = ref.HashGridEncoder(L=16, T=T, F=2, N_min=16, N_max=N_max, tv_scale=0.0)
+        enc_mod.bind_params(**{PARAM: table})  # the reference validates (offsets[-1], F) against this shape
+        enc, tv = enc_mod(pts, 1.0)
+        assert enc.dtype == np.float32 and enc.shape == (N_POINTS, 32) and tv == 0
+        key = f"d{dim}_T{T}_N{N_max}"
+        out[key + "_pts"] = pts
+        out[key + "_enc"] = enc
+        out[key + "_rows"] = np.int64(rows)
+        out[key + "_b"] = np.float64(enc_mod.b)
+        print(key, "rows", rows, "b", enc_mod.b, "|enc| max", float(np.abs(enc).max()))
+    path = os.path.join(ROOT, "tests", "golden", "encoder_reference.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -9,10 +9,11 @@
  *     (oracle/_ref/libvolrend_ref.so, built unmodified from /root/reference by oracle/build_ref.sh)
  *     run on a B200; the captured outputs are committed under tests/golden/ (made by
  *     oracle/make_golden.py) and tests/test_oracle_golden.py checks this file against them.
- *   - hash-grid encoder: "parity unpinned" -- the reference's encoder is pure JAX
- *     (models/encoders.py) and jax is absent from this image; the restatement below follows the
- *     cited lines and is cross-checked against an independent numpy restatement
- *     (oracle/hashgrid_np.py) and first-principles known-answer tests only.
+ *   - hash-grid encoder (pure-JAX HashGridEncoder, models/encoders.py): PINNED against the reference's own
+ *     code -- jax is absent, so oracle/ref_shim.py executes the unmodified HashGridEncoder.__call__ on numpy
+ *     stand-ins; oracle/make_golden_encoder.py committed its outputs (tests/golden/encoder_reference.npz) and
+ *     tests/test_oracle_golden.py requires this file to reproduce them exactly.  The tiny-cuda-nn variant
+ *     (jaxtcnn.hashgrid_encode) stays "parity unpinned": tiny-cuda-nn v1.6 is not on disk.
  *
  * Build: gcc -O2 -fopenmp -ffp-contract=off -fno-fast-math -shared -fPIC  (oracle/Makefile).
  * -ffp-contract=off matters: every fused multiply-add below is an explicit fmaf() placed where

@@ -345,6 +345,32 @@ def test_hashgrid_forward_backward_vs_oracle(oracle, dim, T, N_max):
     assert np.array_equal(n(g) != 0, ref_g != 0)                # exactly the same rows are touched
 
 
+@pytest.mark.parametrize("dim,T,N_max", [(3, 2 ** 19, 2048), (2, 2 ** 19, 2 ** 19), (3, 2 ** 14, 512)])
+def test_hashgrid_vs_reference_code_golden(dim, T, N_max):
+    """The CUDA encoder against golden vectors from the reference's OWN HashGridEncoder.__call__ (models/encoders.py,
+    executed unmodified by oracle/make_golden_encoder.py; tests/golden/encoder_reference.npz): encoded features within
+    the north star's rel 1e-3 (in fact a few ulp), and the backward through the adjoint identity
+    <d_enc, enc_ref(table)> = <d_table, table> -- the encoder is linear in the table, so the table gradient of the
+    reference's autodiff is J^T d_enc for the same J whose action the golden vectors record."""
+    import os
+    from jaxngp_b200 import encoders as E
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "encoder_reference.npz"))
+    key = f"d{dim}_T{T}_N{N_max}"
+    lt = E.make_level_table(16, T, 2, 16, N_max, dim)
+    assert lt.rows == int(g[key + "_rows"]) and abs(lt.b - float(g[key + "_b"])) < 1e-12
+    pts, ref_enc = g[key + "_pts"], g[key + "_enc"]
+    table = inputs.encoder_table(lt.rows, 2, amp=1.0)
+    enc = n(E.hashgrid_forward(lt, t(pts), 1.0, t(table)))
+    assert np.allclose(enc, ref_enc, rtol=1e-3, atol=1e-6)
+    assert np.abs(enc - ref_enc).max() < 2e-6
+    rng = np.random.Generator(np.random.PCG64(45))
+    d_enc = rng.normal(size=ref_enc.shape).astype(np.float32)
+    grad = n(E.hashgrid_backward(lt, t(pts), 1.0, t(d_enc)))
+    lhs = float((d_enc.astype(np.float64) * ref_enc.astype(np.float64)).sum())
+    rhs = float((grad.astype(np.float64) * table.astype(np.float64)).sum())
+    assert abs(lhs - rhs) <= 1e-4 * (abs(lhs) + np.abs(d_enc).sum() * 1e-3)
+
+
 def test_hashgrid_backward_ray_ordered_runs(oracle):
     """Samples in ray order (neighbouring rows share grid cells on the coarse levels) with zero-gradient
     rows sprinkled in: exercises the run aggregation of the scatter kernel."""

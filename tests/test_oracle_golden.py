@@ -96,3 +96,27 @@ def test_inference_loop_golden(oracle):
         it += 1
     assert it == int(g["iterations"]) and ns_total == int(g["ns_total"])
     assert np.allclose(rgbd, g["rgbd"], atol=1e-4) and np.allclose(T, g["T"], atol=1e-4)
+
+
+ENCODER_CONFIGS = [(3, 2 ** 19, 2048), (2, 2 ** 19, 2 ** 19), (3, 2 ** 14, 512)]
+
+
+@pytest.mark.parametrize("dim,T,N_max", ENCODER_CONFIGS)
+def test_hashgrid_encoder_golden_from_reference_code(oracle, dim, T, N_max):
+    """The encoder oracle against the reference's OWN ``HashGridEncoder.__call__`` (models/encoders.py:82-256, run
+    unmodified on numpy by oracle/make_golden_encoder.py through oracle/ref_shim.py): table geometry, level growth
+    factor, and every encoded feature, for the C2/C4 shape, the 2-D imagefit shape (C1) and a small table.  Both CPU
+    restatements (C and numpy) must reproduce the reference's float32 result exactly -- same operations in the same
+    order -- including the points on the cube faces (Q1 spill rows)."""
+    from oracle import hashgrid_np as H
+    g = load("encoder_reference.npz")
+    key = f"d{dim}_T{T}_N{N_max}"
+    lv = H.level_table(16, T, 2, 16, N_max, dim)
+    rows = int(lv["offsets"][-1])
+    assert rows == int(g[key + "_rows"])  # the reference's self.param(..., (offsets[-1], F)) accepted this shape
+    assert abs(float(lv["b"]) - float(g[key + "_b"])) < 1e-12
+    pts, ref_enc = g[key + "_pts"], g[key + "_enc"]
+    table = inputs.encoder_table(rows, 2, amp=1.0)
+    enc_c = oracle.hashgrid_encode(lv, pts, 1.0, table)
+    assert enc_c.dtype == np.float32 and np.array_equal(enc_c, ref_enc)
+    assert np.abs(np.asarray(H.encode(lv, pts, 1.0, table), np.float32) - ref_enc).max() <= 2e-6
