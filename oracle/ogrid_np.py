@@ -1,5 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- numpy restatement of the density-grid update
-(utils/types.py:1149-1239) with the random draws supplied as inputs."""
+(utils/types.py:1149-1239) with the random draws supplied as inputs.  Pinned: the reference's own methods run
+unmodified on numpy stand-ins (oracle/ref_shim.py, oracle/make_golden_ogrid.py -> tests/golden/ogrid_reference.npz)
+and tests/test_oracle_golden.py requires this file to reproduce their densities, masks and bitfields exactly."""
 import numpy as np
 
 from . import oracle as O

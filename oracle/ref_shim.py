@@ -149,3 +149,142 @@ def install():
     module = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(module)
     return module
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Density-grid update (utils/types.py:93-144 OccupancyDensityGrid, :1149-1239 NeRFState.update_ogrid_density /
+# threshold_ogrid): the reference's own source of that class and of those methods, extracted by AST and executed on
+# numpy.  utils/types.py cannot be imported (flax.training, pydantic, PIL, the compiled volrendjax ops ...), and
+# NeRFState is a flax TrainState; the methods only touch a handful of attributes, which `RefStateBase` provides.
+class JArr(np.ndarray):
+    """numpy array with jax's functional update syntax: ``a.at[idx].set(v)`` returns an updated copy."""
+
+    @property
+    def at(self):
+        return _At(self)
+
+
+class _At:
+    def __init__(self, a):
+        self.a = a
+
+    def __getitem__(self, idx):
+        return _AtIdx(self.a, idx)
+
+
+class _AtIdx:
+    def __init__(self, a, idx):
+        self.a, self.idx = a, idx
+
+    def set(self, v):
+        out = self.a.copy()
+        out[self.idx] = v
+        return out
+
+
+def _j(x):
+    return x.view(JArr) if isinstance(x, np.ndarray) and not isinstance(x, JArr) else x
+
+
+class _JnpForTypes(types.ModuleType):
+    """jax.numpy for the extracted code: numpy functions whose array results carry ``.at``."""
+
+    def __getattr__(self, name):
+        target = {"asarray": _asarray, "array": _asarray, "sum": _sum}.get(name, getattr(np, name))
+        if not callable(target) or isinstance(target, type):
+            return target
+
+        @functools.wraps(target)
+        def wrapped(*a, **k):
+            r = target(*a, **k)
+            return [_j(x) for x in r] if isinstance(r, list) else _j(r)
+
+        return wrapped
+
+
+class ScriptedRandom(types.ModuleType):
+    """jax.random with the draws supplied by the caller (the oracle takes them as inputs too): ``choice`` hands out
+    the scripted index arrays in call order, ``uniform`` maps scripted U[0,1) numbers onto [minval, maxval) with
+    jax.random.uniform's arithmetic (u * (maxval - minval) + minval, clamped below at minval)."""
+
+    KeyArray = object
+
+    def __init__(self, choices, uniforms):
+        super().__init__("jax.random")
+        self._choices, self._uniforms = list(choices), list(uniforms)
+
+    def split(self, key, num=2):
+        return [None] * num
+
+    def choice(self, key, a, shape, replace=True, p=None):
+        draw = self._choices.pop(0)
+        assert tuple(draw.shape) == tuple(shape), (draw.shape, shape)
+        if p is not None:  # the scripted cells must be ones the reference could have drawn
+            pos = {int(v): i for i, v in enumerate(np.asarray(a))}
+            assert all(np.asarray(p)[pos[int(v)]] > 0 for v in draw[:64])
+        return _j(np.asarray(draw, dtype=np.asarray(a).dtype))
+
+    def uniform(self, key, shape, dtype, minval=0.0, maxval=1.0):
+        u = np.asarray(self._uniforms.pop(0), np.float32)
+        assert tuple(u.shape) == tuple(shape)
+        lo, hi = np.float32(minval), np.float32(maxval)
+        return np.maximum(lo, u * (hi - lo) + lo).astype(dtype)
+
+
+class RefStateBase:
+    """The attributes NeRFState's grid-update methods read (utils/types.py:1149-1239), and ``replace``."""
+
+    def __init__(self, ogrid, nerf_fn, G, diagonal_n_steps, bound, cascades):
+        self.ogrid, self.nerf_fn = ogrid, nerf_fn
+        self.raymarch = types.SimpleNamespace(density_grid_res=G, diagonal_n_steps=diagonal_n_steps)
+        self.scene_meta = types.SimpleNamespace(bound=bound, cascades=cascades)
+        self.locked_params = {"nerf": None}
+
+    def replace(self, **kw):
+        new = object.__new__(type(self))
+        new.__dict__.update(self.__dict__)
+        new.__dict__.update(kw)
+        return new
+
+
+def install_grid_update(oracle_module, jran):
+    """Returns (OccupancyDensityGrid, RefState): the reference's class and a state class carrying the reference's
+    ``update_ogrid_density`` / ``threshold_ogrid`` / ``density_threshold_from_min_step_size``.  The two compiled ops
+    they call (volrendjax.morton3d_invert, volrendjax.packbits) are served by the C oracle, itself pinned to the
+    reference's CUDA kernels by tests/golden/morton_packbits.npz."""
+    import typing
+    path = os.path.join(REFERENCE, "utils", "types.py")
+    tree = ast.parse(open(path).read())
+    jnp = _JnpForTypes("jax.numpy")
+    jax = _Stub("jax")
+    jax.Array, jax.numpy, jax.random = np.ndarray, jnp, jran
+    jax.jit = lambda fun=None, **kw: fun if fun is not None else (lambda f: f)
+    jax.lax = types.SimpleNamespace(stop_gradient=lambda x: x)
+
+    def flax_dataclass(cls):  # flax.struct.dataclass: a frozen dataclass with .replace
+        cls = dataclasses.dataclass(cls)
+        cls.replace = lambda self, **kw: dataclasses.replace(self, **kw)
+        return cls
+
+    struct = types.SimpleNamespace(field=lambda pytree_node=True, **kw: dataclasses.field(**kw))
+
+    def packbits(density_threshold, density_grid):
+        mask, bits = oracle_module.packbits(float(density_threshold), np.asarray(density_grid, np.float32))
+        return _j(np.asarray(mask).astype(bool)), _j(np.asarray(bits))
+
+    ns = dict(jax=jax, jnp=jnp, jran=jran, np=np, List=typing.List, struct=struct, dataclass=flax_dataclass,
+              morton3d_invert=lambda idx: np.asarray(oracle_module.morton3d_invert(np.asarray(idx, np.uint32))),
+              packbits=packbits, RefStateBase=RefStateBase)
+    exec(compile(_extract_functions(path, {"empty_impl"}), "utils/types.py", "exec"), ns)
+    grid_cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "OccupancyDensityGrid")
+    exec(compile(ast.Module(body=[grid_cls], type_ignores=[]), "utils/types.py", "exec"), ns)
+    state_cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "NeRFState")
+    wanted = {"update_ogrid_density", "threshold_ogrid", "density_threshold_from_min_step_size"}
+    methods = [n for n in state_cls.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert {m.name for m in methods} == wanted
+    ref_state = ast.ClassDef(name="RefState", bases=[ast.Name(id="RefStateBase", ctx=ast.Load())], keywords=[], body=methods,
+                             decorator_list=[], type_params=[])
+    module = ast.Module(body=[ref_state], type_ignores=[])
+    ast.fix_missing_locations(module)
+    exec(compile(module, "utils/types.py", "exec"), ns)
+    return ns["OccupancyDensityGrid"], ns["RefState"]

@@ -120,3 +120,29 @@ def test_hashgrid_encoder_golden_from_reference_code(oracle, dim, T, N_max):
     enc_c = oracle.hashgrid_encode(lv, pts, 1.0, table)
     assert enc_c.dtype == np.float32 and np.array_equal(enc_c, ref_enc)
     assert np.abs(np.asarray(H.encode(lv, pts, 1.0, table), np.float32) - ref_enc).max() <= 2e-6
+
+
+def test_density_grid_update_golden_from_reference_code(oracle):
+    """oracle/ogrid_np.py (the checker of the CUDA grid-update kernels) against the reference's OWN
+    ``OccupancyDensityGrid`` / ``NeRFState.update_ogrid_density`` / ``threshold_ogrid`` (utils/types.py:93-144,
+    1149-1239; executed unmodified on numpy by oracle/make_golden_ogrid.py): two cascades, a full update followed by
+    a sampled one (scripted draws, no repeated cells), thresholding through the mean-density branch after each."""
+    from oracle import ogrid_np
+    from oracle.make_golden_ogrid import density_fn
+    g = load("ogrid_reference.npz")
+    G, K, bound, steps = int(g["G"]), int(g["K"]), float(g["bound"]), int(g["steps"])
+    G3 = G ** 3
+    density = np.zeros(K * G3, np.float32)
+    thr_max = 0.01 * steps / (2 * min(bound, 1) * 3 ** 0.5)  # utils/types.py:1367-1369
+    for tag, update_all in (("all", True), ("sampled", False)):
+        for cas in range(K):
+            sl = slice(cas * G3, (cas + 1) * G3)
+            idx = np.arange(G3, dtype=np.uint32) if update_all else np.concatenate([g[f"{tag}_c{cas}_first"], g[f"{tag}_c{cas}_second"]])
+            coords = ogrid_np.sample_positions(idx, g[f"{tag}_c{cas}_jitter"], G, cas, bound)
+            density[sl] = ogrid_np.decay_and_max(density[sl], idx, density_fn(coords))
+        assert np.array_equal(density, g[f"{tag}_density"]), tag
+        thr = ogrid_np.threshold(density[:G3], thr_max)
+        assert abs(float(thr) - float(g[f"{tag}_threshold"])) <= 1e-6 * float(thr) and float(thr) < thr_max
+        mask, bits = oracle.packbits(float(thr), density)
+        assert np.array_equal(np.asarray(mask).astype(bool), g[f"{tag}_occ_mask"]), tag
+        assert np.array_equal(np.asarray(bits), g[f"{tag}_occupancy"]), tag
