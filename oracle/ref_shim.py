@@ -156,12 +156,34 @@ def install():
 # threshold_ogrid): the reference's own source of that class and of those methods, extracted by AST and executed on
 # numpy.  utils/types.py cannot be imported (flax.training, pydantic, PIL, the compiled volrendjax ops ...), and
 # NeRFState is a flax TrainState; the methods only touch a handful of attributes, which `RefStateBase` provides.
+def _down(x):
+    """jax with x64 disabled never yields 64-bit values: int (+) Python float is float32, mixed int/float32 is float32."""
+    if isinstance(x, np.ndarray):
+        if x.dtype == np.float64:
+            return x.astype(np.float32)
+        if x.dtype == np.int64:
+            return x.astype(np.int32)
+        if x.dtype == np.uint64:
+            return x.astype(np.uint32)
+    return x
+
+
 class JArr(np.ndarray):
-    """numpy array with jax's functional update syntax: ``a.at[idx].set(v)`` returns an updated copy."""
+    """numpy array with jax's functional update syntax (``a.at[idx].set(v)`` returns an updated copy) and jax's
+    32-bit result types for arithmetic."""
 
     @property
     def at(self):
         return _At(self)
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
+        args = [np.asarray(i) if isinstance(i, JArr) else i for i in inputs]
+        if out is not None:
+            kwargs["out"] = tuple(np.asarray(o) if isinstance(o, JArr) else o for o in out)
+        r = getattr(ufunc, method)(*args, **kwargs)
+        if out is not None:
+            return out[0] if len(out) == 1 else out
+        return tuple(_j(_down(x)) for x in r) if isinstance(r, tuple) else _j(_down(r))
 
 
 class _At:
@@ -190,14 +212,17 @@ class _JnpForTypes(types.ModuleType):
     """jax.numpy for the extracted code: numpy functions whose array results carry ``.at``."""
 
     def __getattr__(self, name):
-        target = {"asarray": _asarray, "array": _asarray, "sum": _sum}.get(name, getattr(np, name))
+        target = {"asarray": _asarray, "array": _asarray, "sum": _sum,
+                  "clip": lambda a, a_min=None, a_max=None: np.clip(a, a_min, a_max)}.get(name) or getattr(np, name)
         if not callable(target) or isinstance(target, type):
             return target
 
         @functools.wraps(target)
         def wrapped(*a, **k):
             r = target(*a, **k)
-            return [_j(x) for x in r] if isinstance(r, list) else _j(r)
+            if isinstance(r, (list, tuple)):
+                return type(r)(_j(_down(x)) for x in r)
+            return _j(_down(r))
 
         return wrapped
 
@@ -288,3 +313,56 @@ def install_grid_update(oracle_module, jran):
     ast.fix_missing_locations(module)
     exec(compile(module, "utils/types.py", "exec"), ns)
     return ns["OccupancyDensityGrid"], ns["RefState"]
+
+
+def install_rays():
+    """The reference's ray generation, unmodified: ``make_rays_worldspace`` / ``make_near_far_from_bound``
+    (models/renderers/cuda.py:22-97) and ``Camera.make_ray_directions_from_pixel_coordinates`` (utils/types.py:398-439)
+    for an undistorted perspective camera, plus the per-pixel ray construction nested in ``train_step``
+    (app/nerf/_utils.py:96-115)."""
+    import typing
+    jnp = _JnpForTypes("jax.numpy")
+    jnp.pi = np.float32(np.pi)
+    jnp.linalg = types.SimpleNamespace(norm=lambda a, **k: _j(_down(np.linalg.norm(np.asarray(a), **k))))
+    jax = _Stub("jax")
+    jax.Array, jax.numpy = np.ndarray, jnp
+    jax.jit = lambda fun=None, **kw: fun if fun is not None else (lambda f: f)
+    chex = _Stub("chex")
+    for name in ("assert_type", "assert_rank", "assert_equal_shape"):
+        setattr(chex, name, lambda *a, **k: None)
+    ns = dict(jax=jax, jnp=jnp, chex=chex, np=np, Tuple=typing.Tuple, Camera=object, RigidTransformation=object)
+    types_tree = ast.parse(open(os.path.join(REFERENCE, "utils", "types.py")).read())
+    cam_cls = next(n for n in types_tree.body if isinstance(n, ast.ClassDef) and n.name == "Camera")
+    method = next(n for n in cam_cls.body if isinstance(n, ast.FunctionDef) and n.name == "make_ray_directions_from_pixel_coordinates")
+    ref_cam = ast.ClassDef(name="RefCamera", bases=[], keywords=[], body=[method], decorator_list=[], type_params=[])
+    module = ast.Module(body=[ref_cam], type_ignores=[])
+    ast.fix_missing_locations(module)
+    exec(compile(module, "utils/types.py", "exec"), ns)
+    exec(compile(_extract_functions(os.path.join(REFERENCE, "models", "renderers", "cuda.py"),
+                                    {"make_rays_worldspace", "make_near_far_from_bound"}), "models/renderers/cuda.py", "exec"), ns)
+
+    # the ray construction inside train_step (app/nerf/_utils.py:96-115) is a nested function over the enclosing
+    # scope's `scene`, `view_idcs`, `pixel_idcs`: compiled at module level those become globals of `train_ns`
+    utils_tree = ast.parse(open(os.path.join(REFERENCE, "app", "nerf", "_utils.py")).read())
+    train_step = next(n for n in utils_tree.body if isinstance(n, ast.FunctionDef) and n.name == "train_step")
+    nested = next(n for n in train_step.body if isinstance(n, ast.FunctionDef) and n.name == "make_rays_worldspace")
+    train_ns = dict(jnp=jnp, jax=jax, Tuple=typing.Tuple)
+    exec(compile(ast.Module(body=[nested], type_ignores=[]), "app/nerf/_utils.py", "exec"), train_ns)
+
+    def train_rays(camera, transforms, perm):
+        """view/pixel split as SceneData.get_view_indices / get_pixel_indices (utils/types.py:1029-1039), then the
+        reference's nested make_rays_worldspace."""
+        perm = _j(np.asarray(perm, np.uint32))
+        train_ns["view_idcs"] = jnp.floor_divide(perm, camera.n_pixels)
+        train_ns["pixel_idcs"] = jnp.mod(perm, camera.n_pixels)
+        train_ns["scene"] = types.SimpleNamespace(meta=types.SimpleNamespace(camera=camera), transforms=_j(np.asarray(transforms, np.float32)))
+        return train_ns["make_rays_worldspace"]()
+
+    def make_camera(width, height, fx, fy, cx, cy):
+        cam = ns["RefCamera"]()
+        cam.__dict__.update(width=width, height=height, n_pixels=width * height, fx=fx, fy=fy, cx=cx, cy=cy,
+                            has_distortion=False, _type="PERSPECTIVE")
+        return cam
+
+    return types.SimpleNamespace(make_camera=make_camera, make_rays_worldspace=ns["make_rays_worldspace"],
+                                 make_near_far_from_bound=ns["make_near_far_from_bound"], train_rays=train_rays, array=_j)

@@ -146,3 +146,36 @@ def test_density_grid_update_golden_from_reference_code(oracle):
         mask, bits = oracle.packbits(float(thr), density)
         assert np.array_equal(np.asarray(mask).astype(bool), g[f"{tag}_occ_mask"]), tag
         assert np.array_equal(np.asarray(bits), g[f"{tag}_occupancy"]), tag
+
+
+def test_ray_generation_golden_from_reference_code():
+    """Ray generation and the AABB near/far test against the reference's OWN code (Camera.make_ray_directions_from_
+    pixel_coordinates utils/types.py:398-439, the ray construction nested in train_step app/nerf/_utils.py:96-115,
+    make_rays_worldspace / make_near_far_from_bound models/renderers/cuda.py:22-97; run unmodified on numpy by
+    oracle/make_golden_rays.py).  The numpy restatement that feeds every march test and smoke() is bit-exact; the torch
+    host mirror (renderers.py, the checker of the fused make_training_rays kernel) agrees to one ulp."""
+    import torch
+    from jaxngp_b200 import renderers as R, synthetic as S
+    g = load("rays_reference.npz")
+    cam, tf = S.camera(), S.poses(100)
+    perm = g["perm"].astype(np.int64)
+    hw = cam["width"] * cam["height"]
+    view, pix = perm // hw, perm % hw
+    o, d = S.pixel_rays(tf, view, pix)
+    ts, te = S.near_far(o, d)
+    for got, key in ((o, "train_o"), (d, "train_d"), (ts, "train_t_starts"), (te, "train_t_ends")):
+        assert got.dtype == np.float32 and np.array_equal(got, g[key]), key
+    pt, vt = torch.from_numpy(pix), torch.from_numpy(view)
+    d_cam = R.make_ray_directions(pt % cam["width"], pt // cam["width"], cam)
+    tft = torch.from_numpy(tf)[vt]
+    d_world = (d_cam[:, None, :] * tft[:, :9].reshape(-1, 3, 3)).sum(-1)
+    ts_t, te_t = R.make_near_far_from_bound(1.0, tft[:, 9:], d_world)
+    assert np.abs(d_world.numpy() - g["train_d"]).max() <= 2.4e-7
+    assert np.allclose(ts_t.numpy(), g["train_t_starts"], rtol=1e-6, atol=1e-7)
+    assert np.allclose(te_t.numpy(), g["train_t_ends"], rtol=1e-6, atol=1e-7)
+    small = dict(width=48, height=32, fx=cam["fx"] * 48 / cam["width"], fy=cam["fy"] * 48 / cam["width"], cx=24.0, cy=16.0)
+    fo, fd = R.make_rays_worldspace(small, torch.from_numpy(tf[7]))
+    fts, fte = R.make_near_far_from_bound(1.0, fo, fd)
+    assert np.array_equal(fo.numpy(), g["frame_o"]) and np.abs(fd.numpy() - g["frame_d"]).max() <= 2.4e-7
+    assert np.allclose(fts.numpy(), g["frame_t_starts"], rtol=1e-6, atol=1e-7)
+    assert np.allclose(fte.numpy(), g["frame_t_ends"], rtol=1e-6, atol=1e-7)
