@@ -366,3 +366,94 @@ def install_rays():
 
     return types.SimpleNamespace(make_camera=make_camera, make_rays_worldspace=ns["make_rays_worldspace"],
                                  make_near_far_from_bound=ns["make_near_far_from_bound"], train_rays=train_rays, array=_j)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The NeRF model (models/nerfs.py:27-128 NeRF / CoordinateBasedMLP, :216-238 trunc_exp, :422-454 make_nerf_ngp) and the
+# spherical-harmonics direction encoder (models/encoders.py:365-406), unmodified.  flax's Dense (x @ kernel, no bias
+# here) and sigmoid are library code and are restated; layer order, widths, splits, the concatenation order of
+# [x | SH(dir) | appearance], the activations and trunc_exp's custom backward rule are the reference's.
+_module_stack = []
+
+
+def _compact(fn):
+    """nn.compact: tracks the module being applied so that submodules created inside find their parameters by flax's
+    auto-naming (Dense_0, Dense_1, ... in creation order)."""
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        _module_stack.append(self)
+        object.__setattr__(self, "_auto_index", {})
+        try:
+            return fn(self, *a, **k)
+        finally:
+            _module_stack.pop()
+
+    return wrapper
+
+
+class Dense:
+    """flax.linen.Dense without bias: y = x @ kernel, kernel [in, out] bound on the parent as ``Dense_<i>``."""
+
+    def __init__(self, features, use_bias=True, kernel_init=None, **kw):
+        assert not use_bias, "the reference's MLPs are bias-free (models/nerfs.py:115-127)"
+        self.features = features
+
+    def __call__(self, x):
+        parent = _module_stack[-1]
+        i = parent._auto_index.get("Dense", 0)
+        parent._auto_index["Dense"] = i + 1
+        kernel = parent._bound_params[f"Dense_{i}"]
+        assert kernel.shape == (x.shape[-1], self.features) and kernel.dtype == np.float32, (kernel.shape, x.shape, self.features)
+        return _j(np.matmul(np.asarray(x, np.float32), kernel))
+
+
+class CustomVjp:
+    """jax.custom_vjp: the primal function, with the fwd/bwd rules kept for inspection (``.bwd(aux, g)``)."""
+
+    def __init__(self, fn):
+        self.fn, self.fwd, self.bwd = fn, None, None
+        functools.update_wrapper(self, fn)
+
+    def __call__(self, *a, **k):
+        return self.fn(*a, **k)
+
+    def defvjp(self, fwd, bwd):
+        self.fwd, self.bwd = fwd, bwd
+
+
+def install_nerf():
+    """Imports the reference's models/encoders.py and models/nerfs.py unmodified; returns the ``models.nerfs`` module."""
+    import typing
+    install()  # jax / flax / chex / utils stand-ins + models.encoders
+    jax = sys.modules["jax"]
+    jnp = _JnpForTypes("jax.numpy")  # results carry .at (the SH encoder fills its output with .at[..., i].set)
+    jax.numpy = jnp
+    sys.modules["jax.numpy"] = jnp
+    jax.custom_vjp = CustomVjp
+    nn_mod = sys.modules["flax.linen"]
+    nn_mod.compact, nn_mod.Dense = _compact, Dense
+    nn_mod.relu = lambda x: _j(np.maximum(np.asarray(x), np.float32(0)))
+    nn_mod.sigmoid = lambda x: _j((np.float32(1) / (np.float32(1) + np.exp(-np.asarray(x, np.float32)))).astype(np.float32))
+    nn_mod.initializers = types.SimpleNamespace(glorot_uniform=lambda: None)
+    init_mod = _Stub("jax.nn.initializers")
+    init_mod.Initializer = object
+    jax.nn = _Stub("jax.nn")
+    jax.nn.initializers = init_mod
+    sys.modules.update({"jax.nn": jax.nn, "jax.nn.initializers": init_mod})
+    chex = sys.modules["chex"]
+    chex.assert_axis_dimension = lambda *a, **k: None
+    sys.modules["utils.common"].mkValueError = lambda **kw: ValueError(str(kw))
+    rt = sys.modules["utils.types"]
+    rt.ActivationType = rt.DirectionalEncodingType = rt.PositionalEncodingType = typing.Any
+    # models.encoders must see the .at-capable jnp as well: re-import it under its package name
+    models = types.ModuleType("models")
+    models.__path__ = []
+    sys.modules["models"] = models
+    for name in ("encoders", "nerfs"):
+        spec = importlib.util.spec_from_file_location(f"models.{name}", os.path.join(REFERENCE, "models", f"{name}.py"))
+        module = importlib.util.module_from_spec(spec)
+        sys.modules[f"models.{name}"] = module
+        spec.loader.exec_module(module)
+        setattr(models, name, module)
+    return sys.modules["models.nerfs"]

@@ -4,6 +4,8 @@ march (C oracle) -> hash-grid encode (C oracle) -> MLP (numpy/BLAS restatement o
 -> Adam (app/nerf/_utils.py:19-77).  jax is absent from this image, so this stands in for the
 "JAX-CPU path" named by BASELINE.json; bench.py times it (cpu_baseline, --impl reference) and
 tests/ use it as the checker of the GPU training step.  Never imported by the product.
+Pinned: the MLP, SH basis and trunc_exp reproduce the reference's own models/nerfs.py + models/encoders.py, run
+unmodified on numpy stand-ins (oracle/ref_shim.py, oracle/make_golden_nerf.py -> tests/golden/nerf_reference.npz).
 """
 import numpy as np
 

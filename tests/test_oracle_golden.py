@@ -179,3 +179,35 @@ def test_ray_generation_golden_from_reference_code():
     assert np.array_equal(fo.numpy(), g["frame_o"]) and np.abs(fd.numpy() - g["frame_d"]).max() <= 2.4e-7
     assert np.allclose(fts.numpy(), g["frame_t_starts"], rtol=1e-6, atol=1e-7)
     assert np.allclose(fte.numpy(), g["frame_t_ends"], rtol=1e-6, atol=1e-7)
+
+
+def test_nerf_model_golden_from_reference_code(oracle):
+    """The MLP oracle (oracle/train_np.py: the checker of the fused tensor-core MLP kernels) against the reference's OWN
+    ``make_nerf_ngp`` model (models/nerfs.py NeRF / CoordinateBasedMLP / trunc_exp, models/encoders.py
+    SphericalHarmonicsEncoder; run unmodified on numpy by oracle/make_golden_nerf.py): layer order and widths, the
+    density split, the [x | SH(dir)] concatenation, both activations, the density-only branch, the SH basis, and
+    trunc_exp's backward rule.  The torch host mirror (jaxngp_b200/nerf.py sh4, trunc_exp) is checked too."""
+    import torch
+    from jaxngp_b200 import nerf as nerf_mod
+    from oracle import hashgrid_np as H
+    from oracle import train_np as T
+    g = load("nerf_reference.npz")
+    lv = H.level_table(16, 2 ** 19, 2, 16, 2048, 3)
+    table = inputs.encoder_table(int(lv["offsets"][-1]), 2, amp=1.0)
+    w = {k: g[k] for k in ("density_w0", "density_w1", "rgb_w0", "rgb_w1", "rgb_w2")}
+    enc = oracle.hashgrid_encode(lv, g["xyz"], 1.0, table)
+    drgbs, cache = T.mlp_forward(w, enc, g["dirs"])
+    assert np.allclose(drgbs, g["drgbs"], rtol=2e-6, atol=1e-7), np.abs(drgbs - g["drgbs"]).max()
+    assert np.allclose(drgbs[:, :1], g["density_only"], rtol=2e-6, atol=1e-7)
+    assert np.array_equal(T.sh4(g["dirs"]), g["sh"])  # same expressions, float32 throughout
+    # trunc_exp: forward exp(x), backward exp(clip(x, -15, 15)) * g (models/nerfs.py:222-238)
+    x, gy = g["trunc_exp_x"], g["trunc_exp_g"]
+    assert np.array_equal(np.exp(x), g["trunc_exp_fwd"])
+    assert np.array_equal((np.exp(np.clip(x, -15, 15)) * gy).astype(np.float32), g["trunc_exp_grad"])
+    d_drgbs = np.zeros_like(drgbs)
+    d_drgbs[:, 0] = 1.0  # the oracle's backward applies the same rule to the density channel
+    xt = torch.from_numpy(x.copy()).requires_grad_(True)
+    nerf_mod.trunc_exp(xt).backward(torch.from_numpy(gy.copy()))
+    assert np.allclose(xt.grad.numpy(), g["trunc_exp_grad"], rtol=1e-6, atol=0)
+    sh_t = nerf_mod.sh4(torch.from_numpy(g["dirs"].copy())).numpy()
+    assert np.abs(sh_t - g["sh"]).max() <= 2.4e-7
