@@ -457,3 +457,153 @@ def install_nerf():
         spec.loader.exec_module(module)
         setattr(models, name, module)
     return sys.modules["models.nerfs"]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Loss and optimizer of the training step (app/nerf/_utils.py:19-77 make_optimizer, :117-162 loss_fn nested in
+# train_step; utils/data.py:443-464 blend_rgba_image_array), unmodified.  optax is a third-party dependency that is not
+# on disk (the reference's flake pins nixpkgs' python3Packages.optax): the few primitives the reference configures are
+# restated from their published definitions -- huber_loss, exponential_decay, scale_by_adam with eps_root, scaling by
+# -learning_rate, add_decayed_weights, multi_transform / chain over a pytree of dicts.
+def _tree_map(fn, *trees):
+    t0 = trees[0]
+    if isinstance(t0, dict):
+        return {k: _tree_map(fn, *[t[k] for t in trees]) for k in t0}
+    return fn(*trees)
+
+
+def _mask_lookup(mask, path_value_tree):
+    """optax masks may be prefixes of the parameter tree: a bool at an inner node covers the whole subtree."""
+    if isinstance(path_value_tree, dict):
+        return {k: _mask_lookup(mask[k] if isinstance(mask, dict) else mask, v) for k, v in path_value_tree.items()}
+    return bool(mask)
+
+
+class OptaxShim(types.ModuleType):
+    GradientTransformation = object
+
+    def __init__(self):
+        super().__init__("optax")
+        self.calls = []  # what the reference configured, in call order
+
+    @staticmethod
+    def huber_loss(predictions, targets=None, delta=1.0):
+        err = np.asarray(predictions, np.float32) - np.asarray(targets, np.float32)
+        abs_err = np.abs(err)
+        quad = np.minimum(abs_err, np.float32(delta))
+        return _j((np.float32(0.5) * quad * quad + np.float32(delta) * (abs_err - quad)).astype(np.float32))
+
+    def exponential_decay(self, init_value, transition_steps, decay_rate, transition_begin=0, staircase=False, end_value=None):
+        self.calls.append(("exponential_decay", dict(init_value=init_value, transition_steps=transition_steps, decay_rate=decay_rate,
+                                                     transition_begin=transition_begin, staircase=staircase, end_value=end_value)))
+
+        def schedule(count):
+            decreased = count - transition_begin
+            p = decreased / transition_steps
+            if staircase:
+                p = np.floor(p)
+            value = init_value * decay_rate ** p if decreased > 0 else init_value
+            if end_value is not None:
+                value = max(value, end_value) if decay_rate < 1 else min(value, end_value)
+            return value
+
+        self.last_schedule = schedule
+        return schedule
+
+    def adam(self, learning_rate, b1=0.9, b2=0.999, eps=1e-8, eps_root=0.0):
+        self.calls.append(("adam", dict(learning_rate=learning_rate if not callable(learning_rate) else "schedule", b1=b1, b2=b2,
+                                        eps=eps, eps_root=eps_root)))
+
+        def init(params):
+            return dict(count=0, mu=_tree_map(np.zeros_like, params), nu=_tree_map(np.zeros_like, params))
+
+        def update(grads, state, params=None):
+            count = state["count"] + 1
+            mu = _tree_map(lambda m, g: b1 * m + (1 - b1) * g, state["mu"], grads)
+            nu = _tree_map(lambda v, g: b2 * v + (1 - b2) * g * g, state["nu"], grads)
+            lr = learning_rate(state["count"]) if callable(learning_rate) else learning_rate
+            upd = _tree_map(lambda m, v: (-lr * (m / (1 - b1 ** count)) / (np.sqrt(v / (1 - b2 ** count) + eps_root) + eps)).astype(np.float32),
+                            mu, nu)
+            return upd, dict(count=count, mu=mu, nu=nu)
+
+        return types.SimpleNamespace(init=init, update=update)
+
+    def multi_transform(self, transforms, param_labels):
+        self.calls.append(("multi_transform", dict(labels=param_labels, transforms=sorted(transforms))))
+
+        def init(params):
+            return {k: transforms[param_labels[k]].init(v) for k, v in params.items()}
+
+        def update(grads, state, params=None):
+            out, new_state = {}, {}
+            for k in grads:
+                out[k], new_state[k] = transforms[param_labels[k]].update(grads[k], state[k], None if params is None else params[k])
+            return out, new_state
+
+        return types.SimpleNamespace(init=init, update=update)
+
+    def add_decayed_weights(self, weight_decay=0.0, mask=None):
+        self.calls.append(("add_decayed_weights", dict(weight_decay=weight_decay, mask=mask)))
+
+        def update(updates, state, params):
+            m = _mask_lookup(mask, params)
+            return _tree_map(lambda u, p, on: (u + np.float32(weight_decay) * p).astype(np.float32) if on else u, updates, params, m), state
+
+        return types.SimpleNamespace(init=lambda params: None, update=update)
+
+    def chain(self, *transforms):
+        self.calls.append(("chain", dict(n=len(transforms))))
+
+        def init(params):
+            return [t.init(params) for t in transforms]
+
+        def update(grads, state, params=None):
+            new_state = []
+            for t, s in zip(transforms, state):
+                grads, s = t.update(grads, s, params)
+                new_state.append(s)
+            return grads, new_state
+
+        return types.SimpleNamespace(init=init, update=update)
+
+
+def install_loss_and_optimizer(scripted_random):
+    """Returns a namespace with the reference's ``make_optimizer``, ``blend_rgba_image_array`` and a callable
+    ``loss(pred_rgbds, ray_is_valid, gt_rgba_f32)`` that runs the reference's nested ``loss_fn`` with the renderer
+    replaced by its outputs."""
+    import typing
+    jnp = _JnpForTypes("jax.numpy")
+    jax = _Stub("jax")
+    jax.Array, jax.numpy, jax.random = np.ndarray, jnp, scripted_random
+    jax.tree_util = types.SimpleNamespace(tree_reduce=lambda fn, tree: functools.reduce(fn, list(tree.values())))
+    optax = OptaxShim()
+    chex = _Stub("chex")
+    for name in ("assert_shape", "assert_type"):
+        setattr(chex, name, lambda *a, **k: None)
+    pil = types.SimpleNamespace(Image=type("Image", (), {}))
+    data_ns = dict(jnp=jnp, jax=jax, np=np, chex=chex, Image=pil, Tuple=typing.Tuple)
+    exec(compile(_extract_functions(os.path.join(REFERENCE, "utils", "data.py"), {"blend_rgba_image_array"}), "utils/data.py", "exec"), data_ns)
+    utils_path = os.path.join(REFERENCE, "app", "nerf", "_utils.py")
+    ns = dict(optax=optax)
+    exec(compile(_extract_functions(utils_path, {"make_optimizer"}), "app/nerf/_utils.py", "exec"), ns)
+    tree = ast.parse(open(utils_path).read())
+    train_step = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "train_step")
+    loss_fn = next(n for n in train_step.body if isinstance(n, ast.FunctionDef) and n.name == "loss_fn")
+    train_ns = dict(jnp=jnp, jax=jax, jran=scripted_random, optax=optax,
+                    data=types.SimpleNamespace(blend_rgba_image_array=data_ns["blend_rgba_image_array"]))
+    exec(compile(ast.Module(body=[loss_fn], type_ignores=[]), "app/nerf/_utils.py", "exec"), train_ns)
+
+    def loss(pred_rgbds, ray_is_valid, gt_rgba_f32):
+        n = pred_rgbds.shape[0]
+        valid = _j(np.asarray(ray_is_valid, bool))
+        train_ns.update(
+            make_rays_worldspace=lambda: (_j(np.zeros((n, 3), np.float32)), _j(np.zeros((n, 3), np.float32))),
+            view_idcs=None, total_samples=0,
+            state=types.SimpleNamespace(use_background_model=False, render=types.SimpleNamespace(random_bg=True),
+                                        replace=lambda **kw: None),
+            render_rays_train=lambda **kw: (dict(ray_is_valid=valid, n_valid_rays=valid.sum()), _j(np.asarray(pred_rgbds, np.float32)), 0))
+        value, metrics = train_ns["loss_fn"]({}, _j(np.asarray(gt_rgba_f32, np.float32)), None)
+        return np.float32(value), metrics
+
+    return types.SimpleNamespace(make_optimizer=ns["make_optimizer"], optax=optax, loss=loss,
+                                 blend_rgba_image_array=data_ns["blend_rgba_image_array"], array=_j)

@@ -211,3 +211,46 @@ def test_nerf_model_golden_from_reference_code(oracle):
     assert np.allclose(xt.grad.numpy(), g["trunc_exp_grad"], rtol=1e-6, atol=0)
     sh_t = nerf_mod.sh4(torch.from_numpy(g["dirs"].copy())).numpy()
     assert np.abs(sh_t - g["sh"]).max() <= 2.4e-7
+
+
+def test_loss_and_optimizer_golden_from_reference_code():
+    """oracle/train_np.py's loss and Adam -- the checkers of huber_loss_grad / integrate_loss_fused and of the Adam kernel
+    -- against the reference's OWN loss_fn (nested in train_step, app/nerf/_utils.py:117-162, with
+    blend_rgba_image_array utils/data.py:443-464) and make_optimizer (app/nerf/_utils.py:19-77), run unmodified on numpy
+    by oracle/make_golden_train.py (optax's primitives restated from their definitions): loss value, its gradient
+    (central differences of the reference's loss), background compositing, the staircase learning-rate schedule, and
+    four optimizer steps including the additive decayed-weights term on the MLP weights only."""
+    from oracle import train_np as T
+    g = load("train_reference.npz")
+    gt, bg, pred, valid = g["gt_rgba"], g["bg"], g["pred"], g["valid"]
+    target = gt[:, :3] * gt[:, 3:] + bg * (1 - gt[:, 3:])
+    assert np.array_equal(target.astype(np.float32), g["blend"])
+    loss, grad = T.huber_grad(pred[:, :3], target, valid)
+    assert abs(loss - float(g["loss"])) <= 1e-7 * abs(loss)
+    fd = g["loss_fd_grad"]
+    assert np.abs(grad[:32] - fd).max() <= 2e-3 * np.abs(fd).max() + 1e-7
+    assert (np.abs(fd).sum(-1) == 0).sum() == int((~valid[:32]).sum())  # masked rays carry no gradient
+    opt = T.AdamNp(lr=1e-2)
+    assert np.allclose([opt.lr_at(int(c)) for c in g["lr_counts"]], g["lr_values"], rtol=1e-12)
+    keys = ("position_encoder", "density_mlp", "rgb_mlp")
+    params = {k: g[f"opt_p0_{k}"].copy() for k in keys}
+    for step in range(4):
+        opt.step(params, {k: g[f"opt_g{step}_{k}"] for k in keys}, decay_keys=("density_mlp", "rgb_mlp"))
+        for k in keys:
+            ref = g[f"opt_p{step + 1}_{k}"]
+            assert np.abs(params[k] - ref).max() <= 2e-7 * max(1.0, np.abs(ref).max()) + 1e-9, (step, k)
+    # the weight-decay term is additive (optax.add_decayed_weights chained AFTER the lr-scaled Adam update) and only
+    # on the MLPs: with zero gradients from the start the table would not move while the MLP weights grow by 1e-6 p
+    w0 = g["opt_p0_density_mlp"]
+    probe = T.AdamNp(lr=1e-2)
+    p = {"density_mlp": w0.copy(), "position_encoder": g["opt_p0_position_encoder"].copy()}
+    probe.step(p, {k: np.zeros_like(v) for k, v in p.items()}, decay_keys=("density_mlp",))
+    assert np.array_equal(p["position_encoder"], g["opt_p0_position_encoder"])
+    assert np.allclose(p["density_mlp"], w0 * np.float32(1 + 1e-6), rtol=1e-7)
+    # the CUDA kernel's descriptor carries the same hyper-parameters (trainer.py)
+    import struct
+    from jaxngp_b200 import descriptors as D
+    d = D.make_adam_descriptor(n=8, decay_begin=4, lr_init=1e-2, lr_end=1e-4, decay_rate=1 / 3, transition_steps=10_000,
+                               transition_begin=10_000, staircase=True, b1=0.9, b2=0.99, eps=1e-15, eps_root=1e-15,
+                               weight_decay=1e-6, grad_scale=1.0)
+    assert isinstance(d, bytes) and len(d) > 0
