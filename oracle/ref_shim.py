@@ -176,6 +176,14 @@ class JArr(np.ndarray):
     def at(self):
         return _At(self)
 
+    def __getitem__(self, idx):
+        # jax clamps out-of-bounds gather indices (idle renderer slots carry index >= n_total_rays)
+        first = idx[0] if isinstance(idx, tuple) else idx
+        if isinstance(first, np.ndarray) and first.dtype.kind in "iu" and first.ndim == 1 and self.shape:
+            clamped = np.minimum(np.asarray(first).astype(np.int64), self.shape[0] - 1)
+            idx = (clamped,) + tuple(idx[1:]) if isinstance(idx, tuple) else clamped
+        return super().__getitem__(idx)
+
     def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
         args = [np.asarray(i) if isinstance(i, JArr) else i for i in inputs]
         if out is not None:
@@ -200,7 +208,13 @@ class _AtIdx:
 
     def set(self, v):
         out = self.a.copy()
-        out[self.idx] = v
+        idx = self.idx
+        if isinstance(idx, np.ndarray) and idx.dtype.kind in "iu" and idx.ndim == 1:
+            ok = np.asarray(idx).astype(np.int64) < out.shape[0]  # jax drops out-of-bounds scatter indices
+            if not ok.all():
+                np.asarray(out)[np.asarray(idx)[ok]] = np.asarray(v)[ok] if np.ndim(v) else v
+                return out
+        out[idx] = v
         return out
 
 
@@ -607,3 +621,65 @@ def install_loss_and_optimizer(scripted_random):
 
     return types.SimpleNamespace(make_optimizer=ns["make_optimizer"], optax=optax, loss=loss,
                                  blend_rgba_image_array=data_ns["blend_rgba_image_array"], array=_j)
+
+
+def install_renderer(oracle_module):
+    """The reference's inference renderer, unmodified: ``render_image_inference`` and ``march_and_integrate_inference``
+    (models/renderers/cuda.py:165-373), the Python wrappers ``march_rays_inference`` / ``integrate_rays_inference`` of
+    volume-rendering-jax (marching/__init__.py:96-157, integrating/__init__.py:62-110) and ``f32_to_u8``
+    (utils/data.py:42-43).  The two custom-call primitives the wrappers bind are served by the C oracle.  Returns a
+    namespace with ``render_image_inference`` and the pieces a caller needs to build the ``state`` it reads."""
+    import math
+    import typing
+    rays = install_rays()
+    jnp = _JnpForTypes("jax.numpy")
+    jax = _Stub("jax")
+    jax.Array, jax.numpy = np.ndarray, jnp
+    jax.jit = lambda fun=None, **kw: fun if fun is not None else (lambda f: f)
+    jax.lax = types.SimpleNamespace(stop_gradient=lambda x: x)
+
+    class _Prim:
+        def __init__(self, fn):
+            self.bind = fn
+
+    def march_bind(rays_o, rays_d, t_starts, t_ends, bitfield, next_ray_index_in, terminated, indices, **static):
+        nri, idx, ns, _, xyzs, dss, zs, tso = oracle_module.march_rays_inference(
+            static["diagonal_n_steps"], static["K"], static["G"], static["march_steps_cap"], static["bound"],
+            static["stepsize_portion"], np.asarray(rays_o), np.asarray(rays_d), np.asarray(t_starts), np.asarray(t_ends),
+            np.asarray(bitfield), np.asarray(next_ray_index_in), np.asarray(terminated), np.asarray(indices))
+        return tuple(_j(x) for x in (nri, idx, ns, tso, xyzs, dss, zs))
+
+    def integrate_bind(rays_bg, rays_rgbd, rays_T, n_samples, indices, dss, z_vals, drgbs):
+        cnt, term, rgbd_o, T_o = oracle_module.integrate_rays_inference(
+            np.asarray(rays_bg), np.asarray(rays_rgbd), np.asarray(rays_T), np.asarray(n_samples), np.asarray(indices),
+            np.asarray(dss), np.asarray(z_vals), np.asarray(drgbs, np.float32), raw=True)
+        return _j(cnt), _j(term), _j(rgbd_o), _j(T_o)
+
+    impl = types.SimpleNamespace(march_rays_inference_p=_Prim(march_bind), integrate_rays_inference_p=_Prim(integrate_bind))
+
+    def load_wrapper(rel, name):
+        path = os.path.join(REFERENCE, "deps", "volume-rendering-jax", "src", "volrendjax", rel, "__init__.py")
+        ns = dict(jax=jax, jnp=jnp, Tuple=typing.Tuple, impl=impl)
+        exec(compile(_extract_functions(path, {name}), f"volrendjax/{rel}/__init__.py", "exec"), ns)
+        return ns[name]
+
+    data_ns = dict(jnp=jnp, jax=jax)
+    exec(compile(_extract_functions(os.path.join(REFERENCE, "utils", "data.py"), {"f32_to_u8"}), "utils/data.py", "exec"), data_ns)
+    common_ns = dict(functools=functools, jax=jax, Any=typing.Any, Hashable=typing.Hashable, Sequence=typing.Sequence,
+                     Iterable=typing.Iterable, xc=_Stub("xc"))
+    exec(compile(_extract_functions(os.path.join(REFERENCE, "utils", "common.py"), {"jit_jaxfn_with"}), "utils/common.py", "exec"), common_ns)
+    path = os.path.join(REFERENCE, "models", "renderers", "cuda.py")
+    tree = ast.parse(open(path).read())
+    wanted = {"MarchAndIntegrateInferencePayload", "march_and_integrate_inference", "render_image_inference"}
+    body = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in wanted]
+    assert {n.name for n in body} == wanted
+    placeholder = type("Placeholder", (), {})
+    ns = dict(jax=jax, jnp=jnp, jran=_Stub("jax.random"), math=math, dataclass=dataclasses.dataclass, Callable=typing.Callable,
+              jit_jaxfn_with=common_ns["jit_jaxfn_with"], FrozenVariableDict=typing.Any, RigidTransformation=typing.Any,
+              NeRFState=typing.Any, Camera=placeholder, CameraOverrideOptions=type("CameraOverrideOptions", (), {}),
+              march_rays_inference=load_wrapper("marching", "march_rays_inference"),
+              integrate_rays_inference=load_wrapper("integrating", "integrate_rays_inference"),
+              make_rays_worldspace=rays.make_rays_worldspace, make_near_far_from_bound=rays.make_near_far_from_bound,
+              f32_to_u8=data_ns["f32_to_u8"])
+    exec(compile(ast.Module(body=body, type_ignores=[]), "models/renderers/cuda.py", "exec"), ns)
+    return types.SimpleNamespace(render_image_inference=ns["render_image_inference"], make_camera=rays.make_camera, array=_j)
