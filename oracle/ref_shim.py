@@ -683,3 +683,95 @@ def install_renderer(oracle_module):
               f32_to_u8=data_ns["f32_to_u8"])
     exec(compile(ast.Module(body=body, type_ignores=[]), "models/renderers/cuda.py", "exec"), ns)
     return types.SimpleNamespace(render_image_inference=ns["render_image_inference"], make_camera=rays.make_camera, array=_j)
+
+
+def install_train_forward(oracle_module, scripted_random):
+    """The whole forward of the reference's training step from its own source: the ray construction and ``loss_fn``
+    nested in ``train_step`` (app/nerf/_utils.py:93-162), ``render_rays_train`` (models/renderers/cuda.py:100-162), the
+    ``march_rays`` / ``integrate_rays`` wrappers and the primal of ``__integrate_rays`` (volume-rendering-jax), the
+    ``make_nerf_ngp`` model with the pure-JAX hash-grid encoder, ``blend_rgba_image_array``.  Only the two CUDA
+    primitives (served by the C oracle) and the library calls (flax Dense / sigmoid, optax.huber_loss) are stand-ins.
+    Returns ``forward(perm, transforms, camera, table, weights, bitfield, rgbas_u8, total_samples) -> (loss, metrics,
+    pred_rgbds)``."""
+    import typing
+    nerfs = install_nerf()
+    rays = install_rays()
+    lo = install_loss_and_optimizer(scripted_random)
+    jnp = _JnpForTypes("jax.numpy")
+    jax = _Stub("jax")
+    jax.Array, jax.numpy, jax.random, jax.custom_vjp = np.ndarray, jnp, scripted_random, CustomVjp
+    jax.jit = lambda fun=None, **kw: fun if fun is not None else (lambda f: f)
+    jax.tree_util = types.SimpleNamespace(tree_reduce=lambda fn, tree: functools.reduce(fn, list(tree.values())))
+    vr = os.path.join(REFERENCE, "deps", "volume-rendering-jax", "src", "volrendjax")
+
+    class _Prim:
+        def __init__(self, fn):
+            self.bind = fn
+
+    def march_bind(rays_o, rays_d, t_starts, t_ends, noises, bitfield, **st):
+        out = oracle_module.march_rays(st["total_samples"], st["diagonal_n_steps"], st["K"], st["G"], st["bound"],
+                                       st["stepsize_portion"], np.asarray(rays_o), np.asarray(rays_d), np.asarray(t_starts),
+                                       np.asarray(t_ends), np.asarray(noises), np.asarray(bitfield), raw=True)
+        return tuple(_j(np.asarray(x)) for x in out)
+
+    def integrate_bind(start, ns, bgs, dss, z_vals, drgbs):
+        mbs, rgbd, opac = oracle_module.integrate_rays(0.0, np.asarray(start), np.asarray(ns), np.asarray(bgs), np.asarray(dss),
+                                                       np.asarray(z_vals), np.asarray(drgbs, np.float32))
+        return _j(np.array([mbs], np.uint32)), _j(rgbd), _j(opac)
+
+    impl_int_ns = dict(jax=jax, Tuple=typing.Tuple, integrate_rays_p=_Prim(integrate_bind))
+    exec(compile(_extract_functions(os.path.join(vr, "integrating", "impl.py"), {"__integrate_rays"}), "integrating/impl.py", "exec"), impl_int_ns)
+    impl_int = types.SimpleNamespace(**{"__integrate_rays": impl_int_ns["__integrate_rays"]})
+    int_ns = dict(jax=jax, Tuple=typing.Tuple, impl=impl_int)
+    exec(compile(_extract_functions(os.path.join(vr, "integrating", "__init__.py"), {"integrate_rays"}), "integrating/__init__.py", "exec"), int_ns)
+    march_ns = dict(jax=jax, jnp=jnp, Tuple=typing.Tuple, impl=types.SimpleNamespace(march_rays_p=_Prim(march_bind)))
+    exec(compile(_extract_functions(os.path.join(vr, "marching", "__init__.py"), {"march_rays"}), "marching/__init__.py", "exec"), march_ns)
+    common_ns = dict(functools=functools, jax=jax, Any=typing.Any, Hashable=typing.Hashable, Sequence=typing.Sequence,
+                     Iterable=typing.Iterable, xc=_Stub("xc"))
+    exec(compile(_extract_functions(os.path.join(REFERENCE, "utils", "common.py"), {"jit_jaxfn_with"}), "utils/common.py", "exec"), common_ns)
+    cuda_ns = dict(jax=jax, jnp=jnp, jran=scripted_random, jit_jaxfn_with=common_ns["jit_jaxfn_with"], NeRFState=typing.Any,
+                   make_near_far_from_bound=rays.make_near_far_from_bound, march_rays=march_ns["march_rays"],
+                   integrate_rays=int_ns["integrate_rays"])
+    exec(compile(_extract_functions(os.path.join(REFERENCE, "models", "renderers", "cuda.py"), {"render_rays_train"}),
+                 "models/renderers/cuda.py", "exec"), cuda_ns)
+    utils_path = os.path.join(REFERENCE, "app", "nerf", "_utils.py")
+    tree = ast.parse(open(utils_path).read())
+    train_step = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "train_step")
+    nested = [n for n in train_step.body if isinstance(n, ast.FunctionDef) and n.name in ("make_rays_worldspace", "loss_fn")]
+    assert len(nested) == 2
+    train_ns = dict(jnp=jnp, jax=jax, jran=scripted_random, optax=lo.optax, Tuple=typing.Tuple,
+                    data=types.SimpleNamespace(blend_rgba_image_array=lo.blend_rgba_image_array),
+                    render_rays_train=cuda_ns["render_rays_train"])
+    exec(compile(ast.Module(body=nested, type_ignores=[]), "app/nerf/_utils.py", "exec"), train_ns)
+    model = nerfs.make_nerf_ngp(bound=1.0, inference=False)
+
+    def forward(perm, transforms, camera, table, weights, bitfield, rgbas_u8, total_samples, n_views):
+        model.position_encoder.bind_params(**{"latent codes stored on grid vertices": table})
+        model.density_mlp.bind_params(Dense_0=weights["density_w0"], Dense_1=weights["density_w1"])
+        model.rgb_mlp.bind_params(Dense_0=weights["rgb_w0"], Dense_1=weights["rgb_w1"], Dense_2=weights["rgb_w2"])
+        perm = _j(np.asarray(perm, np.uint32))
+
+        class State:
+            use_background_model = False
+            render = types.SimpleNamespace(random_bg=True)
+            raymarch = types.SimpleNamespace(perturb=True, diagonal_n_steps=1024, density_grid_res=128)
+            scene_meta = types.SimpleNamespace(bound=1.0, cascades=1, stepsize_portion=0.0, camera=camera)
+            ogrid = types.SimpleNamespace(occupancy=_j(np.asarray(bitfield)))
+            nerf_fn = staticmethod(lambda variables, xyzs, dirs, app: model(xyzs, dirs, app))
+            params = None
+
+            def replace(self, **kw):
+                new = State()
+                new.__dict__.update(self.__dict__)
+                new.__dict__.update(kw)
+                return new
+
+        train_ns.update(state=State(), total_samples=total_samples,
+                        scene=types.SimpleNamespace(meta=types.SimpleNamespace(camera=camera), transforms=_j(np.asarray(transforms, np.float32))),
+                        view_idcs=jnp.floor_divide(perm, camera.n_pixels), pixel_idcs=jnp.mod(perm, camera.n_pixels))
+        params = {"nerf": None, "appearance_embeddings": _j(np.zeros((n_views, 0), np.float32))}
+        gt = _j((np.asarray(rgbas_u8[np.asarray(perm)]).astype(np.float32) / np.float32(255)))  # _utils.py:165
+        loss, metrics = train_ns["loss_fn"](params, gt, None)
+        return np.float32(loss), metrics
+
+    return types.SimpleNamespace(forward=forward, make_camera=rays.make_camera)

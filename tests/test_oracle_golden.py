@@ -289,3 +289,29 @@ def test_rendered_frame_golden_from_reference_code(oracle):
     assert np.array_equal(f32_to_u8(rgbd[:, :3]).reshape(Hd, Wd, 3), g["image"])
     depth = rgbd[:, 3:]
     assert np.array_equal(f32_to_u8((depth - depth.min()) / (depth.max() - depth.min() + 1e-15)).reshape(Hd, Wd), g["distance"])
+
+
+def test_training_step_forward_golden_from_reference_code(oracle):
+    """oracle/train_np.train_step -- the checker of the GPU training step and the CPU baseline of bench.py -- against the
+    forward of one whole training step executed from the reference's OWN source (perm -> rays -> march_rays ->
+    HashGridEncoder -> NeRF MLP -> integrate_rays -> Huber loss; app/nerf/_utils.py:93-162, models/renderers/cuda.py,
+    the volume-rendering-jax wrappers, models/nerfs.py, models/encoders.py; oracle/make_golden_train_forward.py): the
+    same rays are valid, the same number of samples is marched and composited (with early termination), same loss."""
+    from jaxngp_b200 import synthetic as S
+    from oracle import train_np as T
+    from oracle.make_golden_train_forward import N_VIEWS, TOTAL_SAMPLES, make_inputs
+    g = load("train_forward_reference.npz")
+    d = make_inputs()
+    cam = d["cam"]
+    perm = d["perm"].astype(np.int64)
+    hw = cam["width"] * cam["height"]
+    o, dd = S.pixel_rays(S.poses(N_VIEWS), perm // hw, perm % hw)
+    ts, te = S.near_far(o, dd)
+    rays = dict(rays_o=o, rays_d=dd, t_starts=ts, t_ends=te, noises=d["noises"])
+    params = dict(table=d["table"], **d["w"])
+    gt = d["rgba_rows"].astype(np.float32) / np.float32(255)
+    m, _ = T.train_step(params, None, d["lv"], S.occupancy_bitfield(), rays, gt, d["bg"], TOTAL_SAMPLES, apply=False)
+    assert m["n_valid_rays"] == int(g["n_valid_rays"]) and 0 < m["n_valid_rays"] < perm.shape[0]
+    assert m["measured_batch_size_before_compaction"] == int(g["measured_batch_size_before_compaction"])
+    assert m["measured_batch_size"] == int(g["measured_batch_size"]) < m["measured_batch_size_before_compaction"]
+    assert abs(m["loss"] - float(g["loss"])) <= 1e-5 * abs(float(g["loss"]))
