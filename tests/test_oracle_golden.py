@@ -1,5 +1,11 @@
-"""Pins the CPU oracle (oracle/ngp_oracle.c) against golden vectors produced by the reference's own
-CUDA kernels on a B200 (oracle/make_golden.py -> tests/golden/*.npz).  Runs without a GPU."""
+"""Pins the CPU oracle, in two layers, against golden vectors of the reference itself.  Runs without a GPU.
+
+1. The compiled ops (morton, packbits, march, integrate, the inference loop): outputs of the reference's own CUDA
+   kernels, built unmodified and run on a B200 (oracle/make_golden.py).
+2. Everything the reference keeps in Python/JAX (hash-grid encoder, NeRF model, loss, optimizer, density-grid update,
+   ray generation, renderer loop and op wrappers, the whole training-step forward and its gradients by finite
+   differences): outputs of the reference's UNMODIFIED source executed on numpy stand-ins for jax/flax/optax
+   (oracle/ref_shim.py, oracle/make_golden_{encoder,nerf,ogrid,rays,train,train_forward,train_grad,render}.py)."""
 import hashlib
 import os
 
