@@ -53,6 +53,34 @@ def main():
         out[key + "_rows"] = np.int64(rows)
         out[key + "_b"] = np.float64(enc_mod.b)
         print(key, "rows", rows, "b", enc_mod.b, "|enc| max", float(np.abs(enc).max()))
+    # TCNNHashGridEncoder.__call__ (models/encoders.py:259-305), the Python half of the tiny-cuda-nn path: what it hands
+    # to jaxtcnn.hashgrid_encode (level offsets WITHOUT the 8-alignment of the pure-JAX encoder, the per-level scale, the
+    # transposed unit-cube coordinates, the parameter shape it requests).  The CUDA half is tiny-cuda-nn v1.6 (absent).
+    import collections
+    import sys as _sys
+    calls = []
+    tcnn = _sys.modules["jaxtcnn"]
+    tcnn.HashGridMetadata = collections.namedtuple("HashGridMetadata", "L F N_min per_level_scale")
+
+    def record(desc, offset_table_data, coords_rm, params):
+        calls.append((desc, np.asarray(offset_table_data), np.asarray(coords_rm), tuple(params.shape)))
+        return np.zeros((desc.L * desc.F, coords_rm.shape[1]), np.float32)
+
+    ref.hashgrid_encode, ref.HashGridMetadata = record, tcnn.HashGridMetadata
+    for T, N_max in ((2 ** 19, 2048), (2 ** 14, 512)):
+        lv = H.level_table(16, T, 2, 16, N_max, 3, align=1)
+        rows = int(lv["offsets"][-1])
+        pts = inputs.encoder_points(16, 3)
+        mod = ref.TCNNHashGridEncoder(L=16, T=T, F=2, N_min=16, N_max=N_max, tv_scale=0.0)
+        mod.bind_params(**{PARAM: np.zeros((rows, 2), np.float32)})  # shape-checked by the reference's self.param
+        enc, tv = mod(pts, 1.0)
+        desc, offs, coords, pshape = calls.pop()
+        assert enc.shape == (16, 32) and offs.dtype == np.uint32 and coords.shape == (3, 16)
+        key = f"tcnn_T{T}_N{N_max}"
+        out[key + "_offsets"] = offs
+        out[key + "_desc"] = np.array([desc.L, desc.F, desc.N_min, desc.per_level_scale], np.float64)
+        out[key + "_coords_rm"] = coords
+        print(key, "rows", int(offs[-1]), "per_level_scale", desc.per_level_scale)
     path = os.path.join(ROOT, "tests", "golden", "encoder_reference.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -357,3 +357,22 @@ def test_training_step_gradients_against_differences_of_the_reference_forward(or
             assert abs(an - fd) > 0.3 * abs(fd), (name, k, an, fd)  # the reference's density VJP is not the derivative
             density += 1
     assert colour >= 7 and density >= 3
+
+
+@pytest.mark.parametrize("T,N_max", [(2 ** 19, 2048), (2 ** 14, 512)])
+def test_tcnn_encoder_python_half_golden_from_reference_code(T, N_max):
+    """What the reference's ``TCNNHashGridEncoder.__call__`` (models/encoders.py:259-305, run unmodified by
+    oracle/make_golden_encoder.py) hands to ``jaxtcnn.hashgrid_encode``: level offsets without the 8-alignment of the
+    pure-JAX encoder (6,098,108 rows at C2), the per-level scale, the transposed unit-cube coordinates.  The host mirror
+    (jaxngp_b200/encoders.py TCNNHashGridEncoder, the oracle's level table with align=1) must pass the same.  The CUDA
+    half of that path is tiny-cuda-nn v1.6, which is not on disk: "parity unpinned" (DESIGN.md section 2)."""
+    from jaxngp_b200 import encoders as E
+    from oracle import hashgrid_np as H
+    g = load("encoder_reference.npz")
+    key = f"tcnn_T{T}_N{N_max}"
+    offs, desc, coords = g[key + "_offsets"], g[key + "_desc"], g[key + "_coords_rm"]
+    lt = E.make_level_table(16, T, 2, 16, N_max, 3, E.TCNNHashGridEncoder.align)
+    assert list(lt.offsets) == offs.tolist() == H.level_table(16, T, 2, 16, N_max, 3, align=1)["offsets"].tolist()
+    assert (int(desc[0]), int(desc[1]), int(desc[2])) == (16, 2, 16) and abs(float(desc[3]) - lt.b) < 1e-12
+    pts = inputs.encoder_points(16, 3)
+    assert np.array_equal(((pts + np.float32(1.0)) / np.float32(2.0)).T, coords)
