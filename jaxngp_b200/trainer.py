@@ -118,6 +118,20 @@ class Trainer:
     def occupancy(self):
         return self.grid.occupancy
 
+    # -- the reference's update cadence (utils/types.py:1380-1396), for callers that run its training loop
+    #    (app/nerf/train.py:46-88): every step at first, every 16 steps from step 240 on
+    @property
+    def update_ogrid_interval(self) -> int:
+        return min(16, self.step // 16 + 1)
+
+    @property
+    def should_call_update_ogrid(self) -> bool:
+        return self.step > 0 and self.step % self.update_ogrid_interval == 0
+
+    @property
+    def should_update_all_ogrid_cells(self) -> bool:
+        return self.step < 256
+
     @property
     def occ_mask(self):
         return self.grid.occ_mask

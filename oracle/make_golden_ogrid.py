@@ -66,6 +66,13 @@ def main():
         out[f"{tag}_occupancy"] = np.asarray(state.ogrid.occupancy).copy()
         print(tag, "occupied fraction", float(out[f"{tag}_occ_mask"].mean()), "threshold", float(out[f"{tag}_threshold"]))
     assert not jran._choices and not jran._uniforms
+    # the update cadence of the training loop (utils/types.py:1380-1396), from the reference's own properties
+    cadence = ref_shim.install_cadence()
+    steps = np.arange(0, 600, dtype=np.int64)
+    out["cadence_steps"] = steps
+    out["cadence_interval"] = np.array([cadence(int(s)).update_ogrid_interval for s in steps], np.int64)
+    out["cadence_call"] = np.array([bool(cadence(int(s)).should_call_update_ogrid) for s in steps])
+    out["cadence_all"] = np.array([bool(cadence(int(s)).should_update_all_ogrid_cells) for s in steps])
     path = os.path.join(ROOT, "tests", "golden", "ogrid_reference.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -775,3 +775,26 @@ def install_train_forward(oracle_module, scripted_random):
         return np.float32(loss), metrics
 
     return types.SimpleNamespace(forward=forward, make_camera=rays.make_camera)
+
+
+def install_cadence():
+    """``NeRFState.update_ogrid_interval`` / ``should_call_update_ogrid`` / ``should_update_all_ogrid_cells``
+    (utils/types.py:1380-1396), unmodified; returns ``state(step)``."""
+    path = os.path.join(REFERENCE, "utils", "types.py")
+    tree = ast.parse(open(path).read())
+    state_cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "NeRFState")
+    wanted = {"update_ogrid_interval", "should_call_update_ogrid", "should_update_all_ogrid_cells"}
+    methods = [n for n in state_cls.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    assert {m.name for m in methods} == wanted
+    cls = ast.ClassDef(name="Cadence", bases=[], keywords=[], body=methods, decorator_list=[], type_params=[])
+    module = ast.Module(body=[cls], type_ignores=[])
+    ast.fix_missing_locations(module)
+    ns = {}
+    exec(compile(module, "utils/types.py", "exec"), ns)
+
+    def state(step):
+        obj = ns["Cadence"]()
+        obj.step = step
+        return obj
+
+    return state

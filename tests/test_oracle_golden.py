@@ -376,3 +376,16 @@ def test_tcnn_encoder_python_half_golden_from_reference_code(T, N_max):
     assert (int(desc[0]), int(desc[1]), int(desc[2])) == (16, 2, 16) and abs(float(desc[3]) - lt.b) < 1e-12
     pts = inputs.encoder_points(16, 3)
     assert np.array_equal(((pts + np.float32(1.0)) / np.float32(2.0)).T, coords)
+
+
+def test_update_cadence_golden_from_reference_code():
+    """The density-grid update cadence of the training loop (utils/types.py:1380-1396 via oracle/make_golden_ogrid.py):
+    interval min(16, step // 16 + 1), full updates for the first 256 steps.  trainer.Trainer mirrors the properties."""
+    from jaxngp_b200.trainer import Trainer
+    g = load("ogrid_reference.npz")
+    probe = Trainer.__new__(Trainer)  # the properties only read .step
+    for step, interval, call, all_cells in zip(g["cadence_steps"], g["cadence_interval"], g["cadence_call"], g["cadence_all"]):
+        probe.step = int(step)
+        assert probe.update_ogrid_interval == int(interval)
+        assert probe.should_call_update_ogrid == bool(call) and probe.should_update_all_ogrid_cells == bool(all_cells)
+    assert int(g["cadence_interval"][240]) == 16 and bool(g["cadence_call"][256])
