@@ -70,7 +70,11 @@ def integrate_rays(
     start, ns = as_u32(rays_sample_startidx, "rays_sample_startidx"), as_u32(rays_n_samples, "rays_n_samples")
     n_rays, total_samples = start.shape[0], dss.shape[0]
     dev = drgbs.device
-    bgs = torch.broadcast_to(torch.as_tensor(bgs, dtype=torch.float32, device=dev), (n_rays, 3))  # impl.py:60
+    bgs = torch.as_tensor(bgs, dtype=torch.float32, device=dev)
+    try:
+        bgs = torch.broadcast_to(bgs, (n_rays, 3))  # impl.py:60 (jnp.broadcast_to raises ValueError when it cannot)
+    except RuntimeError as exc:
+        raise ValueError(f"bgs of shape {tuple(bgs.shape)} cannot be broadcast to ({n_rays}, 3)") from exc
     # integrating/abstract.py:16-29,65-81
     assert_shape(ns, (n_rays,), "rays_n_samples")
     assert_shape(z_vals, (total_samples,), "z_vals")

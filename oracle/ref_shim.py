@@ -798,3 +798,89 @@ def install_cadence():
         return obj
 
     return state
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Abstract-evaluation contracts of the ops (volume-rendering-jax: {marching,integrating,packbits,morton3d}/abstract.py):
+# output shapes / dtypes and the errors raised for malformed operands, unmodified.  chex's assertions are restated
+# (they raise AssertionError); jax.dtypes.canonicalize_dtype maps 64-bit types to 32-bit (x64 is off in the reference).
+class ShapedArray:
+    def __init__(self, shape, dtype):
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+
+def _chex_for_contracts():
+    chex = types.ModuleType("chex")
+
+    def _each(x):
+        return list(x) if isinstance(x, (list, tuple)) else [x]
+
+    def assert_shape(x, shape):
+        for a in _each(x):
+            if tuple(a.shape) != tuple(shape):
+                raise AssertionError(f"shape {a.shape} != {tuple(shape)}")
+
+    def assert_type(x, dtype):
+        for a in _each(x):
+            if np.dtype(a.dtype) != np.dtype(dtype):
+                raise AssertionError(f"dtype {a.dtype} != {np.dtype(dtype)}")
+
+    def assert_rank(x, rank):
+        for a in _each(x):
+            if len(a.shape) != rank:
+                raise AssertionError(f"rank {len(a.shape)} != {rank}")
+
+    def assert_equal_shape(xs):
+        if len({tuple(a.shape) for a in xs}) > 1:
+            raise AssertionError("shapes differ")
+
+    def assert_axis_dimension(x, axis, expected):
+        if x.shape[axis] != expected:
+            raise AssertionError(f"axis {axis} has {x.shape[axis]} != {expected}")
+
+    def assert_scalar_positive(v):
+        if not v > 0:
+            raise AssertionError(f"{v} is not positive")
+
+    def assert_scalar_non_negative(v):
+        if not v >= 0:
+            raise AssertionError(f"{v} is negative")
+
+    for f in (assert_shape, assert_type, assert_rank, assert_equal_shape, assert_axis_dimension, assert_scalar_positive,
+              assert_scalar_non_negative):
+        setattr(chex, f.__name__, f)
+    return chex
+
+
+def install_abstract():
+    """Returns {name: function} with every ``*_abstract`` rule of volume-rendering-jax, and the ShapedArray class."""
+    def canonicalize(dt):
+        dt = np.dtype(dt)
+        return {np.dtype(np.float64): np.dtype(np.float32), np.dtype(np.int64): np.dtype(np.int32),
+                np.dtype(np.uint64): np.dtype(np.uint32)}.get(dt, dt)
+
+    jnp = _numpy_namespace("jax.numpy")
+    jax = _Stub("jax")
+    jax.numpy, jax.ShapedArray = jnp, ShapedArray
+    jax.dtypes = types.SimpleNamespace(canonicalize_dtype=canonicalize)
+    saved = {k: sys.modules.get(k) for k in ("jax", "jax.numpy", "chex")}
+    sys.modules.update({"jax": jax, "jax.numpy": jnp, "chex": _chex_for_contracts()})
+    rules = {}
+    try:
+        for pkg in ("marching", "integrating", "packbits", "morton3d"):
+            path = os.path.join(REFERENCE, "deps", "volume-rendering-jax", "src", "volrendjax", pkg, "abstract.py")
+            spec = importlib.util.spec_from_file_location(f"reference_volrendjax_{pkg}_abstract", path)
+            module = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(module)
+            rules.update({k: v for k, v in vars(module).items() if k.endswith("_abstract")})
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return rules, ShapedArray

@@ -389,3 +389,59 @@ def test_update_cadence_golden_from_reference_code():
         assert probe.update_ogrid_interval == int(interval)
         assert probe.should_call_update_ogrid == bool(call) and probe.should_update_all_ogrid_cells == bool(all_cells)
     assert int(g["cadence_interval"][240]) == 16 and bool(g["cadence_call"][256])
+
+
+def test_op_contracts_golden_from_reference_code():
+    """Abstract-evaluation contracts: the host mirror (jaxngp_b200.volrendjax.*) answers a table of well-formed and
+    malformed operand signatures the way the reference's OWN ``*_abstract`` rules do
+    ({marching,integrating,packbits,morton3d}/abstract.py, run unmodified by oracle/make_golden_contracts.py): the same
+    exception class for every malformed case; for the well-formed ones the checks pass and the call reaches the launch,
+    which refuses CPU tensors (there is no CPU path)."""
+    import json
+    import torch
+    from jaxngp_b200 import _lib, volrendjax as V
+    table = json.load(open(os.path.join(GOLDEN, "contracts_reference.json")))
+    tdt = {"float32": torch.float32, "float16": torch.float16, "uint32": torch.int32, "int32": torch.int32,
+           "uint8": torch.uint8, "int8": torch.int8, "bool": torch.bool}
+
+    def tensor(shape, dtype):
+        if dtype == "int32" and False:
+            pass
+        return torch.zeros(tuple(shape), dtype=tdt[dtype])
+
+    def call(op, ops, st):
+        a = [tensor(s, d) for s, d in ops]
+        if op == "march_rays_abstract":
+            return V.march_rays(st["total_samples"], st["diagonal_n_steps"], st["K"], st["G"], st["bound"], st["stepsize_portion"], *a)
+        if op == "march_rays_inference_abstract":
+            return V.march_rays_inference(st["diagonal_n_steps"], st["K"], st["G"], st["march_steps_cap"], st["bound"],
+                                          st["stepsize_portion"], *a)
+        if op == "integrate_rays_abstract":
+            return V.integrate_rays(0.3, *a)
+        if op == "integrate_rays_inference_abstract":
+            return V.integrate_rays_inference(*a)
+        if op == "pack_density_into_bits_abstract":
+            return V.packbits(*a)
+        if op == "morton3d_abstract":
+            return V.morton3d(*a)
+        if op == "morton3d_invert_abstract":
+            return V.morton3d_invert(*a)
+        raise KeyError(op)
+
+    seen = set()
+    for row in table:
+        # an int32 bitfield is the reference's "wrong dtype" case; uint32 operands travel as int32 in the mirror
+        expected = row["answer"].get("raises", "NgpError")
+        if row["case"] == "integrate bgs shape":
+            # the abstract rule never sees this operand: the reference's wrapper broadcasts bgs to (n_rays, 3) first
+            # (integrating/impl.py:60) and jnp.broadcast_to raises ValueError; the mirror does the same
+            expected = "ValueError"
+        try:
+            call(row["op"], row["operands"], row["static"])
+            got = "no error"
+        except Exception as exc:  # noqa: BLE001 -- the class is what is compared
+            got = type(exc).__name__
+        assert got == expected, (row["case"], got, expected)
+        seen.add(expected)
+    assert {"AssertionError", "NotImplementedError", "ValueError", "NgpError"} <= seen
+    assert _lib.NgpError.__name__ == "NgpError"
