@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- the ops' abstract-evaluation contracts from the reference's OWN code.
 
-Runs every ``*_abstract`` rule of volume-rendering-jax ({marching,integrating,packbits,morton3d}/abstract.py),
-unmodified, on a table of well-formed and malformed operand signatures (oracle/ref_shim.install_abstract) and records
+Runs every ``*_abstract`` rule of volume-rendering-jax ({marching,integrating,packbits,morton3d}/abstract.py) and of
+jax-tcnn (hashgrid_tcnn/abstract.py), unmodified, on a table of well-formed and malformed operand signatures (oracle/ref_shim.install_abstract) and records
 what it answers: output shapes / dtypes, or the exception class it raises.  tests/test_oracle_golden.py replays the
 same table on the host mirror (jaxngp_b200.volrendjax.*).  Writes tests/golden/contracts_reference.json.
 
@@ -62,6 +62,19 @@ def cases():
         ("morton3d float", "morton3d_abstract", [((50, 3), f32)], {}),
         ("morton3d_invert ok", "morton3d_invert_abstract", [((50,), u32)], {}),
         ("morton3d_invert float", "morton3d_invert_abstract", [((50,), f32)], {}),
+    ]
+    # jaxtcnn.hashgrid_encode (deps/jax-tcnn/src/jaxtcnn/hashgrid_tcnn/abstract.py): offsets u32[L+1], coords f32[3, n], params f32[rows, F]
+    tcnn = [((17,), u32), ((3, 70), f32), ((5000, 2), f32)]
+    tcnn_st = dict(L=16, F=2, N_min=16, per_level_scale=1.38)
+    out += [
+        ("tcnn ok", "hashgrid_encode_abstract", tcnn, tcnn_st),
+        ("tcnn 2-D coordinates", "hashgrid_encode_abstract", swap(tcnn, 1, ((2, 70), f32)), tcnn_st),
+        ("tcnn offsets length", "hashgrid_encode_abstract", swap(tcnn, 0, ((16,), u32)), tcnn_st),
+        ("tcnn params width", "hashgrid_encode_abstract", swap(tcnn, 2, ((5000, 4), f32)), tcnn_st),
+        ("tcnn offsets dtype", "hashgrid_encode_abstract", swap(tcnn, 0, ((17,), f32)), tcnn_st),
+        ("tcnn f16 coordinates", "hashgrid_encode_abstract", swap(tcnn, 1, ((3, 70), f16)), tcnn_st),
+        ("tcnn f16 params", "hashgrid_encode_abstract", swap(tcnn, 2, ((5000, 2), f16)), tcnn_st),
+        ("tcnn integer scale", "hashgrid_encode_abstract", tcnn, dict(tcnn_st, per_level_scale=2)),
     ]
     return out
 

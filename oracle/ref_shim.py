@@ -850,8 +850,22 @@ def _chex_for_contracts():
         if not v >= 0:
             raise AssertionError(f"{v} is negative")
 
+    def assert_scalar(v):
+        if not isinstance(v, (int, float)):
+            raise AssertionError(f"{v!r} is not a scalar")
+
+    array_assert_type = assert_type
+
+    def assert_type(x, dtype):  # chex accepts Python scalars too: their type must be (a subtype of) the expected one
+        if all(isinstance(a, (int, float)) for a in _each(x)):
+            for a in _each(x):
+                if not (isinstance(a, dtype) and not (dtype is float and isinstance(a, bool))) or (dtype is float and isinstance(a, int)):
+                    raise AssertionError(f"{a!r} is not of type {dtype}")
+            return
+        array_assert_type(x, dtype)
+
     for f in (assert_shape, assert_type, assert_rank, assert_equal_shape, assert_axis_dimension, assert_scalar_positive,
-              assert_scalar_non_negative):
+              assert_scalar_non_negative, assert_scalar):
         setattr(chex, f.__name__, f)
     return chex
 
@@ -871,8 +885,10 @@ def install_abstract():
     sys.modules.update({"jax": jax, "jax.numpy": jnp, "chex": _chex_for_contracts()})
     rules = {}
     try:
-        for pkg in ("marching", "integrating", "packbits", "morton3d"):
-            path = os.path.join(REFERENCE, "deps", "volume-rendering-jax", "src", "volrendjax", pkg, "abstract.py")
+        paths = {pkg: os.path.join(REFERENCE, "deps", "volume-rendering-jax", "src", "volrendjax", pkg, "abstract.py")
+                 for pkg in ("marching", "integrating", "packbits", "morton3d")}
+        paths["hashgrid_tcnn"] = os.path.join(REFERENCE, "deps", "jax-tcnn", "src", "jaxtcnn", "hashgrid_tcnn", "abstract.py")
+        for pkg, path in paths.items():
             spec = importlib.util.spec_from_file_location(f"reference_volrendjax_{pkg}_abstract", path)
             module = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(module)

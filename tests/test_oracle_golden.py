@@ -393,8 +393,9 @@ def test_update_cadence_golden_from_reference_code():
 
 def test_op_contracts_golden_from_reference_code():
     """Abstract-evaluation contracts: the host mirror (jaxngp_b200.volrendjax.*) answers a table of well-formed and
-    malformed operand signatures the way the reference's OWN ``*_abstract`` rules do
-    ({marching,integrating,packbits,morton3d}/abstract.py, run unmodified by oracle/make_golden_contracts.py): the same
+    malformed operand signatures the way the reference's OWN ``*_abstract`` rules do (volume-rendering-jax
+    {marching,integrating,packbits,morton3d}/abstract.py and jax-tcnn hashgrid_tcnn/abstract.py, run unmodified by
+    oracle/make_golden_contracts.py; jaxngp_b200.jaxtcnn is the mirror of the latter): the same
     exception class for every malformed case; for the well-formed ones the checks pass and the call reaches the launch,
     which refuses CPU tensors (there is no CPU path)."""
     import json
@@ -426,6 +427,9 @@ def test_op_contracts_golden_from_reference_code():
             return V.morton3d(*a)
         if op == "morton3d_invert_abstract":
             return V.morton3d_invert(*a)
+        if op == "hashgrid_encode_abstract":
+            from jaxngp_b200 import jaxtcnn
+            return jaxtcnn.hashgrid_encode(jaxtcnn.HashGridMetadata(**st), *a)
         raise KeyError(op)
 
     seen = set()
@@ -443,5 +447,5 @@ def test_op_contracts_golden_from_reference_code():
             got = type(exc).__name__
         assert got == expected, (row["case"], got, expected)
         seen.add(expected)
-    assert {"AssertionError", "NotImplementedError", "ValueError", "NgpError"} <= seen
+    assert {"AssertionError", "NotImplementedError", "ValueError", "RuntimeError", "NgpError"} <= seen
     assert _lib.NgpError.__name__ == "NgpError"
