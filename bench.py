@@ -126,7 +126,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()  # started early: nvidia-smi needs a moment before its first sample
     tr = Trainer(device=dev, n_rays=N_RAYS, total_samples=TOTAL_SAMPLES, rank=rank, world_size=world,
-                 use_graph=not args.no_graph)
+                 use_graph=not args.no_graph, exchange=args.exchange)
     # converged occupancy of the analytic scene (see DESIGN.md "bench state"): bitfield and its unpacked mask
     tr.grid.occupancy.copy_(tr.scene.bitfield_gt)
     tr.grid.occ_mask.copy_(torch.from_numpy(np.unpackbits(tr.scene.bitfield_gt.cpu().numpy(), bitorder="little").astype(bool)).to(dev))
@@ -219,7 +219,12 @@ def run_ours(args):
                                "2^18 rays = 2^18 sample slots per step per GPU, 128^3 density grid, diagonal_n_steps=1024, "
                                "hash grid L=16 T=2^19 F=2, random-init weights, analytic occupancy",
                    "n_rays_per_gpu": N_RAYS, "total_samples_per_gpu": TOTAL_SAMPLES, "ogrid_update_every": OGRID_EVERY,
-                   "parallelism": f"ray-sharded dp{world}; flat gradient reduce-scatter -> Adam on 1/{world} of the parameters -> parameter all-gather (NCCL)",
+                   "parallelism": f"ray-sharded dp{world}; " + (
+                       f"flat gradient reduce-scatter -> Adam on 1/{world} of the parameters -> parameter all-gather (NCCL)"
+                       if tr.peer_exchange is None else
+                       f"one fused kernel per rank: summed gradient shard read over NVLink "
+                       f"({'multimem.ld_reduce' if tr.peer_exchange.use_multimem else 'peer loads'}) -> Adam on 1/{world} of the "
+                       f"parameters -> stored into every replica ({tr.peer_exchange.n_blocks} CTAs)"),
                    "l2": "per-step working set (table+grads+moments+activations ~0.5 GB) exceeds the 126 MB L2; no flush",
                    "cuda_graph": not args.no_graph},
         "samples_per_step": samples / K,
@@ -648,6 +653,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the C3 render and C4 hash-encoder measurements")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu launch lists)")
+    ap.add_argument("--exchange", default=None, choices=["nccl", "peer", "peer-p2p"],
+                    help="gradient exchange at N>1: NCCL reduce-scatter/all-gather around Adam (default, or "
+                         "NGP_B200_EXCHANGE) or the fused NVLink kernel of csrc/exchange.cu")
     ap.add_argument("--profile", type=int, default=0, help="run N steps between cudaProfilerStart/Stop and exit")
     ap.add_argument("--with-ref-gpu", action="store_true", help="also time the reference's CUDA ops arm in a subprocess")
     args = ap.parse_args()

@@ -263,6 +263,28 @@ typedef struct {
 } NgpAdamDescriptor;
 void ngp_adam_step(cudaStream_t, void **, const char *, size_t);
 
+/* Gradient exchange fused with the optimizer, for ray-sharded data parallelism (the reference trains on one GPU;
+ * this is app/nerf/_utils.py:19-77 applied to the SUM of every rank's gradient).  ONE kernel per rank does
+ * what reduce-scatter -> ngp_adam_step -> all-gather do: it waits until every peer's gradient buffer is complete,
+ * reads this rank's shard of the summed gradient straight from the peers over NVLink (multimem.ld_reduce through the
+ * NVSwitch when multicast pointers are given, otherwise one load per peer in rank order), applies Adam to the shard
+ * (m, v are shard-local), and stores the updated parameters into EVERY rank's parameter buffer (multimem.st, or one
+ * store per peer).  Each element is reduced exactly once, by its owner, so replicas stay bit-identical.  All ranks
+ * must launch it with the same descriptor apart from rank / shard_begin.
+ * in : step u32[1], m f32[n], v f32[n] (n = adam.n, this rank's shard; updated in place),
+ *      grads_ptrs u64[world] (device array: base of rank r's flat gradient buffer, mapped in this process),
+ *      params_ptrs u64[world] (same for the flat parameter buffers; element shard_begin + i of every one is written),
+ *      signal_ptrs u64[world] (rank r's signal pad: zero-initialised u32 words, >= signal_base + n_blocks*world),
+ *      grads_mc, params_mc (multicast bases of the two buffers, read only if use_multimem) */
+typedef struct {
+    NgpAdamDescriptor adam;            /* n = shard length, decay_begin relative to the shard */
+    uint64_t shard_begin;              /* first element of this rank's shard in the flat buffers (multiple of 4) */
+    uint32_t rank, world;              /* world <= 8 */
+    uint32_t use_multimem, n_blocks;   /* n_blocks: same on every rank, <= resident CTAs of the device */
+    uint32_t signal_base, reserved;    /* first u32 word of the pads this op may use */
+} NgpAdamExchangeDescriptor;
+void ngp_adam_step_exchange(cudaStream_t, void **, const char *, size_t);
+
 /* ------------------------------------------------------------------ status */
 int ngp_b200_abi_version(void);
 /* 0 = last call on this host thread succeeded; otherwise a cudaError_t or a negative ngp code */

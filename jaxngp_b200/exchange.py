@@ -1,0 +1,84 @@
+"""Gradient exchange fused with the optimizer over NVLink (``csrc/exchange.cu``).
+
+``dp.py`` exchanges the flat gradient as reduce-scatter -> Adam on the rank's shard -> all-gather (two NCCL launches
+around our optimizer kernel).  ``PeerExchange`` does the same step as ONE kernel per rank: the flat parameter and
+gradient buffers live in symmetric memory (every rank maps every peer's copy, plus one multicast mapping when the
+NVSwitch offers it), and ``ngp_adam_step_exchange`` reads the summed shard straight from the peers, applies Adam and
+writes the new parameters into every replica.
+
+Opt-in (``Trainer(exchange="peer")`` / ``NGP_B200_EXCHANGE=peer``): the NCCL path in ``dp.py`` stays the default until
+this one has been measured on an 8-GPU box.  There is no CPU path; ``tests/test_dp_gloo.py`` covers the host-side
+layout only.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, descriptors
+
+#: first u32 word of the signal pads used by ngp_adam_step_exchange (torch's own barrier()/put_signal use the low words)
+SIGNAL_BASE = 1024
+MAX_WORLD = 8
+
+
+def requested_mode(default="nccl"):
+    """``nccl`` (dp.py), ``peer`` (multicast if available, else per-peer loads) or ``peer-p2p`` (never multicast)."""
+    mode = os.environ.get("NGP_B200_EXCHANGE", default)
+    if mode not in ("nccl", "peer", "peer-p2p"):
+        raise ValueError(f"NGP_B200_EXCHANGE must be nccl, peer or peer-p2p, got {mode!r}")
+    return mode
+
+
+def blocks_for(pad_bytes: int, world: int, want: int = 96) -> int:
+    """CTAs per launch: each needs ``world`` signal words above SIGNAL_BASE; at most one per SM (they spin on peers)."""
+    room = (pad_bytes // 4 - SIGNAL_BASE) // world
+    if room < 1:
+        raise _lib.NgpError(f"signal pad of {pad_bytes} bytes has no room above word {SIGNAL_BASE} for {world} ranks")
+    return max(1, min(want, room, 148))
+
+
+class PeerExchange:
+    """Symmetric flat buffers of one trainer and the fused exchange launch over them.
+
+    ``numel`` is the padded length of the flat buffers (a multiple of 4 * world); rank r owns
+    ``dp.shard_bounds(numel, r, world)``.  Construction is collective: every rank of ``group`` must build it with the
+    same ``numel``."""
+
+    def __init__(self, numel: int, rank: int, world_size: int, device, group=None, mode="peer", n_blocks=None):
+        import torch.distributed._symmetric_memory as symm_mem  # imported here: CPU-only hosts never reach this class
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise _lib.NgpError("the peer exchange needs an initialised NCCL process group (one process per GPU)")
+        if world_size < 2 or world_size > MAX_WORLD:
+            raise _lib.NgpError(f"the peer exchange supports 2..{MAX_WORLD} ranks of one NVLink domain, got {world_size}")
+        if numel % (4 * world_size) != 0:
+            raise _lib.NgpError(f"flat buffer length {numel} is not a multiple of 4 * world_size")
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world, self.device = rank, world_size, torch.device(device)
+        self.params = symm_mem.empty(numel, dtype=torch.float32, device=self.device)
+        self.grads = symm_mem.empty(numel, dtype=torch.float32, device=self.device)
+        self.params.zero_()
+        self.grads.zero_()
+        self._h_params = symm_mem.rendezvous(self.params, group=group)
+        self._h_grads = symm_mem.rendezvous(self.grads, group=group)
+        if self._h_grads.rank != rank or self._h_grads.world_size != world_size:
+            raise _lib.NgpError("symmetric-memory rank/world differ from the trainer's")
+        mc_p, mc_g = int(self._h_params.multicast_ptr), int(self._h_grads.multicast_ptr)
+        self.use_multimem = mode == "peer" and mc_p != 0 and mc_g != 0
+        self._mc_params, self._mc_grads = (mc_p, mc_g) if self.use_multimem else (0, 0)
+        # device arrays of the peers' base pointers, owned by the handles
+        self._grads_ptrs = int(self._h_grads.buffer_ptrs_dev)
+        self._params_ptrs = int(self._h_params.buffer_ptrs_dev)
+        self._signal_ptrs = int(self._h_grads.signal_pad_ptrs_dev)
+        self.n_blocks = blocks_for(int(self._h_grads.signal_pad_size), world_size) if n_blocks is None else int(n_blocks)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)  # every replica zeroed and mapped before the first launch touches a peer
+
+    def step(self, step_dev, adam_m, adam_v, adam_desc: bytes, shard_begin: int):
+        """Enqueue the fused exchange + Adam on the current stream.  ``adam_desc`` is the shard's NgpAdamDescriptor
+        (grad_scale = 1 / world)."""
+        desc = descriptors.make_adam_exchange_descriptor(adam_desc, shard_begin, self.rank, self.world,
+                                                         self.use_multimem, self.n_blocks, SIGNAL_BASE)
+        _lib.call("ngp_adam_step_exchange", [step_dev, adam_m, adam_v, self._grads_ptrs, self._params_ptrs,
+                                             self._signal_ptrs, self._mc_grads, self._mc_params], desc)

@@ -12,7 +12,7 @@ Adam-moment buffers, so data parallelism is a single ``all_reduce`` and the opti
 """
 import torch
 
-from . import _lib, descriptors, dp, encoders, nerf as nerf_mod, ogrid, renderers, synthetic, trainops
+from . import _lib, descriptors, dp, encoders, exchange as exchange_mod, nerf as nerf_mod, ogrid, renderers, synthetic, trainops
 from .volrendjax import integrate_rays, march_rays
 from .volrendjax.integrating import _integrate_bwd, _integrate_fwd
 
@@ -81,10 +81,15 @@ class Scene:
 
 class Trainer:
     def __init__(self, device="cuda:0", n_rays=1 << 18, total_samples=1 << 18, lr=1e-2, seed=1000000007, rank=0,
-                 world_size=1, process_group=None, scene=None, T=1 << 19, use_graph=True, fused_mlp=True, fused_glue=None, fused_encoder=None):
+                 world_size=1, process_group=None, scene=None, T=1 << 19, use_graph=True, fused_mlp=True, fused_glue=None, fused_encoder=None,
+                 exchange=None):
         self.device = torch.device(device)
         self.n_rays, self.total_samples = n_rays, total_samples
         self.rank, self.world_size, self.pg = rank, world_size, process_group
+        # how the flat gradient is exchanged at world_size > 1: "nccl" (dp.py: reduce-scatter, Adam, all-gather) or
+        # "peer" / "peer-p2p" (exchange.py: one fused kernel over NVLink peer memory; opt-in)
+        self.exchange_mode = exchange_mod.requested_mode() if exchange is None else exchange
+        self.peer_exchange = None
         torch.backends.cuda.matmul.allow_tf32 = True  # XLA's default f32 dot precision on Ampere+
         gen = torch.Generator(device=self.device).manual_seed(seed)  # same init on every rank
         self.nerf = nerf_mod.NeRF(bound=synthetic.BOUND, inference=False, device=self.device, generator=gen, T=T)
@@ -143,8 +148,13 @@ class Trainer:
         assert self.table_numel % 4 == 0 and nerf_mod.MLP_NUMEL % 4 == 0
         self.n_params = self.table_numel + nerf_mod.MLP_NUMEL
         total = -(-self.n_params // 32) * 32  # padded so that every rank's shard (world <= 8) is float4-aligned
-        self.flat_params = torch.zeros(total, dtype=torch.float32, device=self.device)
-        self.flat_grads = torch.zeros_like(self.flat_params)
+        if self.world_size > 1 and self.exchange_mode != "nccl":  # symmetric buffers every rank maps (collective)
+            self.peer_exchange = exchange_mod.PeerExchange(total, self.rank, self.world_size, self.device, self.pg,
+                                                           mode=self.exchange_mode)
+            self.flat_params, self.flat_grads = self.peer_exchange.params, self.peer_exchange.grads
+        else:
+            self.flat_params = torch.zeros(total, dtype=torch.float32, device=self.device)
+            self.flat_grads = torch.zeros_like(self.flat_params)
         # optimizer state: this rank's shard only (ZeRO-1, dp.py); the whole buffer on one GPU
         self.shard_lo, self.shard_hi = dp.shard_bounds(total, self.rank, self.world_size)
         self.adam_m = torch.zeros(self.shard_hi - self.shard_lo, dtype=torch.float32, device=self.device)
@@ -257,6 +267,10 @@ class Trainer:
         """Gradient exchange + Adam.  With more than one rank this part stays outside the CUDA graph: the
         collectives are issued eagerly on the current stream after the captured compute graph."""
         lo, hi = self.shard_lo, self.shard_hi
+        if self.peer_exchange is not None:  # the three steps below as one kernel over NVLink (csrc/exchange.cu)
+            self.peer_exchange.step(self.step_dev, self.adam_m, self.adam_v, self.adam_desc, lo)
+            self.step_dev += 1
+            return
         # reduce-scatter [table grad | MLP grads] -> Adam on this rank's shard -> all-gather the parameters
         g = dp.reduce_scatter_flat_gradients(self.flat_grads, self.rank, self.world_size, self.pg)
         _lib.call("ngp_adam_step", [self.step_dev, self.flat_params[lo:hi], g, self.adam_m, self.adam_v], self.adam_desc)

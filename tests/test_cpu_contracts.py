@@ -117,3 +117,63 @@ def test_oracle_hashgrid_two_restatements_agree(oracle):
     p = np.array([[(3 - 0.5) / 15 * 2 - 1, (4 - 0.5) / 15 * 2 - 1, (5 - 0.5) / 15 * 2 - 1]], np.float32)  # level-0 vertex (3,4,5)
     e = oracle.hashgrid_encode(lv, p, 1.0, tab)
     assert np.allclose(e[0, :2], tab[3 + 4 * 16 + 5 * 256], rtol=1e-4)
+
+
+def test_adam_exchange_descriptor_and_argument_checks(monkeypatch):
+    """ngp_adam_step_exchange (csrc/exchange.cu): wire format of its descriptor, and the argument checks that run
+    before anything is enqueued (they need no GPU: a refused call returns before the launch)."""
+    from jaxngp_b200 import _lib, descriptors as D, exchange as X
+
+    class Adam(ctypes.Structure):
+        _fields_ = [("n", ctypes.c_uint64), ("decay_begin", ctypes.c_uint64), ("lr_init", ctypes.c_float),
+                    ("lr_end", ctypes.c_float), ("decay_rate", ctypes.c_float), ("transition_steps", ctypes.c_uint32),
+                    ("transition_begin", ctypes.c_uint32), ("staircase", ctypes.c_uint32), ("b1", ctypes.c_float),
+                    ("b2", ctypes.c_float), ("eps", ctypes.c_float), ("eps_root", ctypes.c_float),
+                    ("weight_decay", ctypes.c_float), ("grad_scale", ctypes.c_float)]
+
+    class Exchange(ctypes.Structure):
+        _fields_ = [("adam", Adam), ("shard_begin", ctypes.c_uint64), ("rank", ctypes.c_uint32), ("world", ctypes.c_uint32),
+                    ("use_multimem", ctypes.c_uint32), ("n_blocks", ctypes.c_uint32), ("signal_base", ctypes.c_uint32),
+                    ("reserved", ctypes.c_uint32)]
+
+    adam = D.make_adam_descriptor(n=1024, decay_begin=512, lr_init=1e-2, lr_end=1e-4, decay_rate=1 / 3, transition_steps=10_000,
+                                  transition_begin=10_000, staircase=True, b1=0.9, b2=0.99, eps=1e-15, eps_root=1e-15,
+                                  weight_decay=1e-6, grad_scale=0.125)
+    raw = D.make_adam_exchange_descriptor(adam, shard_begin=4096, rank=3, world=8, use_multimem=True, n_blocks=96,
+                                          signal_base=X.SIGNAL_BASE)
+    assert len(raw) == ctypes.sizeof(Exchange) == 96 and len(adam) == ctypes.sizeof(Adam) == 64
+    d = Exchange.from_buffer_copy(raw)
+    assert (d.adam.n, d.adam.decay_begin, d.shard_begin, d.rank, d.world, d.use_multimem, d.n_blocks, d.signal_base) == \
+        (1024, 512, 4096, 3, 8, 1, 96, 1024)
+    assert d.adam.grad_scale == 0.125 and d.adam.staircase == 1
+
+    L = _lib.lib()
+    bufs = (ctypes.c_void_p * 8)()
+
+    def status(desc):
+        L.ngp_b200_clear_error()
+        L.ngp_adam_step_exchange(None, bufs, desc, len(desc))
+        st = L.ngp_b200_last_status()
+        L.ngp_b200_clear_error()
+        return st
+
+    assert status(raw[:-4]) == -1                                                                  # descriptor size
+    assert status(D.make_adam_exchange_descriptor(adam, 4098, 3, 8, False, 96, 1024)) == -2         # shard not float4-aligned
+    assert status(D.make_adam_exchange_descriptor(adam, 4096, 8, 8, False, 96, 1024)) == -2         # rank outside the world
+    assert status(D.make_adam_exchange_descriptor(adam, 4096, 0, 9, False, 96, 1024)) == -2         # more than 8 ranks
+    assert status(D.make_adam_exchange_descriptor(adam, 4096, 0, 8, False, 149, 1024)) == -2        # more CTAs than SMs
+    assert status(raw) == -2                                                                        # multimem without multicast bases
+
+    # host side: the mode switch and the CTA budget of the signal pads
+    monkeypatch.delenv("NGP_B200_EXCHANGE", raising=False)
+    assert X.requested_mode() == "nccl"
+    monkeypatch.setenv("NGP_B200_EXCHANGE", "peer")
+    assert X.requested_mode() == "peer"
+    monkeypatch.setenv("NGP_B200_EXCHANGE", "gloo")
+    with pytest.raises(ValueError):
+        X.requested_mode()
+    assert X.blocks_for(9216, 8) == 96 and X.blocks_for(9216, 2) == 96 and X.blocks_for(4096 + 4 * 8 * 5, 8) == 5
+    with pytest.raises(_lib.NgpError):
+        X.blocks_for(4096, 8)
+    with pytest.raises(_lib.NgpError):  # no process group on this host: the peer exchange refuses, nothing falls back
+        X.PeerExchange(1 << 12, 0, 2, "cpu")
