@@ -27,7 +27,7 @@ namespace {
 
 static_assert(sizeof(NgpAdamDescriptor) == 64 && sizeof(NgpAdamExchangeDescriptor) == 96, "descriptor wire format");
 constexpr int kMaxWorld = 8;
-constexpr int kThreads = 512;
+constexpr int kThreads = 256;  // x 128 registers = half an SM: the next batch's march (or a second CTA) fits beside it
 constexpr int kUnroll = 4;
 
 __device__ __forceinline__ uint32_t cas_release_sys(uint32_t *addr, uint32_t expect, uint32_t desired) {
@@ -78,7 +78,7 @@ __device__ __forceinline__ void peer_store4(float4 *addr, float4 v) {
 }
 
 template <bool kMultimem>
-__global__ void __launch_bounds__(kThreads) adam_exchange_kernel(
+__global__ void __launch_bounds__(kThreads, 2) adam_exchange_kernel(
     NgpAdamExchangeDescriptor d, const uint32_t *__restrict__ step_ptr, float *__restrict__ m, float *__restrict__ v,
     const uint64_t *__restrict__ grads_ptrs, const uint64_t *__restrict__ params_ptrs,
     const uint64_t *__restrict__ signal_ptrs, const float *grads_mc, float *params_mc) {

@@ -30,7 +30,7 @@ def requested_mode(default="nccl"):
     return mode
 
 
-def blocks_for(pad_bytes: int, world: int, want: int = 96) -> int:
+def blocks_for(pad_bytes: int, world: int, want: int = 128) -> int:
     """CTAs per launch: each needs ``world`` signal words above SIGNAL_BASE; at most one per SM (they spin on peers)."""
     room = (pad_bytes // 4 - SIGNAL_BASE) // world
     if room < 1:
