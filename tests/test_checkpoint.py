@@ -1,0 +1,139 @@
+"""Checkpoint / array interchange with the reference (jaxngp_b200/checkpoint.py), CPU only.
+
+tests/golden/checkpoint_reference.json was read off the reference's OWN code by oracle/make_golden_checkpoint.py: the
+``params`` keys of ``NeRFState.create`` (app/nerf/train.py:187-197), the pytree-node fields of ``OccupancyDensityGrid``
+(utils/types.py:93-107), the sub-module names of the weight-decay mask (app/nerf/_utils.py:64-76) and every parameter
+name / shape that ``make_nerf_ngp``'s modules request while running unmodified on numpy -- the same run reproduced the
+model outputs of tests/golden/nerf_reference.npz bit for bit from the exported tree."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from jaxngp_b200 import checkpoint as C
+from jaxngp_b200 import nerf as nerf_mod
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROWS, F, G3 = 6098120, 2, 128 ** 3
+
+
+class _Grid:
+    def __init__(self, rng, n=G3):
+        self.density = rng.uniform(0, 3, n).astype(np.float32)
+        self.occ_mask = self.density > 1.5
+        self.occupancy = np.packbits(self.occ_mask, bitorder="little")
+
+
+def _state(rng, rows=ROWS, with_moments=False, n=G3):
+    table = rng.uniform(-1e-4, 1e-4, (rows, F)).astype(np.float32)
+    flat = rng.uniform(-0.3, 0.3, nerf_mod.MLP_NUMEL).astype(np.float32)
+    kw = {}
+    if with_moments:
+        kw = dict(adam_m=rng.normal(size=rows * F + nerf_mod.MLP_NUMEL + 24).astype(np.float32),
+                  adam_v=rng.uniform(size=rows * F + nerf_mod.MLP_NUMEL + 24).astype(np.float32))
+    return C.make_state(1234, table, flat, _Grid(rng, n), n_frames=100, **kw), table, flat
+
+
+def _leaves(tree):
+    return {k: v for k, v in C._flatten(tree)}
+
+
+def test_checkpoint_tree_binds_to_the_reference_model():
+    ref = json.load(open(os.path.join(GOLDEN, "checkpoint_reference.json")))
+    state, table, flat = _state(np.random.default_rng(0))
+    assert set(state["params"]) == set(ref["params_keys"])
+    assert set(state["ogrid"]) == set(ref["ogrid_fields"])
+    assert set(state["params"]["nerf"]) == set(ref["weight_decay_mask"]["nerf"])
+    got = {k: {"shape": list(v.shape), "dtype": v.dtype.name} for k, v in _leaves(state["params"]["nerf"]).items()}
+    assert got == ref["nerf_leaves_requested_by_the_reference"]
+    assert state["params"]["bg"] is None  # train.py:189 when scene_meta.bg is false
+    assert list(state["params"]["appearance_embeddings"].shape) == ref["appearance_embeddings_shape"]
+    assert state["ogrid"]["alive_indices"].dtype == np.uint32 and state["ogrid"]["occ_mask"].dtype == np.bool_
+    # weights in the [in, out] orientation of flax's Dense, in the flat buffer's order
+    off = 0
+    for (module, layer, name), (nm, i, o) in zip(C._MLP_TREE, nerf_mod.MLP_SHAPES):
+        assert name == nm
+        assert np.array_equal(state["params"]["nerf"][module][layer]["kernel"], flat[off:off + i * o].reshape(i, o))
+        off += i * o
+    t2, f2 = C.flat_from_nerf_param_tree(state["params"]["nerf"], ROWS, F)
+    assert np.array_equal(t2, table) and np.array_equal(f2, flat)
+
+
+@pytest.mark.parametrize("container", ["npz", "flax"])
+def test_checkpoint_round_trip(tmp_path, container):
+    rng = np.random.default_rng(1)
+    state, _, _ = _state(rng, rows=4096, with_moments=(container == "npz"), n=32 ** 3)
+    if container == "npz":
+        path = str(tmp_path / "state.npz")
+        C.save_npz(path, state)
+        back = C.load_npz(path)
+    else:
+        path = C.save_flax_checkpoint(str(tmp_path), state)
+        assert os.path.basename(path) == "checkpoint_1234"  # flax.training.checkpoints naming
+        C.save_flax_checkpoint(str(tmp_path), dict(state, step=99))
+        back = C.load_flax_checkpoint(str(tmp_path))  # a directory: the highest step wins
+        assert "opt_state_b200" not in back
+    assert int(back["step"]) == 1234 and back["params"]["bg"] is None
+    a, b = _leaves(state), _leaves(back)
+    if container == "flax":
+        a = {k: v for k, v in a.items() if not k.startswith("opt_state_b200")}
+    assert set(a) == set(b)
+    for k, v in a.items():
+        if isinstance(v, np.ndarray):
+            assert b[k].dtype == v.dtype and b[k].shape == v.shape and np.array_equal(b[k], v), k
+
+
+def test_flax_wire_format_known_answers():
+    """The container against flax.serialization's published encoding, byte for byte on a small tree."""
+    import msgpack
+    blob = C.msgpack_serialize({"step": 3, "t": (np.arange(3, dtype=np.uint8), None), "s": np.float32(1.5)})
+    top = msgpack.unpackb(blob, raw=False, strict_map_key=False)
+    assert top["step"] == 3 and set(top["t"]) == {"0", "1"} and top["t"]["1"] is None  # tuples -> index-keyed dicts
+    arr, scalar = top["t"]["0"], top["s"]
+    assert (arr.code, scalar.code) == (1, 3)  # _MsgpackExtType.ndarray / npscalar
+    assert msgpack.unpackb(arr.data, raw=True) == [[3], b"uint8", b"\x00\x01\x02"]
+    assert msgpack.unpackb(scalar.data, raw=True) == [[], b"float32", np.float32(1.5).tobytes()]
+    back = C.msgpack_restore(blob)
+    assert back["s"] == np.float32(1.5) and isinstance(back["s"], np.float32) and np.array_equal(back["t"]["0"], [0, 1, 2])
+
+
+def test_checkpoint_rejects_what_the_path_does_not_support():
+    state, _, _ = _state(np.random.default_rng(2), rows=512, n=16 ** 3)
+    tree = state["params"]["nerf"]
+    with pytest.raises(C.CheckpointError):  # another table geometry
+        C.flat_from_nerf_param_tree(tree, rows=1024, F=2)
+    wide = {**tree, "rgb_mlp": {**tree["rgb_mlp"], "Dense_0": {"kernel": np.zeros((40, 64), np.float32)}}}
+    with pytest.raises(C.CheckpointError):  # appearance embeddings widen the colour MLP's input (nerfs.py:79-83)
+        C.flat_from_nerf_param_tree(wide)
+    deep = {**tree, "density_mlp": {**tree["density_mlp"], "Dense_2": {"kernel": np.zeros((16, 16), np.float32)}}}
+    with pytest.raises(C.CheckpointError):
+        C.flat_from_nerf_param_tree(deep)
+    with pytest.raises(C.CheckpointError):  # a frequency-encoded model has no hash table
+        C.flat_from_nerf_param_tree({k: v for k, v in tree.items() if k != "position_encoder"})
+    half = {**tree, "position_encoder": {C.TABLE_NAME: tree["position_encoder"][C.TABLE_NAME].astype(np.float16)}}
+    with pytest.raises(C.CheckpointError):
+        C.flat_from_nerf_param_tree(half)
+    with pytest.raises(C.CheckpointError):
+        C.load_flax_checkpoint(os.path.dirname(os.path.abspath(__file__)))  # no checkpoint_<step> file there
+
+
+def test_checkpoint_loads_into_the_host_model():
+    """Parameters travel reference tree -> this package's model buffers in place (no kernel runs: host I/O only)."""
+    import torch
+    model = nerf_mod.NeRF(bound=1.0, inference=True, device="cpu", T=1 << 12)
+    rows, f = model.position_encoder.latents.shape
+    rng = np.random.default_rng(3)
+    state, table, flat = _state(rng, rows=rows, n=16 ** 3)
+    ptr = model.position_encoder.latents.data_ptr()
+    bitfield = C.load_into_model(model, state)
+    assert model.position_encoder.latents.data_ptr() == ptr  # in place: captured graphs keep their pointers
+    assert np.array_equal(model.position_encoder.latents.detach().numpy(), table)
+    assert np.array_equal(model.mlp_flat.detach().numpy()[: nerf_mod.MLP_NUMEL], flat)
+    assert np.array_equal(model.rgb_w2.detach().numpy(), state["params"]["nerf"]["rgb_mlp"]["Dense_2"]["kernel"])
+    assert bitfield.dtype == torch.uint8 and np.array_equal(bitfield.numpy(), state["ogrid"]["occupancy"])
+    back = C.make_state(5, model.position_encoder.latents, model.mlp_flat)
+    assert np.array_equal(back["params"]["nerf"]["density_mlp"]["Dense_1"]["kernel"],
+                          state["params"]["nerf"]["density_mlp"]["Dense_1"]["kernel"]) and "ogrid" not in back
+    with pytest.raises(C.CheckpointError):
+        C.load_into_model(nerf_mod.NeRF(bound=1.0, inference=True, device="cpu", T=1 << 10), state)
