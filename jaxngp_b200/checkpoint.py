@@ -98,7 +98,10 @@ def make_state(step, table, mlp_flat, grid=None, n_frames=0, adam_m=None, adam_v
     buffers laid out like [table | MLP weights] (the trainer's, world_size 1)."""
     state = {"step": int(step),
              "params": {"nerf": nerf_param_tree(table, mlp_flat), "bg": None,
-                        "appearance_embeddings": np.zeros((int(n_frames), 0), np.float32)}}
+                        "appearance_embeddings": np.zeros((int(n_frames), 0), np.float32)},
+             # flax's from_state_dict wants every pytree field of TrainState present; inference (app/nerf/test.py) never
+             # reads this one, and optax's own layout is not restated (module docstring)
+             "opt_state": None}
     if grid is not None:
         density = _np(grid.density).astype(np.float32, copy=False)
         state["ogrid"] = {"density": density, "occ_mask": _np(grid.occ_mask).astype(np.bool_, copy=False),
@@ -114,6 +117,24 @@ def make_state(step, table, mlp_flat, grid=None, n_frames=0, adam_m=None, adam_v
     return state
 
 
+def find_adam_moments(opt_state):
+    """Best effort, for checkpoints WRITTEN BY THE REFERENCE: optax's ``ScaleByAdamState`` serialises as a dict with
+    ``count`` / ``mu`` / ``nu`` wherever the surrounding ``chain`` / ``multi_transform`` / ``masked`` wrappers of the
+    installed optax version put it; the network optimizer's is the one whose ``mu`` carries a ``nerf`` sub-tree
+    (app/nerf/_utils.py:46-56).  Returns (mu["nerf"], nu["nerf"], count) or None."""
+    if not isinstance(opt_state, dict):
+        return None
+    mu, nu = opt_state.get("mu"), opt_state.get("nu")
+    if isinstance(mu, dict) and isinstance(nu, dict) and isinstance(mu.get("nerf"), dict) and isinstance(nu.get("nerf"), dict) \
+            and "position_encoder" in mu["nerf"]:
+        return mu["nerf"], nu["nerf"], opt_state.get("count")
+    for v in opt_state.values():
+        found = find_adam_moments(v)
+        if found is not None:
+            return found
+    return None
+
+
 def state_from_trainer(trainer, n_frames=None) -> dict:
     """Snapshot of a (world_size 1) ``trainer.Trainer``."""
     if trainer.world_size != 1:
@@ -125,7 +146,8 @@ def state_from_trainer(trainer, n_frames=None) -> dict:
 
 def load_into_trainer(trainer, state: dict):
     """Copies parameters, density grid, step and (when present) the Adam moments of ``state`` into the trainer's
-    device buffers.  Captured graphs keep working: buffers are overwritten in place."""
+    device buffers.  Captured graphs keep working: buffers are overwritten in place.  Everything is validated before
+    the first copy, so a refused state leaves the trainer untouched."""
     import torch
 
     table, flat = flat_from_nerf_param_tree(state["params"]["nerf"], *trainer.table.shape)
@@ -134,28 +156,42 @@ def load_into_trainer(trainer, state: dict):
     ae = state["params"].get("appearance_embeddings")
     if ae is not None and np.asarray(ae).size:
         raise CheckpointError("appearance embeddings are outside this path (n_extra_learnable_dims > 0)")
-    dev = trainer.device
-    trainer.table.copy_(torch.from_numpy(table).to(dev))
-    trainer.mlp_flat.copy_(torch.from_numpy(flat).to(dev))
+    grid_arrays = {}
     if "ogrid" in state:
-        g, s = trainer.grid, state["ogrid"]
         for name in ("density", "occ_mask", "occupancy"):
-            src = torch.from_numpy(np.ascontiguousarray(s[name]))
-            dst = getattr(g, name)
-            if src.shape != dst.shape:
-                raise CheckpointError(f"ogrid/{name} has {tuple(src.shape)} entries, this grid {tuple(dst.shape)} (cascades / resolution differ)")
-            dst.copy_(src.to(dev))
-    trainer.step = int(state["step"])
-    trainer.step_dev.fill_(int(state["step"]))
+            src = torch.from_numpy(np.ascontiguousarray(state["ogrid"][name]))
+            dst = getattr(trainer.grid, name)
+            if src.shape != dst.shape or src.dtype != dst.dtype:
+                raise CheckpointError(f"ogrid/{name} is {src.dtype} {tuple(src.shape)}, this grid holds {dst.dtype} "
+                                      f"{tuple(dst.shape)} (cascades / resolution differ)")
+            grid_arrays[name] = src
     opt = state.get("opt_state_b200")
+    if opt is None:  # a checkpoint written by the reference: look for the network optimizer's Adam moments
+        found = find_adam_moments(state.get("opt_state"))
+        if found is not None:
+            opt = {"adam_m": found[0], "adam_v": found[1]}
+    moments = {}
     if opt is not None:
         if trainer.world_size != 1:
             raise CheckpointError("optimizer moments can only be loaded into a world_size-1 trainer")
-        for key, buf in (("adam_m", trainer.adam_m), ("adam_v", trainer.adam_v)):
-            t, f = flat_from_nerf_param_tree(opt[key], *trainer.table.shape)
-            buf[: trainer.table_numel].copy_(torch.from_numpy(t.reshape(-1)).to(dev))
-            buf[trainer.table_numel:trainer.n_params].copy_(torch.from_numpy(f).to(dev))
-    trainer._prefetched = None  # a march prefetched against the old bitfield is dropped (train_step marches again)
+        for key in ("adam_m", "adam_v"):
+            moments[key] = flat_from_nerf_param_tree(opt[key], *trainer.table.shape)
+
+    dev = trainer.device
+    if hasattr(trainer, "drop_prefetch"):
+        trainer.drop_prefetch()  # a march prefetched against the old bitfield must not race with the copies below
+    else:
+        trainer._prefetched = None
+    trainer.table.copy_(torch.from_numpy(table).to(dev))
+    trainer.mlp_flat.copy_(torch.from_numpy(flat).to(dev))
+    for name, src in grid_arrays.items():
+        getattr(trainer.grid, name).copy_(src.to(dev))
+    trainer.step = int(state["step"])
+    trainer.step_dev.fill_(int(state["step"]))
+    for key, (t, f) in moments.items():
+        buf = getattr(trainer, key)
+        buf[: trainer.table_numel].copy_(torch.from_numpy(t.reshape(-1)).to(dev))
+        buf[trainer.table_numel:trainer.n_params].copy_(torch.from_numpy(f).to(dev))
 
 
 def load_into_model(model, state: dict):
@@ -272,6 +308,7 @@ def save_flax_checkpoint(ckpt_dir, state: dict, prefix="checkpoint_") -> str:
     os.makedirs(ckpt_dir, exist_ok=True)
     path = os.path.join(ckpt_dir, f"{prefix}{int(state['step'])}")
     body = {k: v for k, v in state.items() if k != "opt_state_b200"}
+    body.setdefault("opt_state", None)
     tmp = path + ".tmp"
     with open(tmp, "wb") as f:
         f.write(msgpack_serialize(body))

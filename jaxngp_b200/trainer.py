@@ -364,6 +364,13 @@ class Trainer:
         self._prefetched = None
         self._slot = 0
 
+    def drop_prefetch(self):
+        """Forget a march prefetched on the side stream (its inputs are about to change): the main stream first waits
+        for it, so that nothing still writes the slot's buffers when the next ``train_step`` marches into them."""
+        if self._prefetched is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._ev_march[self._slot])
+            self._prefetched = None
+
     def release_graph(self):
         """Drop the captured step graphs (and their private memory pools)."""
         self._graph = self._march_graph = None

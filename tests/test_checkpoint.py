@@ -137,3 +137,73 @@ def test_checkpoint_loads_into_the_host_model():
                           state["params"]["nerf"]["density_mlp"]["Dense_1"]["kernel"]) and "ogrid" not in back
     with pytest.raises(C.CheckpointError):
         C.load_into_model(nerf_mod.NeRF(bound=1.0, inference=True, device="cpu", T=1 << 10), state)
+
+
+def test_adam_moments_are_found_in_a_reference_written_opt_state():
+    """optax's wrappers differ between versions; the network optimizer's ScaleByAdamState is found wherever they put it
+    (here: chain -> multi_transform inner_states -> masked inner_state -> chain, tuples as index-keyed dicts)."""
+    state, _, _ = _state(np.random.default_rng(4), rows=256, n=16 ** 3)
+    assert "opt_state" in state and state["opt_state"] is None  # the field flax's restore insists on
+    mu = {"nerf": C.nerf_param_tree(np.ones((256, 2), np.float32), np.full(nerf_mod.MLP_NUMEL, 2, np.float32)), "bg": None,
+          "appearance_embeddings": {}}
+    nu = {"nerf": C.nerf_param_tree(np.full((256, 2), 3, np.float32), np.full(nerf_mod.MLP_NUMEL, 4, np.float32)), "bg": None,
+          "appearance_embeddings": {}}
+    ae = {"count": np.int32(9), "mu": {"nerf": {}, "bg": None, "appearance_embeddings": np.zeros((100, 0), np.float32)},
+          "nu": {"nerf": {}, "bg": None, "appearance_embeddings": np.zeros((100, 0), np.float32)}}
+    opt_state = {"0": {"inner_states": {"ae": {"inner_state": {"0": ae, "1": {}}},
+                                        "network": {"inner_state": {"0": {"count": np.int32(9), "mu": mu, "nu": nu},
+                                                                    "1": {"count": np.int32(9)}}}}},
+                 "1": {"inner_state": {}}}
+    m, v, count = C.find_adam_moments(opt_state)
+    assert m is mu["nerf"] and v is nu["nerf"] and int(count) == 9
+    assert C.find_adam_moments({"0": {"inner_state": {}}}) is None and C.find_adam_moments(None) is None
+    back = C.msgpack_restore(C.msgpack_serialize(dict(state, opt_state=opt_state)))
+    m2, v2, _ = C.find_adam_moments(back["opt_state"])
+    assert np.array_equal(m2["rgb_mlp"]["Dense_2"]["kernel"], mu["nerf"]["rgb_mlp"]["Dense_2"]["kernel"])
+    assert np.array_equal(v2["position_encoder"][C.TABLE_NAME], nu["nerf"]["position_encoder"][C.TABLE_NAME])
+
+
+def test_checkpoint_round_trip_through_trainer_buffers():
+    """state_from_trainer / load_into_trainer on a stand-in that has the Trainer's buffer attributes (flat [table | MLP]
+    moments, device step counter, density grid) on the CPU: no kernel is involved in a load or a snapshot."""
+    import types
+    import torch
+    rows, n_cells = 512, 16 ** 3
+    rng = np.random.default_rng(5)
+    n_table = rows * F
+    total = -(-(n_table + nerf_mod.MLP_NUMEL) // 32) * 32
+
+    def trainer(seed):
+        g = torch.Generator().manual_seed(seed)
+        flat_params = torch.rand(total, generator=g)
+        grid = types.SimpleNamespace(density=torch.rand(n_cells, generator=g), occ_mask=torch.rand(n_cells, generator=g) > 0.5,
+                                     occupancy=torch.randint(0, 256, (n_cells // 8,), generator=g, dtype=torch.uint8))
+        return types.SimpleNamespace(
+            world_size=1, device=torch.device("cpu"), table=flat_params[:n_table].view(rows, F),
+            mlp_flat=flat_params[n_table:n_table + nerf_mod.MLP_NUMEL], table_numel=n_table,
+            n_params=n_table + nerf_mod.MLP_NUMEL, adam_m=torch.rand(total, generator=g), adam_v=torch.rand(total, generator=g),
+            grid=grid, step=seed, step_dev=torch.full((1,), seed, dtype=torch.int32), scene=types.SimpleNamespace(n_views=100),
+            _prefetched=("stale", 0), flat_params=flat_params)
+
+    src, dst = trainer(41), trainer(7)
+    state = C.state_from_trainer(src)
+    assert state["step"] == 41 and state["params"]["appearance_embeddings"].shape == (100, 0)
+    C.load_into_trainer(dst, state)
+    assert torch.equal(dst.flat_params[: dst.n_params], src.flat_params[: src.n_params])
+    assert torch.equal(dst.adam_m[: dst.n_params], src.adam_m[: src.n_params]) and torch.equal(dst.adam_v[: dst.n_params], src.adam_v[: src.n_params])
+    for name in ("density", "occ_mask", "occupancy"):
+        assert torch.equal(getattr(dst.grid, name), getattr(src.grid, name))
+    assert dst.step == 41 and int(dst.step_dev) == 41 and dst._prefetched is None
+    # sharded optimizer state is refused rather than half-loaded
+    dst.world_size = 2
+    before = dst.flat_params.clone()
+    with pytest.raises(C.CheckpointError):
+        C.load_into_trainer(dst, dict(state, params=dict(state["params"], nerf=C.nerf_param_tree(np.zeros((rows, F), np.float32), np.zeros(nerf_mod.MLP_NUMEL, np.float32)))))
+    assert torch.equal(dst.flat_params, before)  # validated before the first copy
+    with pytest.raises(C.CheckpointError):
+        C.state_from_trainer(dst)
+    dst.world_size = 1
+    with pytest.raises(C.CheckpointError):  # a grid of another resolution
+        C.load_into_trainer(dst, dict(state, ogrid={k: np.concatenate([v, v]) for k, v in state["ogrid"].items()}))
+    with pytest.raises(C.CheckpointError):  # background model
+        C.load_into_trainer(dst, dict(state, params=dict(state["params"], bg={"Dense_0": {}})))
