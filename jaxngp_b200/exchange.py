@@ -64,13 +64,27 @@ class PeerExchange:
         self._h_grads = symm_mem.rendezvous(self.grads, group=group)
         if self._h_grads.rank != rank or self._h_grads.world_size != world_size:
             raise _lib.NgpError("symmetric-memory rank/world differ from the trainer's")
-        mc_p, mc_g = int(self._h_params.multicast_ptr), int(self._h_grads.multicast_ptr)
+        # The handles describe the ALLOCATION a tensor lives in (torch may carve several tensors out of one pooled
+        # block): peer r's copy of a tensor sits at buffer_ptrs[r] + (this tensor's offset inside the local block), and
+        # symmetric allocation makes that offset the same on every rank.  Same for the multicast mapping.
+        def mapped(tensor, handle):
+            bases = [int(p) for p in handle.buffer_ptrs]
+            offset = tensor.data_ptr() - bases[rank]
+            if offset < 0:
+                raise _lib.NgpError("symmetric tensor lies below the block its handle describes")
+            if offset % 16 != 0:
+                raise _lib.NgpError("symmetric tensor is not 16-byte aligned inside its block")
+            mc = int(handle.multicast_ptr)
+            return [b + offset for b in bases], (mc + offset if mc else 0)
+
+        g_ptrs, mc_g = mapped(self.grads, self._h_grads)
+        p_ptrs, mc_p = mapped(self.params, self._h_params)
         self.use_multimem = mode == "peer" and mc_p != 0 and mc_g != 0
         self._mc_params, self._mc_grads = (mc_p, mc_g) if self.use_multimem else (0, 0)
-        # device arrays of the peers' base pointers, owned by the handles
-        self._grads_ptrs = int(self._h_grads.buffer_ptrs_dev)
-        self._params_ptrs = int(self._h_params.buffer_ptrs_dev)
-        self._signal_ptrs = int(self._h_grads.signal_pad_ptrs_dev)
+        # device arrays of u64 addresses (torch has no uint64 arithmetic; int64 carries the same bits)
+        as_dev = lambda ptrs: torch.tensor(ptrs, dtype=torch.int64, device=self.device)  # noqa: E731
+        self._grads_ptrs, self._params_ptrs = as_dev(g_ptrs), as_dev(p_ptrs)
+        self._signal_ptrs = as_dev([int(p) for p in self._h_grads.signal_pad_ptrs])
         self.n_blocks = blocks_for(int(self._h_grads.signal_pad_size), world_size) if n_blocks is None else int(n_blocks)
         torch.cuda.synchronize(self.device)
         dist.barrier(group=group)  # every replica zeroed and mapped before the first launch touches a peer
