@@ -3,7 +3,6 @@
 (utils/types.py:1149-1239).  Every array step runs in this package's kernels (csrc/ogrid.cu,
 gridops.cu); the random draws are inputs, as the reference draws them with jax.random outside the ops.
 """
-import math
 
 import torch
 

@@ -113,7 +113,7 @@ class InferenceRenderer:
 
     def __init__(self, nerf, cam, occupancy_bitfield, *, bg=(1.0, 1.0, 1.0), diagonal_n_steps=1024, K=1, G=128,
                  bound=1.0, stepsize_portion=0.0, march_steps_cap=16, n_rays=262144, pixel_indices=None, skip_empty=True):
-        from . import _lib, descriptors, trainops  # noqa: F401
+        from . import _lib, descriptors
         self.nerf, self.cam, self.bits = nerf, cam, occupancy_bitfield
         dev = occupancy_bitfield.device
         self.dev, self.bound, self.cap = dev, bound, march_steps_cap

@@ -6,7 +6,7 @@ import time
 
 import torch
 
-from jaxngp_b200 import renderers, synthetic
+from jaxngp_b200 import renderers
 from jaxngp_b200.trainer import Scene, Trainer
 
 dev = "cuda:0"
