@@ -1,0 +1,23 @@
+#!/usr/bin/env bash
+# One gpurun call (>= 2 GPUs) that settles the fused gradient exchange of csrc/exchange.cu:
+#   gpurun --gpus 2 --timeout 600 -- 'bash tools_gpu_exchange_session.sh 2'
+# 1. parity + timing of the peer arms against the NCCL arm on the C2 buffer (tools_exchange_check.py)
+# 2. the opt-in GPU test
+# 3. bench.py at N ranks with each exchange, training step only
+# Everything lands in gpurun_out/exchange/.  Each step has its own timeout: the kernel spins on its peers, so a bug shows
+# up as a hang, never as a wrong number.
+set -u
+N=${1:-2}
+OUT=gpurun_out/exchange
+mkdir -p "$OUT"
+run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node "$N" --master-addr 127.0.0.1 --master-port "$1" "${@:2}"; }
+for mode in peer-p2p peer; do
+  timeout 120 bash -c "$(declare -f run); N=$N; run 29511 tools_exchange_check.py --mode $mode" > "$OUT/check_${mode}_n$N.log" 2>&1
+  echo "check $mode: rc=$? $(grep -h '^{' "$OUT/check_${mode}_n$N.log" | tail -1)"
+done
+NGP_B200_TEST_EXCHANGE=1 timeout 300 python -m pytest tests/test_gpu_exchange.py -x -q > "$OUT/pytest_n$N.log" 2>&1
+echo "pytest: rc=$? $(tail -1 "$OUT/pytest_n$N.log")"
+for mode in nccl peer; do
+  timeout 300 bash -c "$(declare -f run); N=$N; run 29513 bench.py --gpus $N --steps 48 --warmup 4 --no-extras --no-cpu-baseline --exchange $mode" > "$OUT/bench_${mode}_n$N.log" 2>&1
+  echo "bench $mode: rc=$? $(grep -h '^{"metric' "$OUT/bench_${mode}_n$N.log" | tail -1 | cut -c1-220)"
+done
