@@ -21,6 +21,7 @@ CONFIGS = (  # (dim, T, N_max): C2 / C4 shape, C1 (imagefit) shape, a small tabl
     (3, 2 ** 19, 2048),
     (2, 2 ** 19, 2 ** 19),
     (3, 2 ** 14, 512),
+    (2, 2 ** 20, 2 ** 19),  # the ImageFitter's own encoder (models/imagefit.py:28-37): ~1 Mi entries per level
 )
 N_POINTS = 256
 PARAM = "latent codes stored on grid vertices"  # models/encoders.py:106

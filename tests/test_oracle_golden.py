@@ -104,7 +104,7 @@ def test_inference_loop_golden(oracle):
     assert np.allclose(rgbd, g["rgbd"], atol=1e-4) and np.allclose(T, g["T"], atol=1e-4)
 
 
-ENCODER_CONFIGS = [(3, 2 ** 19, 2048), (2, 2 ** 19, 2 ** 19), (3, 2 ** 14, 512)]
+ENCODER_CONFIGS = [(3, 2 ** 19, 2048), (2, 2 ** 19, 2 ** 19), (3, 2 ** 14, 512), (2, 2 ** 20, 2 ** 19)]  # last: models/imagefit.py:28-37
 
 
 @pytest.mark.parametrize("dim,T,N_max", ENCODER_CONFIGS)
