@@ -1,0 +1,127 @@
+"""The drop-in boundary against the reference's OWN binding code, CPU only.
+
+tests/golden/lowering_reference.json was recorded by oracle/make_golden_lowering.py, which ran -- unmodified -- all ten
+``*_lowering_rule`` functions of volume-rendering-jax and jax-tcnn (against recording stand-ins for the few MLIR
+constructors they use, with this repo's drop-in extension modules where the reference's compiled ones go) and the
+registration loops of their ``impl.py`` files, and read the module surface off the two ``ffi.cc`` files.  Here:
+
+  * the drop-in modules export what ffi.cc exports, and every capsule carries the address of the matching C symbol;
+  * for the same operand shapes, the host mirror hands libngp_b200.so exactly the buffers the reference's lowering
+    hands XLA -- operands in order, then results in order, same shapes, same element widths -- and the same opaque
+    bytes, under the symbol ``ngp_<target>``.  Nothing is launched: ``_lib.call`` is replaced by a recorder.
+"""
+import ctypes
+import json
+import os
+
+import pytest
+import torch
+
+from jaxngp_b200 import _lib
+from jaxngp_b200 import jaxtcnn
+from jaxngp_b200 import volrendjax as V
+from jaxngp_b200.jaxtcnn import tcnnutils
+from jaxngp_b200.volrendjax import integrating, volrendutils_cuda
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lowering_reference.json")))
+CALLS = GOLDEN["custom_calls"]
+
+# element types as the reference's lowering names them -> what the torch host carries (uint32 travels as int32 bits)
+TORCH = {"float32": torch.float32, "uint32": torch.int32, "uint8": torch.uint8, "bool": torch.bool}
+
+
+def _capsule_pointer(capsule):
+    get_ptr = ctypes.pythonapi.PyCapsule_GetPointer
+    get_ptr.restype, get_ptr.argtypes = ctypes.c_void_p, [ctypes.py_object, ctypes.c_char_p]
+    get_name = ctypes.pythonapi.PyCapsule_GetName
+    get_name.restype, get_name.argtypes = ctypes.c_char_p, [ctypes.py_object]
+    name = get_name(capsule)
+    return name, get_ptr(capsule, name)
+
+
+@pytest.mark.parametrize("package,module", [("volrendjax", volrendutils_cuda), ("jaxtcnn", tcnnutils)])
+def test_drop_in_extension_modules_export_what_ffi_cc_exports(package, module):
+    ffi = GOLDEN["ffi"][package]
+    assert module.__name__.rsplit(".", 1)[1] == ffi["module"]  # importable as `from .. import <module>` in the reference's tree
+    for fn in ffi["functions"]:
+        assert callable(getattr(module, fn)), fn
+    L = _lib.lib()
+    for getter, names in ffi["registrations"].items():
+        regs = getattr(module, getter)()
+        assert list(regs) == names
+        for name, capsule in regs.items():
+            cap_name, ptr = _capsule_pointer(capsule)
+            assert cap_name.decode() == ffi["capsule_name"] == "xla._CUSTOM_CALL_TARGET"
+            assert ptr == ctypes.cast(getattr(L, "ngp_" + name), ctypes.c_void_p).value and ptr
+    registered = {n for n, platform in GOLDEN["registered_by_the_reference_impl"] if platform == "gpu"}
+    assert registered == set(CALLS) and len(GOLDEN["registered_by_the_reference_impl"]) == len(CALLS)
+
+
+def test_descriptor_factories_reject_what_ffi_cc_rejects():
+    with pytest.raises(RuntimeError, match="expected n_bytes to be a positive integer, got 0"):  # ffi.cc:57-59
+        volrendutils_cuda.make_packbits_descriptor(0)
+    with pytest.raises(RuntimeError, match="expected K to be a positive integer, got 0"):  # ffi.cc:79-81
+        volrendutils_cuda.make_marching_descriptor(1, 1, 1, 0, 1, 1.0, 0.0)
+    with pytest.raises(RuntimeError, match="expected K to be a positive integer, got 0"):  # ffi.cc:114-116
+        volrendutils_cuda.make_marching_inference_descriptor(1, 1, 1, 0, 1, 1, 1.0, 0.0)
+
+
+def _operands(target):
+    """CPU tensors shaped like the recorded operands, by the rule's own parameter names."""
+    c = CALLS[target]
+    out = {}
+    for name, (shape, dtype) in c["rule_arguments"].items():  # every array argument of the rule (it may not pass all on)
+        out[name] = torch.zeros(shape, dtype=TORCH[dtype])
+    return out, c["statics"]
+
+
+def _drive(target):
+    a, st = _operands(target)
+    if target == "pack_density_into_bits":
+        V.packbits(a["density_threshold"] + 0.5, a["density_grid"])
+    elif target == "morton3d":
+        V.morton3d(a["xyzs"])
+    elif target == "morton3d_invert":
+        V.morton3d_invert(a["idcs"])
+    elif target == "march_rays":
+        V.march_rays(**st, **a)
+    elif target == "march_rays_inference":
+        a["indices"] = a.pop("indices_in")  # the public wrapper's name (marching/__init__.py:96-110)
+        V.march_rays_inference(**st, **a)
+    elif target == "integrate_rays":
+        integrating._integrate_fwd(a["rays_sample_startidx"], a["rays_n_samples"], a["bgs"], a["dss"], a["z_vals"], a["drgbs"])
+    elif target == "integrate_rays_backward":
+        integrating._integrate_bwd(st["near_distance"], a["rays_sample_startidx"], a["rays_n_samples"], a["bgs"], a["dss"],
+                                   a["z_vals"], a["drgbs"], a["final_rgbds"], a["final_opacities"], a["dL_dfinal_rgbds"])
+    elif target == "integrate_rays_inference":
+        V.integrate_rays_inference(**a)
+    elif target in ("hashgrid_encode", "hashgrid_encode_backward"):
+        desc = jaxtcnn.HashGridMetadata(L=st["L"], F=st["F"], N_min=st["N_min"], per_level_scale=st["per_level_scale"])
+        params = a["params"].requires_grad_(True)
+        enc = jaxtcnn.hashgrid_encode(desc, a["offset_table_data"], a["coords_rm"], params)
+        if target == "hashgrid_encode_backward":
+            enc.backward(torch.ones_like(enc))
+    else:
+        raise KeyError(target)
+
+
+@pytest.mark.parametrize("target", sorted(CALLS))
+def test_host_mirror_issues_the_custom_call_the_reference_lowers_to(monkeypatch, target):
+    seen = []
+
+    def recorder(name, buffers, opaque, stream=None):
+        seen.append((name, [(tuple(b.shape), b.dtype, b.is_contiguous()) for b in buffers], bytes(opaque)))
+
+    monkeypatch.setattr(_lib, "call", recorder)
+    _drive(target)
+    mine = [s for s in seen if s[0] == "ngp_" + target]
+    assert len(mine) == 1, [s[0] for s in seen]
+    _, buffers, opaque = mine[0]
+    ref = CALLS[target]
+    expected = [(tuple(shape), TORCH[dtype]) for shape, dtype in ref["operands"] + ref["results"]]
+    assert [(s, d) for s, d, _ in buffers] == expected
+    assert all(contig for _, _, contig in buffers)
+    # row-major everywhere: the reference asks XLA for its default (descending) layouts
+    for layouts, tensors in ((ref["operand_layouts"], ref["operands"]), (ref["result_layouts"], ref["results"])):
+        assert [list(x) for x in layouts] == [list(range(len(shape) - 1, -1, -1)) for shape, _ in tensors]
+    assert opaque.hex() == ref["opaque"]
