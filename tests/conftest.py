@@ -39,3 +39,13 @@ def ref():
     if not refops.available():
         pytest.skip("oracle/_ref/libvolrend_ref.so not built (needs /root/reference at build time)")
     return refops
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """libngp_b200.so, cross-compiled on first use (nvcc needs no GPU); CPU tests only look at its symbols."""
+    from jaxngp_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        _lib.build()
+    return _lib.lib()

@@ -40,12 +40,12 @@ def _capsule_pointer(capsule):
 
 
 @pytest.mark.parametrize("package,module", [("volrendjax", volrendutils_cuda), ("jaxtcnn", tcnnutils)])
-def test_drop_in_extension_modules_export_what_ffi_cc_exports(package, module):
+def test_drop_in_extension_modules_export_what_ffi_cc_exports(built_lib, package, module):
     ffi = GOLDEN["ffi"][package]
     assert module.__name__.rsplit(".", 1)[1] == ffi["module"]  # importable as `from .. import <module>` in the reference's tree
     for fn in ffi["functions"]:
         assert callable(getattr(module, fn)), fn
-    L = _lib.lib()
+    L = built_lib
     for getter, names in ffi["registrations"].items():
         regs = getattr(module, getter)()
         assert list(regs) == names

@@ -119,7 +119,7 @@ def test_oracle_hashgrid_two_restatements_agree(oracle):
     assert np.allclose(e[0, :2], tab[3 + 4 * 16 + 5 * 256], rtol=1e-4)
 
 
-def test_adam_exchange_descriptor_and_argument_checks(monkeypatch):
+def test_adam_exchange_descriptor_and_argument_checks(monkeypatch, built_lib):
     """ngp_adam_step_exchange (csrc/exchange.cu): wire format of its descriptor, and the argument checks that run
     before anything is enqueued (they need no GPU: a refused call returns before the launch)."""
     from jaxngp_b200 import _lib, descriptors as D, exchange as X
@@ -147,7 +147,7 @@ def test_adam_exchange_descriptor_and_argument_checks(monkeypatch):
         (1024, 512, 4096, 3, 8, 1, 96, 1024)
     assert d.adam.grad_scale == 0.125 and d.adam.staircase == 1
 
-    L = _lib.lib()
+    L = built_lib
     bufs = (ctypes.c_void_p * 8)()
 
     def status(desc):
