@@ -10,6 +10,8 @@ Per step (shapes at BASELINE config C2: n_rays = total_samples = 2^18):
 All parameters live in ONE flat f32 buffer [hash table | MLP weights] with matching flat gradient and
 Adam-moment buffers, so data parallelism is a single ``all_reduce`` and the optimizer a single launch.
 """
+import os
+
 import torch
 
 from . import _lib, descriptors, dp, encoders, exchange as exchange_mod, nerf as nerf_mod, ogrid, renderers, synthetic, trainops
@@ -114,6 +116,11 @@ class Trainer:
             transition_steps=10_000, transition_begin=10_000, staircase=True, b1=0.9, b2=0.99, eps=1e-15,
             eps_root=1e-15, weight_decay=1e-6, grad_scale=1.0 / world_size)
         self.use_graph = use_graph
+        # opt-in (NGP_B200_GRAPH_EXCHANGE=1, unmeasured): at world_size > 1 the gradient exchange + optimizer (NCCL
+        # reduce-scatter, Adam, all-gather, step counter -- or the one fused kernel) replay as ONE captured graph
+        # instead of four eager launches behind the compute graph
+        self.graph_exchange = os.environ.get("NGP_B200_GRAPH_EXCHANGE") == "1"
+        self._exchange_graph = None
         self._graph = self._march_graph = None
         self._static_perm = self._static_out = self._static_marched = None
         self._prefetched = None
@@ -315,7 +322,10 @@ class Trainer:
         self._graph[cur].replay()
         if next_perm is not None and self.world_size > 1:
             self._prefetch(next_perm, cur, main)
-        self._optimizer_step()
+        if self._exchange_graph is not None:
+            self._exchange_graph.replay()
+        else:
+            self._optimizer_step()
         self._slot = 1 - cur
         return self._static_out[cur]
 
@@ -357,6 +367,11 @@ class Trainer:
                 self._graph.append(cg)
                 self._static_marched.append(marched)
                 self._static_out.append(out)
+            if self.graph_exchange and self.world_size > 1:  # every rank captures the same collectives in the same order
+                eg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(eg, stream=self._side):
+                    self._optimizer_step()
+                self._exchange_graph = eg
         main.wait_stream(self._side)
         self.step += 2
         self._ev_march = [torch.cuda.Event(), torch.cuda.Event()]
@@ -373,7 +388,7 @@ class Trainer:
 
     def release_graph(self):
         """Drop the captured step graphs (and their private memory pools)."""
-        self._graph = self._march_graph = None
+        self._graph = self._march_graph = self._exchange_graph = None
         self._static_out = self._static_marched = None
         self._prefetched = None
 

@@ -17,7 +17,9 @@ for mode in peer-p2p peer; do
 done
 NGP_B200_TEST_EXCHANGE=1 timeout 300 python -m pytest tests/test_gpu_exchange.py -x -q > "$OUT/pytest_n$N.log" 2>&1
 echo "pytest: rc=$? $(tail -1 "$OUT/pytest_n$N.log")"
-for mode in nccl peer; do
-  timeout 300 bash -c "$(declare -f run); N=$N; run 29513 bench.py --gpus $N --steps 48 --warmup 4 --no-extras --no-cpu-baseline --exchange $mode" > "$OUT/bench_${mode}_n$N.log" 2>&1
-  echo "bench $mode: rc=$? $(grep -h '^{"metric' "$OUT/bench_${mode}_n$N.log" | tail -1 | cut -c1-220)"
+for graph in 0 1; do  # 1: the exchange + optimizer replayed as one captured graph (NGP_B200_GRAPH_EXCHANGE)
+  for mode in nccl peer; do
+    NGP_B200_GRAPH_EXCHANGE=$graph timeout 300 bash -c "$(declare -f run); N=$N; run 29513 bench.py --gpus $N --steps 48 --warmup 4 --no-extras --no-cpu-baseline --exchange $mode" > "$OUT/bench_${mode}_g${graph}_n$N.log" 2>&1
+    echo "bench $mode graph=$graph: rc=$? $(grep -h '^{"metric' "$OUT/bench_${mode}_g${graph}_n$N.log" | tail -1 | cut -c1-220)"
+  done
 done
