@@ -226,7 +226,7 @@ def run_ours(args):
                        f"({'multimem.ld_reduce' if tr.peer_exchange.use_multimem else 'peer loads'}) -> Adam on 1/{world} of the "
                        f"parameters -> stored into every replica ({tr.peer_exchange.n_blocks} CTAs)"),
                    "l2": "per-step working set (table+grads+moments+activations ~0.5 GB) exceeds the 126 MB L2; no flush",
-                   "cuda_graph": not args.no_graph},
+                   "cuda_graph": not args.no_graph, "exchange_in_graph": tr._exchange_graph is not None},
         "samples_per_step": samples / K,
         "e2e": {"value": samples_e2e / (ms_e2e / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": N_RAYS * 4, "d2h_bytes_per_step": 4, "loss": loss,
