@@ -487,16 +487,19 @@ def cpu_step(ctx, n_rays, seed):
     return time.perf_counter() - t0, m["measured_batch_size_before_compaction"]
 
 
-def cpu_baseline_sample(n_rays=1 << 16, steps=8):
+def cpu_baseline_sample(n_rays=1 << 16, min_steps=8, max_steps=64, cpu_seconds=10.0):
+    """A bounded sample of the C2 workload on the host cores: whole steps until ~10 s of CPU work are in."""
     from oracle import oracle as O
     O.build()
     ctx = cpu_step_setup(n_rays)
     cpu_step(ctx, n_rays, 1)  # warm-up
     tot_t = tot_s = 0.0
-    for k in range(steps):
-        t, s = cpu_step(ctx, n_rays, 100 + k)
+    steps = 0
+    while steps < min_steps or (tot_t < cpu_seconds and steps < max_steps):
+        t, s = cpu_step(ctx, n_rays, 100 + steps)
         tot_t += t
         tot_s += s
+        steps += 1
     return {"value": tot_s / tot_t, "unit": "samples/s", "cores": O.num_threads(), "kind": "port",
             "sample": f"{steps} full training steps of the CPU oracle (C march/encode/integrate + numpy MLP/Adam) at "
                       f"n_rays = total_samples = 2^16 (1/4 of the C2 step), {tot_t:.1f} s of CPU work"}
