@@ -281,7 +281,8 @@ typedef struct {
     uint64_t shard_begin;              /* first element of this rank's shard in the flat buffers (multiple of 4) */
     uint32_t rank, world;              /* world <= 8 */
     uint32_t use_multimem, n_blocks;   /* n_blocks: same on every rank, <= resident CTAs of the device */
-    uint32_t signal_base, reserved;    /* first u32 word of the pads this op may use */
+    uint32_t signal_base, timeout_ms;  /* first u32 word of the pads this op may use; how long a block waits for a
+                                          peer before it traps (0 = 20 s): a missing rank fails the launch, not the GPU */
 } NgpAdamExchangeDescriptor;
 void ngp_adam_step_exchange(cudaStream_t, void **, const char *, size_t);
 

@@ -41,16 +41,34 @@ __device__ __forceinline__ uint32_t cas_acquire_sys(uint32_t *addr, uint32_t exp
     return old;
 }
 
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// A peer that never arrives (crashed rank, mismatched launch) must not hang the GPU: after `timeout_ns` the waiting
+// thread reports and traps, which fails this rank's launch with an error the host sees at its next synchronisation.
+__device__ __noinline__ void peer_timeout(uint32_t rank, uint32_t peer, uint32_t block, int phase) {
+    printf("[ngp_b200] adam_step_exchange: rank %u block %u gave up waiting for rank %u (%s)\n", rank, block, peer,
+           phase == 0 ? "its pad word is still set from the previous round" : "it never signalled");
+    __trap();
+}
+
 // Block b of this rank meets block b of every peer.  Writes of the whole block before the call are visible to every
 // peer thread after its matching call returns (bar.sync orders them before the releasing CAS, which is cumulative).
-__device__ __forceinline__ void meet_peers(uint32_t *const *signal_ptrs, uint32_t slot0, uint32_t rank, uint32_t world) {
+__device__ __forceinline__ void meet_peers(uint32_t *const *signal_ptrs, uint32_t slot0, uint32_t rank, uint32_t world,
+                                           uint64_t timeout_ns) {
     __syncthreads();
     if (threadIdx.x < world) {
         const uint32_t peer = threadIdx.x;
         uint32_t *theirs = signal_ptrs[peer] + slot0 + rank;  // my word in the peer's pad
         uint32_t *mine = signal_ptrs[rank] + slot0 + peer;    // the peer's word in my pad
-        while (cas_release_sys(theirs, 0u, 1u) != 0u) {}
-        while (cas_acquire_sys(mine, 1u, 0u) != 1u) {}
+        const uint64_t t0 = global_ns();
+        for (uint32_t spins = 0; cas_release_sys(theirs, 0u, 1u) != 0u; ++spins)
+            if ((spins & 1023u) == 1023u && global_ns() - t0 > timeout_ns) peer_timeout(rank, peer, blockIdx.x, 0);
+        for (uint32_t spins = 0; cas_acquire_sys(mine, 1u, 0u) != 1u; ++spins)
+            if ((spins & 1023u) == 1023u && global_ns() - t0 > timeout_ns) peer_timeout(rank, peer, blockIdx.x, 1);
     }
     __syncthreads();
 }
@@ -91,7 +109,8 @@ __global__ void __launch_bounds__(kThreads, 2) adam_exchange_kernel(
         s_params[threadIdx.x] = reinterpret_cast<float4 *>(params_ptrs[threadIdx.x]) + d.shard_begin / 4;
     }
     const uint32_t slot0 = d.signal_base + blockIdx.x * d.world;
-    meet_peers(s_signal, slot0, d.rank, d.world);  // (1) every peer's backward has written its gradients
+    const uint64_t timeout_ns = (uint64_t)(d.timeout_ms ? d.timeout_ms : 20000u) * 1000000ull;
+    meet_peers(s_signal, slot0, d.rank, d.world, timeout_ns);  // (1) every peer's backward has written its gradients
 
     const AdamStepConstants c = adam_step_constants(d.adam, __ldg(step_ptr));
     const float4 *g_mc = reinterpret_cast<const float4 *>(grads_mc) + d.shard_begin / 4;
@@ -143,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 2) adam_exchange_kernel(
             }
         }
     }
-    meet_peers(s_signal, slot0, d.rank, d.world);  // (5) replicas complete, gradients no longer read
+    meet_peers(s_signal, slot0, d.rank, d.world, timeout_ns);  // (5) replicas complete, gradients no longer read
 }
 
 }  // namespace

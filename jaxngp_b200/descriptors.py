@@ -85,13 +85,14 @@ def make_adam_descriptor(n, decay_begin, lr_init, lr_end, decay_rate, transition
                        float(eps), float(eps_root), float(weight_decay), float(grad_scale))
 
 
-def make_adam_exchange_descriptor(adam_descriptor, shard_begin, rank, world, use_multimem, n_blocks, signal_base):
+def make_adam_exchange_descriptor(adam_descriptor, shard_begin, rank, world, use_multimem, n_blocks, signal_base,
+                                  timeout_ms=0):
     """NgpAdamExchangeDescriptor (include/ngp_b200.h): the Adam constants of this rank's shard followed by where the
     shard sits in the flat buffers and who takes part in the exchange."""
     assert len(adam_descriptor) == 64
     return adam_descriptor + struct.pack("<Q6I", int(shard_begin), _u32(rank, "rank"), _u32(world, "world"),
                                          int(bool(use_multimem)), _u32(n_blocks, "n_blocks"),
-                                         _u32(signal_base, "signal_base"), 0)
+                                         _u32(signal_base, "signal_base"), _u32(timeout_ms, "timeout_ms"))
 
 
 def make_ogrid_sample_descriptor(n_points, G, mip_bound):

@@ -85,6 +85,9 @@ class PeerExchange:
         as_dev = lambda ptrs: torch.tensor(ptrs, dtype=torch.int64, device=self.device)  # noqa: E731
         self._grads_ptrs, self._params_ptrs = as_dev(g_ptrs), as_dev(p_ptrs)
         self._signal_ptrs = as_dev([int(p) for p in self._h_grads.signal_pad_ptrs])
+        # how long a block waits for a peer before the kernel traps (a rank that never arrives fails the launch with an
+        # error instead of spinning on the GPU until somebody kills the job); 0 = the kernel's default, 20 s
+        self.timeout_ms = int(os.environ.get("NGP_B200_EXCHANGE_TIMEOUT_MS", "0"))
         self.n_blocks = blocks_for(int(self._h_grads.signal_pad_size), world_size) if n_blocks is None else int(n_blocks)
         torch.cuda.synchronize(self.device)
         dist.barrier(group=group)  # every replica zeroed and mapped before the first launch touches a peer
@@ -93,6 +96,6 @@ class PeerExchange:
         """Enqueue the fused exchange + Adam on the current stream.  ``adam_desc`` is the shard's NgpAdamDescriptor
         (grad_scale = 1 / world)."""
         desc = descriptors.make_adam_exchange_descriptor(adam_desc, shard_begin, self.rank, self.world,
-                                                         self.use_multimem, self.n_blocks, SIGNAL_BASE)
+                                                         self.use_multimem, self.n_blocks, SIGNAL_BASE, self.timeout_ms)
         _lib.call("ngp_adam_step_exchange", [step_dev, adam_m, adam_v, self._grads_ptrs, self._params_ptrs,
                                              self._signal_ptrs, self._mc_grads, self._mc_params], desc)

@@ -134,7 +134,7 @@ def test_adam_exchange_descriptor_and_argument_checks(monkeypatch, built_lib):
     class Exchange(ctypes.Structure):
         _fields_ = [("adam", Adam), ("shard_begin", ctypes.c_uint64), ("rank", ctypes.c_uint32), ("world", ctypes.c_uint32),
                     ("use_multimem", ctypes.c_uint32), ("n_blocks", ctypes.c_uint32), ("signal_base", ctypes.c_uint32),
-                    ("reserved", ctypes.c_uint32)]
+                    ("timeout_ms", ctypes.c_uint32)]
 
     adam = D.make_adam_descriptor(n=1024, decay_begin=512, lr_init=1e-2, lr_end=1e-4, decay_rate=1 / 3, transition_steps=10_000,
                                   transition_begin=10_000, staircase=True, b1=0.9, b2=0.99, eps=1e-15, eps_root=1e-15,
