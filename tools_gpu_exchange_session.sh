@@ -4,8 +4,8 @@
 # 1. parity + timing of the peer arms against the NCCL arm on the C2 buffer (tools_exchange_check.py)
 # 2. the opt-in GPU test
 # 3. bench.py at N ranks with each exchange, training step only
-# Everything lands in gpurun_out/exchange/.  Each step has its own timeout: the kernel spins on its peers, so a bug shows
-# up as a hang, never as a wrong number.
+# Everything lands in gpurun_out/exchange/.  The kernel waits on its peers: a rank that never arrives makes the others trap
+# after 20 s (NGP_B200_EXCHANGE_TIMEOUT_MS) with a message naming the missing rank; each step also has its own timeout.
 set -u
 N=${1:-2}
 OUT=gpurun_out/exchange
