@@ -202,7 +202,7 @@ def run_ours(args):
     if not args.no_extras:
         del flush
         tr.release_graph()
-        render = render_bench(dev, rank, world, scene=tr.scene)
+        render = render_bench(dev, rank, world, scene=tr.scene, cap=args.render_cap)
         if rank == 0:
             hashenc = hashenc_bench(dev)
     if rank != 0:
@@ -656,6 +656,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the C3 render and C4 hash-encoder measurements")
     ap.add_argument("--no-graph", action="store_true", help="eager launches (for ncu launch lists)")
+    ap.add_argument("--render-cap", type=int, default=16,
+                    help="march_steps_cap of the C3 renderer (samples per slot and iteration; the frame does not depend on "
+                         "it, the number of loop iterations does -- worth raising when a rank's rays all fit its slots)")
     ap.add_argument("--exchange", default=None, choices=["nccl", "peer", "peer-p2p"],
                     help="gradient exchange at N>1: NCCL reduce-scatter/all-gather around Adam (default, or "
                          "NGP_B200_EXCHANGE) or the fused NVLink kernel of csrc/exchange.cu")
