@@ -88,7 +88,7 @@ class PeerExchange:
         # how long a block waits for a peer before the kernel traps (a rank that never arrives fails the launch with an
         # error instead of spinning on the GPU until somebody kills the job); 0 = the kernel's default, 20 s
         self.timeout_ms = int(os.environ.get("NGP_B200_EXCHANGE_TIMEOUT_MS", "0"))
-        self.n_blocks = blocks_for(int(self._h_grads.signal_pad_size), world_size) if n_blocks is None else int(n_blocks)
+        self.n_blocks = blocks_for(int(symm_mem.get_signal_pad_size()), world_size) if n_blocks is None else int(n_blocks)
         torch.cuda.synchronize(self.device)
         dist.barrier(group=group)  # every replica zeroed and mapped before the first launch touches a peer
 
