@@ -17,6 +17,9 @@ for mode in peer-p2p peer; do
 done
 NGP_B200_TEST_EXCHANGE=1 timeout 300 python -m pytest tests/test_gpu_exchange.py -x -q > "$OUT/pytest_n$N.log" 2>&1
 echo "pytest: rc=$? $(tail -1 "$OUT/pytest_n$N.log")"
+# the other opt-in GPU test written without a GPU (C1 harness vs its CPU restatement); single GPU
+NGP_B200_TEST_IMAGEFIT=1 timeout 300 python -m pytest tests/test_imagefit.py -x -q -m gpu > "$OUT/pytest_imagefit.log" 2>&1
+echo "pytest imagefit: rc=$? $(tail -1 "$OUT/pytest_imagefit.log")"
 for graph in 0 1; do  # 1: the exchange + optimizer replayed as one captured graph (NGP_B200_GRAPH_EXCHANGE)
   for mode in nccl peer; do
     NGP_B200_GRAPH_EXCHANGE=$graph timeout 300 bash -c "$(declare -f run); N=$N; run 29513 bench.py --gpus $N --steps 48 --warmup 4 --no-extras --no-cpu-baseline --exchange $mode" > "$OUT/bench_${mode}_g${graph}_n$N.log" 2>&1
