@@ -207,3 +207,49 @@ def test_checkpoint_round_trip_through_trainer_buffers():
         C.load_into_trainer(dst, dict(state, ogrid={k: np.concatenate([v, v]) for k, v in state["ogrid"].items()}))
     with pytest.raises(C.CheckpointError):  # background model
         C.load_into_trainer(dst, dict(state, params=dict(state["params"], bg={"Dense_0": {}})))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("NGP_B200_TEST_CHECKPOINT") != "1", reason="opt-in until it has run on a GPU once: NGP_B200_TEST_CHECKPOINT=1")
+def test_trainer_resumes_bit_identically_from_a_flax_checkpoint(tmp_path):
+    """Train, write a flax-format checkpoint (+ the .npz with the moments), load them into fresh trainers: parameters,
+    moments and grid arrive as the same bits, and the next step sees the same forward."""
+    import torch
+    from jaxngp_b200.trainer import Scene, Trainer
+    dev = "cuda:0"
+    scene = Scene(dev, n_views=4, width=100, height=100)
+    n_rays = 1 << 12
+
+    def perm(seed):
+        g = torch.Generator(device=dev).manual_seed(seed)
+        return torch.randint(0, scene.n_pixels, (n_rays,), device=dev, generator=g, dtype=torch.int32)
+
+    a = Trainer(device=dev, n_rays=n_rays, total_samples=1 << 15, scene=scene, use_graph=False)
+    for it in range(20):
+        a.train_step(perm(it))
+    a.update_ogrid()
+    state = C.state_from_trainer(a)
+    path = C.save_flax_checkpoint(str(tmp_path), state)
+    C.save_npz(str(tmp_path / "state.npz"), state)
+    from_flax, from_npz = C.load_flax_checkpoint(path), C.load_npz(str(tmp_path / "state.npz"))
+    assert int(from_flax["step"]) == 20 and "opt_state_b200" in from_npz
+
+    b = Trainer(device=dev, n_rays=n_rays, total_samples=1 << 15, scene=scene, use_graph=False, seed=5)
+    C.load_into_trainer(b, from_npz)
+    assert torch.equal(b.flat_params[: b.n_params], a.flat_params[: a.n_params])
+    assert torch.equal(b.adam_m[: b.n_params], a.adam_m[: a.n_params]) and torch.equal(b.grid.occupancy, a.grid.occupancy)
+    noises = torch.rand(n_rays, device=dev)
+    bg = torch.rand(n_rays, 3, device=dev)
+    # same parameters, grid and inputs -> same forward (the backward's atomic scatter order is free, so the parameters
+    # after the step are not compared bit for bit)
+    outs = [t._step_body(perm(99), noises, bg) for t in (a, b)]
+    assert abs(float(outs[0]["loss"]) - float(outs[1]["loss"])) <= 1e-6 * abs(float(outs[0]["loss"]))
+    assert int(outs[0]["measured_batch_size"]) == int(outs[1]["measured_batch_size"])
+    # the flax file alone (no moments) restores the model: same rendering inputs
+    c = Trainer(device=dev, n_rays=n_rays, total_samples=1 << 15, scene=scene, use_graph=False, seed=6)
+    before = C.state_from_trainer(b)["params"]["nerf"]
+    C.load_into_trainer(c, from_flax)
+    assert int(c.step_dev.item()) == 20 and float(c.adam_m.abs().max()) == 0  # moments stay at their initial zeros
+    after = C.state_from_trainer(c)["params"]["nerf"]
+    assert np.array_equal(after["rgb_mlp"]["Dense_1"]["kernel"], state["params"]["nerf"]["rgb_mlp"]["Dense_1"]["kernel"])
+    assert not np.array_equal(after["rgb_mlp"]["Dense_1"]["kernel"], before["rgb_mlp"]["Dense_1"]["kernel"])  # b has stepped since

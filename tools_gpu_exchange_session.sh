@@ -20,6 +20,8 @@ echo "pytest: rc=$? $(tail -1 "$OUT/pytest_n$N.log")"
 # the other opt-in GPU test written without a GPU (C1 harness vs its CPU restatement); single GPU
 NGP_B200_TEST_IMAGEFIT=1 timeout 300 python -m pytest tests/test_imagefit.py -x -q -m gpu > "$OUT/pytest_imagefit.log" 2>&1
 echo "pytest imagefit: rc=$? $(tail -1 "$OUT/pytest_imagefit.log")"
+NGP_B200_TEST_CHECKPOINT=1 timeout 300 python -m pytest tests/test_checkpoint.py -x -q -m gpu > "$OUT/pytest_checkpoint.log" 2>&1
+echo "pytest checkpoint: rc=$? $(tail -1 "$OUT/pytest_checkpoint.log")"
 for graph in 0 1; do  # 1: the exchange + optimizer replayed as one captured graph (NGP_B200_GRAPH_EXCHANGE)
   for mode in nccl peer; do
     NGP_B200_GRAPH_EXCHANGE=$graph timeout 300 bash -c "$(declare -f run); N=$N; run 29513 bench.py --gpus $N --steps 48 --warmup 4 --no-extras --no-cpu-baseline --exchange $mode" > "$OUT/bench_${mode}_g${graph}_n$N.log" 2>&1
