@@ -106,7 +106,9 @@ def make_state(step, table, mlp_flat, grid=None, n_frames=0, adam_m=None, adam_v
         density = _np(grid.density).astype(np.float32, copy=False)
         state["ogrid"] = {"density": density, "occ_mask": _np(grid.occ_mask).astype(np.bool_, copy=False),
                           "occupancy": _np(grid.occupancy).astype(np.uint8, copy=False),
-                          "alive_indices": np.arange(density.shape[0], dtype=np.uint32)}  # types.py:139 (re-marked after a load, train.py:206)
+                          # types.py:139; the reference re-marks after a load anyway (train.py:206)
+                          "alive_indices": (np.arange(density.shape[0], dtype=np.uint32) if getattr(grid, "alive_indices", None) is None
+                                            else _np(grid.alive_indices).astype(np.int64).astype(np.uint32))}
         if state["ogrid"]["occupancy"].shape[0] * 8 != density.shape[0] or state["ogrid"]["occ_mask"].shape != density.shape:
             raise CheckpointError("density grid arrays disagree in size")
     if adam_m is not None and adam_v is not None:

@@ -20,6 +20,16 @@ class OccupancyDensityGrid:
         self.density = torch.zeros(n, dtype=torch.float32, device=device)
         self.occ_mask = torch.zeros(n, dtype=torch.bool, device=device)
         self.occupancy = torch.full((n // 8,), 255, dtype=torch.uint8, device=device)
+        # cells some training camera sees (mark_untrained_density_grid); None = every cell, as at creation (types.py:139)
+        self.alive_indices = None      # int32 [n_alive], global Morton indices, cascade by cascade
+        self.alive_indices_offset = None  # python list, K + 1 entries (types.py:1353-1358)
+
+    def alive_in_cascade(self, cas: int):
+        """Aligned (in-cascade) indices of the trainable cells of one cascade, or None when all of them are."""
+        if self.alive_indices is None:
+            return None
+        lo, hi = self.alive_indices_offset[cas], self.alive_indices_offset[cas + 1]
+        return self.alive_indices[lo:hi] % self.G3
 
     @property
     def G3(self):
@@ -68,15 +78,19 @@ def update_ogrid_density(grid: OccupancyDensityGrid, density_fn, cas: int, updat
     selections (parity tests); cells are assumed alive (no camera culling in synthetic scenes)."""
     G3, dev = grid.G3, grid.density.device
     sl = slice(cas * G3, (cas + 1) * G3)
+    alive = grid.alive_in_cascade(cas)  # None unless mark_untrained_density_grid culled cells (:1158-1160)
+    n_alive = G3 if alive is None else int(alive.shape[0])
     if update_all:  # :1166-1169
-        idx = torch.arange(G3, dtype=torch.int32, device=dev)
+        idx = torch.arange(G3, dtype=torch.int32, device=dev) if alive is None else alive
     else:  # :1170-1191
-        M = max(1, G3 // 2)
+        M = max(1, n_alive // 2)
         half = max(1, M // 2)
         if draws is not None:
             first, second = draws["first"], draws["second"]
         else:
-            first = torch.randint(0, G3, (half,), device=dev, generator=generator, dtype=torch.int32)
+            first = torch.randint(0, n_alive, (half,), device=dev, generator=generator, dtype=torch.int32)
+            if alive is not None:  # uniform among the trainable cells
+                first = alive[first.long()]
             # uniform over the currently occupied cells: inverse-CDF over the mask (jran.choice with p)
             csum = torch.cumsum(grid.occ_mask[sl].to(torch.int32), 0)
             total = csum[-1]
@@ -101,3 +115,76 @@ def threshold_ogrid(grid: OccupancyDensityGrid, diagonal_n_steps: int, bound: fl
         grid.occ_mask.copy_(occ_mask)
         grid.occupancy.copy_(occupancy)
     return thr, occ_mask, occupancy
+
+
+_CELL_CORNERS = ((0, 0, 0), (0, 0, 1), (0, 1, 0), (0, 1, 1), (1, 0, 0), (1, 0, 1), (1, 1, 0), (1, 1, 1))
+
+
+def _morton3d_invert_host(idx: torch.Tensor) -> torch.Tensor:
+    """Morton index -> (x, y, z), torch integer ops on any device (marching.cu:70-77's bit compaction).  Used by the
+    one-time culling below so that it does not depend on a stream or a launch."""
+    def compact(x):
+        x = x & 0x49249249
+        x = (x | (x >> 2)) & 0xC30C30C3
+        x = (x | (x >> 4)) & 0x0F00F00F
+        x = (x | (x >> 8)) & 0xFF0000FF
+        x = (x | (x >> 16)) & 0x0000FFFF
+        return x
+    idx = idx.to(torch.int64)
+    return torch.stack([compact(idx), compact(idx >> 1), compact(idx >> 2)], dim=-1)
+
+
+def visible_cells(K: int, G: int, bound: float, transforms: torch.Tensor, cam: dict) -> torch.Tensor:
+    """``NeRFState.mark_untrained_density_grid`` (utils/types.py:1241-1326), undistorted cameras: bool [K * G^3], true
+    where one of the cell's 8 corners is in front of some training camera and projects into its frame.
+    ``transforms`` [V, 12]: rot_cw row-major then t_cw (trainer.Scene).  One-time setup, a few torch ops per view."""
+    if cam.get("distortion") or cam.get("has_distortion"):
+        raise NotImplementedError("camera distortion models are outside this path (utils/types.py:1286-1297)")
+    dev = transforms.device
+    G3 = G ** 3
+    cells = _morton3d_invert_host(torch.arange(G3, device=dev)).to(torch.float32)
+    corners = torch.tensor(_CELL_CORNERS, dtype=torch.float32, device=dev)
+    f = torch.tensor([cam["fx"], cam["fy"]], dtype=torch.float32, device=dev)
+    c = torch.tensor([cam["cx"], cam["cy"]], dtype=torch.float32, device=dev)
+    wh = torch.tensor([cam["width"], cam["height"]], dtype=torch.float32, device=dev)
+    alive = torch.zeros(K * G3, dtype=torch.bool, device=dev)
+    for cas in range(K):
+        mip_bound = float(min(2 ** cas, bound))
+        xyz = (cells / G - 0.5) * (2 * mip_bound)                       # :1249-1252
+        verts = xyz[:, None, :] + (2 * mip_bound / G) * corners[None]   # :1253-1263
+        part = alive[cas * G3:(cas + 1) * G3]
+        for tf in transforms.to(torch.float32):
+            rot, t = tf[:9].reshape(3, 3), tf[9:]
+            p_cam = ((verts - t)[..., None, :] * rot.T).sum(-1)          # world -> camera (:1275-1276)
+            front = p_cam[..., 2] < 0                                    # the camera looks along -z
+            uv = ((p_cam[..., :2] / (-p_cam[..., 2:])) * f + c) / wh     # :1281,1298-1302
+            inside = ((uv >= 0) & (uv < 1)).all(-1)
+            part |= (front & inside).any(-1)                             # :1310-1312
+            if bool(part.all()):
+                break
+    return alive
+
+
+def mark_untrained_density_grid(grid: OccupancyDensityGrid, transforms: torch.Tensor, cam: dict, bound: float,
+                                diagonal_n_steps: int, step: int) -> torch.Tensor:
+    """utils/types.py:1241-1362: cull the cells no training camera sees (density -1, never sampled or decayed again),
+    re-threshold (-0.5 at step 0: every trainable cell starts occupied) and re-pack the bitfield, in place.
+    Returns the alive marker.  Called once at start / after loading a checkpoint (app/nerf/train.py:206)."""
+    alive = visible_cells(grid.K, grid.G, bound, transforms, cam)
+    if step > 0:  # :1343 reads the grid BEFORE the culling: mean over the cells that were trainable until now
+        thr = threshold(grid.density[: grid.G3], density_threshold_from_min_step_size(diagonal_n_steps, bound))
+    else:
+        thr = -0.5
+    grid.density.copy_(torch.where(alive, grid.density, torch.full_like(grid.density, -1.0)))
+    occ_mask, occupancy = packbits(thr, grid.density)
+    grid.occ_mask.copy_(occ_mask)
+    grid.occupancy.copy_(occupancy)
+    if bool(alive.all()):
+        grid.alive_indices = grid.alive_indices_offset = None
+    else:
+        grid.alive_indices = torch.nonzero(alive).reshape(-1).to(torch.int32)
+        per_cascade = alive.view(grid.K, grid.G3).sum(dim=1).tolist()
+        grid.alive_indices_offset = [0]
+        for n in per_cascade:
+            grid.alive_indices_offset.append(grid.alive_indices_offset[-1] + int(n))
+    return alive

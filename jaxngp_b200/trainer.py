@@ -392,6 +392,14 @@ class Trainer:
         self._static_out = self._static_marched = None
         self._prefetched = None
 
+    def mark_untrained_density_grid(self):
+        """utils/types.py:1241-1362, called by the reference once before training and after a checkpoint load
+        (app/nerf/train.py:206): cells no training camera sees are culled for good.  Not part of ``__init__``: the
+        procedural scene's cameras see every cell of its single cascade, and bench.py installs the analytic occupancy."""
+        self.drop_prefetch()
+        return ogrid.mark_untrained_density_grid(self.grid, self.scene.transforms, self.scene.cam, synthetic.BOUND,
+                                                 synthetic.DIAGONAL_N_STEPS, self.step)
+
     # -- density grid update (utils/types.py:1149-1239) --------------------------------------------
     def _density_fn(self, xyz):
         if self.fused_encoder:

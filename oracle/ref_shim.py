@@ -286,9 +286,26 @@ class RefStateBase:
         return new
 
 
-def install_grid_update(oracle_module, jran):
+class _Progress:
+    """tqdm stand-in: iterates, swallows the progress-bar calls."""
+
+    def __init__(self, iterable, **kw):
+        self._it = iterable
+
+    def __iter__(self):
+        return iter(self._it)
+
+    def set_description_str(self, *a, **k):
+        pass
+
+    def close(self):
+        pass
+
+
+def install_grid_update(oracle_module, jran, extra_methods=()):
     """Returns (OccupancyDensityGrid, RefState): the reference's class and a state class carrying the reference's
-    ``update_ogrid_density`` / ``threshold_ogrid`` / ``density_threshold_from_min_step_size``.  The two compiled ops
+    ``update_ogrid_density`` / ``threshold_ogrid`` / ``density_threshold_from_min_step_size`` (plus ``extra_methods``
+    of NeRFState, e.g. ``mark_untrained_density_grid``).  The two compiled ops
     they call (volrendjax.morton3d_invert, volrendjax.packbits) are served by the C oracle, itself pinned to the
     reference's CUDA kernels by tests/golden/morton_packbits.npz."""
     import typing
@@ -313,12 +330,12 @@ def install_grid_update(oracle_module, jran):
 
     ns = dict(jax=jax, jnp=jnp, jran=jran, np=np, List=typing.List, struct=struct, dataclass=flax_dataclass,
               morton3d_invert=lambda idx: np.asarray(oracle_module.morton3d_invert(np.asarray(idx, np.uint32))),
-              packbits=packbits, RefStateBase=RefStateBase)
+              packbits=packbits, RefStateBase=RefStateBase, tqdm=_Progress, tqdm_format="")
     exec(compile(_extract_functions(path, {"empty_impl"}), "utils/types.py", "exec"), ns)
     grid_cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "OccupancyDensityGrid")
     exec(compile(ast.Module(body=[grid_cls], type_ignores=[]), "utils/types.py", "exec"), ns)
     state_cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "NeRFState")
-    wanted = {"update_ogrid_density", "threshold_ogrid", "density_threshold_from_min_step_size"}
+    wanted = {"update_ogrid_density", "threshold_ogrid", "density_threshold_from_min_step_size"} | set(extra_methods)
     methods = [n for n in state_cls.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
     assert {m.name for m in methods} == wanted
     ref_state = ast.ClassDef(name="RefState", bases=[ast.Name(id="RefStateBase", ctx=ast.Load())], keywords=[], body=methods,

@@ -449,3 +449,36 @@ def test_op_contracts_golden_from_reference_code():
         seen.add(expected)
     assert {"AssertionError", "NotImplementedError", "ValueError", "RuntimeError", "NgpError"} <= seen
     assert _lib.NgpError.__name__ == "NgpError"
+
+
+def test_mark_untrained_density_grid_golden_from_reference_code(oracle):
+    """The one-time camera-visibility culling (utils/types.py:1241-1362) against the reference's OWN method, run
+    unmodified by oracle/make_golden_mark_untrained.py: the numpy restatement and the torch host code that the product
+    runs (device-agnostic integer / float32 ops, here on the CPU) reproduce the alive marker, the culled densities, the
+    alive index table and -- through the restated thresholds -- the occupancy of both a fresh (step 0) and a trained state."""
+    import torch
+    from jaxngp_b200 import ogrid as product_ogrid
+    from jaxngp_b200 import synthetic as S
+    from oracle import ogrid_np
+    g = load("mark_untrained_reference.npz")
+    G, K, bound = int(g["G"]), int(g["K"]), float(g["bound"])
+    G3 = G ** 3
+    cam = S.camera()
+    alive_ref = np.zeros(K * G3, bool)
+    alive_ref[g["step0_alive_indices"]] = True
+    assert np.array_equal(g["step0_alive_indices"], g["step300_alive_indices"])
+    assert np.array_equal(np.diff(g["step0_alive_indices_offset"]), alive_ref.reshape(K, G3).sum(1))
+    alive_np = ogrid_np.visible_cells(K, G, bound, g["poses"], cam)
+    assert np.array_equal(alive_np, alive_ref)
+    alive_t = product_ogrid.visible_cells(K, G, bound, torch.from_numpy(g["poses"]), cam).numpy()
+    assert np.array_equal(alive_t, alive_ref)
+    thr_max = 0.01 * 1024 / (2 * min(bound, 1) * 3 ** 0.5)
+    for step in (0, 300):
+        marked, mask, bits, alive_idx = ogrid_np.mark_untrained(g["density_in"], alive_np, step, thr_max, G3)
+        assert np.array_equal(marked, g[f"step{step}_density"]) and np.array_equal(alive_idx, g[f"step{step}_alive_indices"])
+        assert np.array_equal(mask, g[f"step{step}_occ_mask"]) and np.array_equal(bits, g[f"step{step}_occupancy"])
+    assert np.array_equal(g["step0_occ_mask"], alive_ref)  # threshold -0.5: every trainable cell starts occupied
+    # Morton inversion of the host code = the compiled op's
+    idx = np.arange(0, G3, 7, dtype=np.uint32)
+    assert np.array_equal(product_ogrid._morton3d_invert_host(torch.from_numpy(idx.astype(np.int64))).numpy(),
+                          oracle.morton3d_invert(idx).astype(np.int64))

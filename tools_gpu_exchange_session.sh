@@ -22,6 +22,8 @@ NGP_B200_TEST_IMAGEFIT=1 timeout 300 python -m pytest tests/test_imagefit.py -x 
 echo "pytest imagefit: rc=$? $(tail -1 "$OUT/pytest_imagefit.log")"
 NGP_B200_TEST_CHECKPOINT=1 timeout 300 python -m pytest tests/test_checkpoint.py -x -q -m gpu > "$OUT/pytest_checkpoint.log" 2>&1
 echo "pytest checkpoint: rc=$? $(tail -1 "$OUT/pytest_checkpoint.log")"
+NGP_B200_TEST_CULLING=1 timeout 300 python -m pytest tests/test_gpu_optin_ogrid.py -x -q > "$OUT/pytest_culling.log" 2>&1
+echo "pytest culling: rc=$? $(tail -1 "$OUT/pytest_culling.log")"
 for graph in 0 1; do  # 1: the exchange + optimizer replayed as one captured graph (NGP_B200_GRAPH_EXCHANGE)
   for mode in nccl peer; do
     NGP_B200_GRAPH_EXCHANGE=$graph timeout 300 bash -c "$(declare -f run); N=$N; run 29513 bench.py --gpus $N --steps 48 --warmup 4 --no-extras --no-cpu-baseline --exchange $mode" > "$OUT/bench_${mode}_g${graph}_n$N.log" 2>&1
