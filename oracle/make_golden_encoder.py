@@ -54,6 +54,17 @@ def main():
         out[key + "_rows"] = np.int64(rows)
         out[key + "_b"] = np.float64(enc_mod.b)
         print(key, "rows", rows, "b", enc_mod.b, "|enc| max", float(np.abs(enc).max()))
+    # the total-variation branch (models/encoders.py:234-254, tv_scale > 0): the regulariser's value on 64 points
+    for dim, T, N_max in ((3, 2 ** 14, 512), (2, 2 ** 12, 256)):
+        lv = H.level_table(16, T, 2, 16, N_max, dim)
+        rows = int(lv["offsets"][-1])
+        pts = inputs.encoder_points(64, dim)
+        table = inputs.encoder_table(rows, 2, amp=1.0)
+        enc_mod = ref.HashGridEncoder(L=16, T=T, F=2, N_min=16, N_max=N_max, tv_scale=0.25)
+        enc_mod.bind_params(**{PARAM: table})
+        _, tv = enc_mod(pts, 1.0)
+        out[f"tv_d{dim}_T{T}_N{N_max}"] = np.float32(tv)
+        print("tv", dim, T, N_max, float(tv))
     # TCNNHashGridEncoder.__call__ (models/encoders.py:259-305), the Python half of the tiny-cuda-nn path: what it hands
     # to jaxtcnn.hashgrid_encode (level offsets WITHOUT the 8-alignment of the pure-JAX encoder, the per-level scale, the
     # transposed unit-cube coordinates, the parameter shape it requests).  The CUDA half is tiny-cuda-nn v1.6 (absent).

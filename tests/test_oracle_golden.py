@@ -482,3 +482,22 @@ def test_mark_untrained_density_grid_golden_from_reference_code(oracle):
     idx = np.arange(0, G3, 7, dtype=np.uint32)
     assert np.array_equal(product_ogrid._morton3d_invert_host(torch.from_numpy(idx.astype(np.int64))).numpy(),
                           oracle.morton3d_invert(idx).astype(np.int64))
+
+
+@pytest.mark.parametrize("dim,T,N_max", [(3, 2 ** 14, 512), (2, 2 ** 12, 256)])
+def test_total_variation_branch_golden_from_reference_code(dim, T, N_max):
+    """The encoder's optional regulariser (models/encoders.py:234-254, ``tv_scale > 0``; off in make_nerf_ngp) from the
+    reference's unmodified ``HashGridEncoder.__call__``: the host module's torch restatement (index ops, not a kernel:
+    it is off the hot path) gives the same value."""
+    import torch
+    from jaxngp_b200 import encoders as E
+    from oracle import hashgrid_np as H
+    g = load("encoder_reference.npz")
+    lv = H.level_table(16, T, 2, 16, N_max, dim)
+    table = inputs.encoder_table(int(lv["offsets"][-1]), 2, amp=1.0)
+    module = E.HashGridEncoder(16, T, 2, 16, N_max, tv_scale=0.25, dim=dim, device="cpu")
+    with torch.no_grad():
+        module.latents.copy_(torch.from_numpy(table))
+        tv = module.tv_scale * module._total_variation(torch.from_numpy(inputs.encoder_points(64, dim)), 1.0)
+    ref = float(g[f"tv_d{dim}_T{T}_N{N_max}"])
+    assert ref > 0 and abs(float(tv) - ref) <= 1e-6 * ref
