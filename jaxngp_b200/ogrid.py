@@ -75,7 +75,7 @@ def update_ogrid_density(grid: OccupancyDensityGrid, density_fn, cas: int, updat
                          max_inference: int, draws=None, generator=None, out_density=None):
     """``NeRFState.update_ogrid_density`` (utils/types.py:1149-1225) for one cascade.  ``density_fn(xyz)``
     evaluates the NeRF's density branch.  ``draws`` = dict(first, second, jitter) overrides the random
-    selections (parity tests); cells are assumed alive (no camera culling in synthetic scenes)."""
+    selections (parity tests).  After ``mark_untrained_density_grid`` culled cells, only trainable cells are sampled."""
     G3, dev = grid.G3, grid.density.device
     sl = slice(cas * G3, (cas + 1) * G3)
     alive = grid.alive_in_cascade(cas)  # None unless mark_untrained_density_grid culled cells (:1158-1160)
