@@ -212,7 +212,55 @@ def main():
         reg.append([name, platform])
     assert {n for n, _ in reg} == set(calls), (reg, sorted(calls))
 
-    out = {"custom_calls": calls, "registered_by_the_reference_impl": reg,
+    # the custom_vjp of integrate_rays (integrating/impl.py:50-146), unmodified: which residuals and cotangents its bwd rule
+    # hands the backward primitive, and which primal argument each returned cotangent is bound to
+    import typing
+    bound = {}
+
+    class _Prim:
+        def __init__(self, name, results):
+            self.name, self.results = name, results
+
+        def bind(self, *operands, **statics):
+            bound[self.name] = ([o if isinstance(o, str) else "<array>" for o in operands], sorted(statics))
+            return tuple(self.results)
+
+    class _CustomVjp:
+        def __init__(self, fn):
+            self.fn = fn
+
+        def __call__(self, *a, **k):
+            return self.fn(*a, **k)
+
+        def defvjp(self, fwd, bwd):
+            self.fwd, self.bwd = fwd, bwd
+
+    jax_stub = types.SimpleNamespace(custom_vjp=_CustomVjp, Array=object,
+                                     numpy=types.SimpleNamespace(broadcast_to=lambda a, shape: a))
+    ns = dict(jax=jax_stub, Tuple=typing.Tuple,
+              integrate_rays_p=_Prim("integrate_rays", ["measured_batch_size", "final_rgbds", "final_opacities"]),
+              integrate_rays_bwd_p=_Prim("integrate_rays_backward", ["dL_dbgs", "dL_dz_vals", "dL_ddrgbs"]))
+    tree = ast.parse(open(os.path.join(VR, "src", "volrendjax", "integrating", "impl.py")).read())
+    wanted = {"__integrate_rays", "__fwd_integrate_rays", "__bwd_integrate_rays"}
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in wanted]
+    body += [n for n in tree.body if isinstance(n, ast.Expr) and "defvjp" in ast.unparse(n)]
+    assert len(body) == 4
+    exec(compile(ast.Module(body=body, type_ignores=[]), "integrating/impl.py", "exec"), ns)
+    vjp = ns["__integrate_rays"]
+    primal_names = ["near_distance", "rays_sample_startidx", "rays_n_samples", "bgs", "dss", "z_vals", "drgbs"]
+
+    class _Named(str):  # a string standing in for an array: only .shape is asked of it (the bgs broadcast)
+        shape = (N,)
+
+    primals = {n: _Named(n) for n in primal_names}
+    _, aux = vjp.fwd(**primals)
+    cotangents = vjp.bwd(aux, ("dL_dmeasured_batch_size", "dL_dfinal_rgbds", "dL_dfinal_opacities"))
+    integrate_vjp = {"primal_arguments": primal_names,
+                     "backward_operands": bound["integrate_rays_backward"][0], "backward_statics": bound["integrate_rays_backward"][1],
+                     "cotangent_bound_to": {n: c for n, c in zip(primal_names, cotangents)}}
+    print("integrate_rays bwd binds:", integrate_vjp["cotangent_bound_to"])
+
+    out = {"custom_calls": calls, "registered_by_the_reference_impl": reg, "integrate_rays_vjp": integrate_vjp,
            "ffi": {"volrendjax": _ffi_surface(os.path.join(VR, "lib", "ffi.cc")),
                    "jaxtcnn": _ffi_surface(os.path.join(TC, "lib", "ffi.cc"))}}
     path = os.path.join(ROOT, "tests", "golden", "lowering_reference.json")

@@ -125,3 +125,39 @@ def test_host_mirror_issues_the_custom_call_the_reference_lowers_to(monkeypatch,
     for layouts, tensors in ((ref["operand_layouts"], ref["operands"]), (ref["result_layouts"], ref["results"])):
         assert [list(x) for x in layouts] == [list(range(len(shape) - 1, -1, -1)) for shape, _ in tensors]
     assert opaque.hex() == ref["opaque"]
+
+
+def test_integrate_rays_vjp_against_the_reference_rule(monkeypatch):
+    """The reference's OWN bwd rule of integrate_rays (integrating/impl.py:111-141, run unmodified with named stand-ins):
+    same residuals and cotangent handed to the backward primitive, in the same order -- and the documented difference
+    (SURVEY quirk Q5): the reference returns ``dL_dbgs`` in the slot of ``dss`` and nothing for ``bgs``; here each
+    cotangent goes to the argument it belongs to."""
+    vjp = GOLDEN["integrate_rays_vjp"]
+    assert vjp["backward_operands"] == ["rays_sample_startidx", "rays_n_samples", "bgs", "dss", "z_vals", "drgbs",
+                                        "final_rgbds", "final_opacities", "dL_dfinal_rgbds"]
+    assert vjp["backward_statics"] == ["near_distance"]
+    assert vjp["cotangent_bound_to"] == {"near_distance": None, "rays_sample_startidx": None, "rays_n_samples": None,
+                                         "bgs": None, "dss": "dL_dbgs", "z_vals": "dL_dz_vals", "drgbs": "dL_ddrgbs"}
+    calls = []
+
+    def recorder(name, buffers, opaque, stream=None):
+        calls.append((name, [b.data_ptr() for b in buffers]))
+        for b in buffers[-3:]:
+            b.fill_(1.0)  # stand-in results so that autograd has something to route
+
+    monkeypatch.setattr(_lib, "call", recorder)
+    n, s = 6, 40
+    start = torch.zeros(n, dtype=torch.int32)
+    ns = torch.zeros(n, dtype=torch.int32)
+    bgs = torch.zeros(n, 3, requires_grad=True)
+    dss, z_vals = torch.zeros(s, requires_grad=True), torch.zeros(s, requires_grad=True)
+    drgbs = torch.zeros(s, 4, requires_grad=True)
+    _, final_rgbds, _ = V.integrate_rays(0.3, start, ns, bgs, dss, z_vals, drgbs)
+    final_rgbds.sum().backward()
+    fwd, bwd = calls
+    assert (fwd[0], bwd[0]) == ("ngp_integrate_rays", "ngp_integrate_rays_backward")
+    # backward operands = the forward's six inputs, its two ray outputs, then the cotangent: the reference's order
+    assert bwd[1][:6] == fwd[1][:6] and bwd[1][6:8] == fwd[1][7:9] and len(bwd[1]) == 12
+    assert bgs.grad is not None and bgs.grad.shape == (n, 3)      # dL_dbgs -> bgs (the reference: -> dss)
+    assert dss.grad is None                                       # the op has no gradient for dss
+    assert z_vals.grad.shape == (s,) and drgbs.grad.shape == (s, 4)
