@@ -650,7 +650,7 @@ def main():
         faulthandler.dump_traceback_later(float(os.environ["NGP_FAULT_DUMP"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=48)
+    ap.add_argument("--steps", type=int, default=256)  # ~0.15 s per timed region: a few nvidia-smi samples land inside
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
