@@ -74,7 +74,10 @@ def flat_from_nerf_param_tree(tree: dict, rows: int = None, F: int = None):
     if table.dtype != np.float32 or table.ndim != 2:
         raise CheckpointError(f"hash table must be float32 [rows, F], got {table.dtype} {table.shape}")
     if (rows is not None and table.shape[0] != rows) or (F is not None and table.shape[1] != F):
-        raise CheckpointError(f"hash table is {table.shape}, this model expects ({rows}, {F})")
+        raise CheckpointError(
+            f"hash table is {table.shape}, this model expects ({rows}, {F}).  Tables written by the training encoder have "
+            "8-aligned level sizes (models/encoders.py:96), the tiny-cuda-nn layout of the inference model does not (:275): "
+            "build the model with inference=False to load a checkpoint trained with the pure-JAX encoder")
     parts = {}
     for module, layer, name in _MLP_TREE:
         try:
