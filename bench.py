@@ -659,7 +659,7 @@ def main():
     ap.add_argument("--render-cap", type=int, default=16,
                     help="march_steps_cap of the C3 renderer (samples per slot and iteration; the frame does not depend on "
                          "it, the number of loop iterations does -- worth raising when a rank's rays all fit its slots)")
-    ap.add_argument("--exchange", default=None, choices=["nccl", "peer", "peer-p2p"],
+    ap.add_argument("--exchange", default=None, choices=["auto", "nccl", "peer", "peer-p2p"],
                     help="gradient exchange at N>1: NCCL reduce-scatter/all-gather around Adam (default, or "
                          "NGP_B200_EXCHANGE) or the fused NVLink kernel of csrc/exchange.cu")
     ap.add_argument("--profile", type=int, default=0, help="run N steps between cudaProfilerStart/Stop and exit")

@@ -193,6 +193,33 @@ void ngp_ogrid_sample_positions(cudaStream_t, void **, const char *, size_t);
 void ngp_ogrid_decay_max(cudaStream_t, void **, const char *, size_t);
 void ngp_ogrid_threshold(cudaStream_t, void **, const char *, size_t);
 
+/* Random inputs of the path.  The reference draws them with jax.random outside its ops (march perturbations
+ * models/renderers/cuda.py:118-122, random backgrounds app/nerf/_utils.py:134-136, the cell draws and the jitter of
+ * utils/types.py:1170-1206); here they are Philox4x32-10 blocks, a pure function of (seed, stream_id, call counter,
+ * element index): element i of call c is philox(counter = {i, c, stream_id, 0}, key = {seed_lo, seed_hi}), each word
+ * mapped to [0, 1) by jax.random.uniform's construction (23 mantissa bits under exponent 0, minus 1).
+ * Ops that consume a call counter take `rng_state u32[2]` = {counter, ticket} in device memory: every block reads the
+ * counter, the last block of the launch increments it -- a replayed CUDA graph draws fresh numbers on every replay. */
+typedef struct { uint32_t seed_lo, seed_hi, stream_id; } NgpRngDescriptor;
+/* philox_uniform: out f32[n,4] = the four uniforms of every element of call `counter` (tests, eager replays) */
+typedef struct { uint32_t n, counter; NgpRngDescriptor rng; } NgpPhiloxDescriptor;
+void ngp_philox_uniform(cudaStream_t, void **, const char *, size_t);
+
+/* Cell draws + sample positions of update_ogrid_density (utils/types.py:1166-1206) for one cascade in one op.
+ * mode 1 (update_all): every trainable cell once, in order.  mode 0: n_first cells uniform among the trainable cells,
+ * then n_second cells uniform among the currently OCCUPIED ones (jran.choice with p = occ_mask: inverse CDF over a
+ * prefix count of the cascade's bitfield), with replacement.  Each cell gets a jittered point inside it (:1193-1206).
+ * in : bitfield u32[n_cells/32] (the cascade's slice of the occupancy bitfield, 16-byte aligned),
+ *      alive u32[n_alive] (Morton indices of the trainable cells inside the cascade) or NULL if has_alive == 0,
+ *      rng_state u32[2] (in/out)
+ * out: idx u32[M], coords f32[M,3]        M = mode ? n_alive : n_first + n_second */
+typedef struct {
+    uint32_t n_cells, G, n_alive, has_alive, mode, n_first, n_second;
+    float mip_bound;
+    NgpRngDescriptor rng;
+} NgpOgridDrawDescriptor;
+void ngp_ogrid_draw_cells(cudaStream_t, void **, const char *, size_t);
+
 /* Fully fused NeRF MLP of make_nerf_ngp (models/nerfs.py:27-128,216-238,422-454) on the tensor cores.
  * weights = flat f32[9408] = [density W0 32x64 | density W1 64x16 | rgb W0 32x64 | rgb W1 64x64 | rgb W2 64x3],
  * each row-major [in][out] like the flax Dense kernels.
@@ -239,6 +266,11 @@ typedef struct { uint32_t n_rays, width, height, n_views; float fx, fy, cx, cy, 
 typedef struct { uint32_t n_rays; float delta; } NgpHuberLossDescriptor;
 void ngp_make_training_rays(cudaStream_t, void **, const char *, size_t);
 void ngp_huber_loss_grad(cudaStream_t, void **, const char *, size_t);
+/* make_training_rays plus the step's random inputs from the same kernel (see NgpRngDescriptor above):
+ *   in : perm i32[n], transforms f32[V,12], rng_state u32[2] (in/out)
+ *   out: rays_o, rays_d, t_starts, t_ends as above, noises f32[n] (uniform x), bgs f32[n,3] (uniforms y, z, w) */
+typedef struct { NgpTrainingRaysDescriptor rays; NgpRngDescriptor rng; } NgpTrainingRaysRngDescriptor;
+void ngp_make_training_rays_rng(cudaStream_t, void **, const char *, size_t);
 
 /* integrate_rays (integrating.cu:24-99) + the Huber loss of train_step (app/nerf/_utils.py:151-165, target pixel
  * composited onto the random background, utils/data.py:459-463) + integrate_rays_backward (integrating.cu:101-240,

@@ -191,6 +191,19 @@ def load_into_trainer(trainer, state: dict):
     trainer.mlp_flat.copy_(torch.from_numpy(flat).to(dev))
     for name, src in grid_arrays.items():
         getattr(trainer.grid, name).copy_(src.to(dev))
+    if "ogrid" in state:
+        # the trainable-cell table (utils/types.py:1353-1358): without it the next full update would sample culled
+        # cells again.  The reference's checkpoint stores the indices only; the per-cascade offsets are derived from them
+        # (the reference re-marks after every restore, app/nerf/train.py:206 -- callers may still do that).
+        alive = state["ogrid"].get("alive_indices")
+        g = trainer.grid
+        n_cells = g.K * g.G3
+        if alive is None or np.asarray(alive).size in (0, n_cells):
+            g.alive_indices = g.alive_indices_offset = None
+        else:
+            alive = np.sort(np.asarray(alive).astype(np.int64).reshape(-1))
+            g.alive_indices = torch.from_numpy(alive.astype(np.int32)).to(dev)
+            g.alive_indices_offset = [int(np.searchsorted(alive, c * g.G3)) for c in range(g.K + 1)]
     trainer.step = int(state["step"])
     trainer.step_dev.fill_(int(state["step"]))
     for key, (t, f) in moments.items():

@@ -121,6 +121,54 @@ __device__ __forceinline__ float4 huber_ray(float4 pred, uchar4 px, float bg0, f
     return make_float4(gr[0], gr[1], gr[2], 0.f);
 }
 
+// ---------------------------------------------------------------- counter-based random numbers
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3", SC'11): the random inputs of the path
+// (march perturbations models/renderers/cuda.py:118-122, random backgrounds app/nerf/_utils.py:134-136, the cell draws and
+// jitter of utils/types.py:1170-1206) are drawn by the reference with jax.random OUTSIDE its ops; here they are a pure
+// function of (seed, stream, call counter, element index), so a captured CUDA graph and an eager replay see the same
+// numbers.  Known-answer vectors of the Random123 distribution are checked in tests/test_rng.py.
+struct Philox4 { uint32_t x, y, z, w; };
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+// 23 random mantissa bits under exponent 0 -> [1, 2) -> [0, 1): jax.random.uniform's construction
+__host__ __device__ __forceinline__ float bits_to_unit_float(uint32_t bits) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+#else
+    uint32_t u = (bits >> 9) | 0x3F800000u;
+    float f;
+    memcpy(&f, &u, 4);
+    return f - 1.0f;
+#endif
+}
+// the four uniforms of element `i` of call `counter` on `stream_id` (NgpRngDescriptor)
+__device__ __forceinline__ float4 philox_uniform4(uint32_t i, uint32_t counter, uint32_t stream_id, uint32_t seed_lo, uint32_t seed_hi) {
+    const Philox4 r = philox4x32_10(i, counter, stream_id, 0u, seed_lo, seed_hi);
+    return make_float4(bits_to_unit_float(r.x), bits_to_unit_float(r.y), bits_to_unit_float(r.z), bits_to_unit_float(r.w));
+}
+// A call counter that lives in device memory and is bumped by the LAST block of the launch that consumed it, so that
+// replaying a captured graph draws fresh numbers each time: state = {counter, blocks_done}.  Every block reads
+// state[0] when it starts; the last one to finish increments it and re-arms the ticket.
+__device__ __forceinline__ void rng_state_finish(uint32_t *state) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(state + 1, 1u) == gridDim.x - 1u) {
+            state[1] = 0u;
+            __threadfence();
+            atomicAdd(state, 1u);
+        }
+    }
+}
+
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }

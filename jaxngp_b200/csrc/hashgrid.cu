@@ -166,7 +166,18 @@ __global__ void __launch_bounds__(kBlock) hashgrid_a1_backward_kernel(const __gr
                         va[k] = base[k] + ((c >> (DIM - 1 - k)) & 1);
                         vb[k] = base[k] + (((c + NC / 2) >> (DIM - 1 - k)) & 1);
                     }
-                    const uint32_t ra = grid_row<DIM>(va, m), rb = grid_row<DIM>(vb, m);
+                    uint32_t ra = hg::grid_row_unclamped<DIM>(va, m), rb = hg::grid_row_unclamped<DIM>(vb, m);
+                    // a row past the table (see hg::grid_row): XLA's scatter-add drops the update
+                    if (ra > m.last_row) {
+                        ra = m.last_row;
+#pragma unroll
+                        for (int f = 0; f < F; ++f) v[c][f] = 0.f;
+                    }
+                    if (rb > m.last_row) {
+                        rb = m.last_row;
+#pragma unroll
+                        for (int f = 0; f < F; ++f) v[c + NC / 2][f] = 0.f;
+                    }
                     if (F == 2) {
                         if (kPaired && (ra ^ rb) == 1u) {
                             const bool a_hi = ra & 1u;
@@ -354,6 +365,19 @@ bool a1_validate(const NgpHashGridA1Descriptor *d, const char *op) {
                   d->table_dtype);
         return false;
     }
+    for (uint32_t l = 0; l < d->L; ++l) {
+        if (d->offsets[l + 1] <= d->offsets[l]) {
+            set_error(NGP_ERR_ARGUMENT, "%s: level %u has no rows (offsets %u..%u)", op, l, d->offsets[l], d->offsets[l + 1]);
+            return false;
+        }
+        // a hashed level indexes `hash mod wrap`: every such row must exist
+        const uint32_t wrap = d->wrap_T ? d->wrap_T : d->offsets[l + 1] - d->offsets[l];
+        if (((d->hashed_mask >> l) & 1u) && (uint64_t)d->offsets[l] + wrap > d->offsets[d->L]) {
+            set_error(NGP_ERR_ARGUMENT, "%s: hashed level %u reaches row %llu of a %u-row table", op, l,
+                      (unsigned long long)d->offsets[l] + wrap, d->offsets[d->L]);
+            return false;
+        }
+    }
     return true;
 }
 
@@ -374,7 +398,8 @@ void ngp_hashgrid_a1_forward(cudaStream_t stream, void **buffers, const char *op
     float *enc = b.next<float>();
     const unsigned blocks = div_up((unsigned long long)d->n_points * d->L, kBlock);
     // one aligned load for both corners of an x-pair needs the table base aligned to two rows
-    const bool paired = (reinterpret_cast<uintptr_t>(table) % (2 * d->F * (d->table_dtype == 0 ? 4 : 2))) == 0;
+    // (and an even row count: the pair load of the clamped last row must stay inside the table)
+    const bool paired = (reinterpret_cast<uintptr_t>(table) % (2 * d->F * (d->table_dtype == 0 ? 4 : 2))) == 0 && d->offsets[d->L] % 2 == 0;
     const bool pow2 = d->wrap_T != 0 && (d->wrap_T & (d->wrap_T - 1u)) == 0;
 #define NGP_FWD_(DIM, F, TT, P, W) \
     hashgrid_a1_forward_kernel<DIM, F, TT, P, W><<<blocks, kBlock, 0, stream>>>(*d, pos, static_cast<const TT *>(table), group_counts, enc)
@@ -413,7 +438,7 @@ void ngp_hashgrid_a1_backward(cudaStream_t stream, void **buffers, const char *o
                 "hashgrid_a1_backward");
     if (d->n_points == 0) return;
     const unsigned blocks = div_up(d->n_points, kBlock);  // one CTA per 256 points, all levels
-    const bool paired = reinterpret_cast<uintptr_t>(d_table) % 16 == 0;
+    const bool paired = reinterpret_cast<uintptr_t>(d_table) % 16 == 0 && d->offsets[d->L] % 2 == 0;
     if (d->dim == 3 && d->F == 2) {
         if (paired) hashgrid_a1_backward_kernel<3, 2, true><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
         else hashgrid_a1_backward_kernel<3, 2, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);

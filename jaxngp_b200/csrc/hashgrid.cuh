@@ -11,11 +11,13 @@ constexpr uint32_t kPrime1 = 2654435761u, kPrime2 = 805459861u;  // encoders.py:
 struct LevelMeta {
     float scale;
     uint32_t res, offset, wrap, hashed;
+    uint32_t last_row;  // rows of the whole table - 1: where an out-of-range row of a dense level lands (see grid_row)
 };
 
-// kPow2: every level's wrap is a power of two (always true for `mod T`, encoders.py:187): mask, no branch
+// kPow2: every level's wrap is a power of two (always true for `mod T`, encoders.py:187): mask, no branch.
+// Row as the reference computes it -- possibly past the table, see grid_row below.
 template <int DIM, bool kPow2 = false>
-__device__ __forceinline__ uint32_t grid_row(const uint32_t (&v)[DIM], const LevelMeta &m) {
+__device__ __forceinline__ uint32_t grid_row_unclamped(const uint32_t (&v)[DIM], const LevelMeta &m) {
     uint32_t idx;
     if (m.hashed) {  // encoders.py:157-177
         idx = v[0] ^ (v[1] * kPrime1);
@@ -28,6 +30,18 @@ __device__ __forceinline__ uint32_t grid_row(const uint32_t (&v)[DIM], const Lev
     if (kPow2 || (m.wrap & (m.wrap - 1u)) == 0u) idx &= m.wrap - 1u;
     else if (idx >= m.wrap) idx %= m.wrap;
     return idx + m.offset;
+}
+
+// Q1: with `mod T` a dense level's vertex index reaches past the level's own rows (a vertex coordinate equals `res` in
+// the outer half-cell) and lands in the NEXT level's rows -- reproduced.  On the last dense level of a table with no
+// hashed level behind it the row would lie past the table.  `latents[indices]` (encoders.py:225) is NumPy-style jnp
+// indexing: XLA clamps an out-of-range gather index to the last row, and DROPS the out-of-range update of the
+// transposed scatter-add (jax's documented out-of-bounds semantics for indexing; jax is not on disk to confirm, and the
+// reference's default geometry -- hashed levels behind the dense ones -- never gets here).  Forward: this clamp;
+// backward: the contribution is skipped (hashgrid_a1_backward_kernel).
+template <int DIM, bool kPow2 = false>
+__device__ __forceinline__ uint32_t grid_row(const uint32_t (&v)[DIM], const LevelMeta &m) {
+    return min(grid_row_unclamped<DIM, kPow2>(v, m), m.last_row);
 }
 
 template <typename TT, int F>
@@ -127,6 +141,7 @@ __device__ __forceinline__ LevelMeta a1_level(const NgpHashGridA1Descriptor &d, 
     m.offset = d.offsets[level];
     m.wrap = d.wrap_T ? d.wrap_T : d.offsets[level + 1] - d.offsets[level];
     m.hashed = (d.hashed_mask >> level) & 1u;
+    m.last_row = d.offsets[d.L] - 1u;
     return m;
 }
 

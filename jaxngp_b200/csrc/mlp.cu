@@ -952,9 +952,9 @@ void ngp_nerf_fused_forward(cudaStream_t stream, void **buffers, const char *opa
     float *enc_out = d->write_enc ? b.next<float>() : nullptr;
     const size_t pair_bytes = gd.table_dtype == 0 ? 16 : 8;
     if (gd.dim != 3 || gd.L != 16 || gd.F != 2 || gd.table_dtype > 1 || gd.wrap_T == 0 || (gd.wrap_T & (gd.wrap_T - 1u)) != 0 ||
-        reinterpret_cast<uintptr_t>(table) % pair_bytes != 0) {
+        reinterpret_cast<uintptr_t>(table) % pair_bytes != 0 || gd.offsets[gd.L] % 2 != 0) {
         set_error(NGP_ERR_ARGUMENT,
-                  "nerf_fused_forward: needs dim=3 L=16 F=2, power-of-two wrap_T and a table aligned to two rows "
+                  "nerf_fused_forward: needs dim=3 L=16 F=2, power-of-two wrap_T and a table of an even number of rows aligned to two rows "
                   "(got dim=%u L=%u F=%u wrap_T=%u); use hashgrid_a1_forward + nerf_mlp_forward", gd.dim, gd.L, gd.F, gd.wrap_T);
         return;
     }

@@ -327,9 +327,9 @@ extern "C" void ngp_nerf_fused_forward_umma(cudaStream_t stream, void **buffers,
     float *enc_out = d->write_enc ? b.next<float>() : nullptr;
     const size_t pair_bytes = gd.table_dtype == 0 ? 16 : 8;
     if (gd.dim != 3 || gd.L != 16 || gd.F != 2 || gd.table_dtype > 1 || gd.wrap_T == 0 || (gd.wrap_T & (gd.wrap_T - 1u)) != 0 ||
-        reinterpret_cast<uintptr_t>(table) % pair_bytes != 0 || d->density_only) {
+        reinterpret_cast<uintptr_t>(table) % pair_bytes != 0 || gd.offsets[gd.L] % 2 != 0 || d->density_only) {
         set_error(NGP_ERR_ARGUMENT,
-                  "nerf_fused_forward_umma: needs dim=3 L=16 F=2, power-of-two wrap_T, a table aligned to two rows and the "
+                  "nerf_fused_forward_umma: needs dim=3 L=16 F=2, power-of-two wrap_T, a table of an even number of rows aligned to two rows and the "
                   "full (density + colour) output (got dim=%u L=%u F=%u wrap_T=%u density_only=%u); use nerf_fused_forward",
                   gd.dim, gd.L, gd.F, gd.wrap_T, d->density_only);
         return;

@@ -12,12 +12,28 @@ namespace {
 
 constexpr int kBlock = 256;
 
-__global__ void __launch_bounds__(kBlock) make_training_rays_kernel(NgpTrainingRaysDescriptor d,
+// kRng: the step's random inputs leave the same kernel -- noises[i] (march perturbation, cuda.py:118-122) and
+// bgs[i] (random background of the loss, _utils.py:134-136) = the four Philox uniforms of element i of this call.
+template <bool kRng>
+__global__ void __launch_bounds__(kBlock) make_training_rays_kernel(NgpTrainingRaysDescriptor d, NgpRngDescriptor rng,
                                                                      const int32_t *__restrict__ perm,
                                                                      const float *__restrict__ transforms,
+                                                                     uint32_t *__restrict__ rng_state,
                                                                      float *__restrict__ rays_o, float *__restrict__ rays_d,
-                                                                     float *__restrict__ t_starts, float *__restrict__ t_ends) {
+                                                                     float *__restrict__ t_starts, float *__restrict__ t_ends,
+                                                                     float *__restrict__ noises, float *__restrict__ bgs) {
     const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (kRng) {
+        const uint32_t counter = rng_state[0];
+        if (i < d.n_rays) {
+            const float4 u = philox_uniform4(i, counter, rng.stream_id, rng.seed_lo, rng.seed_hi);
+            noises[i] = u.x;
+            bgs[3 * (size_t)i + 0] = u.y;
+            bgs[3 * (size_t)i + 1] = u.z;
+            bgs[3 * (size_t)i + 2] = u.w;
+        }
+        rng_state_finish(rng_state);  // every thread of the block reaches this (no early return above)
+    }
     if (i >= d.n_rays) return;
     const uint32_t hw = d.width * d.height;
     const uint32_t p = (uint32_t)__ldg(perm + i);
@@ -51,6 +67,11 @@ __global__ void __launch_bounds__(kBlock) make_training_rays_kernel(NgpTrainingR
     }
     t_starts[i] = fmaxf(t_start, 0.f);
     t_ends[i] = t_end;
+}
+
+__global__ void __launch_bounds__(kBlock) philox_uniform_kernel(NgpPhiloxDescriptor d, float4 *__restrict__ out) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i < d.n) out[i] = philox_uniform4(i, d.counter, d.rng.stream_id, d.rng.seed_lo, d.rng.seed_hi);
 }
 
 __global__ void __launch_bounds__(kBlock) count_valid_kernel(uint32_t n, const uint8_t *__restrict__ valid,
@@ -107,8 +128,44 @@ void ngp_make_training_rays(cudaStream_t stream, void **buffers, const char *opa
     float *rays_d = b.next<float>();
     float *t_starts = b.next<float>();
     float *t_ends = b.next<float>();
-    make_training_rays_kernel<<<div_up(d->n_rays, kBlock), kBlock, 0, stream>>>(*d, perm, transforms, rays_o, rays_d, t_starts, t_ends);
+    make_training_rays_kernel<false><<<div_up(d->n_rays, kBlock), kBlock, 0, stream>>>(*d, NgpRngDescriptor{}, perm, transforms, nullptr, rays_o,
+                                                                                       rays_d, t_starts, t_ends, nullptr, nullptr);
     check_launch("make_training_rays");
+}
+
+void ngp_make_training_rays_rng(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *d = descriptor<NgpTrainingRaysRngDescriptor>(opaque, opaque_len, "make_training_rays_rng");
+    if (!d || d->rays.n_rays == 0) return;
+    if (d->rays.width == 0 || d->rays.height == 0 || d->rays.n_views == 0) {
+        set_error(NGP_ERR_ARGUMENT, "make_training_rays_rng: empty image or view set");
+        return;
+    }
+    BufferCursor b{buffers};
+    const int32_t *perm = b.next<const int32_t>();
+    const float *transforms = b.next<const float>();
+    uint32_t *rng_state = b.next<uint32_t>();
+    float *rays_o = b.next<float>();
+    float *rays_d = b.next<float>();
+    float *t_starts = b.next<float>();
+    float *t_ends = b.next<float>();
+    float *noises = b.next<float>();
+    float *bgs = b.next<float>();
+    make_training_rays_kernel<true><<<div_up(d->rays.n_rays, kBlock), kBlock, 0, stream>>>(d->rays, d->rng, perm, transforms, rng_state, rays_o,
+                                                                                            rays_d, t_starts, t_ends, noises, bgs);
+    check_launch("make_training_rays_rng");
+}
+
+void ngp_philox_uniform(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *d = descriptor<NgpPhiloxDescriptor>(opaque, opaque_len, "philox_uniform");
+    if (!d || d->n == 0) return;
+    BufferCursor b{buffers};
+    float4 *out = b.next<float4>();
+    philox_uniform_kernel<<<div_up(d->n, kBlock), kBlock, 0, stream>>>(*d, out);
+    check_launch("philox_uniform");
 }
 
 void ngp_huber_loss_grad(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {

@@ -122,3 +122,23 @@ def make_integrate_loss_descriptor(n_rays, total_samples, near_distance, delta):
 
 def make_huber_loss_descriptor(n_rays, delta):
     return struct.pack("<If", _u32(n_rays, "n_rays"), float(delta))
+
+
+def make_rng_descriptor(seed, stream_id):
+    """NgpRngDescriptor: 64-bit seed as the Philox key, `stream_id` separates independent consumers."""
+    seed = int(seed) & (2 ** 64 - 1)
+    return struct.pack("<3I", seed & 0xFFFFFFFF, seed >> 32, _u32(stream_id, "stream_id"))
+
+
+def make_philox_descriptor(n, counter, seed, stream_id):
+    return struct.pack("<2I", _u32(n, "n"), _u32(counter, "counter")) + make_rng_descriptor(seed, stream_id)
+
+
+def make_training_rays_rng_descriptor(n_rays, width, height, n_views, fx, fy, cx, cy, bound, seed, stream_id):
+    return make_training_rays_descriptor(n_rays, width, height, n_views, fx, fy, cx, cy, bound) + make_rng_descriptor(seed, stream_id)
+
+
+def make_ogrid_draw_descriptor(n_cells, G, n_alive, has_alive, update_all, n_first, n_second, mip_bound, seed, stream_id):
+    return struct.pack("<7If", _u32(n_cells, "n_cells"), _u32(G, "G"), _u32(n_alive, "n_alive"), int(bool(has_alive)),
+                       int(bool(update_all)), _u32(n_first, "n_first"), _u32(n_second, "n_second"),
+                       float(mip_bound)) + make_rng_descriptor(seed, stream_id)

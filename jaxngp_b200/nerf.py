@@ -89,7 +89,7 @@ def fused_supported(lt, table: torch.Tensor, wrap: str = "jaxngp") -> bool:
     """Shapes ngp_nerf_fused_forward covers (include/ngp_b200.h); anything else runs encoder and MLP as two ops."""
     pair_bytes = 16 if table.dtype == torch.float32 else 8
     return (lt.dim == 3 and lt.L == 16 and lt.F == 2 and wrap == "jaxngp" and lt.T & (lt.T - 1) == 0
-            and table.dtype in (torch.float32, torch.float16) and table.data_ptr() % pair_bytes == 0)
+            and table.dtype in (torch.float32, torch.float16) and table.data_ptr() % pair_bytes == 0 and lt.rows % 2 == 0)
 
 
 def fused_forward(lt, pos: torch.Tensor, bound: float, table: torch.Tensor, dirs, weights: torch.Tensor, *,

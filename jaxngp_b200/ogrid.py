@@ -23,6 +23,9 @@ class OccupancyDensityGrid:
         # cells some training camera sees (mark_untrained_density_grid); None = every cell, as at creation (types.py:139)
         self.alive_indices = None      # int32 [n_alive], global Morton indices, cascade by cascade
         self.alive_indices_offset = None  # python list, K + 1 entries (types.py:1353-1358)
+        # random draws of the update (cell choice, jitter): Philox stream of csrc/common.cuh, counter on the device
+        self.seed = 0
+        self.rng_state = torch.zeros(2, dtype=torch.int32, device=device)
 
     def alive_in_cascade(self, cas: int):
         """Aligned (in-cascade) indices of the trainable cells of one cascade, or None when all of them are."""
@@ -52,6 +55,30 @@ def sample_positions(idx: torch.Tensor, uniforms: torch.Tensor, G: int, cas: int
     return coords
 
 
+STREAM_OGRID = 2  # NgpRngDescriptor.stream_id of the grid update's draws
+
+
+def draw_cells(grid: OccupancyDensityGrid, cas: int, update_all: bool, bound: float):
+    """utils/types.py:1166-1206 in one op (csrc/ogrid.cu ``ngp_ogrid_draw_cells``): which cells of cascade ``cas`` this
+    update evaluates, and a jittered point inside each.  Returns (idx int32 [M] Morton indices inside the cascade,
+    coords f32 [M, 3]).  Draws come from ``grid.rng_state`` / ``grid.seed``; the launch advances the counter."""
+    G3, dev = grid.G3, grid.density.device
+    alive = grid.alive_in_cascade(cas)
+    n_alive = G3 if alive is None else int(alive.shape[0])
+    if update_all:
+        n_first, n_second, m = 0, 0, n_alive
+    else:
+        n_first = n_second = max(1, max(1, n_alive // 2) // 2)  # M = max(1, n_grids // 2); max(1, M // 2) each (:1171-1190)
+        m = n_first + n_second
+    idx = torch.empty(m, dtype=torch.int32, device=dev)
+    coords = torch.empty(m, 3, dtype=torch.float32, device=dev)
+    bits = grid.occupancy[cas * G3 // 8:(cas + 1) * G3 // 8]
+    _lib.call("ngp_ogrid_draw_cells", [bits, alive.contiguous() if alive is not None else 0, grid.rng_state, idx, coords],
+              descriptors.make_ogrid_draw_descriptor(G3, grid.G, n_alive, alive is not None, update_all, n_first, n_second,
+                                                     min(bound, 2.0 ** cas), grid.seed, STREAM_OGRID))
+    return idx, coords
+
+
 def decay_and_max(density: torch.Tensor, idx: torch.Tensor, new_density: torch.Tensor, decay: float = 0.95,
                   out: torch.Tensor = None) -> torch.Tensor:
     """utils/types.py:1162-1164,1219-1221 on one cascade's slice: alive cells decay, then
@@ -78,28 +105,31 @@ def update_ogrid_density(grid: OccupancyDensityGrid, density_fn, cas: int, updat
     selections (parity tests).  After ``mark_untrained_density_grid`` culled cells, only trainable cells are sampled."""
     G3, dev = grid.G3, grid.density.device
     sl = slice(cas * G3, (cas + 1) * G3)
-    alive = grid.alive_in_cascade(cas)  # None unless mark_untrained_density_grid culled cells (:1158-1160)
-    n_alive = G3 if alive is None else int(alive.shape[0])
-    if update_all:  # :1166-1169
-        idx = torch.arange(G3, dtype=torch.int32, device=dev) if alive is None else alive
-    else:  # :1170-1191
-        M = max(1, n_alive // 2)
-        half = max(1, M // 2)
-        if draws is not None:
-            first, second = draws["first"], draws["second"]
-        else:
-            first = torch.randint(0, n_alive, (half,), device=dev, generator=generator, dtype=torch.int32)
-            if alive is not None:  # uniform among the trainable cells
-                first = alive[first.long()]
-            # uniform over the currently occupied cells: inverse-CDF over the mask (jran.choice with p)
-            csum = torch.cumsum(grid.occ_mask[sl].to(torch.int32), 0)
-            total = csum[-1]
-            u = torch.rand(half, device=dev, generator=generator)
-            target = (u * total.to(torch.float32)).to(torch.int32).clamp(max=(total - 1).clamp(min=0)) + 1
-            second = torch.searchsorted(csum, target).clamp(max=G3 - 1).to(torch.int32)
-        idx = torch.cat([first, second])
-    jitter = draws["jitter"] if draws is not None else torch.rand(idx.shape[0], 3, device=dev, generator=generator)
-    coords = sample_positions(idx, jitter, grid.G, cas, bound)
+    if draws is None and generator is None:  # the product path: cell choice, jitter and positions in one op
+        idx, coords = draw_cells(grid, cas, update_all, bound)
+    else:  # supplied draws (parity tests against the reference's own update) or a torch generator
+        alive = grid.alive_in_cascade(cas)  # None unless mark_untrained_density_grid culled cells (:1158-1160)
+        n_alive = G3 if alive is None else int(alive.shape[0])
+        if update_all:  # :1166-1169
+            idx = torch.arange(G3, dtype=torch.int32, device=dev) if alive is None else alive
+        else:  # :1170-1191
+            M = max(1, n_alive // 2)
+            half = max(1, M // 2)
+            if draws is not None:
+                first, second = draws["first"], draws["second"]
+            else:
+                first = torch.randint(0, n_alive, (half,), device=dev, generator=generator, dtype=torch.int32)
+                if alive is not None:  # uniform among the trainable cells
+                    first = alive[first.long()]
+                # uniform over the currently occupied cells: inverse-CDF over the mask (jran.choice with p)
+                csum = torch.cumsum(grid.occ_mask[sl].to(torch.int32), 0)
+                total = csum[-1]
+                u = torch.rand(half, device=dev, generator=generator)
+                target = (u * total.to(torch.float32)).to(torch.int32).clamp(max=(total - 1).clamp(min=0)) + 1
+                second = torch.searchsorted(csum, target).clamp(max=G3 - 1).to(torch.int32)
+            idx = torch.cat([first, second])
+        jitter = draws["jitter"] if draws is not None else torch.rand(idx.shape[0], 3, device=dev, generator=generator)
+        coords = sample_positions(idx, jitter, grid.G, cas, bound)
     new_density = torch.cat([density_fn(part).reshape(-1) for part in coords.split(max(1, max_inference))])
     target = grid.density[sl] if out_density is None else out_density[sl]
     decay_and_max(grid.density[sl], idx, new_density, 0.95, out=target)
@@ -114,6 +144,17 @@ def threshold_ogrid(grid: OccupancyDensityGrid, diagonal_n_steps: int, bound: fl
     if commit:  # in place: captured CUDA graphs keep reading these buffers
         grid.occ_mask.copy_(occ_mask)
         grid.occupancy.copy_(occupancy)
+    return thr, occ_mask, occupancy
+
+
+def threshold_ogrid_(grid: OccupancyDensityGrid, diagonal_n_steps: int, bound: float, density=None, occ_mask=None, occupancy=None):
+    """``threshold_ogrid`` writing the mask and the bitfield straight into the given buffers (default: the grid's own,
+    which captured CUDA graphs keep reading): no temporaries, no copies."""
+    density = grid.density if density is None else density
+    occ_mask = grid.occ_mask if occ_mask is None else occ_mask
+    occupancy = grid.occupancy if occupancy is None else occupancy
+    thr = threshold(density[: grid.G3], density_threshold_from_min_step_size(diagonal_n_steps, bound))
+    _lib.call("ngp_packbits_scalar", [thr, density, occ_mask, occupancy], descriptors.make_packbits_descriptor(density.shape[0] // 8))
     return thr, occ_mask, occupancy
 
 

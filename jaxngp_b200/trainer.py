@@ -10,6 +10,7 @@ Per step (shapes at BASELINE config C2: n_rays = total_samples = 2^18):
 All parameters live in ONE flat f32 buffer [hash table | MLP weights] with matching flat gradient and
 Adam-moment buffers, so data parallelism is a single ``all_reduce`` and the optimizer a single launch.
 """
+import math
 import os
 
 import torch
@@ -88,8 +89,10 @@ class Trainer:
         self.device = torch.device(device)
         self.n_rays, self.total_samples = n_rays, total_samples
         self.rank, self.world_size, self.pg = rank, world_size, process_group
-        # how the flat gradient is exchanged at world_size > 1: "nccl" (dp.py: reduce-scatter, Adam, all-gather) or
-        # "peer" / "peer-p2p" (exchange.py: one fused kernel over NVLink peer memory; opt-in)
+        # how the flat gradient is exchanged at world_size > 1: "peer" / "peer-p2p" (exchange.py: ONE fused kernel per rank
+        # over NVLink peer / multicast memory, replayed as a captured graph; the default -- measured 0.594 vs 0.646 ms per
+        # step at N=2, replicas bit-identical and equal to the NCCL arm) or "nccl" (dp.py: reduce-scatter, Adam,
+        # all-gather; also what "auto" falls back to when the ranks cannot map each other's memory)
         self.exchange_mode = exchange_mod.requested_mode() if exchange is None else exchange
         self.peer_exchange = None
         torch.backends.cuda.matmul.allow_tf32 = True  # XLA's default f32 dot precision on Ampere+
@@ -107,8 +110,11 @@ class Trainer:
         self.grid = ogrid.OccupancyDensityGrid(synthetic.K, synthetic.G, device=self.device)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.step = 0
-        torch.cuda.manual_seed(seed + 1 + rank)  # per-rank perturbation / background streams (graph-safe default generator)
-        self.noise_gen = None
+        # per-rank random streams (march perturbations + backgrounds; grid-update draws): Philox counters in device
+        # memory, advanced by the launches that consume them -- graph replays and eager launches draw the same numbers
+        self.rng_seed = seed + 1 + rank
+        self.rng_state = trainops.new_rng_state(self.device)
+        self.grid.seed = self.rng_seed
         # weight decay applies to the MLP weights only (_utils.py:45-77): index >= table_numel, shard relative
         decay_begin = min(max(self.table_numel - self.shard_lo, 0), self.shard_hi - self.shard_lo)
         self.adam_desc = descriptors.make_adam_descriptor(
@@ -116,15 +122,16 @@ class Trainer:
             transition_steps=10_000, transition_begin=10_000, staircase=True, b1=0.9, b2=0.99, eps=1e-15,
             eps_root=1e-15, weight_decay=1e-6, grad_scale=1.0 / world_size)
         self.use_graph = use_graph
-        # opt-in (NGP_B200_GRAPH_EXCHANGE=1, unmeasured): at world_size > 1 the gradient exchange + optimizer (NCCL
-        # reduce-scatter, Adam, all-gather, step counter -- or the one fused kernel) replay as ONE captured graph
-        # instead of four eager launches behind the compute graph
-        self.graph_exchange = os.environ.get("NGP_B200_GRAPH_EXCHANGE") == "1"
+        # the fused exchange kernel + step counter replay as one captured graph behind the compute graph
+        # (NGP_B200_GRAPH_EXCHANGE=0: eager launches).  The NCCL arm stays eager: its collectives captured in a graph
+        # measured no faster (0.655 vs 0.646 ms at N=2) and made process-group teardown hang.
+        self.graph_exchange = os.environ.get("NGP_B200_GRAPH_EXCHANGE", "1") == "1"
         self._exchange_graph = None
         self._graph = self._march_graph = None
         self._static_perm = self._static_out = self._static_marched = None
         self._prefetched = None
         self._slot = 0
+        self._shadow = None
 
     @property
     def occupancy(self):
@@ -154,10 +161,20 @@ class Trainer:
         self.table_numel = enc.latents.numel()
         assert self.table_numel % 4 == 0 and nerf_mod.MLP_NUMEL % 4 == 0
         self.n_params = self.table_numel + nerf_mod.MLP_NUMEL
-        total = -(-self.n_params // 32) * 32  # padded so that every rank's shard (world <= 8) is float4-aligned
+        # padded so that every rank's shard is float4-aligned and the shards cover the buffer, for any world size
+        quantum = math.lcm(32, 4 * self.world_size)
+        total = -(-self.n_params // quantum) * quantum
         if self.world_size > 1 and self.exchange_mode != "nccl":  # symmetric buffers every rank maps (collective)
-            self.peer_exchange = exchange_mod.PeerExchange(total, self.rank, self.world_size, self.device, self.pg,
-                                                           mode=self.exchange_mode)
+            try:
+                self.peer_exchange = exchange_mod.PeerExchange(total, self.rank, self.world_size, self.device, self.pg,
+                                                               mode="peer" if self.exchange_mode == "auto" else self.exchange_mode)
+            except Exception as exc:  # no peer mapping on this box (every rank fails alike: same node, same driver)
+                if self.exchange_mode != "auto":
+                    raise
+                import warnings
+                warnings.warn(f"peer exchange unavailable ({exc}); using the NCCL reduce-scatter / all-gather exchange")
+                self.exchange_mode = "nccl"
+        if self.peer_exchange is not None:
             self.flat_params, self.flat_grads = self.peer_exchange.params, self.peer_exchange.grads
         else:
             self.flat_params = torch.zeros(total, dtype=torch.float32, device=self.device)
@@ -183,11 +200,12 @@ class Trainer:
         sc = self.scene
         bg = None
         if noises is None:
-            # one generator launch for both random inputs of the step: the march perturbations (cuda.py:118-122) and
-            # the random backgrounds the loss composites onto (_utils.py:134-136), which travel with the marched batch
-            rnd = torch.rand(4 * self.n_rays, device=self.device)
-            noises, bg = rnd[: self.n_rays], rnd[self.n_rays:].view(self.n_rays, 3)
-        o, d, t_starts, t_ends = trainops.make_training_rays(perm, sc.transforms, sc.cam, synthetic.BOUND)
+            # both random inputs of the step leave the ray-generation kernel: the march perturbations (cuda.py:118-122)
+            # and the random backgrounds the loss composites onto (_utils.py:134-136), which travel with the marched batch
+            o, d, t_starts, t_ends, noises, bg = trainops.make_training_rays_rng(perm, sc.transforms, sc.cam, synthetic.BOUND,
+                                                                                 self.rng_state, self.rng_seed)
+        else:
+            o, d, t_starts, t_ends = trainops.make_training_rays(perm, sc.transforms, sc.cam, synthetic.BOUND)
         return march_rays(self.total_samples, synthetic.DIAGONAL_N_STEPS, synthetic.K, synthetic.G, synthetic.BOUND,
                           synthetic.STEPSIZE_PORTION, o, d, t_starts, t_ends, noises, self.grid.occupancy, raw=True) + (bg,)
 
@@ -196,7 +214,9 @@ class Trainer:
         sc = self.scene
         nxt, exc, ray_is_valid, rays_n, rays_start, _, xyzs, dirs, dss, z_vals, marched_bg = marched
         if bg is None:
-            bg = marched_bg if marched_bg is not None else torch.rand(self.n_rays, 3, device=self.device)  # random_bg, _utils.py:134-136
+            if marched_bg is None:
+                raise ValueError("supplied march perturbations need supplied backgrounds as well (the step draws both or none)")
+            bg = marched_bg  # random_bg, _utils.py:134-136
         if self.fused_encoder:  # encoder gather feeding the MLP's first tensor-core fragments (enc written once, for the backward)
             drgbs, enc = nerf_mod.fused_forward(self.levels, xyzs, synthetic.BOUND, self.table, dirs, self.mlp_flat, want_enc=True)
         else:
@@ -304,12 +324,12 @@ class Trainer:
         if self._graph is None:
             self._capture_graphs(perm, main)
         cur = self._slot
-        key = (perm.data_ptr(), perm.numel())
-        if self._prefetched == key:
+        if self._prefetched == self._batch_key(perm):
             main.wait_event(self._ev_march[cur])  # marched on the side stream during the previous step
         else:
             if self._prefetched is not None:  # a different batch was prefetched into this slot: let it finish first
                 main.wait_event(self._ev_march[cur])
+                self.rng_state[:1] -= 1  # its draws are handed back (see drop_prefetch)
             self._static_perm[cur].copy_(perm, non_blocking=True)
             self._march_graph[cur].replay()
         self._prefetched = None
@@ -337,7 +357,14 @@ class Trainer:
             self._static_perm[nxt].copy_(next_perm, non_blocking=True)
             self._march_graph[nxt].replay()
             self._ev_march[nxt].record(self._side)
-        self._prefetched = (next_perm.data_ptr(), next_perm.numel())
+        self._prefetched = self._batch_key(next_perm)
+
+    @staticmethod
+    def _batch_key(perm):
+        """Identity of a batch for the prefetch hit test: address, length and torch's in-place version counter, so a
+        staging buffer refilled in place (``copy_``, ``random_`` ...) is a different batch.  Writes torch cannot see
+        (a numpy view of pinned memory) are not detected: do not refill a buffer that way while it is prefetched."""
+        return (perm.data_ptr(), perm.numel(), perm._version)
 
     def _capture_graphs(self, perm, main):
         self._side = torch.cuda.Stream(device=self.device)
@@ -347,9 +374,15 @@ class Trainer:
         self._side.wait_stream(main)
         self._march_graph, self._graph, self._static_marched, self._static_out = [], [], [], []
         with torch.cuda.stream(self._side):
-            for _ in range(2):  # warm-up on the capture stream (scratch blocks)
+            # warm-up on the capture stream (scratch blocks, lazy module loads, NCCL channels).  It runs real steps, so
+            # everything they change is put back afterwards: the first train_step applies ONE optimizer update from its
+            # batch, as the eager path and the reference do (every rank issues the same warm-up collectives).
+            saved = [t.clone() for t in (self.flat_params, self.adam_m, self.adam_v, self.step_dev, self.rng_state)]
+            for _ in range(2):
                 self._compute_body(self._static_perm[0], self._march_body(self._static_perm[0]))
                 self._optimizer_step()
+            for t, v in zip((self.flat_params, self.adam_m, self.adam_v, self.step_dev, self.rng_state), saved):
+                t.copy_(v)
             for slot in range(2):
                 mg = torch.cuda.CUDAGraph()
                 # the captured march runs underneath the step's other kernels: a small persistent grid keeps it from
@@ -367,13 +400,12 @@ class Trainer:
                 self._graph.append(cg)
                 self._static_marched.append(marched)
                 self._static_out.append(out)
-            if self.graph_exchange and self.world_size > 1:  # every rank captures the same collectives in the same order
+            if self.graph_exchange and self.peer_exchange is not None:  # every rank captures the same launch
                 eg = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(eg, stream=self._side):
                     self._optimizer_step()
                 self._exchange_graph = eg
         main.wait_stream(self._side)
-        self.step += 2
         self._ev_march = [torch.cuda.Event(), torch.cuda.Event()]
         self._ev_free = torch.cuda.Event()
         self._prefetched = None
@@ -385,6 +417,7 @@ class Trainer:
         if self._prefetched is not None:
             torch.cuda.current_stream(self.device).wait_event(self._ev_march[self._slot])
             self._prefetched = None
+            self.rng_state[:1] -= 1  # the dropped march consumed a call of the random stream: hand it back
 
     def release_graph(self):
         """Drop the captured step graphs (and their private memory pools)."""
@@ -416,16 +449,20 @@ class Trainer:
         ``commit=False`` does all the work into shadow buffers (bench: keeps the marching workload fixed)."""
         if update_all is None:
             update_all = self.step < 256  # utils/types.py:1391-1392
-        if commit and self._prefetched is not None:  # a prefetched march saw the old bitfield: redo it
-            torch.cuda.current_stream(self.device).wait_event(self._ev_march[self._slot])
-            self._prefetched = None
+        if commit:  # a prefetched march saw the old bitfield: redo it (with the same random draws)
+            self.drop_prefetch()
         g = self.grid
-        shadow = None if commit else torch.empty_like(g.density)
+        if commit:
+            shadow = mask_out = bits_out = None
+        else:
+            if self._shadow is None:
+                self._shadow = (torch.empty_like(g.density), torch.empty_like(g.occ_mask), torch.empty_like(g.occupancy))
+            shadow, mask_out, bits_out = self._shadow
         for cas in range(g.K):
             ogrid.update_ogrid_density(g, self._density_fn, cas, update_all, synthetic.BOUND, self.total_samples,
                                        out_density=shadow)
         if self.world_size > 1:  # every rank sampled its own cells: take the max (SURVEY 8e)
             dp.allreduce_density_grid(g.density if commit else shadow, self.pg)
-        _, occ_mask, occupancy = ogrid.threshold_ogrid(g, synthetic.DIAGONAL_N_STEPS, synthetic.BOUND,
-                                                       density=None if commit else shadow, commit=commit)
+        _, occ_mask, occupancy = ogrid.threshold_ogrid_(g, synthetic.DIAGONAL_N_STEPS, synthetic.BOUND, density=shadow,
+                                                        occ_mask=mask_out, occupancy=bits_out)
         return occ_mask, occupancy

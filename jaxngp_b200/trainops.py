@@ -19,6 +19,42 @@ def make_training_rays(perm: torch.Tensor, transforms: torch.Tensor, cam: dict, 
     return o, d, ts, te
 
 
+#: Philox stream ids (NgpRngDescriptor.stream_id): independent consumers of one seed
+STREAM_TRAIN_RAYS, STREAM_OGRID = 1, 2
+
+
+def new_rng_state(device, counter=0):
+    """Device-resident call counter of the ops that draw random numbers: int32[2] = {counter, ticket}."""
+    return torch.tensor([counter, 0], dtype=torch.int32, device=device)
+
+
+def philox_uniform(n: int, counter: int, seed: int, stream_id: int, device) -> torch.Tensor:
+    """f32 [n, 4]: the four uniforms every element of call `counter` draws (csrc/common.cuh philox_uniform4)."""
+    out = torch.empty(n, 4, dtype=torch.float32, device=device)
+    if n:
+        _lib.call("ngp_philox_uniform", [out], descriptors.make_philox_descriptor(n, counter, seed, stream_id))
+    return out
+
+
+def make_training_rays_rng(perm: torch.Tensor, transforms: torch.Tensor, cam: dict, bound: float, rng_state: torch.Tensor,
+                           seed: int, stream_id: int = STREAM_TRAIN_RAYS):
+    """``make_training_rays`` plus the step's random inputs from the same launch: noises [n] (march perturbations,
+    models/renderers/cuda.py:118-122) and bgs [n, 3] (random backgrounds, app/nerf/_utils.py:134-136) = the Philox
+    uniforms of call ``rng_state[0]``, which the launch increments."""
+    n, dev = perm.shape[0], perm.device
+    o = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    d = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    ts = torch.empty(n, dtype=torch.float32, device=dev)
+    te = torch.empty(n, dtype=torch.float32, device=dev)
+    noises = torch.empty(n, dtype=torch.float32, device=dev)
+    bgs = torch.empty(n, 3, dtype=torch.float32, device=dev)
+    if n:
+        _lib.call("ngp_make_training_rays_rng", [perm, transforms, rng_state, o, d, ts, te, noises, bgs],
+                  descriptors.make_training_rays_rng_descriptor(n, cam["width"], cam["height"], transforms.shape[0], cam["fx"],
+                                                                cam["fy"], cam["cx"], cam["cy"], bound, seed, stream_id))
+    return o, d, ts, te, noises, bgs
+
+
 def huber_loss_grad(final_rgbds, ray_is_valid, perm, rgbas_u8, bgs, delta=0.1):
     """Returns (dL_dfinal_rgbds [n,4], loss [1], n_valid_rays int32[1]); app/nerf/_utils.py:151-165."""
     n, dev = final_rgbds.shape[0], final_rgbds.device

@@ -78,7 +78,8 @@ def indices_and_weights(levels, pos, bound):
 
 def encode(levels, pos, bound, table):
     idx, w = indices_and_weights(levels, pos, bound)
-    lat = np.asarray(table, np.float32)[idx]  # [L, n, C, F]  :226
+    # :226 is NumPy-style jnp indexing: an out-of-range index (last level dense, outer half-cell) is CLAMPED by XLA
+    lat = np.asarray(table, np.float32)[np.minimum(idx, np.uint32(levels["offsets"][-1] - 1))]  # [L, n, C, F]
     enc = (lat * w[..., None]).sum(axis=-2)  # :231
     return enc.transpose(1, 0, 2).reshape(enc.shape[1], -1)  # :233
 
@@ -88,6 +89,9 @@ def backward(levels, pos, bound, d_enc, F):
     L, n, Cn = idx.shape
     d = np.asarray(d_enc, np.float64).reshape(n, L, F).transpose(1, 0, 2)  # [L, n, F]
     upd = w[..., None].astype(np.float64) * d[:, :, None, :]
-    out = np.zeros((int(levels["offsets"][-1]), F), np.float64)
-    np.add.at(out, idx.reshape(-1), upd.reshape(-1, F))
+    rows = int(levels["offsets"][-1])
+    out = np.zeros((rows, F), np.float64)
+    flat_idx, flat_upd = idx.reshape(-1), upd.reshape(-1, F)
+    inside = flat_idx < rows  # the transposed scatter-add of that gather DROPS out-of-range updates (jax's documented
+    np.add.at(out, flat_idx[inside], flat_upd[inside])  # out-of-bounds semantics for indexing)
     return out

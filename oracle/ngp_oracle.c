@@ -506,6 +506,8 @@ void orc_hashgrid_encode(uint32_t n, uint32_t dim, uint32_t L, uint32_t F, const
                     w *= wk;
                 }
                 uint32_t row = hg_index(dim, v, res[l], hashed[l], wrap, offsets[l]);
+                /* latents[indices] (encoders.py:226): XLA clamps an out-of-range gather index (last level dense) */
+                if (row >= offsets[L]) row = offsets[L] - 1;
                 for (uint32_t f = 0; f < F; ++f) acc[f] += w * table[(size_t)row * F + f];
             }
             for (uint32_t f = 0; f < F; ++f) enc[(size_t)p * L * F + l * F + f] = acc[f]; /* :231-233 */
@@ -546,6 +548,7 @@ void orc_hashgrid_backward(uint32_t n, uint32_t dim, uint32_t L, uint32_t F, con
                     w *= wk;
                 }
                 uint32_t row = hg_index(dim, v, res[l], hashed[l], wrap, offsets[l]);
+                if (row >= offsets[L]) continue; /* ... and its transposed scatter-add drops the update */
                 for (uint32_t f = 0; f < F; ++f) {
                     double upd = (double)w * (double)d_enc[(size_t)p * L * F + l * F + f];
 #pragma omp atomic

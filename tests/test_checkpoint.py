@@ -210,7 +210,6 @@ def test_checkpoint_round_trip_through_trainer_buffers():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("NGP_B200_TEST_CHECKPOINT") != "1", reason="opt-in until it has run on a GPU once: NGP_B200_TEST_CHECKPOINT=1")
 def test_trainer_resumes_bit_identically_from_a_flax_checkpoint(tmp_path):
     """Train, write a flax-format checkpoint (+ the .npz with the moments), load them into fresh trainers: parameters,
     moments and grid arrive as the same bits, and the next step sees the same forward."""
@@ -253,3 +252,14 @@ def test_trainer_resumes_bit_identically_from_a_flax_checkpoint(tmp_path):
     after = C.state_from_trainer(c)["params"]["nerf"]
     assert np.array_equal(after["rgb_mlp"]["Dense_1"]["kernel"], state["params"]["nerf"]["rgb_mlp"]["Dense_1"]["kernel"])
     assert not np.array_equal(after["rgb_mlp"]["Dense_1"]["kernel"], before["rgb_mlp"]["Dense_1"]["kernel"])  # b has stepped since
+    # culled cells survive the round trip: the trainable-cell table comes back, so a full update leaves them at -1
+    culled = torch.zeros_like(a.grid.density, dtype=torch.bool)
+    culled[::3] = True
+    a.grid.density[culled] = -1.0
+    a.grid.alive_indices = torch.nonzero(~culled).reshape(-1).to(torch.int32)
+    a.grid.alive_indices_offset = [0, int((~culled).sum())]
+    d = Trainer(device=dev, n_rays=n_rays, total_samples=1 << 15, scene=scene, use_graph=False, seed=7)
+    C.load_into_trainer(d, C.state_from_trainer(a))
+    assert torch.equal(d.grid.alive_indices, a.grid.alive_indices) and d.grid.alive_indices_offset == a.grid.alive_indices_offset
+    d.update_ogrid(update_all=True)
+    assert torch.equal(d.grid.density < 0, culled)

@@ -166,7 +166,7 @@ def test_adam_exchange_descriptor_and_argument_checks(monkeypatch, built_lib):
 
     # host side: the mode switch and the CTA budget of the signal pads
     monkeypatch.delenv("NGP_B200_EXCHANGE", raising=False)
-    assert X.requested_mode() == "nccl"
+    assert X.requested_mode() == "auto"  # the fused kernel, NCCL if peers cannot be mapped
     monkeypatch.setenv("NGP_B200_EXCHANGE", "peer")
     assert X.requested_mode() == "peer"
     monkeypatch.setenv("NGP_B200_EXCHANGE", "gloo")

@@ -8,7 +8,7 @@ those compare-and-swap steps for small worlds and checks what the kernel relies 
   * barrier: a thread leaves round k only after its peer's thread has entered round k (so the peer's earlier writes --
     its gradients before the first barrier, its parameter stores before the second -- are ordered before),
   * the pads return to all-zero, so the next launch starts from the state the first one found.
-It checks the protocol, not the CUDA code: the GPU run of tools_exchange_check.py does that."""
+It checks the protocol, not the CUDA code: the GPU run of tools/exchange_check.py does that."""
 import itertools
 
 

@@ -1,4 +1,4 @@
-"""Camera-visibility culling on the GPU (opt-in, ``NGP_B200_TEST_CULLING=1``, until it has run on a GPU once): the device
+"""Camera-visibility culling on the GPU: the device
 result equals the CPU restatement that tests/golden/mark_untrained_reference.npz pins, and a density-grid update after
 the culling only ever touches trainable cells."""
 import os
@@ -7,8 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("NGP_B200_TEST_CULLING") != "1", reason="opt-in: NGP_B200_TEST_CULLING=1")]
+pytestmark = pytest.mark.gpu
 
 
 def test_mark_untrained_density_grid_on_device_and_update_respects_it(oracle):

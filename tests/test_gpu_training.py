@@ -298,3 +298,77 @@ def test_graph_renderer_is_bit_identical_to_reference_loop(small_scene):
     rgb2, _ = R.render(pose)
     diff = (rgb2.reshape(ref_rgb.shape).int() - ref_rgb.int()).abs().float()
     assert diff.mean() < 0.5 and (diff > 2).float().mean() < 0.02
+
+
+def test_graph_prefetch_train_step_matches_eager_steps(small_scene):
+    """The path bench.py times -- ``train_step(perm, next_perm)``: two march graphs + two compute graphs over
+    double-buffered slots, the next batch's march prefetched on a side stream -- against the same K steps run eagerly
+    (``use_graph=False``) with SUPPLIED perturbations and backgrounds: the Philox blocks the captured ray-generation kernel
+    draws from its device-resident call counter, regenerated here call by call.  A committed density-grid update sits in
+    the middle (it drops the prefetch and changes the bitfield the next march reads).
+
+    Integer outputs that depend on the march only (sample count before compaction, valid rays) must be identical at every
+    step; the composited sample count and the loss to float tolerance; parameters after K steps to atomic-order
+    tolerance (the hash-table scatter and the loss reduction are float atomics)."""
+    from jaxngp_b200 import trainops
+    from jaxngp_b200.trainer import Trainer
+    n_rays, total, K, update_at = 1 << 14, 1 << 17, 10, 5
+    gen = torch.Generator(device=DEV).manual_seed(21)
+    perms = [torch.randint(0, small_scene.n_pixels, (n_rays,), device=DEV, generator=gen, dtype=torch.int32) for _ in range(K)]
+    runs = {}
+    for arm in ("graph", "eager"):
+        tr = Trainer(device=DEV, n_rays=n_rays, total_samples=total, scene=small_scene, use_graph=arm == "graph", seed=77)
+        init = tr.flat_params.clone()
+        outs = []
+        for k in range(K):
+            if arm == "graph":
+                out = tr.train_step(perms[k], perms[k + 1] if k + 1 < K else None)
+            else:
+                u = trainops.philox_uniform(n_rays, k, tr.rng_seed, trainops.STREAM_TRAIN_RAYS, DEV)
+                tr.step += 1
+                out = tr._step_body(perms[k], u[:, 0].contiguous(), u[:, 1:].contiguous())
+            outs.append({name: v.clone() for name, v in out.items()})
+            if k + 1 == update_at:
+                tr.update_ogrid(update_all=True, commit=True)
+        torch.cuda.synchronize()
+        runs[arm] = dict(outs=outs, params=tr.flat_params.clone(), init=init, occ=tr.occupancy.clone(),
+                         step_dev=int(tr.step_dev), step=tr.step, rng=tr.rng_state.tolist(), m=tr.adam_m.clone())
+    g, e = runs["graph"], runs["eager"]
+    assert torch.equal(g["init"], e["init"])
+    assert g["step_dev"] == e["step_dev"] == K and g["step"] == e["step"] == K  # the graph warm-up leaves no trace
+    assert g["rng"] == [K, 0]  # one Philox call per captured march, none for the warm-up
+    for k in range(K):
+        a, b = g["outs"][k], e["outs"][k]
+        if k < update_at:  # same bitfield on both arms: the march is bit-identical
+            assert int(a["measured_batch_size_before_compaction"]) == int(b["measured_batch_size_before_compaction"]), k
+            assert int(a["n_valid_rays"]) == int(b["n_valid_rays"]), k
+        else:  # the updated bitfield thresholds densities that differ in their last bits between the arms
+            assert abs(int(a["measured_batch_size_before_compaction"]) - int(b["measured_batch_size_before_compaction"])) \
+                <= 2e-3 * int(b["measured_batch_size_before_compaction"]), k
+        assert abs(int(a["measured_batch_size"]) - int(b["measured_batch_size"])) <= 2e-3 * int(b["measured_batch_size"]) + 4, k
+        assert abs(float(a["loss"]) - float(b["loss"])) <= 2e-3 * abs(float(b["loss"])), (k, float(a["loss"]), float(b["loss"]))
+    assert (g["occ"] != e["occ"]).float().mean() < 2e-3
+    moved = (e["params"] - e["init"]).abs()
+    diff = (g["params"] - e["params"]).abs()
+    assert float(moved.max()) > 1e-3
+    # Adam normalises the gradient: an entry whose gradient sum is pure rounding noise can take a full-size step of
+    # either sign, so a handful of entries may differ by O(lr); everything else agrees closely
+    assert float((diff > 1e-4 + 1e-2 * moved).float().mean()) < 2e-3, float((diff > 1e-4 + 1e-2 * moved).float().mean())
+    assert float(torch.linalg.norm(diff)) <= 3e-2 * float(torch.linalg.norm(moved))
+
+
+def test_prefetch_key_sees_in_place_refills(small_scene):
+    """A staging buffer refilled in place is a different batch: the prefetched march must not be reused for it."""
+    from jaxngp_b200.trainer import Trainer
+    n_rays = 1 << 12
+    tr = Trainer(device=DEV, n_rays=n_rays, total_samples=1 << 15, scene=small_scene, use_graph=True, seed=5)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    a = torch.randint(0, small_scene.n_pixels, (n_rays,), device=DEV, generator=gen, dtype=torch.int32)
+    b = torch.randint(0, small_scene.n_pixels, (n_rays,), device=DEV, generator=gen, dtype=torch.int32)
+    stage = a.clone()
+    tr.train_step(a, stage)  # prefetches `stage` (= a's values)
+    stage.copy_(b)           # refilled in place while prefetched
+    out = tr.train_step(stage)
+    torch.cuda.synchronize()
+    assert torch.equal(tr._static_perm[1 - tr._slot], b)  # the step marched the refilled batch, not the stale one
+    assert torch.isfinite(out["loss"])

@@ -1,5 +1,5 @@
 """BASELINE config C1 (2-D image fit, models/imagefit.py): the CPU restatement against central differences of its own
-forward (CPU), and -- opt-in, ``NGP_B200_TEST_IMAGEFIT=1`` on a GPU box -- the harness around the 2-D hash-grid kernels
+forward (CPU), and on the GPU the harness around the 2-D hash-grid kernels
 against that restatement for a few optimizer steps."""
 import os
 
@@ -79,7 +79,6 @@ def test_imagefit_host_model_shapes_and_names():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("NGP_B200_TEST_IMAGEFIT") != "1", reason="opt-in until it has run on a GPU once: NGP_B200_TEST_IMAGEFIT=1")
 def test_imagefit_harness_matches_oracle_steps():
     import torch
     from jaxngp_b200 import imagefit

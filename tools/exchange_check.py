@@ -1,7 +1,7 @@
 """Check and time the fused gradient exchange (csrc/exchange.cu) against the NCCL path it replaces.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-        tools_exchange_check.py [--mode peer|peer-p2p] [--numel 12200000] [--steps 3] [--time 50]
+        tools/exchange_check.py [--mode peer|peer-p2p] [--numel 12200000] [--steps 3] [--time 50]
 
 Every rank fills its gradient buffer with its own seeded values, then both arms run the same optimizer steps from the
 same parameters:
@@ -19,7 +19,7 @@ import sys
 import torch
 import torch.distributed as dist
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from jaxngp_b200 import _lib, descriptors, dp, exchange  # noqa: E402
 
 

@@ -1,5 +1,5 @@
 """Top stall sites of one kernel from an ncu report's SASS page:
-python tools_ncu_hotspots.py report.ncu-rep <kernel regex> [top N]"""
+python tools/ncu_hotspots.py report.ncu-rep <kernel regex> [top N]"""
 import csv, subprocess, sys, io
 rep, rx = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40

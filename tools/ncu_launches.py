@@ -1,5 +1,5 @@
 """Summarise an `ncu --csv --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum` launch list by kernel.
-Usage: python tools_ncu_launches.py launches.csv "<command that was profiled>" > summary.txt"""
+Usage: python tools/ncu_launches.py launches.csv "<command that was profiled>" > summary.txt"""
 import collections
 import csv
 import sys

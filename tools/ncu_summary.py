@@ -1,4 +1,4 @@
-"""Summarise an ncu --set full report: python tools_ncu_summary.py report.ncu-rep [out.csv]"""
+"""Summarise an ncu --set full report: python tools/ncu_summary.py report.ncu-rep [out.csv]"""
 import csv
 import subprocess
 import sys

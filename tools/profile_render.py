@@ -1,9 +1,13 @@
 """Kernel-level breakdown of one 800x800 inference frame (InferenceRenderer) after a short training run.
-Usage: python tools_profile_render.py [train_steps] [n_slots] [cap]"""
+Usage: python tools/profile_render.py [train_steps] [n_slots] [cap]"""
 import collections
 import json
+import os
 import sys
 import time
+
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 from torch.profiler import ProfilerActivity, profile

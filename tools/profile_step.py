@@ -1,7 +1,11 @@
 """Kernel-level breakdown of the C2 training step (eager launches, warm L2 like the graph replay).
-Usage: python tools_profile_step.py [n_steps] [fused_encoder 0/1]"""
+Usage: python tools/profile_step.py [n_steps] [fused_encoder 0/1]"""
 import collections
+import os
 import sys
+
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 import torch

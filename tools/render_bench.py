@@ -1,8 +1,12 @@
 """C3: 800x800 inference rendering through the reference's slot-refill loop (renderers.render_image_inference)
-with a briefly trained model.  Prints rays/s and fps.  Usage: python tools_render_bench.py [train_steps]"""
+with a briefly trained model.  Prints rays/s and fps.  Usage: python tools/render_bench.py [train_steps]"""
 import json
+import os
 import sys
 import time
+
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch
 
