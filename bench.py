@@ -21,6 +21,21 @@ import sys
 import threading
 import time
 
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+if "--impl" in sys.argv and "reference" in sys.argv[sys.argv.index("--impl") + 1:][:1]:
+    # the CPU arm uses every host core it can: torchrun exports OMP_NUM_THREADS=1 to its workers, which would pin
+    # numpy's BLAS and the C oracle's OpenMP loops to one thread -- undo that before numpy loads its thread pools
+    os.environ["OMP_NUM_THREADS"] = str(host_cores())
+    os.environ.pop("MKL_NUM_THREADS", None)
+    os.environ.pop("OPENBLAS_NUM_THREADS", None)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -185,10 +200,21 @@ def run_ours(args):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
+    # K steps per timed region, as asked; the region is repeated R times (same batches, fresh random draws) and the
+    # MEDIAN region is reported with the spread beside it: 20 steps are an 11 ms sample otherwise
+    R = args.repeats if args.repeats > 0 else (25 if K * 25 <= 2000 else max(5, 2000 // K))
     sampler.mark(0)
-    ms, samples, _, _ = timed(K, W, e2e=False)
-    ms_e2e, samples_e2e, loss, _ = timed(K, W, e2e=True)
+    regions = [timed(K, W, e2e=False) for _ in range(R)]
+    regions_e2e = [timed(K, W, e2e=True) for _ in range(max(3, R // 3))]
     sampler.mark(1)
+    med = sorted(regions, key=lambda r: r[0])[len(regions) // 2]
+    ms, samples = med[0], med[1]
+    med_e = sorted(regions_e2e, key=lambda r: r[0])[len(regions_e2e) // 2]
+    ms_e2e, samples_e2e, loss = med_e[0], med_e[1], med_e[2]
+    spread = {"repeats": R, "ms_per_step_min": min(r[0] for r in regions) / K, "ms_per_step_median": ms / K,
+              "ms_per_step_max": max(r[0] for r in regions) / K, "e2e_repeats": len(regions_e2e),
+              "e2e_ms_per_step_min": min(r[0] for r in regions_e2e) / K, "e2e_ms_per_step_max": max(r[0] for r in regions_e2e) / K,
+              "timed_s_total": (sum(r[0] for r in regions) + sum(r[0] for r in regions_e2e)) / 1e3}
     clocks = sampler.stop() if rank == 0 else None
 
     # launches per step: count the kernels of one eager (un-graphed) step with the torch profiler's CUPTI view
@@ -197,6 +223,7 @@ def run_ours(args):
     # dominant kernel in isolation, on the step's own sample positions: CUDA events on the launching
     # stream, L2 flushed between iterations
     roof = dominant_kernel_roofline(tr, perms_dev[W], flush) if rank == 0 else None
+    per_op = per_op_vs_reference(tr, perms_dev[W], flush) if rank == 0 and world == 1 and not args.no_extras else None
 
     render = hashenc = None
     if not args.no_extras:
@@ -227,20 +254,41 @@ def run_ours(args):
                        f"parameters -> stored into every replica ({tr.peer_exchange.n_blocks} CTAs)"),
                    "l2": "per-step working set (table+grads+moments+activations ~0.5 GB) exceeds the 126 MB L2; no flush",
                    "cuda_graph": not args.no_graph, "exchange_in_graph": tr._exchange_graph is not None},
-        "samples_per_step": samples / K,
+        "samples_per_step": samples / K, "timing": spread,
         "e2e": {"value": samples_e2e / (ms_e2e / 1e3), "unit": "samples/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": N_RAYS * 4, "d2h_bytes_per_step": 4, "loss": loss,
                 "note": "every step: pixel indices copied from pinned host memory, loss copied back to pinned host memory "
                         "(read by the host one step later, while the next step runs)"},
         "gpu_launches": tr_counts["ours"] * K,
         "launches_per_step": tr_counts,
-        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "render": render, "hashenc": hashenc,
+        "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "per_op_vs_ref": per_op, "render": render, "hashenc": hashenc,
     }
-    if args.with_ref_gpu:
-        line["ref_gpu"] = run_subprocess_json(["--impl", "reference-gpu", "--steps", str(min(K, 10)), "--warmup", "3"])
+    if render is not None:  # BASELINE's second metric, where the driver's per-N records can see it
+        line["render_fps"], line["render_rays_per_s"] = render["fps"], render["rays_per_s"]
+        line["render_e2e_fps"] = render["e2e"]["fps"]
+    if hashenc is not None:
+        line["hashenc_fwd_bwd_gbs_T19"] = hashenc["sweep"][0]["fwd_bwd_gbs"]
+    if world == 1 and not args.no_ref_gpu and not args.no_extras:
+        # the comparator the north star names: the reference's own CUDA ops on this B200 (whole training step)
+        torch.cuda.empty_cache()
+        ref = run_subprocess_json(["--impl", "reference-gpu", "--steps", str(min(K, 10)), "--warmup", "3"])
+        line["ref_gpu"] = ref
+        if "value" in ref:
+            line["vs_ref_gpu"] = {"ratio": value / ref["value"], "ours_samples_per_s": value, "reference_samples_per_s": ref["value"],
+                                  "comparator": ref.get("config", {}).get("workload")}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def csrc_sha256():
+    """Digest of the kernel sources (what a committed ncu capture must have been taken from to be quoted)."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "jaxngp_b200", "csrc", "*.cu*"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
 
 
 def count_launches(tr, perm):
@@ -259,6 +307,20 @@ def count_launches(tr, perm):
         return {"ours": 6, "library": None, "note": f"profiler unavailable: {exc}"}
     ours = [n for n in names if "ngp::" in n or n.startswith("ngp")]
     return {"ours": len(ours), "library": len(names) - len(ours), "ours_names": sorted(set(n.split("(")[0][-60:] for n in ours))}
+
+
+def time_once(fn, flush):
+    """One launch timed alone: L2 flushed (a 256 MB fill), then a ~150 us spin kernel so that the host has enqueued
+    `fn`'s launches before the start event completes (otherwise Python's launch latency sits inside the interval)."""
+    import torch
+    flush.fill_(1)
+    torch.cuda._sleep(300_000)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
 
 
 def dominant_kernel_roofline(tr, perm, flush):
@@ -305,28 +367,28 @@ def dominant_kernel_roofline(tr, perm, flush):
     res = {}
     for name, fn, nbytes, note in kernels:
         times = []
-        for _ in range(3 + 10):
-            flush.fill_(1)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1))
-        t_ms = float(np.mean(times[3:]))
+        for _ in range(3 + 20):
+            times.append(time_once(fn, flush))
+        t_ms = float(np.median(times[3:]))
         res[name] = {"ms": round(t_ms, 4), "algorithmic_bytes": int(nbytes), "achieved_gbs": round(nbytes / (t_ms * 1e-3) / 1e9, 1),
                      "frac_of_hbm": round(nbytes / (t_ms * 1e-3) / 1e9 / hbm, 3), "per_unit": note}
     res["nerf_fused_forward"]["achieved_tflops"] = round(n * 18816 / (res["nerf_fused_forward"]["ms"] * 1e-3) / 1e12, 2)
     res["nerf_mlp_backward"]["achieved_tflops"] = round(n * 56448 / (res["nerf_mlp_backward"]["ms"] * 1e-3) / 1e12, 2)
     top = max(res, key=lambda k: res[k]["ms"])
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/), if present
-    traffic = None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel: an ncu counter, so it cannot be taken
+    # inside this run.  It is reported only from a committed capture of THIS build -- profiles/dram_traffic_r*.json carries
+    # the sha256 of the csrc/ sources it was taken from -- and is null the moment a kernel source changes.
+    traffic = traffic_src = None
     try:
         import glob
-        traffic = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "dram_traffic_r*.json")))[-1])).get(top)
+        cap = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "dram_traffic_r*.json")))[-1]))
+        if cap.get("csrc_sha256") == csrc_sha256():
+            traffic, traffic_src = cap.get(top), "ncu --set full capture of this build: profiles/" + cap.get("file", "dram_traffic")
+        else:
+            traffic_src = "no ncu capture of this build (kernel sources changed since the last one): null"
     except Exception:
-        pass
-    common = {"kernel": top, "traffic": traffic, "sample_slots": n, "samples": used, "rays_with_samples": n_hit,
+        traffic_src = "no committed ncu capture"
+    common = {"kernel": top, "traffic": traffic, "traffic_source": traffic_src, "sample_slots": n, "samples": used, "rays_with_samples": n_hit,
               "note": "each kernel timed alone with an L2 flush before every launch (isolated times sum to more than the "
                       "graph-replayed step, whose kernels find their inputs in L2); limiter per kernel in DESIGN.md section 5",
               "kernels": res}
@@ -339,6 +401,75 @@ def dominant_kernel_roofline(tr, perm, flush):
     return {"bound": "hbm", "achieved": res[top]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
             "frac": res[top]["frac_of_hbm"], "peak_source": src, **common}
 
+
+
+# ------------------------------------------------------------------------------------------- per op, ours vs theirs
+def per_op_vs_reference(tr, perm, flush, iters=20):
+    """Every compiled op of the reference (deps/volume-rendering-jax/lib/impl/{marching,integrating,packbits}.cu,
+    compiled unmodified into oracle/_ref) against this library's drop-in for it, on IDENTICAL inputs at the BASELINE
+    sizes: C2 (2^18 rays, 2^18 sample budget) for the training ops, C3 (640,000 rays of one 800x800 frame, 262,144
+    slots x 16 steps, first loop iteration) for the inference ops, the 128^3 grid for packbits / morton.  Each launch
+    timed alone with CUDA events on the launching stream, L2 flushed before it; median of `iters`.  ratio = theirs / ours."""
+    import torch
+    from tests import refops
+    if not refops.available():
+        return {"unavailable": "oracle/_ref/libvolrend_ref.so not built (needs /root/reference at build time)"}
+    from jaxngp_b200 import nerf as nerf_mod, renderers, synthetic, trainops, volrendjax as V
+    from jaxngp_b200.volrendjax.integrating import _integrate_bwd, _integrate_fwd
+    dev, sc = perm.device, tr.scene
+    o, d, ts, te, noises, bg = trainops.make_training_rays_rng(perm, sc.transforms, sc.cam, synthetic.BOUND,
+                                                               trainops.new_rng_state(dev), seed=1)
+    st = (TOTAL_SAMPLES, synthetic.DIAGONAL_N_STEPS, synthetic.K, synthetic.G, synthetic.BOUND, 0.0)
+    bits = tr.occupancy
+    nxt, exc, valid, rn, rs, idcs, xyzs, dirs, dss, zs = V.march_rays(*st, o, d, ts, te, noises, bits, raw=True)
+    drgbs = nerf_mod.fused_forward(tr.levels, xyzs, 1.0, tr.table, dirs, tr.mlp_flat)
+    drgbs = torch.cat([drgbs[:, :1] + 4.0 * (xyzs.norm(dim=-1, keepdim=True) < 0.45), drgbs[:, 1:]], -1).contiguous()  # visible medium
+    _, fin, opac = _integrate_fwd(rs, rn, bg, dss, zs, drgbs)
+    d_fin = torch.randn(N_RAYS, 4, device=dev)
+    # C3: one frame's rays, every slot free
+    fo, fd = renderers.make_rays_worldspace(sc.cam, sc.transforms[3])
+    fts, fte = renderers.make_near_far_from_bound(synthetic.BOUND, fo, fd)
+    N, n_slots, cap = fo.shape[0], 262144, 16
+    ist = (synthetic.DIAGONAL_N_STEPS, synthetic.K, synthetic.G, cap, synthetic.BOUND, 0.0)
+    nri = torch.zeros(1, dtype=torch.int32, device=dev)
+    term = torch.ones(n_slots, dtype=torch.bool, device=dev)
+    idx0 = torch.zeros(n_slots, dtype=torch.int32, device=dev)
+    m_inf = V.march_rays_inference(*ist, fo, fd, fts, fte, bits, nri, term, idx0)
+    _, idx1, ns1, _, ixyz, idss, izs = m_inf[:7]
+    idrgbs = torch.rand(n_slots, cap, 4, device=dev) * torch.tensor([6.0, 1.0, 1.0, 1.0], device=dev)
+    fbg, frgbd, fT = torch.ones(N, 3, device=dev), torch.zeros(N, 4, device=dev), torch.ones(N, device=dev)
+    G3 = synthetic.G ** 3
+    density = torch.rand(G3, device=dev)
+    thr = torch.full((G3,), 0.4, device=dev)
+    cells = torch.randint(0, synthetic.G, (G3, 3), device=dev, dtype=torch.int32)
+    codes = torch.randint(0, G3, (G3,), device=dev, dtype=torch.int32)
+    used = int((nxt - exc)[0])
+    ops = (
+        ("march_rays (C2)", lambda m: m.march_rays(*st, o, d, ts, te, noises, bits, raw=True), f"{N_RAYS} rays, {used} samples"),
+        ("integrate_rays (C2)", lambda m: m.integrate_rays(synthetic.NEAR, rs, rn, bg, dss, zs, drgbs), f"{used} samples"),
+        ("integrate_rays_backward (C2)", lambda m: m.integrate_rays_backward(synthetic.NEAR, rs, rn, bg, dss, zs, drgbs, fin, opac, d_fin)
+         if m is refops else _integrate_bwd(synthetic.NEAR, rs, rn, bg, dss, zs, drgbs, fin, opac, d_fin), f"{used} samples"),
+        ("march_rays_inference (C3, first iteration)", lambda m: m.march_rays_inference(*ist, fo, fd, fts, fte, bits, nri, term, idx0),
+         f"{N} rays, {n_slots} slots x {cap}"),
+        ("integrate_rays_inference (C3)", lambda m: m.integrate_rays_inference(fbg, frgbd, fT, ns1, idx1, idss, izs, idrgbs),
+         f"{n_slots} slots x {cap}"),
+        ("pack_density_into_bits (128^3)", lambda m: m.packbits(thr, density), f"{G3} cells"),
+        ("morton3d (128^3)", lambda m: m.morton3d(cells), f"{G3} points"),
+        ("morton3d_invert (128^3)", lambda m: m.morton3d_invert(codes), f"{G3} codes"),
+    )
+    table = {}
+    for name, fn, size in ops:
+        row = {"inputs": size}
+        for arm, mod in (("ours_ms", V), ("reference_ms", refops)):
+            for _ in range(3):
+                fn(mod)
+            row[arm] = round(float(np.median([time_once(lambda: fn(mod), flush) for _ in range(iters)])), 4)
+        row["ratio"] = round(row["reference_ms"] / row["ours_ms"], 2)
+        table[name] = row
+    return {"method": "CUDA events around one launch, L2 flushed, median of %d; ratio = reference_ms / ours_ms (> 1: ours faster). "
+                      "Both arms go through the same torch/ctypes wrappers (output allocation included); the reference's "
+                      "march_rays_inference also synchronises its stream and copies a counter (marching.cu:561-562)" % iters,
+            "reference": "deps/volume-rendering-jax/lib/impl/*.cu compiled unmodified for sm_100a (oracle/build_ref.sh)", "ops": table}
 
 # ------------------------------------------------------------------------------------------- extras (C3, C4)
 def render_bench(dev, rank, world, scene=None, frames=10, train_steps=300, n_slots=262144, cap=16):
@@ -370,26 +501,43 @@ def render_bench(dev, rank, world, scene=None, frames=10, train_steps=300, n_slo
         rgb, _ = R.render(scene.transforms[v])
         return gather(rgb.reshape(rows.numel(), Wd, 3)) if world > 1 else rgb
 
-    for v in views[:2]:
-        frame(v)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    samples = 0
-    e0.record()
-    for v in views[2:]:
-        img = frame(v)
-        samples += int(R.samples_done)
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    smp = torch.tensor([samples], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(smp)
+    host_frame = torch.empty((H if world > 1 else rows.numel()) * Wd * 3, dtype=torch.uint8).pin_memory()
+    poses_host = scene.transforms.cpu().pin_memory()
+
+    def run(e2e):
+        """frames rendered back to back; e2e: the pose comes from pinned host memory and the finished u8 frame is copied
+        back to pinned host memory every frame (the copy of frame k overlaps nothing: it is waited for before frame k+1,
+        as a viewer would)."""
+        for v in views[:2]:
+            frame(v)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        smp = torch.zeros((), dtype=torch.int64, device=dev)
+        e0.record()
+        for v in views[2:]:
+            if e2e:
+                pose = poses_host[v].to(dev, non_blocking=True)
+                rgb, _ = R.render(pose)
+                img = gather(rgb.reshape(rows.numel(), Wd, 3)) if world > 1 else rgb
+                host_frame.copy_(img.reshape(-1), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+            else:
+                img = frame(v)
+            smp += R.samples_done
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(smp)
+        return float(ms) / frames, int(smp), img
+
+    ms_frame, smp, img = run(False)
+    ms_frame_e2e, _, _ = run(True)
     # quality of the frame just rendered against the analytic ground truth of that view (white background)
     v = views[-1]
     gt = scene.rgbas_u8[v * H * Wd:(v + 1) * H * Wd].float() / 255
@@ -399,9 +547,11 @@ def render_bench(dev, rank, world, scene=None, frames=10, train_steps=300, n_slo
         full = torch.zeros(H * Wd, 3, device=dev)
         full[pixels.long()] = img.reshape(-1, 3).float() / 255
     psnr = float(-10 * torch.log10(((full - gt_rgb) ** 2).mean()))
-    ms_frame = float(ms) / frames
     return {"metric": "800x800 inference render rays/s", "rays_per_s": 640000 / (ms_frame * 1e-3), "fps": 1e3 / ms_frame,
-            "ms_per_frame": ms_frame, "frames": frames, "n_gpus": world, "samples_per_frame": int(smp) / frames,
+            "ms_per_frame": ms_frame, "frames": frames, "n_gpus": world, "samples_per_frame": smp / frames,
+            "e2e": {"fps": 1e3 / ms_frame_e2e, "rays_per_s": 640000 / (ms_frame_e2e * 1e-3), "ms_per_frame": ms_frame_e2e,
+                    "h2d_bytes_per_frame": 48, "d2h_bytes_per_frame": int(host_frame.numel()),
+                    "note": "pose copied from pinned host memory, finished u8 frame copied to pinned host memory and waited for, every frame"},
             "slots_per_gpu": R.n, "march_steps_cap": cap, "model": f"trained {train_steps} steps in this run (C2 step)",
             "psnr_last_frame": psnr, "sharding": "interleaved 32-row bands, all-gather of the u8 image per frame"}
 
@@ -491,6 +641,7 @@ def cpu_baseline_sample(n_rays=1 << 16, min_steps=8, max_steps=64, cpu_seconds=1
     """A bounded sample of the C2 workload on the host cores: whole steps until ~10 s of CPU work are in."""
     from oracle import oracle as O
     O.build()
+    O.set_num_threads(host_cores())
     ctx = cpu_step_setup(n_rays)
     cpu_step(ctx, n_rays, 1)  # warm-up
     tot_t = tot_s = 0.0
@@ -511,6 +662,7 @@ def run_reference_cpu(args):
         return
     from oracle import oracle as O
     O.build()
+    O.set_num_threads(host_cores())  # torchrun exports OMP_NUM_THREADS=1: this arm uses every core it may run on
     n_rays = 1 << 16
     ctx = cpu_step_setup(n_rays)
     K, W = args.steps, max(1, min(args.warmup, 2))
@@ -628,9 +780,11 @@ def run_reference_gpu(args):
     print(json.dumps({"impl": "reference-gpu", "metric": METRIC, "value": int(samples) / (ms / 1e3), "unit": "samples/s",
                       "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
                       "data": "synthetic", "dtype": "f32 (tf32 matmuls)",
-                      "config": {"workload": "C2 training step: reference march_rays/integrate_rays CUDA kernels compiled "
-                                             "unmodified for sm_100a + torch restatement of the pure-JAX HashGridEncoder "
-                                             "(no density-grid update in the loop)"}}))
+                      "config": {"workload": "C2 training step: the reference's march_rays / integrate_rays / integrate_rays_backward "
+                                             "CUDA kernels compiled unmodified for sm_100a + an EAGER torch restatement of its "
+                                             "pure-JAX HashGridEncoder, MLP, loss and Adam (jax is absent; XLA would fuse the "
+                                             "encoder's [L,n,8,*] intermediates, so this is a soft comparator for the JAX half "
+                                             "and an exact one for the CUDA half -- see per_op_vs_ref); no density-grid update"}}))
 
 
 def run_subprocess_json(extra):
@@ -662,8 +816,9 @@ def main():
     ap.add_argument("--exchange", default=None, choices=["auto", "nccl", "peer", "peer-p2p"],
                     help="gradient exchange at N>1: NCCL reduce-scatter/all-gather around Adam (default, or "
                          "NGP_B200_EXCHANGE) or the fused NVLink kernel of csrc/exchange.cu")
+    ap.add_argument("--repeats", type=int, default=0, help="timed K-step regions (0 = 25, fewer when K is large); the median is reported")
     ap.add_argument("--profile", type=int, default=0, help="run N steps between cudaProfilerStart/Stop and exit")
-    ap.add_argument("--with-ref-gpu", action="store_true", help="also time the reference's CUDA ops arm in a subprocess")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-CUDA-ops arm (a subprocess, N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_cpu(args)

@@ -65,6 +65,60 @@ __global__ void __launch_bounds__(kBlock) hashgrid_a1_forward_kernel(const __gri
     else *reinterpret_cast<float4 *>(out) = make_float4(acc[0], acc[1], acc[F - 2], acc[F - 1]);
 }
 
+
+// ---------------------------------------------------------------- level-major passes (tables larger than L2)
+// When the whole table no longer fits in L2 (T >= 2^20 at L = 16, F = 2: 87 MB .. 1 GB), the point-major kernels above
+// keep EVERY level's rows live at once and each 8-byte gather / reduction misses to DRAM as a 32-byte sector.  The
+// grouped kernels run the same arithmetic level group by level group (grid.y = group, scheduled after grid.x): the rows
+// in flight are those of `kLPG` consecutive levels only, sized by the launcher to stay L2-resident, so a level's rows
+// are fetched from DRAM once per pass instead of once per access.  Same per-(point, level) code => same bits.
+//
+// Forward, kLPG >= 4: a point's kLPG * F floats are >= 32 contiguous bytes of its output row: full sectors.
+// Forward, kLPG < 4 : partial sectors would be read-modify-written at DRAM on every pass; the pass writes a level-major
+// scratch [L][n][F] instead (coalesced) and hashgrid_transpose_kernel lays the rows out afterwards.
+template <int DIM, int F, typename TT, bool kPaired, bool kPow2, int kLPG, bool kScratch>
+__global__ void __launch_bounds__(kBlock) hashgrid_a1_forward_group_kernel(const __grid_constant__ NgpHashGridA1Descriptor d,
+                                                                            const float *__restrict__ pos,
+                                                                            const TT *__restrict__ table,
+                                                                            float *__restrict__ out) {
+    __shared__ LevelMeta s_meta[kLPG];
+    const uint32_t l0 = blockIdx.y * kLPG;
+    if (threadIdx.x < kLPG && l0 + threadIdx.x < d.L) s_meta[threadIdx.x] = a1_level(d, l0 + threadIdx.x);
+    __syncthreads();
+    const uint64_t tid = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+    const uint32_t point = (uint32_t)(tid / kLPG), j = (uint32_t)(tid % kLPG), level = l0 + j;
+    if (point >= d.n_points || level >= d.L) return;
+    const LevelMeta m = s_meta[j];
+    float x[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) x[k] = __ldg(pos + (size_t)point * DIM + k);
+    float p01[DIM], acc[F];
+    hg::unit_pos<DIM>(x, d.bound, p01);
+    hg::encode_point_level<DIM, F, TT, kPaired, kPow2>(table, m, p01, acc);
+    float *dst = kScratch ? out + ((size_t)level * d.n_points + point) * F : out + ((size_t)point * d.L + level) * F;
+    // streaming stores (evict-first): the L2 is for the level group's rows
+    if (F == 2) __stcs(reinterpret_cast<float2 *>(dst), make_float2(acc[0], acc[1]));
+    else __stcs(reinterpret_cast<float4 *>(dst), make_float4(acc[0], acc[1], acc[F - 2], acc[F - 1]));
+}
+
+// scratch [L][n][F] -> enc [n][L*F] through a shared-memory tile: both sides coalesced
+template <int F>
+__global__ void __launch_bounds__(kBlock) hashgrid_transpose_kernel(uint32_t n, uint32_t L, const float *__restrict__ scratch,
+                                                                     float *__restrict__ enc) {
+    constexpr int kPts = 64;
+    extern __shared__ float s_tile[];  // [kPts][L*F + 1]
+    const uint32_t p0 = blockIdx.x * kPts, LF = L * F, pitch = LF + 1;
+    for (uint32_t e = threadIdx.x; e < L * kPts * F; e += kBlock) {  // level-major read: kPts * F consecutive floats per level
+        const uint32_t l = e / (kPts * F), r = e % (kPts * F), pt = r / F, f = r % F;
+        if (p0 + pt < n) s_tile[pt * pitch + l * F + f] = __ldcs(scratch + ((size_t)l * n + p0 + pt) * F + f);
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < kPts * LF; e += kBlock) {
+        const uint32_t pt = e / LF, c = e % LF;
+        if (p0 + pt < n) __stcs(enc + (size_t)(p0 + pt) * LF + c, s_tile[pt * pitch + c]);
+    }
+}
+
 // Backward: level-major warps.  A CTA owns 256 consecutive points; warp w walks levels w, w+8 and its
 // lanes are 32 CONSECUTIVE points at ONE level.  Samples arrive ray by ray (march_rays emits each
 // ray's samples contiguously), so neighbouring lanes usually sit in the same grid cell on the coarse
@@ -72,11 +126,13 @@ __global__ void __launch_bounds__(kBlock) hashgrid_a1_forward_kernel(const __gri
 // reduction and only the run's first lane issues the 8 reductions.  L2 reductions are issued per
 // active lane (~1.3 cycles each), so this removes ~55 % of them on ray-ordered samples; on
 // incoherent points the run detection costs three shuffles and a vote per level.
+// `lpg` levels per pass (grid.y = level group, see "level-major passes" above): the CTA's work items are (32-point
+// sub-tile, level of the group), dealt to its warps round-robin; lpg = L in one pass is the mapping just described.
 template <int DIM, int F, bool kPaired>
 __global__ void __launch_bounds__(kBlock) hashgrid_a1_backward_kernel(const __grid_constant__ NgpHashGridA1Descriptor d,
                                                                        const float *__restrict__ pos,
                                                                        const float *__restrict__ d_enc,
-                                                                       float *__restrict__ d_table) {
+                                                                       float *__restrict__ d_table, uint32_t lpg) {
     __shared__ LevelMeta s_meta[NGP_HG_MAX_LEVELS];
     if (threadIdx.x < d.L) s_meta[threadIdx.x] = a1_level(d, threadIdx.x);
     __syncthreads();
@@ -85,27 +141,37 @@ __global__ void __launch_bounds__(kBlock) hashgrid_a1_backward_kernel(const __gr
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t tile_begin = blockIdx.x * kBlock;
 
-    for (uint32_t sub = 0; sub < kWarps; ++sub) {
-        const uint32_t point = tile_begin + sub * 32u + lane;
-        const bool in_range = point < d.n_points;
-        float p01[DIM];
+    const uint32_t l0 = blockIdx.y * lpg, l1 = min(l0 + lpg, d.L);
+    uint32_t sub_loaded = 0xFFFFFFFFu;
+    bool in_range = false;
+    uint32_t point = 0;
+    float p01[DIM];
+    for (uint32_t task = warp; task < kWarps * lpg; task += kWarps) {
+        const uint32_t sub = task / lpg, level = l0 + task % lpg;
+        if (level >= l1) continue;
+        if (sub != sub_loaded) {
+            sub_loaded = sub;
+            point = tile_begin + sub * 32u + lane;
+            in_range = point < d.n_points;
 #pragma unroll
-        for (int k = 0; k < DIM; ++k) {
-            const float x = in_range ? __ldg(pos + (size_t)point * DIM + k) : 0.f;
-            p01[k] = __fdiv_rn(__fadd_rn(x, d.bound), __fmul_rn(2.f, d.bound));  // encoders.py:87
+            for (int k = 0; k < DIM; ++k) {
+                const float x = in_range ? __ldg(pos + (size_t)point * DIM + k) : 0.f;
+                p01[k] = __fdiv_rn(__fadd_rn(x, d.bound), __fmul_rn(2.f, d.bound));  // encoders.py:87
+            }
         }
-        for (uint32_t level = warp; level < d.L; level += kWarps) {
+        {
             const LevelMeta m = s_meta[level];
             float g[F];
 #pragma unroll
             for (int f = 0; f < F; ++f) g[f] = 0.f;
             if (in_range) {
                 const float *gin = d_enc + ((size_t)point * d.L + level) * F;
+                // streamed once (evict-first): the L2 is for the gradient rows the reductions below hit
                 if (F == 2) {
-                    const float2 v = __ldg(reinterpret_cast<const float2 *>(gin));
+                    const float2 v = __ldcs(reinterpret_cast<const float2 *>(gin));
                     g[0] = v.x; g[1] = v.y;
                 } else {
-                    const float4 v = __ldg(reinterpret_cast<const float4 *>(gin));
+                    const float4 v = __ldcs(reinterpret_cast<const float4 *>(gin));
                     g[0] = v.x; g[1] = v.y; g[F - 2] = v.z; g[F - 1] = v.w;
                 }
             }
@@ -358,6 +424,29 @@ __global__ void __launch_bounds__(kBlock) zero_rows_kernel(const uint32_t *__res
     for (size_t i = n4 * 4 + (size_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (size_t)gridDim.x * kBlock) out[i] = 0.f;
 }
 
+// Levels per pass for a table that does not fit in L2 (see "level-major passes"): the largest power of two whose level
+// groups each stay under `budget` bytes of rows; 0 = the whole table fits, use the single-pass kernels.
+// NGP_B200_HG_LPG / NGP_B200_HG_BWD_LPG override it (tuning; 16 = force the single pass).
+constexpr size_t kL2TableBudget = 72u << 20;  // of B200's 126 MB L2: rows in flight next to the streamed inputs / outputs
+// (measured, tools/hashenc_sweep.py: 64 MB groups -- 4 levels at T = 2^21, 2 at 2^22, 1 at 2^23 -- are the fastest)
+unsigned levels_per_pass(const NgpHashGridA1Descriptor *d, size_t row_bytes, const char *env) {
+    if (const char *e = getenv(env)) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) return (unsigned)v;
+        if (v >= 16) return 0;
+    }
+    if ((size_t)d->offsets[d->L] * row_bytes <= (64u << 20)) return 0;
+    for (unsigned lpg = 8; lpg > 1; lpg >>= 1) {
+        bool ok = true;
+        for (uint32_t l0 = 0; l0 < d->L && ok; l0 += lpg) {
+            const uint32_t l1 = l0 + lpg < d->L ? l0 + lpg : d->L;
+            ok = (size_t)(d->offsets[l1] - d->offsets[l0]) * row_bytes <= kL2TableBudget;
+        }
+        if (ok) return lpg;
+    }
+    return 1;
+}
+
 bool a1_validate(const NgpHashGridA1Descriptor *d, const char *op) {
     if (d->L == 0 || d->L > NGP_HG_MAX_LEVELS || (d->dim != 2 && d->dim != 3) || (d->F != 2 && d->F != 4) ||
         d->table_dtype > 1) {
@@ -401,6 +490,37 @@ void ngp_hashgrid_a1_forward(cudaStream_t stream, void **buffers, const char *op
     // (and an even row count: the pair load of the clamped last row must stay inside the table)
     const bool paired = (reinterpret_cast<uintptr_t>(table) % (2 * d->F * (d->table_dtype == 0 ? 4 : 2))) == 0 && d->offsets[d->L] % 2 == 0;
     const bool pow2 = d->wrap_T != 0 && (d->wrap_T & (d->wrap_T - 1u)) == 0;
+    // tables beyond L2: level-major passes (dim 3, F 2, power-of-two wrap, pair-aligned table: the NeRF geometry)
+    const unsigned lpg = (d->dim == 3 && d->F == 2 && paired && pow2 && !d->rows_per_group)
+                             ? levels_per_pass(d, d->F * (d->table_dtype == 0 ? 4 : 2), "NGP_B200_HG_LPG") : 0;
+    if (lpg) {
+        const dim3 grid(div_up((unsigned long long)d->n_points * lpg, kBlock), div_up(d->L, lpg), 1);
+        float *dst = enc;
+        const bool scratch = lpg < 4;
+        if (scratch) {
+            dst = static_cast<float *>(workspace(stream, (size_t)d->n_points * d->L * d->F * sizeof(float)));
+            if (!dst) return;
+        }
+#define NGP_FWD_G(TT, LPG, SCR) \
+    hashgrid_a1_forward_group_kernel<3, 2, TT, true, true, LPG, SCR><<<grid, kBlock, 0, stream>>>(*d, pos, static_cast<const TT *>(table), dst)
+#define NGP_FWD_GT(TT)                                   \
+    do {                                                 \
+        if (lpg == 8) NGP_FWD_G(TT, 8, false);           \
+        else if (lpg == 4) NGP_FWD_G(TT, 4, false);      \
+        else if (lpg == 2) NGP_FWD_G(TT, 2, true);       \
+        else NGP_FWD_G(TT, 1, true);                     \
+    } while (0)
+        if (d->table_dtype == 0) NGP_FWD_GT(float); else NGP_FWD_GT(__half);
+#undef NGP_FWD_GT
+#undef NGP_FWD_G
+        if (!check_launch("hashgrid_a1_forward(level-major)")) return;
+        if (scratch) {
+            const size_t smem = 64 * (d->L * d->F + 1) * sizeof(float);
+            hashgrid_transpose_kernel<2><<<div_up(d->n_points, 64), kBlock, smem, stream>>>(d->n_points, d->L, dst, enc);
+            check_launch("hashgrid_a1_forward(transpose)");
+        }
+        return;
+    }
 #define NGP_FWD_(DIM, F, TT, P, W) \
     hashgrid_a1_forward_kernel<DIM, F, TT, P, W><<<blocks, kBlock, 0, stream>>>(*d, pos, static_cast<const TT *>(table), group_counts, enc)
 #define NGP_FWD(DIM, F, TT)                              \
@@ -437,16 +557,19 @@ void ngp_hashgrid_a1_backward(cudaStream_t stream, void **buffers, const char *o
     NGP_CUDA_OK(cudaMemsetAsync(d_table, 0, (size_t)d->offsets[d->L] * d->F * sizeof(float), stream),
                 "hashgrid_a1_backward");
     if (d->n_points == 0) return;
-    const unsigned blocks = div_up(d->n_points, kBlock);  // one CTA per 256 points, all levels
+    // one CTA per 256 points; all levels in one pass, or level-major passes when the gradient table exceeds L2
+    unsigned lpg = levels_per_pass(d, d->F * sizeof(float), "NGP_B200_HG_BWD_LPG");
+    if (lpg == 0) lpg = d->L;
+    const dim3 blocks(div_up(d->n_points, kBlock), div_up(d->L, lpg), 1);
     const bool paired = reinterpret_cast<uintptr_t>(d_table) % 16 == 0 && d->offsets[d->L] % 2 == 0;
     if (d->dim == 3 && d->F == 2) {
-        if (paired) hashgrid_a1_backward_kernel<3, 2, true><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
-        else hashgrid_a1_backward_kernel<3, 2, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
-    } else if (d->dim == 3) hashgrid_a1_backward_kernel<3, 4, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
+        if (paired) hashgrid_a1_backward_kernel<3, 2, true><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg);
+        else hashgrid_a1_backward_kernel<3, 2, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg);
+    } else if (d->dim == 3) hashgrid_a1_backward_kernel<3, 4, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg);
     else if (d->F == 2) {
-        if (paired) hashgrid_a1_backward_kernel<2, 2, true><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
-        else hashgrid_a1_backward_kernel<2, 2, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
-    } else hashgrid_a1_backward_kernel<2, 4, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table);
+        if (paired) hashgrid_a1_backward_kernel<2, 2, true><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg);
+        else hashgrid_a1_backward_kernel<2, 2, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg);
+    } else hashgrid_a1_backward_kernel<2, 4, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg);
     check_launch("hashgrid_a1_backward");
 }
 

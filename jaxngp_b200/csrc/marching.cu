@@ -567,7 +567,8 @@ __global__ void __launch_bounds__(kInferWarps * 32, 8) march_rays_inference_kern
     const uint32_t *indices_in, const uint32_t *__restrict__ block_total,
     const uint32_t *__restrict__ rank_in_block, uint32_t *__restrict__ next_ray_index, uint32_t *indices_out,
     uint32_t *__restrict__ n_samples, float *t_starts_out, float *__restrict__ xyzs,
-    float *__restrict__ dss, float *__restrict__ z_vals, float *__restrict__ ray_dirs) {
+    float *__restrict__ dss, float *__restrict__ z_vals, float *__restrict__ ray_dirs,
+    const float *__restrict__ t_admitted) {
     constexpr uint32_t kW = W, kWMask = W == 32 ? 0xFFFFFFFFu : 0xFFFFu;
     const uint32_t lane = threadIdx.x & (kW - 1u);
     const uint32_t shift = W == 32 ? 0u : (threadIdx.x & 16u);  // position of this slot's lanes in the warp
@@ -583,7 +584,9 @@ __global__ void __launch_bounds__(kInferWarps * 32, 8) march_rays_inference_kern
     const uint32_t counter_in = __ldg(next_ray_index_in);
     const bool mine = terminated[i] != 0;
     uint32_t ray_idx;
-    if (mine || i == p.n_rays - 1) {  // terminated slots before this slot's 1024-block
+    if (t_admitted) {  // admission and the empty-space prefix were done by march_rays_inference_admit_kernel
+        ray_idx = indices_out[i];
+    } else if (mine || i == p.n_rays - 1) {  // terminated slots before this slot's 1024-block
         const uint32_t nb = mine ? i / kRankSlots : 0u, nb_all = div_up_dev(p.n_rays, kRankSlots);
         uint32_t before = 0, all = 0;
         for (uint32_t j = lane; j < nb_all; j += kW) {
@@ -600,7 +603,7 @@ __global__ void __launch_bounds__(kInferWarps * 32, 8) march_rays_inference_kern
     } else {
         ray_idx = indices_in[i];
     }
-    if (lane == 0) indices_out[i] = ray_idx;
+    if (lane == 0 && !t_admitted) indices_out[i] = ray_idx;
 
     const uint32_t cap = p.march_steps_cap;
     float *__restrict__ o_xyzs = xyzs + (size_t)i * cap * 3;
@@ -611,7 +614,7 @@ __global__ void __launch_bounds__(kInferWarps * 32, 8) march_rays_inference_kern
     float t_cur = 0.f, t_end = 0.f;
     bool live = ray_idx < p.n_total_rays;
     if (live) {
-        t_cur = t_starts[ray_idx];  // plain load: the in-place variant writes this element back below
+        t_cur = t_admitted ? __ldg(t_admitted + i) : t_starts[ray_idx];  // plain load: the in-place variant writes this element back below
         t_end = __ldg(t_ends + ray_idx);
         live = !(t_end < t_cur);  // marching.cu:317 (strict)
     }
@@ -702,6 +705,62 @@ __global__ void __launch_bounds__(kInferWarps * 32, 8) march_rays_inference_kern
             o_z[k] = 0.f;
         }
     }
+}
+
+// ---------------------------------------------------------------- admission + empty-space prefix, one thread per slot
+// Front end of the drop-in march_rays_inference: hands fresh rays to terminated slots in slot order (same rule as the
+// cooperative kernel) and runs the empty-space prefix of the slot's ray (march_rays_skip_empty_kernel's rule: the
+// visit sequence touches ~1 chain point in 5 while nothing is occupied, which a thread hopping voxel to voxel walks
+// far cheaper than 16 lanes evaluating consecutive chain points).  A frame's first pass starts every ray at the near
+// plane: measured 1.55 ms -> see DESIGN for the cooperative kernel alone on 262,144 fresh slots against 0.49 ms for
+// the reference's thread-per-slot loop.  The cooperative kernel then starts at t_admitted[slot]: same samples, same final t.
+__global__ void __launch_bounds__(128) march_rays_inference_admit_kernel(
+    NgpMarchingInferenceDescriptor p, const float *__restrict__ rays_o, const float *__restrict__ rays_d,
+    const float *__restrict__ t_starts, const float *__restrict__ t_ends, const uint8_t *__restrict__ bitfield,
+    const uint32_t *__restrict__ next_ray_index_in, const uint8_t *__restrict__ terminated,
+    const uint32_t *__restrict__ indices_in, const uint32_t *__restrict__ block_total,
+    const uint32_t *__restrict__ rank_in_block, uint32_t *__restrict__ next_ray_index, uint32_t *__restrict__ indices_out,
+    float *__restrict__ t_admitted) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t counter_in = __ldg(next_ray_index_in);
+    // a warp's 32 slots lie in one 1024-slot rank block: the terminated slots before that block, summed cooperatively
+    const uint32_t warp_first = i - lane;
+    if (warp_first >= p.n_rays) return;
+    const uint32_t nb = warp_first / kRankSlots, nb_all = div_up_dev(p.n_rays, kRankSlots);
+    const bool last_warp = warp_first + 32u >= p.n_rays;
+    uint32_t before = 0, all = 0;
+    for (uint32_t j = lane; j < (last_warp ? nb_all : nb); j += 32u) {
+        const uint32_t c = __ldg(block_total + j);
+        if (j < nb) before += c;
+        all += c;
+    }
+    before = __reduce_add_sync(0xffffffffu, before);
+    if (last_warp) {
+        all = __reduce_add_sync(0xffffffffu, all);
+        if (lane == 0) *next_ray_index = counter_in + all;
+    }
+    if (i >= p.n_rays) return;
+    const uint32_t ray_idx = terminated[i] ? counter_in + before + __ldg(rank_in_block + i) : __ldg(indices_in + i);
+    indices_out[i] = ray_idx;
+    float t = 0.f;
+    if (ray_idx < p.n_total_rays) {
+        t = __ldg(t_starts + ray_idx);
+        const float t_end = __ldg(t_ends + ray_idx);
+        if (!(t_end < t)) {  // marching.cu:317
+            const Grid g = make_grid(p.diagonal_n_steps, p.K, p.G, p.bound, p.stepsize_portion, bitfield);
+            const Ray ray = load_ray(rays_o, rays_d, ray_idx);
+            float t_prev = t;
+            while (t < t_end) {
+                const Step s = march_step<true>(g, ray, t);
+                if (s.occupied) break;
+                t_prev = t;
+                t = s.t_next;
+            }
+            if (!(t < t_end)) t = t_prev;  // see march_rays_skip_empty_kernel
+        }
+    }
+    t_admitted[i] = t;
 }
 
 // ---------------------------------------------------------------- empty-space pre-advance (inference)
@@ -844,19 +903,26 @@ static void launch_march_rays_inference(cudaStream_t stream, void **buffers, con
         return;
     }
     const unsigned rank_blocks = div_up(desc->n_rays, kRankSlots);
-    auto *ws = static_cast<uint32_t *>(workspace(stream, ((size_t)rank_blocks + desc->n_rays + 1) * sizeof(uint32_t)));
+    auto *ws = static_cast<uint32_t *>(workspace(stream, ((size_t)rank_blocks + 2 * (size_t)desc->n_rays + 1) * sizeof(uint32_t)));
     if (!ws) return;
     uint32_t *block_total = ws, *rank_in_block = ws + rank_blocks, *snapshot = ws + rank_blocks + desc->n_rays;
+    float *t_admitted = in_place ? nullptr : reinterpret_cast<float *>(snapshot + 1);
     march_rays_inference_rank_kernel<<<rank_blocks, kRankBlock, 0, stream>>>(desc->n_rays, terminated, block_total, rank_in_block,
                                                                              next_in, in_place ? snapshot : nullptr);
     if (!check_launch(op)) return;
+    if (!in_place) {  // the renderer's in-place path pre-advances every ray once per frame (ngp_march_rays_skip_empty)
+        march_rays_inference_admit_kernel<<<div_up(desc->n_rays, 128), 128, 0, stream>>>(
+            *desc, rays_o, rays_d, t_starts, t_ends, bitfield, next_in, terminated, indices_in, block_total, rank_in_block,
+            next_out, indices_out, t_admitted);
+        if (!check_launch(op)) return;
+    }
     // half a warp per slot when one 16-point chunk of the chain covers the cap, else a whole warp
     const bool half = desc->march_steps_cap <= 16;
     const unsigned grid = div_up(desc->n_rays, half ? 2 * kInferWarps : kInferWarps);
 #define NGP_MARCH_INF(IP, W, counter, dirs_ptr)                                                                        \
     march_rays_inference_kernel<IP, W><<<grid, kInferWarps * 32, 0, stream>>>(                                         \
         *desc, rays_o, rays_d, t_starts, t_ends, bitfield, counter, terminated, indices_in, block_total, rank_in_block, \
-        next_out, indices_out, n_samples, t_starts_out, xyzs, dss, z_vals, dirs_ptr)
+        next_out, indices_out, n_samples, t_starts_out, xyzs, dss, z_vals, dirs_ptr, t_admitted)
     if (in_place) {
         if (half) NGP_MARCH_INF(true, 16, snapshot, ray_dirs); else NGP_MARCH_INF(true, 32, snapshot, ray_dirs);
     } else {

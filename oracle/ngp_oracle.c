@@ -33,6 +33,14 @@
 #define T_THRESHOLD 1e-4f /* deps/volume-rendering-jax/lib/impl/integrating.cu:12 */
 #define TWO_SQRT3 3.4641015529632568359f /* 2 * (float)SQRT3, volrend.h:18, marching.cu:20-21 */
 
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

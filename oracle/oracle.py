@@ -32,6 +32,12 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n):
+    """torchrun exports OMP_NUM_THREADS=1 to its workers: callers that want all host cores say so explicitly."""
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 

@@ -56,22 +56,26 @@ def _canonical(rn, rs, payload, order_rn, order_rs):
 
 @pytest.mark.parametrize("budget", [1 << 18, 1 << 26])
 def test_march_rays_c2_vs_reference_kernel(ref, budget):
-    """Every ray both kernels marched carries bit-identical payloads (the reference hands out ranges in atomic arrival
-    order: compare after gathering by each side's own start index); without overflow also every counter and flag."""
+    """Every ray marched here carries the reference kernel's payload bit for bit.  The reference hands out sample ranges
+    in atomic arrival order, so payloads are compared after gathering by each side's own start index, and the reference
+    runs with a budget nothing overflows (which rays a full budget serves is arrival-order luck there, ray order here;
+    what a served ray receives does not depend on the budget).  Without overflow on our side: every counter and flag too."""
     from jaxngp_b200 import volrendjax as V
     st, arrays = _rays(7)
     a = {k: _t(v) for k, v in arrays.items()}
     got = V.march_rays(total_samples=budget, **st, **a, raw=True)
-    exp = ref.march_rays(total_samples=budget, **st, **a, raw=True)
+    exp = ref.march_rays(total_samples=1 << 26, **st, **a, raw=True)
+    assert int(exp[1][0]) == 0
     g_rn, g_rs, e_rn, e_rs = (x.long() & 0xFFFFFFFF for x in (got[3], got[4], exp[3], exp[4]))
-    overflow = int(exp[1][0]) != 0 or int(got[1][0]) != 0
-    if not overflow:
+    if int(got[1][0]) == 0:
         assert int(got[0][0]) == int(exp[0][0])
         assert torch.equal(got[2], exp[2]) and torch.equal(g_rn, e_rn)
-    both = got[2] & exp[2] & (g_rn > 0) & (e_rn > 0)
-    assert int(both.sum()) > 1000
-    assert torch.equal(g_rn[both], e_rn[both])
-    order_rn = torch.where(both, g_rn, torch.zeros_like(g_rn))
+    else:
+        assert budget == 1 << 18
+    served = got[2] & (g_rn > 0)
+    assert int(served.sum()) > (1000 if budget == 1 << 18 else 100000), int(served.sum())
+    assert bool(exp[2][served].all()) and torch.equal(g_rn[served], e_rn[served])
+    order_rn = torch.where(served, g_rn, torch.zeros_like(g_rn))
     for k in (5, 6, 7, 8, 9):  # idcs, xyzs, dirs, dss, z_vals
         ours, _ = _canonical(g_rn, g_rs, got[k], order_rn, g_rs)
         theirs, _ = _canonical(e_rn, e_rs, exp[k], order_rn, g_rs)
@@ -127,7 +131,7 @@ def test_hashgrid_c2_table_all_dense_levels_clamp_like_xla():
         pts[1024:1536, dim - 1] = np.float32(0.99999994)
         tab = rng.uniform(-1, 1, (lt.rows, 2)).astype(np.float32)
         idx, _ = H.indices_and_weights(lv, pts, 1.0)
-        assert int(idx.max()) == lt.rows - 1  # the clamp was hit
+        assert dim == 2 or int(idx.max()) >= lt.rows  # 3-D case: rows past the table are asked for (scale 63 -> vertex 64 = res)
         enc = E.hashgrid_forward(lt, _t(pts), 1.0, _t(tab)).cpu().numpy()
         assert np.allclose(enc, H.encode(lv, pts, 1.0, tab), atol=2e-6)
         d_enc = rng.normal(size=(4096, 2 * L)).astype(np.float32)
