@@ -235,6 +235,10 @@ void ngp_nerf_mlp_forward(cudaStream_t, void **, const char *, size_t);
 void ngp_nerf_mlp_backward(cudaStream_t, void **, const char *, size_t);
 /* Same contract, weight gradients on mma.sync instead of tcgen05/TMEM (the cross-check arm of the tests). */
 void ngp_nerf_mlp_backward_mma(cudaStream_t, void **, const char *, size_t);
+/* Same contract, EVERY matrix product on tcgen05 (csrc/mlp_bwd_tc.cu): forward recompute and delta chain with the A
+ * operand in tensor memory (each accumulator rewritten in place by its epilogue), weight gradients from shared-memory
+ * panels.  Same tf32 operand rounding; results agree with the two kernels above to f32 accumulation-order error. */
+void ngp_nerf_mlp_backward_tc(cudaStream_t, void **, const char *, size_t);
 
 /* HashGridEncoder fused in front of the MLP forward: the [n,32] encoding feeds the first layer's
  * tensor-core fragments directly.  Bit-identical to hashgrid_a1_forward followed by nerf_mlp_forward.
@@ -295,6 +299,12 @@ typedef struct {
 } NgpAdamDescriptor;
 void ngp_adam_step(cudaStream_t, void **, const char *, size_t);
 
+/* out[0] = sa * a[0] + sb * b[0] + c on device-resident 32-bit scalars (a, b, out may alias): the step counter after an
+ * optimizer step, and train_step's `next_sample_write_location - number_of_exceeded_samples` (marching/__init__.py:91).
+ * in : a u32[1], b u32[1]        out: out u32[1] */
+typedef struct { int32_t sa, sb, c; } NgpU32AxpyDescriptor;
+void ngp_u32_axpy(cudaStream_t, void **, const char *, size_t);
+
 /* Gradient exchange fused with the optimizer, for ray-sharded data parallelism (the reference trains on one GPU;
  * this is app/nerf/_utils.py:19-77 applied to the SUM of every rank's gradient).  ONE kernel per rank does
  * what reduce-scatter -> ngp_adam_step -> all-gather do: it waits until every peer's gradient buffer is complete,
@@ -317,6 +327,28 @@ typedef struct {
                                           peer before it traps (0 = 20 s): a missing rank fails the launch, not the GPU */
 } NgpAdamExchangeDescriptor;
 void ngp_adam_step_exchange(cudaStream_t, void **, const char *, size_t);
+
+/* ------------------------------------------------------------------ section A, status-returning form
+ * XLA's API_VERSION_STATUS_RETURNING custom-call signature (the api_version jax's `custom_call` lowering emits by
+ * default): the four arguments above plus an XlaCustomCallStatus*.  Each `_status` entry point runs the op of the same
+ * name and, if it failed and `status` is non-null, reports the failure through XLA's XlaCustomCallStatusSetFailure
+ * (resolved in the process at first use, or supplied with ngp_b200_set_status_failure_fn), so the error surfaces as an
+ * XlaRuntimeError instead of the C++ exception the reference throws through XLA's C frames (volrend.h:9-16).
+ * Register these under the reference's target names (jaxngp_b200/jax_ffi.py); the four-argument symbols stay for
+ * hosts that call them directly. */
+typedef struct XlaCustomCallStatus_ XlaCustomCallStatus;
+typedef void (*ngp_set_failure_fn)(XlaCustomCallStatus *, const char *message, size_t message_len);
+void ngp_b200_set_status_failure_fn(ngp_set_failure_fn fn);
+void ngp_pack_density_into_bits_status(cudaStream_t, void **, const char *, size_t, XlaCustomCallStatus *);
+void ngp_march_rays_status(cudaStream_t, void **, const char *, size_t, XlaCustomCallStatus *);
+void ngp_march_rays_inference_status(cudaStream_t, void **, const char *, size_t, XlaCustomCallStatus *);
+void ngp_morton3d_status(cudaStream_t, void **, const char *, size_t, XlaCustomCallStatus *);
+void ngp_morton3d_invert_status(cudaStream_t, void **, const char *, size_t, XlaCustomCallStatus *);
+void ngp_integrate_rays_status(cudaStream_t, void **, const char *, size_t, XlaCustomCallStatus *);
+void ngp_integrate_rays_backward_status(cudaStream_t, void **, const char *, size_t, XlaCustomCallStatus *);
+void ngp_integrate_rays_inference_status(cudaStream_t, void **, const char *, size_t, XlaCustomCallStatus *);
+void ngp_hashgrid_encode_status(cudaStream_t, void **, const char *, size_t, XlaCustomCallStatus *);
+void ngp_hashgrid_encode_backward_status(cudaStream_t, void **, const char *, size_t, XlaCustomCallStatus *);
 
 /* ------------------------------------------------------------------ status */
 int ngp_b200_abi_version(void);

@@ -21,11 +21,17 @@ OPS = (
     "ngp_pack_density_into_bits", "ngp_packbits_scalar", "ngp_march_rays", "ngp_march_rays_inference", "ngp_march_rays_skip_empty", "ngp_march_rays_inference_inplace", "ngp_integrate_rays_inference_inplace",
     "ngp_morton3d", "ngp_morton3d_invert", "ngp_integrate_rays", "ngp_integrate_rays_backward",
     "ngp_integrate_rays_inference", "ngp_hashgrid_encode", "ngp_hashgrid_encode_backward",
-    "ngp_hashgrid_a1_forward", "ngp_hashgrid_a1_backward", "ngp_adam_step", "ngp_adam_step_exchange", "ngp_ogrid_sample_positions", "ngp_ogrid_decay_max", "ngp_ogrid_threshold", "ngp_nerf_mlp_forward", "ngp_nerf_mlp_backward", "ngp_nerf_mlp_backward_mma", "ngp_nerf_fused_forward", "ngp_nerf_fused_forward_umma", "ngp_umma_selftest", "ngp_make_training_rays", "ngp_huber_loss_grad", "ngp_integrate_loss_fused",
-    "ngp_make_training_rays_rng", "ngp_philox_uniform", "ngp_ogrid_draw_cells",
+    "ngp_hashgrid_a1_forward", "ngp_hashgrid_a1_backward", "ngp_adam_step", "ngp_adam_step_exchange", "ngp_ogrid_sample_positions", "ngp_ogrid_decay_max", "ngp_ogrid_threshold", "ngp_nerf_mlp_forward", "ngp_nerf_mlp_backward", "ngp_nerf_mlp_backward_mma", "ngp_nerf_mlp_backward_tc", "ngp_nerf_fused_forward", "ngp_nerf_fused_forward_umma", "ngp_umma_selftest", "ngp_make_training_rays", "ngp_huber_loss_grad", "ngp_integrate_loss_fused",
+    "ngp_make_training_rays_rng", "ngp_philox_uniform", "ngp_ogrid_draw_cells", "ngp_u32_axpy",
 )
+#: the reference's ten registered targets (volume-rendering-jax lib/ffi.cc:25-51, jax-tcnn lib/ffi.cc:25-30)
+DROP_IN_TARGETS = ("pack_density_into_bits", "march_rays", "march_rays_inference", "morton3d", "morton3d_invert",
+                   "integrate_rays", "integrate_rays_backward", "integrate_rays_inference", "hashgrid_encode",
+                   "hashgrid_encode_backward")
+#: their status-returning forms (five arguments: + XlaCustomCallStatus*)
+STATUS_FORMS = tuple(f"ngp_{t}_status" for t in DROP_IN_TARGETS)
 STATUS_SYMBOLS = ("ngp_b200_abi_version", "ngp_b200_last_status", "ngp_b200_last_error", "ngp_b200_clear_error",
-                  "ngp_b200_set_march_ctas_per_sm")
+                  "ngp_b200_set_march_ctas_per_sm", "ngp_b200_set_status_failure_fn") + STATUS_FORMS
 
 _lib = None
 launch_count = 0  # number of custom calls issued through this binding (bench.py reports it)
@@ -63,6 +69,12 @@ def lib():
         _lib.ngp_b200_clear_error.restype = None
         _lib.ngp_b200_set_march_ctas_per_sm.restype = None
         _lib.ngp_b200_set_march_ctas_per_sm.argtypes = [C.c_int]
+        for name in STATUS_FORMS:
+            fn = getattr(_lib, name)
+            fn.restype = None
+            fn.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t, C.c_void_p]
+        _lib.ngp_b200_set_status_failure_fn.restype = None
+        _lib.ngp_b200_set_status_failure_fn.argtypes = [C.c_void_p]
     return _lib
 
 

@@ -48,8 +48,27 @@ __global__ void __launch_bounds__(256) adam_kernel(NgpAdamDescriptor d, const ui
     }
 }
 
+// out = sa * a + sb * b + c on device-resident u32 scalars: the step counter after an optimizer step (a = out = step,
+// c = 1) and train_step's `next - exceeded` (marching/__init__.py:91) without a host round trip or a library launch
+__global__ void u32_axpy_kernel(NgpU32AxpyDescriptor d, const uint32_t *a, const uint32_t *b, uint32_t *out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out = (uint32_t)(d.sa * (int32_t)*a + d.sb * (int32_t)*b + d.c);
+}
+
 }  // namespace
 }  // namespace ngp
+
+extern "C" void ngp_u32_axpy(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *d = descriptor<NgpU32AxpyDescriptor>(opaque, opaque_len, "u32_axpy");
+    if (!d) return;
+    BufferCursor b{buffers};
+    const uint32_t *a = b.next<const uint32_t>();
+    const uint32_t *bb = b.next<const uint32_t>();
+    uint32_t *out = b.next<uint32_t>();
+    u32_axpy_kernel<<<1, 32, 0, stream>>>(*d, a, bb, out);
+    check_launch("u32_axpy");
+}
 
 extern "C" void ngp_adam_step(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
     using namespace ngp;

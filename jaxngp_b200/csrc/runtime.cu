@@ -1,4 +1,7 @@
 // runtime.cu -- status channel and per-stream scratch pool of libngp_b200.
+#include <dlfcn.h>
+
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -71,7 +74,48 @@ void *workspace(cudaStream_t stream, size_t bytes) {
 
 }  // namespace ngp
 
+// ---- status-returning custom-call form.  XLA's API_VERSION_STATUS_RETURNING (what jax's `custom_call` lowering asks for
+// by default) passes an XlaCustomCallStatus* as a fifth argument; a callee with the four-argument signature the
+// reference registers (ffi.cc:17-51) simply never looks at it, which is why a failure there can only throw through C
+// frames.  The `_status` entry points run the same op and, when it failed and a status object was given, mark it failed
+// with the recorded message through XLA's own `XlaCustomCallStatusSetFailure` -- looked up in the process at first use
+// (jaxlib exports it from its xla_extension), or handed in with ngp_b200_set_status_failure_fn.
+namespace ngp {
+namespace {
+std::atomic<ngp_set_failure_fn> g_set_failure{nullptr};
+std::atomic<bool> g_looked_up{false};
+}  // namespace
+void report_status(XlaCustomCallStatus *status) {
+    if (t_status == NGP_OK || status == nullptr) return;
+    ngp_set_failure_fn fn = g_set_failure.load();
+    if (!fn && !g_looked_up.exchange(true)) {
+        fn = reinterpret_cast<ngp_set_failure_fn>(dlsym(RTLD_DEFAULT, "XlaCustomCallStatusSetFailure"));
+        if (fn) g_set_failure.store(fn);
+    }
+    if (fn) fn(status, t_message, strlen(t_message));
+}
+}  // namespace ngp
+
+#define NGP_STATUS_FORM(op)                                                                                          \
+    extern "C" void op##_status(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len,          \
+                                XlaCustomCallStatus *status) {                                                       \
+        op(stream, buffers, opaque, opaque_len);                                                                     \
+        ngp::report_status(status);                                                                                  \
+    }
+NGP_STATUS_FORM(ngp_pack_density_into_bits)
+NGP_STATUS_FORM(ngp_march_rays)
+NGP_STATUS_FORM(ngp_march_rays_inference)
+NGP_STATUS_FORM(ngp_morton3d)
+NGP_STATUS_FORM(ngp_morton3d_invert)
+NGP_STATUS_FORM(ngp_integrate_rays)
+NGP_STATUS_FORM(ngp_integrate_rays_backward)
+NGP_STATUS_FORM(ngp_integrate_rays_inference)
+NGP_STATUS_FORM(ngp_hashgrid_encode)
+NGP_STATUS_FORM(ngp_hashgrid_encode_backward)
+#undef NGP_STATUS_FORM
+
 extern "C" {
+void ngp_b200_set_status_failure_fn(ngp_set_failure_fn fn) { ngp::g_set_failure.store(fn); }
 int ngp_b200_abi_version(void) { return NGP_B200_ABI_VERSION; }
 int ngp_b200_last_status(void) { return ngp::t_status; }
 const char *ngp_b200_last_error(void) { return ngp::t_message; }

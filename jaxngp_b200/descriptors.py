@@ -142,3 +142,7 @@ def make_ogrid_draw_descriptor(n_cells, G, n_alive, has_alive, update_all, n_fir
     return struct.pack("<7If", _u32(n_cells, "n_cells"), _u32(G, "G"), _u32(n_alive, "n_alive"), int(bool(has_alive)),
                        int(bool(update_all)), _u32(n_first, "n_first"), _u32(n_second, "n_second"),
                        float(mip_bound)) + make_rng_descriptor(seed, stream_id)
+
+
+def make_u32_axpy_descriptor(sa, sb, c):
+    return struct.pack("<3i", int(sa), int(sb), int(c))

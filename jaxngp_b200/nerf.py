@@ -115,14 +115,20 @@ def fused_forward(lt, pos: torch.Tensor, bound: float, table: torch.Tensor, dirs
     return (out, enc) if want_enc else out
 
 
-def mlp_backward(enc, dirs, weights, d_drgbs, d_weights=None, impl="umma"):
+BACKWARD_IMPLS = {"tc": "ngp_nerf_mlp_backward_tc", "umma": "ngp_nerf_mlp_backward", "mma": "ngp_nerf_mlp_backward_mma"}
+DEFAULT_BACKWARD_IMPL = "umma"
+
+
+def mlp_backward(enc, dirs, weights, d_drgbs, d_weights=None, impl=None):
     """Fused backward: returns (d_enc [n, 32], d_weights [9408]); recomputes the forward on chip.
-    ``impl``: "umma" = weight gradients on tcgen05 with TMEM-resident accumulators (default), "mma" = all mma.sync."""
+    ``impl``: "tc" = every matrix product on tcgen05, chain operands in tensor memory (csrc/mlp_bwd_tc.cu);
+    "umma" = mma.sync register chain + weight gradients on tcgen05; "mma" = all mma.sync (cross-check arm)."""
+    impl = impl or DEFAULT_BACKWARD_IMPL
     n = enc.shape[0]
     d_enc = torch.empty(n, 32, dtype=torch.float32, device=enc.device)
     if d_weights is None:
         d_weights = torch.empty(MLP_NUMEL, dtype=torch.float32, device=enc.device)
-    _lib.call("ngp_nerf_mlp_backward" if impl == "umma" else "ngp_nerf_mlp_backward_mma", [enc, dirs, weights, d_drgbs, d_enc, d_weights],
+    _lib.call(BACKWARD_IMPLS[impl], [enc, dirs, weights, d_drgbs, d_enc, d_weights],
               descriptors.make_nerf_mlp_descriptor(n))
     return d_enc, d_weights
 

@@ -232,8 +232,9 @@ class Trainer:
                                            final_opac, d_final)
         d_enc, _ = nerf_mod.mlp_backward(enc, dirs, self.mlp_flat, d_drgbs, d_weights=self.mlp_grad)
         encoders.hashgrid_backward(self.levels, xyzs, synthetic.BOUND, d_enc, out=self.table_grad)
-        return dict(loss=loss[0], n_valid_rays=n_valid[0], measured_batch_size_before_compaction=(nxt - exc)[0],
-                    measured_batch_size=effective[0])  # marching/__init__.py:91
+        used = trainops.u32_axpy(nxt, exc, 1, -1, 0)  # next - exceeded, marching/__init__.py:91
+        return dict(loss=loss[0], n_valid_rays=n_valid[0], measured_batch_size_before_compaction=used[0],
+                    measured_batch_size=effective[0])
 
     def _step_body(self, perm, noises=None, bg=None, apply=True):
         if not self.fused_glue:
@@ -296,13 +297,13 @@ class Trainer:
         lo, hi = self.shard_lo, self.shard_hi
         if self.peer_exchange is not None:  # the three steps below as one kernel over NVLink (csrc/exchange.cu)
             self.peer_exchange.step(self.step_dev, self.adam_m, self.adam_v, self.adam_desc, lo)
-            self.step_dev += 1
+            trainops.u32_axpy(self.step_dev, self.step_dev, 1, 0, 1, out=self.step_dev)
             return
         # reduce-scatter [table grad | MLP grads] -> Adam on this rank's shard -> all-gather the parameters
         g = dp.reduce_scatter_flat_gradients(self.flat_grads, self.rank, self.world_size, self.pg)
         _lib.call("ngp_adam_step", [self.step_dev, self.flat_params[lo:hi], g, self.adam_m, self.adam_v], self.adam_desc)
         dp.all_gather_flat_parameters(self.flat_params, self.rank, self.world_size, self.pg)
-        self.step_dev += 1
+        trainops.u32_axpy(self.step_dev, self.step_dev, 1, 0, 1, out=self.step_dev)
 
     def train_step(self, perm, next_perm=None):
         """perm: int32 [n_rays] indices into the scene's pixels (device or pinned host tensor).  Returns

@@ -55,6 +55,14 @@ def make_training_rays_rng(perm: torch.Tensor, transforms: torch.Tensor, cam: di
     return o, d, ts, te, noises, bgs
 
 
+def u32_axpy(a: torch.Tensor, b: torch.Tensor, sa: int, sb: int, c: int, out: torch.Tensor = None) -> torch.Tensor:
+    """out[0] = sa * a[0] + sb * b[0] + c on device scalars (int32 tensors carrying uint32 bits), one 1-thread launch."""
+    if out is None:
+        out = torch.empty(1, dtype=torch.int32, device=a.device)
+    _lib.call("ngp_u32_axpy", [a, b, out], descriptors.make_u32_axpy_descriptor(sa, sb, c))
+    return out
+
+
 def huber_loss_grad(final_rgbds, ray_is_valid, perm, rgbas_u8, bgs, delta=0.1):
     """Returns (dL_dfinal_rgbds [n,4], loss [1], n_valid_rays int32[1]); app/nerf/_utils.py:151-165."""
     n, dev = final_rgbds.shape[0], final_rgbds.device

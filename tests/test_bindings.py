@@ -161,3 +161,50 @@ def test_integrate_rays_vjp_against_the_reference_rule(monkeypatch):
     assert bgs.grad is not None and bgs.grad.shape == (n, 3)      # dL_dbgs -> bgs (the reference: -> dss)
     assert dss.grad is None                                       # the op has no gradient for dss
     assert z_vals.grad.shape == (s,) and drgbs.grad.shape == (s, 4)
+
+
+def test_status_returning_forms_and_jax_registration_shim(built_lib, monkeypatch):
+    """The five-argument entry points (XLA's API_VERSION_STATUS_RETURNING) and ``jaxngp_b200/jax_ffi.py``: every drop-in
+    target has a ``_status`` form behind a capsule of the right name; a failing call (descriptor of the wrong size: caught
+    before anything touches a device) reports its message through the status callback exactly once, a null status pointer
+    is tolerated, and ``register()`` hands all ten capsules to ``jax.ffi.register_ffi_target(..., api_version=0)`` -- here
+    a recording stand-in, since jax is not installed."""
+    import sys
+    import types
+    from jaxngp_b200 import jax_ffi
+    L = built_lib
+    caps = jax_ffi.capsules()
+    assert sorted(caps) == sorted(CALLS)  # the reference's ten registered targets
+    for target, capsule in caps.items():
+        name, ptr = _capsule_pointer(capsule)
+        assert name == b"xla._CUSTOM_CALL_TARGET"
+        assert ptr == ctypes.cast(getattr(L, f"ngp_{target}_status"), ctypes.c_void_p).value and ptr
+    seen = []
+    CB = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t)
+    cb = CB(lambda status, msg, n: seen.append((status, msg[:n].decode())))
+    L.ngp_b200_set_status_failure_fn(ctypes.cast(cb, ctypes.c_void_p))
+    try:
+        bufs = (ctypes.c_void_p * 16)()
+        token = ctypes.c_uint64(0)  # stands in for the XlaCustomCallStatus object
+        L.ngp_march_rays_status(None, bufs, b"\x00" * 5, 5, ctypes.byref(token))
+        assert len(seen) == 1 and seen[0][0] == ctypes.addressof(token)
+        assert "march_rays: invalid opaque object size, expected 28, got 5" in seen[0][1]  # serde.h:35-40's message
+        L.ngp_b200_clear_error()
+        L.ngp_march_rays_status(None, bufs, b"\x00" * 5, 5, None)  # no status object: recorded, not reported
+        assert len(seen) == 1 and L.ngp_b200_last_status() == -1
+        L.ngp_b200_clear_error()
+        # a well-formed call that has nothing to do reports nothing
+        from jaxngp_b200 import descriptors as D
+        desc = D.make_morton3d_descriptor(0)
+        L.ngp_morton3d_status(None, bufs, desc, len(desc), ctypes.byref(token))
+        assert len(seen) == 1 and L.ngp_b200_last_status() == 0
+    finally:
+        L.ngp_b200_set_status_failure_fn(None)
+        L.ngp_b200_clear_error()
+    # register() against a recording jax
+    calls = []
+    fake = types.ModuleType("jax")
+    fake.ffi = types.SimpleNamespace(register_ffi_target=lambda name, capsule, platform, api_version: calls.append((name, platform, api_version, capsule)))
+    monkeypatch.setitem(sys.modules, "jax", fake)
+    assert jax_ffi.register() == sorted(CALLS)
+    assert sorted(c[0] for c in calls) == sorted(CALLS) and {c[1:3] for c in calls} == {("CUDA", 0)}

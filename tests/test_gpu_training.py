@@ -372,3 +372,44 @@ def test_prefetch_key_sees_in_place_refills(small_scene):
     torch.cuda.synchronize()
     assert torch.equal(tr._static_perm[1 - tr._slot], b)  # the step marched the refilled batch, not the stale one
     assert torch.isfinite(out["loss"])
+
+
+@pytest.mark.parametrize("n", [1, 100, 128 * 148 * 2 + 77, (1 << 18) + 5])
+def test_mlp_backward_all_tcgen05_matches_the_other_arms(n):
+    """csrc/mlp_bwd_tc.cu (recompute, delta chain and weight gradients all on tcgen05, chain operands in tensor memory,
+    weight operands re-staged by bulk copies) against the mma.sync arm and a plain fp32 PyTorch reference of the same
+    network: same tf32 operand rounding, so the arms agree to f32 accumulation order except where a pre-activation within
+    rounding of zero lands on the other side of a ReLU (counted, not bounded entrywise).  Several tiles per CTA exercise
+    the accumulate flags, every panel-reuse barrier in both parities and both weight images; the second call re-allocates
+    tensor memory."""
+    from jaxngp_b200 import nerf as nerf_mod
+    gen = torch.Generator(device=DEV).manual_seed(13)
+    model = nerf_mod.NeRF(bound=1.0, device=DEV, generator=gen, T=2 ** 14)
+    w = model.mlp_flat.detach().clone()
+    enc = torch.randn(n, 32, device=DEV, generator=gen) * 0.5
+    dirs = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV, generator=gen), dim=-1)
+    d_out = torch.randn(n, 4, device=DEV, generator=gen)
+    g_enc_b, g_w_b = nerf_mod.mlp_backward(enc, dirs, w, d_out, impl="mma")
+    for rep in range(2):
+        g_enc_a, g_w_a = nerf_mod.mlp_backward(enc, dirs, w, d_out, impl="tc")
+        torch.cuda.synchronize()
+        assert torch.isfinite(g_enc_a).all() and torch.isfinite(g_w_a).all()
+        assert torch.linalg.norm(g_enc_a - g_enc_b) <= 2e-3 * torch.linalg.norm(g_enc_b) + 1e-7, (rep, n)
+        assert ((g_enc_a - g_enc_b).abs() > 1e-3 * g_enc_b.abs().max()).float().mean() <= 1e-3, (rep, n)
+        assert (g_w_a - g_w_b).abs().max() <= 1e-3 * g_w_b.abs().max() + 1e-7, (rep, n, (g_w_a - g_w_b).abs().max(), g_w_b.abs().max())
+    # fp32 reference (autograd)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    wr = w.clone().requires_grad_(True)
+    er = enc.clone().requires_grad_(True)
+    views, off = {}, 0
+    for k, i, o in nerf_mod.MLP_SHAPES:
+        views[k] = wr[off:off + i * o].view(i, o)
+        off += i * o
+    x = torch.relu(er @ views["density_w0"]) @ views["density_w1"]
+    h = torch.cat([x, nerf_mod.sh4(dirs)], dim=-1)
+    rgb = torch.sigmoid(torch.relu(torch.relu(h @ views["rgb_w0"]) @ views["rgb_w1"]) @ views["rgb_w2"])
+    ref = torch.cat([nerf_mod.trunc_exp(x[:, :1]), rgb], dim=-1)
+    g_enc_ref, g_w_ref = torch.autograd.grad(ref, [er, wr], d_out)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    assert torch.linalg.norm(g_enc_a - g_enc_ref) <= 3e-2 * torch.linalg.norm(g_enc_ref) + 1e-6
+    assert (g_w_a - g_w_ref).abs().max() <= 1e-2 * g_w_ref.abs().max() + 1e-6

@@ -77,7 +77,10 @@ def main():
     err_m = float((m - m_ref).abs().max())
     err_v = float((v - v_ref).abs().max())
     scale = float(p_ref.abs().max())
-    ok = replicas_identical and err_p <= 1e-5 * max(scale, 1.0) and err_m <= 1e-5 and err_v <= 1e-5
+    # replicas must hold the SAME bits.  Against the NCCL arm only the summation order of the per-rank gradients differs
+    # (ring order there, the switch's order here): moments agree to f32 rounding; Adam divides by sqrt(v), so an element whose
+    # summed gradient is nearly cancelling moves by a visible fraction of lr = 1e-2 either way (measured 4e-5 at 8 ranks)
+    ok = replicas_identical and err_p <= 2e-4 * max(scale, 1.0) and err_m <= 1e-6 and err_v <= 1e-6
 
     timing = {}
     if args.time > 0:
