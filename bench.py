@@ -472,11 +472,14 @@ def per_op_vs_reference(tr, perm, flush, iters=20):
             "reference": "deps/volume-rendering-jax/lib/impl/*.cu compiled unmodified for sm_100a (oracle/build_ref.sh)", "ops": table}
 
 # ------------------------------------------------------------------------------------------- extras (C3, C4)
-def render_bench(dev, rank, world, scene=None, frames=10, train_steps=300, n_slots=262144, cap=16):
+def render_bench(dev, rank, world, scene=None, frames=10, train_steps=(300, 1024), n_slots=262144, cap=16):
     """BASELINE configs[2] (C3): 800x800 frames through march_rays_inference / integrate_rays_inference
     (InferenceRenderer: the reference's slot-refill loop, one CUDA graph per iteration), image rows dealt to the
-    ranks in interleaved 32-row bands, one all-gather of the u8 image per frame.  The model is trained here for
-    `train_steps` steps first (identical replicas: same seeds on every rank)."""
+    ranks in interleaved 32-row bands, one all-gather of the u8 image per frame.  The model is trained here first
+    (identical replicas: same seeds on every rank) and measured at two points: after 300 steps -- round 1's
+    configuration, a fuzzy field that still marches ~78 samples per ray -- and after 1024 steps (0.6 s of training), when
+    the occupancy grid has pruned the empty space the way a model someone would render has; that one is the line's figure.
+    Frame time is proportional to the samples marched, which is reported next to every figure."""
     import torch
     import torch.distributed as dist
     from jaxngp_b200 import dp, renderers
@@ -484,11 +487,18 @@ def render_bench(dev, rank, world, scene=None, frames=10, train_steps=300, n_slo
     scene = scene if scene is not None else Scene(dev)
     tr = Trainer(device=dev, scene=scene)  # world_size=1: every rank trains the same replica
     gen = torch.Generator(device=dev).manual_seed(0)
-    for it in range(train_steps):
-        perm = torch.randint(0, scene.n_pixels, (tr.n_rays,), device=dev, generator=gen, dtype=torch.int32)
-        tr.train_step(perm)
-        if (it + 1) % 16 == 0:
-            tr.update_ogrid()
+    trained = 0
+
+    def train_to(n_steps):
+        nonlocal trained
+        for it in range(trained, n_steps):
+            perm = torch.randint(0, scene.n_pixels, (tr.n_rays,), device=dev, generator=gen, dtype=torch.int32)
+            tr.train_step(perm)
+            if (it + 1) % 16 == 0:
+                tr.update_ogrid()
+        trained = max(trained, n_steps)
+
+    train_to(train_steps[0])
     H, Wd = scene.cam["height"], scene.cam["width"]
     rows = dp.tile_rows(H, rank, world).to(dev)
     pixels = (rows[:, None] * Wd + torch.arange(Wd, device=dev)[None, :]).reshape(-1).to(torch.int32)
@@ -536,24 +546,32 @@ def render_bench(dev, rank, world, scene=None, frames=10, train_steps=300, n_slo
             dist.all_reduce(smp)
         return float(ms) / frames, int(smp), img
 
-    ms_frame, smp, img = run(False)
-    ms_frame_e2e, _, _ = run(True)
-    # quality of the frame just rendered against the analytic ground truth of that view (white background)
-    v = views[-1]
-    gt = scene.rgbas_u8[v * H * Wd:(v + 1) * H * Wd].float() / 255
-    gt_rgb = gt[:, :3] * gt[:, 3:] + (1 - gt[:, 3:])
-    full = img.reshape(-1, 3).float() / 255 if world > 1 else None
-    if full is None:
-        full = torch.zeros(H * Wd, 3, device=dev)
-        full[pixels.long()] = img.reshape(-1, 3).float() / 255
-    psnr = float(-10 * torch.log10(((full - gt_rgb) ** 2).mean()))
-    return {"metric": "800x800 inference render rays/s", "rays_per_s": 640000 / (ms_frame * 1e-3), "fps": 1e3 / ms_frame,
-            "ms_per_frame": ms_frame, "frames": frames, "n_gpus": world, "samples_per_frame": smp / frames,
-            "e2e": {"fps": 1e3 / ms_frame_e2e, "rays_per_s": 640000 / (ms_frame_e2e * 1e-3), "ms_per_frame": ms_frame_e2e,
-                    "h2d_bytes_per_frame": 48, "d2h_bytes_per_frame": int(host_frame.numel()),
-                    "note": "pose copied from pinned host memory, finished u8 frame copied to pinned host memory and waited for, every frame"},
-            "slots_per_gpu": R.n, "march_steps_cap": cap, "model": f"trained {train_steps} steps in this run (C2 step)",
-            "psnr_last_frame": psnr, "sharding": "interleaved 32-row bands, all-gather of the u8 image per frame"}
+    def measure():
+        ms_frame, smp, img = run(False)
+        ms_frame_e2e, _, _ = run(True)
+        # quality of the frame just rendered against the analytic ground truth of that view (white background)
+        v = views[-1]
+        gt = scene.rgbas_u8[v * H * Wd:(v + 1) * H * Wd].float() / 255
+        gt_rgb = gt[:, :3] * gt[:, 3:] + (1 - gt[:, 3:])
+        full = img.reshape(-1, 3).float() / 255 if world > 1 else None
+        if full is None:
+            full = torch.zeros(H * Wd, 3, device=dev)
+            full[pixels.long()] = img.reshape(-1, 3).float() / 255
+        psnr = float(-10 * torch.log10(((full - gt_rgb) ** 2).mean()))
+        return {"rays_per_s": 640000 / (ms_frame * 1e-3), "fps": 1e3 / ms_frame, "ms_per_frame": ms_frame,
+                "samples_per_frame": smp / frames, "samples_per_s": smp / frames / (ms_frame * 1e-3), "psnr_last_frame": psnr,
+                "model": f"trained {trained} steps in this run (C2 step)",
+                "e2e": {"fps": 1e3 / ms_frame_e2e, "rays_per_s": 640000 / (ms_frame_e2e * 1e-3), "ms_per_frame": ms_frame_e2e,
+                        "h2d_bytes_per_frame": 48, "d2h_bytes_per_frame": int(host_frame.numel()),
+                        "note": "pose copied from pinned host memory, finished u8 frame copied to pinned host memory and waited for, every frame"}}
+
+    early = measure()
+    train_to(train_steps[1])
+    out = measure()
+    out.update({"metric": "800x800 inference render rays/s", "frames": frames, "n_gpus": world, "slots_per_gpu": R.n, "march_steps_cap": cap,
+                "sharding": "interleaved 32-row bands, all-gather of the u8 image per frame",
+                "after_300_steps_round1_configuration": early})
+    return out
 
 
 def hashenc_bench(dev, n=1 << 22, log2_T=(19, 20, 21, 22, 23, 24), iters=10):

@@ -7,44 +7,34 @@
 //             exactly as the reference chains optax.add_decayed_weights behind adam (_utils.py:45-77)
 //
 // The step counter lives in device memory so the whole training step can sit in one CUDA graph.
-#include "common.cuh"
+#include "adam.cuh"
 
 namespace ngp {
 namespace {
 
+// two float4 per thread and iteration: 8 independent 16-byte loads in flight before the first dependent instruction
 __global__ void __launch_bounds__(256) adam_kernel(NgpAdamDescriptor d, const uint32_t *__restrict__ step_ptr,
                                                    float *__restrict__ params, const float *__restrict__ grads,
                                                    float *__restrict__ m, float *__restrict__ v) {
-    const uint32_t t = __ldg(step_ptr) + 1u;  // optax counts from 1 for the bias correction
-    // learning-rate schedule evaluated at count = t - 1 (optax schedules see the pre-increment count)
-    float lr = d.lr_init;
-    const float count = (float)(t - 1u);
-    if (d.transition_steps > 0) {
-        float p = fmaxf(count - (float)d.transition_begin, 0.f) / (float)d.transition_steps;
-        if (d.staircase) p = floorf(p);
-        lr = (count <= (float)d.transition_begin) ? d.lr_init : d.lr_init * powf(d.decay_rate, p);
-        lr = d.decay_rate < 1.f ? fmaxf(lr, d.lr_end) : fminf(lr, d.lr_end);
-    }
-    const float bc1 = 1.f - powf(d.b1, (float)t), bc2 = 1.f - powf(d.b2, (float)t);
-    const size_t n4 = d.n / 4;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-        float4 p = reinterpret_cast<float4 *>(params)[i];
-        float4 g = __ldg(reinterpret_cast<const float4 *>(grads) + i);
-        float4 mm = reinterpret_cast<float4 *>(m)[i];
-        float4 vv = reinterpret_cast<float4 *>(v)[i];
-        const float wd = (i * 4 >= d.decay_begin) ? d.weight_decay : 0.f;
-        float *pp = &p.x, *gg = &g.x, *pm = &mm.x, *pv = &vv.x;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float gk = gg[k] * d.grad_scale;
-            pm[k] = d.b1 * pm[k] + (1.f - d.b1) * gk;
-            pv[k] = d.b2 * pv[k] + (1.f - d.b2) * gk * gk;
-            const float upd = -lr * (pm[k] / bc1) / (sqrtf(pv[k] / bc2 + d.eps_root) + d.eps);
-            pp[k] = pp[k] + (upd + wd * pp[k]);
+    const AdamStepConstants c = adam_step_constants(d, __ldg(step_ptr));
+    const size_t n4 = d.n / 4, stride = (size_t)gridDim.x * blockDim.x;
+    float4 *p4 = reinterpret_cast<float4 *>(params), *m4 = reinterpret_cast<float4 *>(m), *v4 = reinterpret_cast<float4 *>(v);
+    const float4 *g4 = reinterpret_cast<const float4 *>(grads);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += 2 * stride) {
+        const size_t j = i + stride;
+        const bool two = j < n4;
+        // The moments are touched by this kernel only: they stream through L2 evict-first (ld.cs / st.cs), so that the
+        // gradients the backward just left in L2 are read from there and the parameters written here stay resident for
+        // the next step's gathers instead of being pushed out by 195 MB of moments.
+        float4 p0 = p4[i], g0 = __ldg(g4 + i), m0 = __ldcs(m4 + i), v0 = __ldcs(v4 + i);
+        float4 p1 = p0, g1 = g0, m1 = m0, v1 = v0;
+        if (two) { p1 = p4[j]; g1 = __ldg(g4 + j); m1 = __ldcs(m4 + j); v1 = __ldcs(v4 + j); }
+        adam_update4(d, c, (i * 4 >= d.decay_begin) ? d.weight_decay : 0.f, p0, g0, m0, v0);
+        p4[i] = p0; __stcs(m4 + i, m0); __stcs(v4 + i, v0);
+        if (two) {
+            adam_update4(d, c, (j * 4 >= d.decay_begin) ? d.weight_decay : 0.f, p1, g1, m1, v1);
+            p4[j] = p1; __stcs(m4 + j, m1); __stcs(v4 + j, v1);
         }
-        reinterpret_cast<float4 *>(params)[i] = p;
-        reinterpret_cast<float4 *>(m)[i] = mm;
-        reinterpret_cast<float4 *>(v)[i] = vv;
     }
 }
 
