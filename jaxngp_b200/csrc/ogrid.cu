@@ -14,6 +14,28 @@ namespace ngp {
 namespace {
 
 constexpr int kBlock = 256;
+constexpr int kScanBlock = 1024;
+constexpr uint32_t kChunkWords = 32, kChunkCells = 1024;  // cell draws: the bitfield in chunks of 1024 cells
+
+// occupied cells per chunk, one thread per chunk (grids up to 256^3: the draw kernel scans these counts in shared memory)
+__global__ void __launch_bounds__(kBlock) ogrid_chunk_count_kernel(uint32_t n_chunks, uint32_t n_words, const uint32_t *__restrict__ bits,
+                                                                   uint32_t *__restrict__ counts) {
+    const uint32_t c = blockIdx.x * kBlock + threadIdx.x;
+    if (c >= n_chunks) return;
+    const uint32_t w0 = c * kChunkWords;
+    uint32_t cnt = 0;
+    if (w0 + kChunkWords <= n_words) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(bits + w0);
+#pragma unroll
+        for (int k = 0; k < (int)kChunkWords / 4; ++k) {
+            const uint4 v = __ldg(p + k);
+            cnt += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+        }
+    } else {
+        for (uint32_t w = w0; w < n_words; ++w) cnt += __popc(__ldg(bits + w));
+    }
+    counts[c] = cnt;
+}
 
 // sample position of cell `m` (Morton index inside the cascade) with jitter draws u (:1193-1206)
 __device__ __forceinline__ void ogrid_cell_position(uint32_t m, uint32_t G, float mip_bound, const float (&u)[3], float *out) {
@@ -145,8 +167,6 @@ __global__ void __launch_bounds__(kBlock) ogrid_threshold_kernel(uint32_t n, flo
 // ---------------------------------------------------------------- cell draws of update_ogrid_density (:1166-1206)
 // The bitfield of a cascade (Morton order, LSB first: bit i = cell i) is cut into chunks of 1024 cells (32 words);
 // `prefix[c]` = occupied cells in chunks [0, c).  One CTA scans them: 2048 chunks at G = 128.
-constexpr int kScanBlock = 1024;
-constexpr uint32_t kChunkWords = 32, kChunkCells = 1024;
 
 __global__ void __launch_bounds__(kScanBlock) ogrid_chunk_prefix_kernel(uint32_t n_chunks, uint32_t n_words,
                                                                          const uint32_t *__restrict__ bits,
@@ -205,11 +225,46 @@ __global__ void __launch_bounds__(kScanBlock) ogrid_chunk_prefix_kernel(uint32_t
 // among the OCCUPIED cells (jran.choice with p = occ_mask: the k-th occupied cell, k = ceil(total * (1 - u)) as
 // jax's inverse-CDF search does; an empty grid yields the first trainable cell like searchsorted on an all-zero CDF).
 // The fourth..sixth uniforms of the same Philox block are the jitter inside the cell.
+// kSmemPrefix: `prefix` holds per-chunk COUNTS (ogrid_chunk_count_kernel) and every block scans them into its own
+// shared-memory prefix first (<= kMaxSmemChunks chunks: grids up to 256^3); otherwise `prefix` is the global exclusive
+// prefix of ogrid_chunk_prefix_kernel.
+constexpr uint32_t kMaxSmemChunks = 16384;
+template <bool kSmemPrefix>
 __global__ void __launch_bounds__(kBlock) ogrid_draw_cells_kernel(NgpOgridDrawDescriptor d, const uint32_t *__restrict__ bits,
                                                                    const uint32_t *__restrict__ alive,
                                                                    const uint32_t *__restrict__ prefix,
                                                                    uint32_t *__restrict__ rng_state,
                                                                    uint32_t *__restrict__ idx_out, float *__restrict__ coords) {
+    extern __shared__ uint32_t s_prefix[];  // [n_chunks + 1] when kSmemPrefix
+    const uint32_t n_chunks = (d.n_cells + kChunkCells - 1u) / kChunkCells;
+    const uint32_t *pre = prefix;
+    if (kSmemPrefix) {  // block-wide exclusive scan of the chunk counts: kBlock threads x `per` consecutive chunks each
+        __shared__ uint32_t s_warp[kBlock / 32];
+        const uint32_t per = (n_chunks + kBlock - 1u) / kBlock, c0 = threadIdx.x * per;
+        uint32_t sum = 0;
+        for (uint32_t k = 0; k < per; ++k)
+            if (c0 + k < n_chunks) sum += __ldg(prefix + c0 + k);
+        uint32_t incl = sum;
+        const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += t;
+        }
+        if (lane == 31u) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t base = 0;
+        for (uint32_t w = 0; w < warp; ++w) base += s_warp[w];
+        uint32_t run = base + incl - sum;
+        for (uint32_t k = 0; k < per; ++k)
+            if (c0 + k < n_chunks) {
+                s_prefix[c0 + k] = run;
+                run += __ldg(prefix + c0 + k);
+            }
+        if (threadIdx.x == kBlock - 1u) s_prefix[n_chunks] = base + incl;
+        __syncthreads();
+        pre = s_prefix;
+    }
     const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
     const uint32_t counter = rng_state[0];
     const uint32_t n_draws = d.mode ? d.n_alive : d.n_first + d.n_second;
@@ -220,8 +275,7 @@ __global__ void __launch_bounds__(kBlock) ogrid_draw_cells_kernel(NgpOgridDrawDe
             const uint32_t k = d.mode ? i : __umulhi(r.x, d.n_alive);  // uniform in [0, n_alive)
             cell = alive ? __ldg(alive + k) : k;
         } else {
-            const uint32_t n_chunks = (d.n_cells + kChunkCells - 1u) / kChunkCells;
-            const uint32_t total = __ldg(prefix + n_chunks);
+            const uint32_t total = pre[n_chunks];
             if (total == 0u) {
                 cell = alive ? __ldg(alive) : 0u;
             } else {
@@ -231,20 +285,38 @@ __global__ void __launch_bounds__(kBlock) ogrid_draw_cells_kernel(NgpOgridDrawDe
                 uint32_t lo = 0, hi = n_chunks;  // last chunk with prefix[c] <= k
                 while (hi - lo > 1u) {
                     const uint32_t mid = (lo + hi) >> 1;
-                    if (__ldg(prefix + mid) <= k) lo = mid; else hi = mid;
+                    if (pre[mid] <= k) lo = mid; else hi = mid;
                 }
-                uint32_t rest = k - __ldg(prefix + lo);
-                const uint32_t w0 = lo * kChunkWords;
-                const uint32_t n_words = (d.n_cells + 31u) / 32u;
+                uint32_t rest = k - pre[lo];
+                const uint32_t w0 = lo * kChunkWords, n_words = (d.n_cells + 31u) / 32u;
                 cell = 0u;
-                for (uint32_t w = w0; w < min(w0 + kChunkWords, n_words); ++w) {
-                    const uint32_t word = __ldg(bits + w);
-                    const uint32_t pc = __popc(word);
-                    if (rest < pc) {
-                        cell = w * 32u + __fns(word, 0u, (int)rest + 1);
-                        break;
+                if (w0 + kChunkWords <= n_words) {  // the chunk's 32 words as 8 independent 16-byte loads, then registers only
+                    uint4 q[kChunkWords / 4];
+#pragma unroll
+                    for (int j = 0; j < (int)kChunkWords / 4; ++j) q[j] = __ldg(reinterpret_cast<const uint4 *>(bits + w0) + j);
+                    bool found = false;
+#pragma unroll
+                    for (int j = 0; j < (int)kChunkWords / 4; ++j) {
+                        const uint32_t ws[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t pc = __popc(ws[e]);
+                            if (!found && rest < pc) {
+                                cell = (w0 + 4u * j + e) * 32u + __fns(ws[e], 0u, (int)rest + 1);
+                                found = true;
+                            }
+                            if (!found) rest -= pc;
+                        }
                     }
-                    rest -= pc;
+                } else {
+                    for (uint32_t w = w0; w < n_words; ++w) {
+                        const uint32_t word = __ldg(bits + w), pc = __popc(word);
+                        if (rest < pc) {
+                            cell = w * 32u + __fns(word, 0u, (int)rest + 1);
+                            break;
+                        }
+                        rest -= pc;
+                    }
                 }
             }
         }
@@ -324,18 +396,31 @@ void ngp_ogrid_draw_cells(cudaStream_t stream, void **buffers, const char *opaqu
     const uint32_t n_draws = d->mode ? d->n_alive : d->n_first + d->n_second;
     if (n_draws == 0) return;
     uint32_t *prefix = nullptr;
+    bool smem_prefix = false;
+    const uint32_t n_chunks = div_up(d->n_cells, kChunkCells);
     if (!d->mode && d->n_second) {
         if (reinterpret_cast<uintptr_t>(bits) % 16 != 0) {
             set_error(NGP_ERR_ARGUMENT, "ogrid_draw_cells: the bitfield must be 16-byte aligned");
             return;
         }
-        const uint32_t n_chunks = div_up(d->n_cells, kChunkCells);
         prefix = static_cast<uint32_t *>(workspace(stream, (size_t)(n_chunks + 1) * sizeof(uint32_t)));
         if (!prefix) return;
-        ogrid_chunk_prefix_kernel<<<1, kScanBlock, 0, stream>>>(n_chunks, d->n_cells / 32u, bits, prefix);
+        smem_prefix = n_chunks <= kMaxSmemChunks;
+        if (smem_prefix) ogrid_chunk_count_kernel<<<div_up(n_chunks, kBlock), kBlock, 0, stream>>>(n_chunks, d->n_cells / 32u, bits, prefix);
+        else ogrid_chunk_prefix_kernel<<<1, kScanBlock, 0, stream>>>(n_chunks, d->n_cells / 32u, bits, prefix);
         if (!check_launch("ogrid_draw_cells(prefix)")) return;
     }
-    ogrid_draw_cells_kernel<<<div_up(n_draws, kBlock), kBlock, 0, stream>>>(*d, bits, alive, prefix, rng_state, idx, coords);
+    if (smem_prefix) {
+        const size_t smem = (size_t)(n_chunks + 1) * sizeof(uint32_t);
+        static bool configured = false;  // benign race: idempotent
+        if (!configured) {
+            cudaFuncSetAttribute(ogrid_draw_cells_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((kMaxSmemChunks + 1) * sizeof(uint32_t)));
+            configured = true;
+        }
+        ogrid_draw_cells_kernel<true><<<div_up(n_draws, kBlock), kBlock, smem, stream>>>(*d, bits, alive, prefix, rng_state, idx, coords);
+    } else {
+        ogrid_draw_cells_kernel<false><<<div_up(n_draws, kBlock), kBlock, 0, stream>>>(*d, bits, alive, prefix, rng_state, idx, coords);
+    }
     check_launch("ogrid_draw_cells");
 }
 

@@ -94,13 +94,14 @@ def fused_supported(lt, table: torch.Tensor, wrap: str = "jaxngp") -> bool:
 
 def fused_forward(lt, pos: torch.Tensor, bound: float, table: torch.Tensor, dirs, weights: torch.Tensor, *,
                   wrap: str = "jaxngp", group_counts: torch.Tensor = None, rows_per_group: int = 0, want_enc: bool = False,
-                  impl: str = "mma"):
+                  impl: str = "mma", out: torch.Tensor = None):
     """Hash-grid encoder fused in front of the MLP forward (csrc/mlp.cu ``nerf_fused_forward_kernel``): bit-identical
     to ``encoders.hashgrid_forward`` + ``mlp_forward``, without the [n, 32] round trip through HBM.
     Returns ``drgbs`` (``dirs=None``: densities [n]); with ``want_enc`` also the encoding (kept for the backward)."""
     n = pos.shape[0]
     density_only = dirs is None
-    out = torch.empty((n,) if density_only else (n, 4), dtype=torch.float32, device=pos.device)
+    if out is None:  # `out`: a caller-owned slice to write into (the grid update evaluates its points in chunks)
+        out = torch.empty((n,) if density_only else (n, 4), dtype=torch.float32, device=pos.device)
     enc = torch.empty(n, 32, dtype=torch.float32, device=pos.device) if want_enc else None
     if n:
         desc = encoders._a1_descriptor(lt, n, bound, wrap, table.dtype, rows_per_group) + \

@@ -4,6 +4,8 @@
 gridops.cu); the random draws are inputs, as the reference draws them with jax.random outside the ops.
 """
 
+import inspect
+
 import torch
 
 from . import _lib, descriptors
@@ -102,7 +104,8 @@ def update_ogrid_density(grid: OccupancyDensityGrid, density_fn, cas: int, updat
                          max_inference: int, draws=None, generator=None, out_density=None):
     """``NeRFState.update_ogrid_density`` (utils/types.py:1149-1225) for one cascade.  ``density_fn(xyz)``
     evaluates the NeRF's density branch.  ``draws`` = dict(first, second, jitter) overrides the random
-    selections (parity tests).  After ``mark_untrained_density_grid`` culled cells, only trainable cells are sampled."""
+    selections (parity tests).  After ``mark_untrained_density_grid`` culled cells, only trainable cells are sampled.
+    ``density_fn(xyz, out)`` may write the densities of ``xyz`` into ``out`` and return it (no concatenation afterwards)."""
     G3, dev = grid.G3, grid.density.device
     sl = slice(cas * G3, (cas + 1) * G3)
     if draws is None and generator is None:  # the product path: cell choice, jitter and positions in one op
@@ -130,7 +133,15 @@ def update_ogrid_density(grid: OccupancyDensityGrid, density_fn, cas: int, updat
             idx = torch.cat([first, second])
         jitter = draws["jitter"] if draws is not None else torch.rand(idx.shape[0], 3, device=dev, generator=generator)
         coords = sample_positions(idx, jitter, grid.G, cas, bound)
-    new_density = torch.cat([density_fn(part).reshape(-1) for part in coords.split(max(1, max_inference))])
+    # :1208-1217: the points go through the model in chunks of `max_inference`; every chunk writes its slice of one buffer
+    new_density = torch.empty(coords.shape[0], dtype=torch.float32, device=dev)
+    chunk = max(1, max_inference)
+    takes_out = len(inspect.signature(density_fn).parameters) >= 2
+    for begin in range(0, coords.shape[0], chunk):
+        part = new_density[begin:begin + chunk]
+        res = density_fn(coords[begin:begin + chunk], part) if takes_out else density_fn(coords[begin:begin + chunk])
+        if res is not part:  # a density function that ignores the output slice
+            part.copy_(res.reshape(-1))
     target = grid.density[sl] if out_density is None else out_density[sl]
     decay_and_max(grid.density[sl], idx, new_density, 0.95, out=target)
     return idx, coords, new_density

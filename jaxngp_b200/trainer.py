@@ -435,9 +435,9 @@ class Trainer:
                                                  synthetic.DIAGONAL_N_STEPS, self.step)
 
     # -- density grid update (utils/types.py:1149-1239) --------------------------------------------
-    def _density_fn(self, xyz):
+    def _density_fn(self, xyz, out=None):
         if self.fused_encoder:
-            return nerf_mod.fused_forward(self.levels, xyz.contiguous(), synthetic.BOUND, self.table, None, self.mlp_flat)
+            return nerf_mod.fused_forward(self.levels, xyz.contiguous(), synthetic.BOUND, self.table, None, self.mlp_flat, out=out)
         enc = encoders.hashgrid_forward(self.levels, xyz.contiguous(), synthetic.BOUND, self.table)
         if self.fused_mlp:
             return nerf_mod.mlp_forward(enc, None, self.mlp_flat)
