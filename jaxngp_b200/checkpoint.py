@@ -197,13 +197,15 @@ def load_into_trainer(trainer, state: dict):
         # (the reference re-marks after every restore, app/nerf/train.py:206 -- callers may still do that).
         alive = state["ogrid"].get("alive_indices")
         g = trainer.grid
-        n_cells = g.K * g.G3
+        n_cells = int(g.density.shape[0])
+        cascades = int(getattr(g, "K", 1))
+        cells_per_cascade = n_cells // cascades
         if alive is None or np.asarray(alive).size in (0, n_cells):
             g.alive_indices = g.alive_indices_offset = None
         else:
             alive = np.sort(np.asarray(alive).astype(np.int64).reshape(-1))
             g.alive_indices = torch.from_numpy(alive.astype(np.int32)).to(dev)
-            g.alive_indices_offset = [int(np.searchsorted(alive, c * g.G3)) for c in range(g.K + 1)]
+            g.alive_indices_offset = [int(np.searchsorted(alive, c * cells_per_cascade)) for c in range(cascades + 1)]
     trainer.step = int(state["step"])
     trainer.step_dev.fill_(int(state["step"]))
     for key, (t, f) in moments.items():
