@@ -502,13 +502,18 @@ def render_bench(dev, rank, world, scene=None, frames=10, train_steps=(300, 1024
     H, Wd = scene.cam["height"], scene.cam["width"]
     rows = dp.tile_rows(H, rank, world).to(dev)
     pixels = (rows[:, None] * Wd + torch.arange(Wd, device=dev)[None, :]).reshape(-1).to(torch.int32)
+    # the default renderer (the whole slot-refill loop as one persistent kernel) and, beside it, round 1's renderer (one
+    # CUDA-graph replay per loop iteration, host check a batch behind)
     R = renderers.InferenceRenderer(tr.nerf, scene.cam, tr.occupancy, n_rays=min(n_slots, pixels.numel()), march_steps_cap=cap,
                                     pixel_indices=pixels)
+    R_loop = renderers.InferenceRenderer(tr.nerf, scene.cam, tr.occupancy, n_rays=min(n_slots, pixels.numel()), march_steps_cap=cap,
+                                         pixel_indices=pixels, persistent=False)
+    active = [R]
     views = [(7 * k + 3) % scene.n_views for k in range(frames + 2)]
     gather = dp.ImageGather(H, Wd, 3, rank, world, dev) if world > 1 else None
 
     def frame(v):
-        rgb, _ = R.render(scene.transforms[v])
+        rgb, _ = active[0].render(scene.transforms[v])
         return gather(rgb.reshape(rows.numel(), Wd, 3)) if world > 1 else rgb
 
     host_frame = torch.empty((H if world > 1 else rows.numel()) * Wd * 3, dtype=torch.uint8).pin_memory()
@@ -529,13 +534,13 @@ def render_bench(dev, rank, world, scene=None, frames=10, train_steps=(300, 1024
         for v in views[2:]:
             if e2e:
                 pose = poses_host[v].to(dev, non_blocking=True)
-                rgb, _ = R.render(pose)
+                rgb, _ = active[0].render(pose)
                 img = gather(rgb.reshape(rows.numel(), Wd, 3)) if world > 1 else rgb
                 host_frame.copy_(img.reshape(-1), non_blocking=True)
                 torch.cuda.current_stream().synchronize()
             else:
                 img = frame(v)
-            smp += R.samples_done
+            smp += active[0].samples_done
         e1.record()
         if world > 1:
             dist.barrier()
@@ -547,6 +552,9 @@ def render_bench(dev, rank, world, scene=None, frames=10, train_steps=(300, 1024
         return float(ms) / frames, int(smp), img
 
     def measure():
+        active[0] = R_loop
+        ms_loop, smp_loop, img_loop = run(False)
+        active[0] = R
         ms_frame, smp, img = run(False)
         ms_frame_e2e, _, _ = run(True)
         # quality of the frame just rendered against the analytic ground truth of that view (white background)
@@ -561,6 +569,11 @@ def render_bench(dev, rank, world, scene=None, frames=10, train_steps=(300, 1024
         return {"rays_per_s": 640000 / (ms_frame * 1e-3), "fps": 1e3 / ms_frame, "ms_per_frame": ms_frame,
                 "samples_per_frame": smp / frames, "samples_per_s": smp / frames / (ms_frame * 1e-3), "psnr_last_frame": psnr,
                 "model": f"trained {trained} steps in this run (C2 step)",
+                "renderer": "persistent whole-frame kernel (ngp_render_frame)" if R.persistent else "loop (graph replay per iteration)",
+                "loop_renderer": {"fps": 1e3 / ms_loop, "ms_per_frame": ms_loop, "samples_per_frame": smp_loop / frames,
+                                  "same_image": bool(torch.equal(img, img_loop)),
+                                  "note": "round 1's renderer on the same model and views: one CUDA-graph replay per slot-refill "
+                                          "iteration (march, compaction, tcgen05 encoder + MLP, integrate), host check a batch behind"},
                 "e2e": {"fps": 1e3 / ms_frame_e2e, "rays_per_s": 640000 / (ms_frame_e2e * 1e-3), "ms_per_frame": ms_frame_e2e,
                         "h2d_bytes_per_frame": 48, "d2h_bytes_per_frame": int(host_frame.numel()),
                         "note": "pose copied from pinned host memory, finished u8 frame copied to pinned host memory and waited for, every frame"}}

@@ -253,6 +253,18 @@ void ngp_nerf_fused_forward(cudaStream_t, void **, const char *, size_t);
  * kernel; results agree to f32 accumulation-order error (rel 1e-5), not bit for bit. */
 void ngp_nerf_fused_forward_umma(cudaStream_t, void **, const char *, size_t);
 
+/* Whole-frame inference kernel: render_image_inference's slot-refill loop (models/renderers/cuda.py:244-373:
+ * march_rays_inference -> NeRF -> integrate_rays_inference -> scatter, until every ray has terminated) as ONE persistent
+ * launch -- ray slots, samples and compositing state stay on the SM; a free slot takes the next ray with one atomicAdd.
+ * Same march code, same encoder + tcgen05 MLP code and the same compositing expressions as the ops it replaces.
+ * `march.march_steps_cap` must be 16 and `march.n_rays` is unused; rays arrive pre-advanced by ngp_march_rays_skip_empty.
+ * in : rays_o f32[N,3], rays_d f32[N,3], t_starts f32[N], t_ends f32[N], bitfield u8[K*G^3/8], rays_bg f32[N,3],
+ *      table (f32|f16)[rows,2], weights f32[9408]
+ * scratch (zeroed by the op): next_ray u32[1], counters u64[2] (rays terminated, samples marched)
+ * out: rays_rgbd f32[N,4] (colour composited onto the background, depth) */
+typedef struct { NgpHashGridA1Descriptor grid; NgpMarchingInferenceDescriptor march; } NgpRenderFrameDescriptor;
+void ngp_render_frame(cudaStream_t, void **, const char *, size_t);
+
 /* Diagnostic: known-answer test of the tcgen05 (kind::tf32) operand formats of csrc/umma.cuh -- forward, dgrad and
  * wgrad GEMM shapes on swizzled shared-memory panels with TMEM accumulators.  No descriptor (opaque_len = 0).
  * in : A f32[128,32], W f32[32,64], G f32[128,64]     out: A.W f32[128,64], G.W^T f32[128,32], G^T.A f32[64,32] */

@@ -119,6 +119,25 @@ __global__ void __launch_bounds__(kBlock) hashgrid_transpose_kernel(uint32_t n, 
     }
 }
 
+// enc-shaped [n][L*F] -> level-major [L][n][F] (the backward's input for one- and two-level passes: read in place, a pass
+// would pull a 32-byte sector through L2 for every 8 bytes it uses -- four times the stream, next to the level's rows)
+template <int F>
+__global__ void __launch_bounds__(kBlock) hashgrid_transpose_in_kernel(uint32_t n, uint32_t L, const float *__restrict__ rows,
+                                                                        float *__restrict__ scratch) {
+    constexpr int kPts = 64;
+    extern __shared__ float s_tile[];  // [kPts][L*F + 1]
+    const uint32_t p0 = blockIdx.x * kPts, LF = L * F, pitch = LF + 1;
+    for (uint32_t e = threadIdx.x; e < kPts * LF; e += kBlock) {
+        const uint32_t pt = e / LF, c = e % LF;
+        if (p0 + pt < n) s_tile[pt * pitch + c] = __ldcs(rows + (size_t)(p0 + pt) * LF + c);
+    }
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < L * kPts * F; e += kBlock) {
+        const uint32_t l = e / (kPts * F), r = e % (kPts * F), pt = r / F, f = r % F;
+        if (p0 + pt < n) scratch[((size_t)l * n + p0 + pt) * F + f] = s_tile[pt * pitch + l * F + f];
+    }
+}
+
 // Backward: level-major warps.  A CTA owns 256 consecutive points; warp w walks levels w, w+8 and its
 // lanes are 32 CONSECUTIVE points at ONE level.  Samples arrive ray by ray (march_rays emits each
 // ray's samples contiguously), so neighbouring lanes usually sit in the same grid cell on the coarse
@@ -132,7 +151,7 @@ template <int DIM, int F, bool kPaired>
 __global__ void __launch_bounds__(kBlock) hashgrid_a1_backward_kernel(const __grid_constant__ NgpHashGridA1Descriptor d,
                                                                        const float *__restrict__ pos,
                                                                        const float *__restrict__ d_enc,
-                                                                       float *__restrict__ d_table, uint32_t lpg) {
+                                                                       float *__restrict__ d_table, uint32_t lpg, bool level_major_in) {
     __shared__ LevelMeta s_meta[NGP_HG_MAX_LEVELS];
     if (threadIdx.x < d.L) s_meta[threadIdx.x] = a1_level(d, threadIdx.x);
     __syncthreads();
@@ -165,7 +184,8 @@ __global__ void __launch_bounds__(kBlock) hashgrid_a1_backward_kernel(const __gr
 #pragma unroll
             for (int f = 0; f < F; ++f) g[f] = 0.f;
             if (in_range) {
-                const float *gin = d_enc + ((size_t)point * d.L + level) * F;
+                const float *gin = level_major_in ? d_enc + ((size_t)level * d.n_points + point) * F
+                                                  : d_enc + ((size_t)point * d.L + level) * F;
                 // streamed once (evict-first): the L2 is for the gradient rows the reductions below hit
                 if (F == 2) {
                     const float2 v = __ldcs(reinterpret_cast<const float2 *>(gin));
@@ -562,14 +582,29 @@ void ngp_hashgrid_a1_backward(cudaStream_t stream, void **buffers, const char *o
     if (lpg == 0) lpg = d->L;
     const dim3 blocks(div_up(d->n_points, kBlock), div_up(d->L, lpg), 1);
     const bool paired = reinterpret_cast<uintptr_t>(d_table) % 16 == 0 && d->offsets[d->L] % 2 == 0;
+    // one- and two-level passes read d_enc from a level-major copy (see hashgrid_transpose_in_kernel)
+    bool lm = lpg <= 2 && lpg < d->L;
+    if (lm) {
+        auto *scratch = static_cast<float *>(workspace(stream, (size_t)d->n_points * d->L * d->F * sizeof(float)));
+        if (!scratch) return;
+        const size_t smem = 64 * (d->L * d->F + 1) * sizeof(float);
+        if (smem > 48 * 1024) {
+            lm = false;  // (L * F > 191: not a geometry of this path) -- read in place
+        } else {
+            if (d->F == 2) hashgrid_transpose_in_kernel<2><<<div_up(d->n_points, 64), kBlock, smem, stream>>>(d->n_points, d->L, d_enc, scratch);
+            else hashgrid_transpose_in_kernel<4><<<div_up(d->n_points, 64), kBlock, smem, stream>>>(d->n_points, d->L, d_enc, scratch);
+            if (!check_launch("hashgrid_a1_backward(transpose)")) return;
+            d_enc = scratch;
+        }
+    }
     if (d->dim == 3 && d->F == 2) {
-        if (paired) hashgrid_a1_backward_kernel<3, 2, true><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg);
-        else hashgrid_a1_backward_kernel<3, 2, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg);
-    } else if (d->dim == 3) hashgrid_a1_backward_kernel<3, 4, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg);
+        if (paired) hashgrid_a1_backward_kernel<3, 2, true><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg, lm);
+        else hashgrid_a1_backward_kernel<3, 2, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg, lm);
+    } else if (d->dim == 3) hashgrid_a1_backward_kernel<3, 4, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg, lm);
     else if (d->F == 2) {
-        if (paired) hashgrid_a1_backward_kernel<2, 2, true><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg);
-        else hashgrid_a1_backward_kernel<2, 2, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg);
-    } else hashgrid_a1_backward_kernel<2, 4, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg);
+        if (paired) hashgrid_a1_backward_kernel<2, 2, true><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg, lm);
+        else hashgrid_a1_backward_kernel<2, 2, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg, lm);
+    } else hashgrid_a1_backward_kernel<2, 4, false><<<blocks, kBlock, 0, stream>>>(*d, pos, d_enc, d_table, lpg, lm);
     check_launch("hashgrid_a1_backward");
 }
 

@@ -19,6 +19,7 @@
 // shared-memory loads, HMMA issue and fragment conversions the tensor core now does asynchronously.
 #include "common.cuh"
 #include "hashgrid.cuh"
+#include "marching.cuh"
 #include "umma.cuh"
 
 namespace ngp {
@@ -108,6 +109,138 @@ __global__ void __launch_bounds__(256) compact_live_groups_kernel(uint32_t n_gro
     if (live) live_list[base + __popc(votes & ((1u << lane) - 1u))] = i;
 }
 
+// One 128-sample tile through the gather and the five tcgen05 layers: thread r of `group` owns row r (position x,
+// direction dir; rows with live = false gather nothing and produce garbage nobody reads).  o = (density, rgb).
+// Shared by the forward op (tiles of the sample array) and the whole-frame kernel (tiles of a group's eight ray slots).
+template <typename TT, bool kWriteEnc>
+__device__ __forceinline__ void tile_forward(const TT *__restrict__ table, const hg::LevelMeta *s_meta, float bound, const float (&x)[3],
+                                             const float (&dir)[3], bool live, float *__restrict__ enc_row, uint8_t *PA, uint8_t *PB,
+                                             uint32_t pa, uint32_t pb, uint32_t wa, uint32_t tmem_d, uint32_t tmem_row, uint64_t *bar,
+                                             uint32_t &phase, uint32_t group, uint32_t r, float4 &o) {
+    constexpr uint32_t kI64 = umma::make_idesc(128, 64, false, true), kI32 = umma::make_idesc(128, 32, false, true);
+    // ---- gather: this thread's sample on all 16 levels
+    float p01[3];
+    hg::unit_pos<3>(x, bound, p01);
+#pragma unroll 2
+    for (int lv = 0; lv < 16; lv += 2) {  // partially rolled: the fully unrolled gather overflows the instruction cache
+        float e0[2], e1[2];
+        hg::encode_point_level_pred<TT>(table, s_meta[lv], p01, live, e0);
+        hg::encode_point_level_pred<TT>(table, s_meta[lv + 1], p01, live, e1);
+        if (kWriteEnc && live) *reinterpret_cast<float4 *>(enc_row + 2 * lv) = make_float4(e0[0], e0[1], e1[0], e1[1]);
+        store_chunk(PA, r, 2 * lv, tf32r(e0[0]), tf32r(e0[1]), tf32r(e1[0]), tf32r(e1[1]));
+    }
+    const float dx = dir[0], dy = dir[1], dz = dir[2];
+    uint32_t v[32];
+    // ---- layer 0: enc[32] -> 64, ReLU
+    umma::fence_smem_to_async();
+    group_barrier(group);
+    if (r == 0) {
+        umma::fence_after_sync();
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks)
+            umma::mma_tf32(tmem_d, umma::desc_k_major(pa, ks), umma::desc_mn_major(wa + WB0, ks, 32 * 128), kI64, ks > 0);
+        umma::commit(bar);
+    }
+    umma::mbar_wait(bar, phase);
+    phase ^= 1u;
+    umma::fence_after_sync();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        umma::tmem_ld32(tmem_row + 32 * h, v);
+        umma::tmem_ld_wait();
+        relu_store32(PB, r, 32 * h, v);
+    }
+    // ---- layer 1: 64 -> 16 (padded to 32), no activation; density = exp(x[0]); hin = [x | SH4(dir)]
+    umma::fence_before_sync();
+    umma::fence_smem_to_async();
+    group_barrier(group);
+    if (r == 0) {
+        umma::fence_after_sync();
+#pragma unroll
+        for (uint32_t ks = 0; ks < 8; ++ks)
+            umma::mma_tf32(tmem_d, umma::desc_k_major(pb + (ks >> 2) * kPA, ks & 3u), umma::desc_mn_major(wa + WB1, ks, 64 * 128), kI32, ks > 0);
+        umma::commit(bar);
+    }
+    umma::mbar_wait(bar, phase);
+    phase ^= 1u;
+    umma::fence_after_sync();
+    umma::tmem_ld32(tmem_row, v);
+    umma::tmem_ld_wait();
+    const float density = expf(__uint_as_float(v[0]));
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        store_chunk(PA, r, 4 * c, tf32r(__uint_as_float(v[4 * c])), tf32r(__uint_as_float(v[4 * c + 1])),
+                    tf32r(__uint_as_float(v[4 * c + 2])), tf32r(__uint_as_float(v[4 * c + 3])));
+    {
+        float s[16];
+        sh16(dx, dy, dz, s);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            store_chunk(PA, r, 16 + 4 * c, tf32r(s[4 * c]), tf32r(s[4 * c + 1]), tf32r(s[4 * c + 2]), tf32r(s[4 * c + 3]));
+    }
+    // ---- layer 2: hin[32] -> 64, ReLU
+    umma::fence_before_sync();
+    umma::fence_smem_to_async();
+    group_barrier(group);
+    if (r == 0) {
+        umma::fence_after_sync();
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks)
+            umma::mma_tf32(tmem_d, umma::desc_k_major(pa, ks), umma::desc_mn_major(wa + WB2, ks, 32 * 128), kI64, ks > 0);
+        umma::commit(bar);
+    }
+    umma::mbar_wait(bar, phase);
+    phase ^= 1u;
+    umma::fence_after_sync();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        umma::tmem_ld32(tmem_row + 32 * h, v);
+        umma::tmem_ld_wait();
+        relu_store32(PB, r, 32 * h, v);
+    }
+    // ---- layer 3: 64 -> 64, ReLU (the MMA has been awaited, so its A panel can take the result)
+    umma::fence_before_sync();
+    umma::fence_smem_to_async();
+    group_barrier(group);
+    if (r == 0) {
+        umma::fence_after_sync();
+#pragma unroll
+        for (uint32_t ks = 0; ks < 8; ++ks)
+            umma::mma_tf32(tmem_d, umma::desc_k_major(pb + (ks >> 2) * kPA, ks & 3u), umma::desc_mn_major(wa + WB3, ks, 64 * 128), kI64, ks > 0);
+        umma::commit(bar);
+    }
+    umma::mbar_wait(bar, phase);
+    phase ^= 1u;
+    umma::fence_after_sync();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        umma::tmem_ld32(tmem_row + 32 * h, v);
+        umma::tmem_ld_wait();
+        relu_store32(PB, r, 32 * h, v);
+    }
+    // ---- layer 4: 64 -> 3 (padded to 32), sigmoid
+    umma::fence_before_sync();
+    umma::fence_smem_to_async();
+    group_barrier(group);
+    if (r == 0) {
+        umma::fence_after_sync();
+#pragma unroll
+        for (uint32_t ks = 0; ks < 8; ++ks)
+            umma::mma_tf32(tmem_d, umma::desc_k_major(pb + (ks >> 2) * kPA, ks & 3u), umma::desc_mn_major(wa + WB4, ks, 64 * 128), kI32, ks > 0);
+        umma::commit(bar);
+    }
+    umma::mbar_wait(bar, phase);
+    phase ^= 1u;
+    umma::fence_after_sync();
+    umma::tmem_ld32(tmem_row, v);
+    umma::tmem_ld_wait();
+    o.x = density;
+    o.y = 1.f / (1.f + expf(-__uint_as_float(v[0])));
+    o.z = 1.f / (1.f + expf(-__uint_as_float(v[1])));
+    o.w = 1.f / (1.f + expf(-__uint_as_float(v[2])));
+    umma::fence_before_sync();  // the next tile's first MMA overwrites the accumulator these loads read
+}
+
 template <typename TT, bool kWriteEnc>
 __global__ void __launch_bounds__(kThreadsU, 1) nerf_fused_forward_umma_kernel(const __grid_constant__ NgpNerfFusedDescriptor d,
                                                                                const float *__restrict__ pos,
@@ -144,7 +277,6 @@ __global__ void __launch_bounds__(kThreadsU, 1) nerf_fused_forward_umma_kernel(c
     const uint32_t tmem_row = tmem_d + ((32u * gw) << 16);            // this warp's 32 lanes of it (tcgen05.ld address)
     const uint32_t pa = umma::smem_u32(PA), pb = umma::smem_u32(PB), wa = umma::smem_u32(wsm);
     uint64_t *bar = &bars[group];
-    constexpr uint32_t kI64 = umma::make_idesc(128, 64, false, true), kI32 = umma::make_idesc(128, 32, false, true);
 
     const uint32_t n = d.grid.n_points, rpg = d.grid.rows_per_group;
     const float bound = d.grid.bound;
@@ -166,142 +298,204 @@ __global__ void __launch_bounds__(kThreadsU, 1) nerf_fused_forward_umma_kernel(c
                 live = my_k < __ldg(group_counts + dir_row) && row < n;
             }
         }
-        // ---- gather: this thread's sample on all 16 levels
-        float x[3] = {0.f, 0.f, 0.f}, p01[3];
+        float x[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 1.f};
         if (live) {
             x[0] = __ldg(pos + (size_t)row * 3 + 0);
             x[1] = __ldg(pos + (size_t)row * 3 + 1);
             x[2] = __ldg(pos + (size_t)row * 3 + 2);
+            dir[0] = __ldg(dirs + (size_t)dir_row * 3 + 0);
+            dir[1] = __ldg(dirs + (size_t)dir_row * 3 + 1);
+            dir[2] = __ldg(dirs + (size_t)dir_row * 3 + 2);
         }
-        hg::unit_pos<3>(x, bound, p01);
-#pragma unroll 2
-        for (int lv = 0; lv < 16; lv += 2) {  // partially rolled: the fully unrolled gather overflows the instruction cache
-            float e0[2], e1[2];
-            hg::encode_point_level_pred<TT>(table, s_meta[lv], p01, live, e0);
-            hg::encode_point_level_pred<TT>(table, s_meta[lv + 1], p01, live, e1);
-            if (kWriteEnc && live)
-                *reinterpret_cast<float4 *>(enc_out + (size_t)row * 32 + 2 * lv) = make_float4(e0[0], e0[1], e1[0], e1[1]);
-            store_chunk(PA, r, 2 * lv, tf32r(e0[0]), tf32r(e0[1]), tf32r(e1[0]), tf32r(e1[1]));
+        float4 o;
+        tile_forward<TT, kWriteEnc>(table, s_meta, bound, x, dir, live, kWriteEnc ? enc_out + (size_t)row * 32 : nullptr, PA, PB, pa, pb, wa,
+                                    tmem_d, tmem_row, bar, phase, group, r, o);
+        if (live) reinterpret_cast<float4 *>(out)[row] = o;
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc(tmem_slot, kTmemCols);
+}
+
+
+// ---------------------------------------------------------------- whole-frame inference kernel
+// render_image_inference (models/renderers/cuda.py:244-373) as ONE persistent launch: the reference's slot-refill loop
+// -- march_rays_inference -> NeRF -> integrate_rays_inference -> scatter, repeated until every ray has terminated, with
+// a host check per iteration (cuda.py:318-361) -- runs inside the kernel.  A tile group (128 threads) owns EIGHT ray
+// slots, one per half-warp; per pass
+//   refill   : a free slot takes the next ray of the frame (one atomicAdd: arrival order, like the reference's kernel)
+//   march    : the half-warp marches up to 16 samples of its ray (march::march_chunk<16>, the code of the drop-in op);
+//              sample w lands in lane w through a shared-memory staging row
+//   NeRF     : the group's 8 x 16 rows go through the gather and the five tcgen05 layers (tile_forward: the code of
+//              the forward op); thread = sample, density / colour stay in registers
+//   integrate: the half-warp composites its 16 samples in order (integrating.cu:278-314: same expressions, the
+//              transmittance chain replayed through shuffles, exact early stop), then terminates the ray (pixel out,
+//              slot free) or keeps (T, colour, t) in registers for the next pass.
+// No sample, no slot state and no counter leaves the SM between passes; four groups per CTA interleave, so one group's
+// dependent bitfield loads and compositing chain run under the others' gathers.  Rays must arrive pre-advanced through
+// the empty space in front of them (ngp_march_rays_skip_empty), as for the loop renderer.
+constexpr uint32_t kSlots = 8, kCap = 16;
+constexpr float kTThresholdFrame = 1e-4f;  // integrating.cu:12
+
+template <typename TT>
+__global__ void __launch_bounds__(kThreadsU, 1) nerf_render_frame_kernel(const __grid_constant__ NgpRenderFrameDescriptor d,
+                                                                         const float *__restrict__ rays_o,
+                                                                         const float *__restrict__ rays_d,
+                                                                         const float *__restrict__ t_starts,
+                                                                         const float *__restrict__ t_ends,
+                                                                         const uint8_t *__restrict__ bitfield,
+                                                                         const float *__restrict__ rays_bg,
+                                                                         const TT *__restrict__ table,
+                                                                         const float *__restrict__ weights,
+                                                                         uint32_t *__restrict__ next_ray,
+                                                                         float4 *__restrict__ rays_rgbd,
+                                                                         unsigned long long *__restrict__ counters) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *base = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *wsm = base;
+    __shared__ uint64_t bars[kGroups];
+    __shared__ uint32_t tmem_slot;
+    __shared__ hg::LevelMeta s_meta[16];
+    __shared__ float s_stage[kGroups][kSlots][kCap][5];   // x, y, z, ds, t of the samples a slot marched this pass
+    __shared__ uint32_t s_count[kGroups][kSlots], s_idle[kGroups][kSlots];
+    const uint32_t tid = threadIdx.x, group = tid / kGroupThreads, r = tid % kGroupThreads, gw = r >> 5;
+    const uint32_t slot = r >> 4, lane = r & 15u, shift = tid & 16u, mask = 0xFFFFu << shift;
+    uint8_t *PB = base + kWBytes + group * kGroupBytes, *PA = PB;
+
+    stage_weight(wsm + WB0, weights + G_W0, 32, 64, 64);
+    stage_weight(wsm + WB1, weights + G_W1, 64, 16, 32);
+    stage_weight(wsm + WB2, weights + G_W2, 32, 64, 64);
+    stage_weight(wsm + WB3, weights + G_W3, 64, 64, 64);
+    stage_weight(wsm + WB4, weights + G_W4, 64, 3, 32);
+    if (tid < 16) s_meta[tid] = hg::a1_level(d.grid, tid);
+    if (tid < kGroups) umma::mbar_init(&bars[tid], 1);
+    if (tid == 0) umma::fence_mbar_init();
+    if (tid < 32) umma::tmem_alloc(&tmem_slot, kTmemCols);
+    umma::fence_smem_to_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_d = tmem_slot + group * kTmemColsPerGroup, tmem_row = tmem_d + ((32u * gw) << 16);
+    const uint32_t pa = umma::smem_u32(PA), pb = umma::smem_u32(PB), wa = umma::smem_u32(wsm);
+    uint64_t *bar = &bars[group];
+
+    const NgpMarchingInferenceDescriptor &mp = d.march;
+    const march::Grid g = march::make_grid(mp.diagonal_n_steps, mp.K, mp.G, mp.bound, mp.stepsize_portion, bitfield);
+    const uint32_t N = mp.n_total_rays;
+    const float bound = d.grid.bound;
+    // slot state, uniform across the slot's 16 lanes
+    bool have_ray = false, exhausted = false, live = false;
+    uint32_t ray_idx = 0, phase = 0;
+    march::Ray ray = {};
+    float t_cur = 0.f, t_end = 0.f, T = 1.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned long long n_samples_total = 0, n_rays_done = 0;
+    float *stage = &s_stage[group][slot][0][0];
+
+    for (;;) {
+        // ---- refill (cuda.py:326-361's admission, one ray per free slot)
+        if (!have_ray && !exhausted) {
+            uint32_t next = 0;
+            if (lane == 0) next = atomicAdd(next_ray, 1u);
+            next = __shfl_sync(mask, next, 0, 16);
+            if (next >= N) {
+                exhausted = true;
+            } else {
+                ray_idx = next;
+                ray = march::load_ray(rays_o, rays_d, next);
+                t_cur = __ldg(t_starts + next);
+                t_end = __ldg(t_ends + next);
+                T = 1.f;
+                acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                have_ray = true;
+            }
         }
-        float dx = 0.f, dy = 0.f, dz = 1.f;
-        if (live) {
-            dx = __ldg(dirs + (size_t)dir_row * 3 + 0);
-            dy = __ldg(dirs + (size_t)dir_row * 3 + 1);
-            dz = __ldg(dirs + (size_t)dir_row * 3 + 2);
+        // ---- march up to kCap samples of this slot's ray.  marching.cu:317 is evaluated on EVERY pass (strict): a ray whose
+        // previous pass ended past t_end -- its far-plane sample was that pass's 16th -- must not meet the far-plane rule again
+        uint32_t n = 0;
+        live = have_ray && !(t_end < t_cur);
+        if (live)
+            n = march::march_chunk<16>(
+                g, ray, t_cur, t_end, kCap, lane, mask, shift,
+                [&](uint32_t w, const march::EvalPoint &s, float t) {
+                    stage[w * 5 + 0] = s.px;
+                    stage[w * 5 + 1] = s.py;
+                    stage[w * 5 + 2] = s.pz;
+                    stage[w * 5 + 3] = s.ds;
+                    stage[w * 5 + 4] = t;
+                },
+                [&](uint32_t w, float ds) { stage[w * 5 + 3] = ds; });
+        if (lane == 0) {
+            s_count[group][slot] = n;
+            s_idle[group][slot] = (!have_ray && exhausted) ? 1u : 0u;
         }
-        uint32_t v[32];
-        // ---- layer 0: enc[32] -> 64, ReLU
-        umma::fence_smem_to_async();
-        group_barrier(group);
-        if (r == 0) {
-            umma::fence_after_sync();
+        group_barrier(group);  // staging rows and counts of the whole group are visible
+        uint32_t n_group = 0, idle = 0;
 #pragma unroll
-            for (uint32_t ks = 0; ks < 4; ++ks)
-                umma::mma_tf32(tmem_d, umma::desc_k_major(pa, ks), umma::desc_mn_major(wa + WB0, ks, 32 * 128), kI64, ks > 0);
-            umma::commit(bar);
+        for (uint32_t k = 0; k < kSlots; ++k) {
+            n_group += s_count[group][k];
+            idle += s_idle[group][k];
         }
-        umma::mbar_wait(bar, phase);
-        phase ^= 1u;
-        umma::fence_after_sync();
+        if (idle == kSlots) break;  // group-uniform: every slot is free and the frame has no rays left
+        const bool row_live = lane < n;
+        float x[3] = {0.f, 0.f, 0.f}, ds = 0.f, z = 0.f;
+        if (row_live) {
+            x[0] = stage[lane * 5 + 0];
+            x[1] = stage[lane * 5 + 1];
+            x[2] = stage[lane * 5 + 2];
+            ds = stage[lane * 5 + 3];
+            z = stage[lane * 5 + 4];
+        }
+        // ---- NeRF on the group's rows (skipped, group-uniformly, when no slot marched a sample this pass)
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n_group) {
+            const float dir[3] = {ray.dx, ray.dy, ray.dz};
+            tile_forward<TT, false>(table, s_meta, bound, x, dir, row_live, nullptr, PA, PB, pa, pb, wa, tmem_d, tmem_row, bar, phase, group, r, o);
+        }
+        // ---- integrate this slot's samples in order (integrating.cu:278-314), all 16 lanes in lockstep
+        if (have_ray) {
+            const float alpha = row_live ? 1.f - __expf(-o.x * ds) : 0.f;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            umma::tmem_ld32(tmem_row + 32 * h, v);
-            umma::tmem_ld_wait();
-            relu_store32(PB, r, 32 * h, v);
+            for (uint32_t s = 0; s < kCap; ++s) {
+                const float a = __shfl_sync(mask, alpha, s, 16);
+                const float cr = __shfl_sync(mask, o.y, s, 16), cg = __shfl_sync(mask, o.z, s, 16), cb = __shfl_sync(mask, o.w, s, 16);
+                const float zz = __shfl_sync(mask, z, s, 16);
+                if (T > kTThresholdFrame && s < n) {
+                    const float w = T * a;
+                    acc.x += w * cr;
+                    acc.y += w * cg;
+                    acc.z += w * cb;
+                    acc.w += w * zz;
+                    T *= (1.f - a);
+                }
+            }
+            bool term;
+            float4 out;
+            if (T <= kTThresholdFrame) {  // integrating.cu:293-301
+                const float idenom = 1.f / (1.f - T);
+                term = true;
+                out = make_float4(acc.x * idenom, acc.y * idenom, acc.z * idenom, acc.w * idenom);
+            } else {  // integrating.cu:302-314
+                term = n < kCap;
+                out = acc;
+                if (term) {
+                    out.x = acc.x + T * __ldg(rays_bg + 3 * (size_t)ray_idx + 0);
+                    out.y = acc.y + T * __ldg(rays_bg + 3 * (size_t)ray_idx + 1);
+                    out.z = acc.z + T * __ldg(rays_bg + 3 * (size_t)ray_idx + 2);
+                }
+            }
+            n_samples_total += n;
+            if (term) {
+                if (lane == 0) rays_rgbd[ray_idx] = out;
+                ++n_rays_done;
+                have_ray = false;
+            }
         }
-        // ---- layer 1: 64 -> 16 (padded to 32), no activation; density = exp(x[0]); hin = [x | SH4(dir)]
-        umma::fence_before_sync();
-        umma::fence_smem_to_async();
-        group_barrier(group);
-        if (r == 0) {
-            umma::fence_after_sync();
-#pragma unroll
-            for (uint32_t ks = 0; ks < 8; ++ks)
-                umma::mma_tf32(tmem_d, umma::desc_k_major(pb + (ks >> 2) * kPA, ks & 3u), umma::desc_mn_major(wa + WB1, ks, 64 * 128), kI32, ks > 0);
-            umma::commit(bar);
-        }
-        umma::mbar_wait(bar, phase);
-        phase ^= 1u;
-        umma::fence_after_sync();
-        umma::tmem_ld32(tmem_row, v);
-        umma::tmem_ld_wait();
-        const float density = expf(__uint_as_float(v[0]));
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            store_chunk(PA, r, 4 * c, tf32r(__uint_as_float(v[4 * c])), tf32r(__uint_as_float(v[4 * c + 1])),
-                        tf32r(__uint_as_float(v[4 * c + 2])), tf32r(__uint_as_float(v[4 * c + 3])));
-        {
-            float s[16];
-            sh16(dx, dy, dz, s);
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                store_chunk(PA, r, 16 + 4 * c, tf32r(s[4 * c]), tf32r(s[4 * c + 1]), tf32r(s[4 * c + 2]), tf32r(s[4 * c + 3]));
-        }
-        // ---- layer 2: hin[32] -> 64, ReLU
-        umma::fence_before_sync();
-        umma::fence_smem_to_async();
-        group_barrier(group);
-        if (r == 0) {
-            umma::fence_after_sync();
-#pragma unroll
-            for (uint32_t ks = 0; ks < 4; ++ks)
-                umma::mma_tf32(tmem_d, umma::desc_k_major(pa, ks), umma::desc_mn_major(wa + WB2, ks, 32 * 128), kI64, ks > 0);
-            umma::commit(bar);
-        }
-        umma::mbar_wait(bar, phase);
-        phase ^= 1u;
-        umma::fence_after_sync();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            umma::tmem_ld32(tmem_row + 32 * h, v);
-            umma::tmem_ld_wait();
-            relu_store32(PB, r, 32 * h, v);
-        }
-        // ---- layer 3: 64 -> 64, ReLU (the MMA has been awaited, so its A panel can take the result)
-        umma::fence_before_sync();
-        umma::fence_smem_to_async();
-        group_barrier(group);
-        if (r == 0) {
-            umma::fence_after_sync();
-#pragma unroll
-            for (uint32_t ks = 0; ks < 8; ++ks)
-                umma::mma_tf32(tmem_d, umma::desc_k_major(pb + (ks >> 2) * kPA, ks & 3u), umma::desc_mn_major(wa + WB3, ks, 64 * 128), kI64, ks > 0);
-            umma::commit(bar);
-        }
-        umma::mbar_wait(bar, phase);
-        phase ^= 1u;
-        umma::fence_after_sync();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            umma::tmem_ld32(tmem_row + 32 * h, v);
-            umma::tmem_ld_wait();
-            relu_store32(PB, r, 32 * h, v);
-        }
-        // ---- layer 4: 64 -> 3 (padded to 32), sigmoid
-        umma::fence_before_sync();
-        umma::fence_smem_to_async();
-        group_barrier(group);
-        if (r == 0) {
-            umma::fence_after_sync();
-#pragma unroll
-            for (uint32_t ks = 0; ks < 8; ++ks)
-                umma::mma_tf32(tmem_d, umma::desc_k_major(pb + (ks >> 2) * kPA, ks & 3u), umma::desc_mn_major(wa + WB4, ks, 64 * 128), kI32, ks > 0);
-            umma::commit(bar);
-        }
-        umma::mbar_wait(bar, phase);
-        phase ^= 1u;
-        umma::fence_after_sync();
-        umma::tmem_ld32(tmem_row, v);
-        umma::tmem_ld_wait();
-        if (live) {
-            float4 o;
-            o.x = density;
-            o.y = 1.f / (1.f + expf(-__uint_as_float(v[0])));
-            o.z = 1.f / (1.f + expf(-__uint_as_float(v[1])));
-            o.w = 1.f / (1.f + expf(-__uint_as_float(v[2])));
-            reinterpret_cast<float4 *>(out)[row] = o;
-        }
-        umma::fence_before_sync();  // the next tile's first MMA overwrites the accumulator these loads read
+        group_barrier(group);  // everyone has read this pass's staging rows and counts before the next pass overwrites them
+    }
+    if (lane == 0) {
+        if (n_rays_done) atomicAdd(counters + 0, n_rays_done);
+        if (n_samples_total) atomicAdd(counters + 1, n_samples_total);
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -310,6 +504,55 @@ __global__ void __launch_bounds__(kThreadsU, 1) nerf_fused_forward_umma_kernel(c
 
 }  // namespace
 }  // namespace ngp
+
+extern "C" void ngp_render_frame(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *d = descriptor<NgpRenderFrameDescriptor>(opaque, opaque_len, "render_frame");
+    if (!d) return;
+    const NgpHashGridA1Descriptor &gd = d->grid;
+    BufferCursor b{buffers};
+    const float *rays_o = b.next<const float>();
+    const float *rays_d = b.next<const float>();
+    const float *t_starts = b.next<const float>();
+    const float *t_ends = b.next<const float>();
+    const uint8_t *bitfield = b.next<const uint8_t>();
+    const float *rays_bg = b.next<const float>();
+    const void *table = b.next<const void>();
+    const float *weights = b.next<const float>();
+    uint32_t *next_ray = b.next<uint32_t>();
+    unsigned long long *counters = b.next<unsigned long long>();
+    float4 *rays_rgbd = b.next<float4>();
+    const size_t pair_bytes = gd.table_dtype == 0 ? 16 : 8;
+    if (gd.dim != 3 || gd.L != 16 || gd.F != 2 || gd.table_dtype > 1 || gd.wrap_T == 0 || (gd.wrap_T & (gd.wrap_T - 1u)) != 0 ||
+        reinterpret_cast<uintptr_t>(table) % pair_bytes != 0 || gd.offsets[gd.L] % 2 != 0 || gd.rows_per_group != 0) {
+        set_error(NGP_ERR_ARGUMENT, "render_frame: needs dim=3 L=16 F=2, power-of-two wrap_T and a table of an even number of rows aligned to "
+                  "two rows (got dim=%u L=%u F=%u wrap_T=%u)", gd.dim, gd.L, gd.F, gd.wrap_T);
+        return;
+    }
+    if (d->march.K == 0 || d->march.G == 0 || d->march.G > 1024 || d->march.march_steps_cap != kCap) {
+        set_error(NGP_ERR_ARGUMENT, "render_frame: expected K > 0, 0 < G <= 1024 and march_steps_cap = %u, got K=%u G=%u cap=%u", kCap,
+                  d->march.K, d->march.G, d->march.march_steps_cap);
+        return;
+    }
+    NGP_CUDA_OK(cudaMemsetAsync(next_ray, 0, sizeof(uint32_t), stream), "render_frame");
+    NGP_CUDA_OK(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), stream), "render_frame");
+    if (d->march.n_total_rays == 0) return;
+    const unsigned blocks = min(div_up(d->march.n_total_rays, kGroups * kSlots), 148u);  // persistent: one CTA per SM
+#define NGP_FRAME(TT)                                                                                                  \
+    do {                                                                                                               \
+        static bool configured = false; /* benign race: idempotent */                                                  \
+        if (!configured) {                                                                                             \
+            cudaFuncSetAttribute(nerf_render_frame_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdUmmaSmem); \
+            configured = true;                                                                                         \
+        }                                                                                                              \
+        nerf_render_frame_kernel<TT><<<blocks, kThreadsU, kFwdUmmaSmem, stream>>>(                                      \
+            *d, rays_o, rays_d, t_starts, t_ends, bitfield, rays_bg, static_cast<const TT *>(table), weights, next_ray, rays_rgbd, counters); \
+    } while (0)
+    if (gd.table_dtype == 0) NGP_FRAME(float); else NGP_FRAME(__half);
+#undef NGP_FRAME
+    check_launch("render_frame");
+}
 
 extern "C" void ngp_nerf_fused_forward_umma(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
     using namespace ngp;

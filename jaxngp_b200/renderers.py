@@ -112,7 +112,8 @@ class InferenceRenderer:
     bit-identical to ``render_image_inference``."""
 
     def __init__(self, nerf, cam, occupancy_bitfield, *, bg=(1.0, 1.0, 1.0), diagonal_n_steps=1024, K=1, G=128,
-                 bound=1.0, stepsize_portion=0.0, march_steps_cap=16, n_rays=262144, pixel_indices=None, skip_empty=True):
+                 bound=1.0, stepsize_portion=0.0, march_steps_cap=16, n_rays=262144, pixel_indices=None, skip_empty=True,
+                 persistent=None):
         from . import _lib, descriptors
         self.nerf, self.cam, self.bits = nerf, cam, occupancy_bitfield
         dev = occupancy_bitfield.device
@@ -145,6 +146,20 @@ class InferenceRenderer:
         self._graph = None
         self._host_counters = self._host_events = None
         self._max_passes = 2 * _max_loop_passes(N, n, diagonal_n_steps, bound, self.cap)
+        # The whole slot-refill loop as ONE persistent kernel (csrc/mlp_fwd_umma.cu nerf_render_frame_kernel, SURVEY 8
+        # f4): default wherever it applies -- the fused tcgen05 encoder + MLP geometry, 16 samples per slot and pass.
+        from . import encoders, nerf as nerf_mod
+        enc_mod = getattr(nerf, "position_encoder", None)
+        can = (enc_mod is not None and self.cap == 16 and getattr(nerf, "fused", False) and getattr(nerf, "grouped_impl", "umma") == "umma"
+               and nerf_mod.fused_supported(enc_mod.levels, enc_mod.latents, enc_mod.wrap))
+        self.persistent = can if persistent is None else bool(persistent)
+        if self.persistent and not can:
+            raise ValueError("the persistent frame kernel needs the fused hash-grid + MLP geometry (dim 3, L 16, F 2, power-of-two T), "
+                             "march_steps_cap = 16 and grouped_impl = 'umma'")
+        if self.persistent:
+            self._frame_desc = lambda: (encoders._a1_descriptor(enc_mod.levels, 0, bound, enc_mod.wrap, enc_mod.latents.dtype)
+                                        + self._march_desc)
+            self._next_ray = torch.zeros(1, dtype=i32, device=dev)
 
     def _iteration(self):
         """One pass of the slot-refill loop (cuda.py:180-241): three custom calls, no torch glue -- the scatters back
@@ -182,6 +197,13 @@ class InferenceRenderer:
         if self.skip_empty:  # walk every ray to its first occupied point once, thread per ray (same samples, bit for bit)
             _lib.call("ngp_march_rays_skip_empty", [self.o, self.d, self.t_starts, self.t_ends, self.bits, self.t_starts],
                       self._march_desc)
+        if self.persistent:  # one launch: refill, march, encoder + MLP and compositing never leave the SM
+            enc_mod = self.nerf.position_encoder
+            _lib.call("ngp_render_frame",
+                      [self.o, self.d, self.t_starts, self.t_ends, self.bits, self.rays_bg, enc_mod.latents.detach(),
+                       self.nerf.mlp_flat.detach(), self._next_ray, self.counters, self.rays_rgbd], self._frame_desc())
+            rgb = (self.rays_rgbd[: self.N, :3].clamp(0, 1) * 255 + 0.5).to(torch.uint8)
+            return rgb, self.rays_rgbd[: self.N, 3]
         self.rays_rgbd.zero_()
         self.rays_T.fill_(1.0)
         self.terminated.fill_(True)

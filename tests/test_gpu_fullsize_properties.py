@@ -135,9 +135,26 @@ def test_frame_c3_fast_renderer_equals_reference_loop():
     assert float((ref_rgb.float().mean())) < 250  # the object is visible (not an all-background frame)
     # default: dense layers on tcgen05 (f32 accumulation order differs): at most one grey level on a few pixels
     tr.nerf.grouped_impl = "umma"
-    R2 = renderers.InferenceRenderer(tr.nerf, scene.cam, tr.occupancy)
+    R2 = renderers.InferenceRenderer(tr.nerf, scene.cam, tr.occupancy, persistent=False)
     rgb2, depth2 = R2.render_rays(o, d, ts, te)
     assert int(R2.counters[0]) == 640000
     diff = (rgb2.reshape(ref_rgb.shape).int() - ref_rgb.int()).abs()
     assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 1e-2, (int(diff.max()), float((diff > 0).float().mean()))
     assert torch.allclose(depth2.reshape(ref_depth.shape), ref_depth, atol=1e-3)
+    # the whole loop as ONE persistent kernel (the default renderer): same march code, same encoder + MLP code, same
+    # compositing expressions as the tcgen05 loop above -- every ray once, the same samples, the same image
+    R3 = renderers.InferenceRenderer(tr.nerf, scene.cam, tr.occupancy)
+    assert R3.persistent
+    for _ in range(2):  # second frame: counters and the ray ticket start over
+        rgb3, depth3 = R3.render_rays(o, d, ts, te)
+        assert int(R3.counters[0]) == 640000
+        assert int(R3.counters[1]) == int(R2.counters[1])  # same samples marched: same termination decisions
+        assert torch.equal(rgb3, rgb2)
+        assert torch.allclose(depth3, depth2, atol=1e-6)
+    # rays it owns only (tile sharding): a strided subset renders the same pixels
+    pix = torch.arange(0, 640000, 7, device=DEV, dtype=torch.int32)
+    R4 = renderers.InferenceRenderer(tr.nerf, scene.cam, tr.occupancy, pixel_indices=pix)
+    rgb4, _ = R4.render(pose)
+    R5 = renderers.InferenceRenderer(tr.nerf, scene.cam, tr.occupancy, pixel_indices=pix, persistent=False)
+    rgb5, _ = R5.render(pose)
+    assert torch.equal(rgb4, rgb5) and int(R4.counters[0]) == pix.numel()

@@ -413,3 +413,28 @@ def test_mlp_backward_all_tcgen05_matches_the_other_arms(n):
     torch.backends.cuda.matmul.allow_tf32 = True
     assert torch.linalg.norm(g_enc_a - g_enc_ref) <= 3e-2 * torch.linalg.norm(g_enc_ref) + 1e-6
     assert (g_w_a - g_w_ref).abs().max() <= 1e-2 * g_w_ref.abs().max() + 1e-6
+
+
+def test_persistent_frame_kernel_matches_the_loop_renderer(small_scene):
+    """ngp_render_frame (the slot-refill loop inside one persistent kernel) against the graph-replayed loop on small
+    frames: random high-frequency field, frames with fewer rays than one CTA's slots, empty frames, a ray budget that is
+    not a multiple of the slot count."""
+    from jaxngp_b200 import nerf as nerf_mod, renderers
+    gen = torch.Generator(device=DEV).manual_seed(19)
+    model = nerf_mod.NeRF(bound=1.0, device=DEV, generator=gen)
+    with torch.no_grad():
+        model.position_encoder.latents.uniform_(-1.0, 1.0, generator=gen)
+    cam, bits = small_scene.cam, small_scene.bitfield_gt
+    n_pix = cam["width"] * cam["height"]
+    for pixels in (None, torch.arange(0, n_pix, 3, device=DEV, dtype=torch.int32), torch.arange(5, device=DEV, dtype=torch.int32)):
+        loop = renderers.InferenceRenderer(model, cam, bits, pixel_indices=pixels, persistent=False)
+        one = renderers.InferenceRenderer(model, cam, bits, pixel_indices=pixels)
+        assert one.persistent and not loop.persistent
+        for view in (1, 2):
+            a, da = loop.render(small_scene.transforms[view])
+            b, db = one.render(small_scene.transforms[view])
+            assert int(one.counters[0]) == one.N and int(one.counters[1]) == int(loop.counters[1])
+            assert torch.equal(a, b) and torch.allclose(da, db, atol=1e-6)
+    empty = renderers.InferenceRenderer(model, cam, torch.zeros_like(bits))  # nothing occupied: every pixel is background
+    rgb, _ = empty.render(small_scene.transforms[0])
+    assert int(empty.counters[0]) == empty.N and int(empty.counters[1]) == 0 and bool((rgb == 255).all())
