@@ -173,6 +173,8 @@ typedef struct {
 void ngp_hashgrid_a1_forward(cudaStream_t, void **, const char *, size_t);
 /* in : pos f32[n,dim], d_enc f32[n,L*F]                 out: d_table f32[rows,F] (zero-filled, then scatter-added) */
 void ngp_hashgrid_a1_backward(cudaStream_t, void **, const char *, size_t);
+/* same, without the zero-fill: scatter-ADDS into d_table (a batch processed in chunks) */
+void ngp_hashgrid_a1_backward_acc(cudaStream_t, void **, const char *, size_t);
 
 /* packbits with a scalar threshold read from device memory (drops the broadcast array the
  * reference materialises, packbits/__init__.py:25-28).
@@ -233,6 +235,8 @@ typedef struct {
 } NgpNerfMlpDescriptor;
 void ngp_nerf_mlp_forward(cudaStream_t, void **, const char *, size_t);
 void ngp_nerf_mlp_backward(cudaStream_t, void **, const char *, size_t);
+/* Same contract, but d_weights is ADDED to instead of defined (a batch processed in chunks: first chunk = the op above). */
+void ngp_nerf_mlp_backward_acc(cudaStream_t, void **, const char *, size_t);
 /* Same contract, weight gradients on mma.sync instead of tcgen05/TMEM (the cross-check arm of the tests). */
 void ngp_nerf_mlp_backward_mma(cudaStream_t, void **, const char *, size_t);
 /* Same contract, EVERY matrix product on tcgen05 (csrc/mlp_bwd_tc.cu): forward recompute and delta chain with the A

@@ -565,7 +565,18 @@ void ngp_hashgrid_a1_forward(cudaStream_t stream, void **buffers, const char *op
     check_launch("hashgrid_a1_forward");
 }
 
+static void launch_hashgrid_a1_backward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len, bool accumulate);
+
 void ngp_hashgrid_a1_backward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    launch_hashgrid_a1_backward(stream, buffers, opaque, opaque_len, false);
+}
+
+// same, ADDING to d_table instead of zero-filling it first (a batch processed in chunks)
+void ngp_hashgrid_a1_backward_acc(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    launch_hashgrid_a1_backward(stream, buffers, opaque, opaque_len, true);
+}
+
+static void launch_hashgrid_a1_backward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len, bool accumulate) {
     using namespace ngp;
     clear_error();
     auto *d = descriptor<NgpHashGridA1Descriptor>(opaque, opaque_len, "hashgrid_a1_backward");
@@ -574,8 +585,16 @@ void ngp_hashgrid_a1_backward(cudaStream_t stream, void **buffers, const char *o
     const float *pos = b.next<const float>();
     const float *d_enc = b.next<const float>();
     float *d_table = b.next<float>();
-    NGP_CUDA_OK(cudaMemsetAsync(d_table, 0, (size_t)d->offsets[d->L] * d->F * sizeof(float), stream),
-                "hashgrid_a1_backward");
+    if (!accumulate)
+        NGP_CUDA_OK(cudaMemsetAsync(d_table, 0, (size_t)d->offsets[d->L] * d->F * sizeof(float), stream), "hashgrid_a1_backward");
+    {   // the scatter runs beside kernels that fill the SM's shared memory (the chunked backward of trainer.py pairs it
+        // with the 225 KB MLP backward): an SM hosts CTAs of one carve-out at a time, so ask for the same one
+        static bool configured = false;  // benign race: idempotent
+        if (!configured) {
+            cudaFuncSetAttribute(hashgrid_a1_backward_kernel<3, 2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            configured = true;
+        }
+    }
     if (d->n_points == 0) return;
     // one CTA per 256 points; all levels in one pass, or level-major passes when the gradient table exceeds L2
     unsigned lpg = levels_per_pass(d, d->F * sizeof(float), "NGP_B200_HG_BWD_LPG");

@@ -888,7 +888,7 @@ void ngp_nerf_mlp_forward(cudaStream_t stream, void **buffers, const char *opaqu
     check_launch("nerf_mlp_forward");
 }
 
-void ngp_nerf_mlp_backward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+static void launch_nerf_mlp_backward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len, bool accumulate) {
     using namespace ngp;
     clear_error();
     auto *d = descriptor<NgpNerfMlpDescriptor>(opaque, opaque_len, "nerf_mlp_backward");
@@ -900,7 +900,7 @@ void ngp_nerf_mlp_backward(cudaStream_t stream, void **buffers, const char *opaq
     const float *d_drgbs = b.next<const float>();
     float *d_enc = b.next<float>();
     float *d_weights = b.next<float>();
-    NGP_CUDA_OK(cudaMemsetAsync(d_weights, 0, kGlobalWeights * sizeof(float), stream), "nerf_mlp_backward");
+    if (!accumulate) NGP_CUDA_OK(cudaMemsetAsync(d_weights, 0, kGlobalWeights * sizeof(float), stream), "nerf_mlp_backward");
     if (d->n_samples == 0) return;
     static bool configured = false;
     if (!configured) {
@@ -910,6 +910,15 @@ void ngp_nerf_mlp_backward(cudaStream_t stream, void **buffers, const char *opaq
     const unsigned blocks = min(div_up(d->n_samples, kBlockSamples), 148u);
     nerf_mlp_backward_umma_kernel<<<blocks, kThreads, kBwdUmmaSmem, stream>>>(d->n_samples, enc, dirs, weights, d_drgbs, d_enc, d_weights);
     check_launch("nerf_mlp_backward");
+}
+
+void ngp_nerf_mlp_backward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    launch_nerf_mlp_backward(stream, buffers, opaque, opaque_len, false);
+}
+
+// same, ADDING to d_weights instead of defining it (a batch processed in chunks: the first chunk defines, the others add)
+void ngp_nerf_mlp_backward_acc(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    launch_nerf_mlp_backward(stream, buffers, opaque, opaque_len, true);
 }
 
 void ngp_nerf_mlp_backward_mma(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {

@@ -87,12 +87,13 @@ def hashgrid_forward(lt: LevelTable, pos: torch.Tensor, bound: float, table: tor
 
 
 def hashgrid_backward(lt: LevelTable, pos: torch.Tensor, bound: float, d_enc: torch.Tensor, wrap: str = "jaxngp",
-                      out: torch.Tensor = None):
+                      out: torch.Tensor = None, accumulate: bool = False):
     """d_table[rows, F] = scatter-add of w_c * d_enc (the autodiff of the gather at encoders.py:226-231)."""
     n = pos.shape[0]
     if out is None:
         out = torch.empty(lt.rows, lt.F, dtype=torch.float32, device=pos.device)
-    _lib.call("ngp_hashgrid_a1_backward", [pos, d_enc, out], _a1_descriptor(lt, n, bound, wrap, torch.float32))
+    _lib.call("ngp_hashgrid_a1_backward_acc" if accumulate else "ngp_hashgrid_a1_backward", [pos, d_enc, out],
+              _a1_descriptor(lt, n, bound, wrap, torch.float32))
     return out
 
 

@@ -120,17 +120,22 @@ BACKWARD_IMPLS = {"tc": "ngp_nerf_mlp_backward_tc", "umma": "ngp_nerf_mlp_backwa
 DEFAULT_BACKWARD_IMPL = "umma"
 
 
-def mlp_backward(enc, dirs, weights, d_drgbs, d_weights=None, impl=None):
+def mlp_backward(enc, dirs, weights, d_drgbs, d_weights=None, impl=None, d_enc=None, accumulate=False):
     """Fused backward: returns (d_enc [n, 32], d_weights [9408]); recomputes the forward on chip.
     ``impl``: "tc" = every matrix product on tcgen05, chain operands in tensor memory (csrc/mlp_bwd_tc.cu);
     "umma" = mma.sync register chain + weight gradients on tcgen05; "mma" = all mma.sync (cross-check arm)."""
     impl = impl or DEFAULT_BACKWARD_IMPL
     n = enc.shape[0]
-    d_enc = torch.empty(n, 32, dtype=torch.float32, device=enc.device)
+    if d_enc is None:
+        d_enc = torch.empty(n, 32, dtype=torch.float32, device=enc.device)
     if d_weights is None:
         d_weights = torch.empty(MLP_NUMEL, dtype=torch.float32, device=enc.device)
-    _lib.call(BACKWARD_IMPLS[impl], [enc, dirs, weights, d_drgbs, d_enc, d_weights],
-              descriptors.make_nerf_mlp_descriptor(n))
+    op = BACKWARD_IMPLS[impl]
+    if accumulate:  # d_weights += ... (a batch processed in chunks; the hybrid kernel only)
+        if impl != "umma":
+            raise ValueError("accumulate=True is implemented for impl='umma'")
+        op = "ngp_nerf_mlp_backward_acc"
+    _lib.call(op, [enc, dirs, weights, d_drgbs, d_enc, d_weights], descriptors.make_nerf_mlp_descriptor(n))
     return d_enc, d_weights
 
 

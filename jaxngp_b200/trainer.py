@@ -103,6 +103,16 @@ class Trainer:
         self.fused_glue = fused_mlp if fused_glue is None else fused_glue
         self.prefetch_march_ctas_per_sm = 1
         self.fused_loss = True  # ngp_integrate_loss_fused instead of integrate_rays / huber_loss_grad / integrate_rays_backward
+        # The backward as a two-stream software pipeline over `bwd_chunks` slices of the sample array: the MLP backward of
+        # slice c+1 (latency-bound: one 225 KB CTA per SM, a quarter of the issue slots) runs while the table scatter of
+        # slice c (bound by the L2's reduction rate, 1 KB of shared memory per CTA) fills the same SMs beside it.
+        # Measured on C2 (ms per step): 1 slice 0.562, 2 slices 0.533, 4 slices 0.552, 8 slices 0.658 -- each slice re-stages
+        # the MLP kernel (weights, tensor memory, 9,408 atomics per CTA to flush), and beside the MLP's registers an SM
+        # holds two scatter CTAs instead of five, so only part of the scatter hides; uneven splits measured worse.
+        self.bwd_chunks = int(os.environ.get("NGP_B200_BWD_CHUNKS", "2"))
+        # optional explicit split in "waves" of 148 x 128 samples (one block per SM of the MLP kernel), e.g. "9,5"
+        self.bwd_waves = [int(w) for w in os.environ.get("NGP_B200_BWD_WAVES", "").split(",") if w]
+        self._bwd_side = None
         self._flatten_parameters()
         self.fused_encoder = (fused_mlp and nerf_mod.fused_supported(self.levels, self.table)) if fused_encoder is None else fused_encoder
         self.scene = scene if scene is not None else Scene(self.device)
@@ -230,11 +240,46 @@ class Trainer:
             d_final, loss, n_valid = trainops.huber_loss_grad(final_rgbds, ray_is_valid, perm, sc.rgbas_u8, bg)
             _, _, d_drgbs = _integrate_bwd(synthetic.NEAR, rays_start, rays_n, bg, dss, z_vals, drgbs, final_rgbds,
                                            final_opac, d_final)
-        d_enc, _ = nerf_mod.mlp_backward(enc, dirs, self.mlp_flat, d_drgbs, d_weights=self.mlp_grad)
-        encoders.hashgrid_backward(self.levels, xyzs, synthetic.BOUND, d_enc, out=self.table_grad)
+        self._backward(enc, dirs, xyzs, d_drgbs)
         used = trainops.u32_axpy(nxt, exc, 1, -1, 0)  # next - exceeded, marching/__init__.py:91
         return dict(loss=loss[0], n_valid_rays=n_valid[0], measured_batch_size_before_compaction=used[0],
                     measured_batch_size=effective[0])
+
+    def _backward(self, enc, dirs, xyzs, d_drgbs):
+        """MLP backward + hash-table scatter into the flat gradient buffer, as one pass or as the pipeline of ``bwd_chunks``
+        slices described in ``__init__`` (per-sample work: any split of the sample array gives the same sums, to atomic order)."""
+        n, chunks = xyzs.shape[0], self.bwd_chunks
+        if not self.fused_mlp or chunks <= 1 or n < 128 * 148 * chunks:
+            d_enc, _ = nerf_mod.mlp_backward(enc, dirs, self.mlp_flat, d_drgbs, d_weights=self.mlp_grad)
+            encoders.hashgrid_backward(self.levels, xyzs, synthetic.BOUND, d_enc, out=self.table_grad)
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._bwd_side is None:
+            self._bwd_side = torch.cuda.Stream(device=self.device)
+        side = self._bwd_side
+        d_enc = torch.empty(n, 32, dtype=torch.float32, device=self.device)
+        if self.bwd_waves:  # explicit split in waves of 148 x 128 samples (one block per SM of the persistent MLP kernel)
+            sizes = [w * 128 * 148 for w in self.bwd_waves]
+        else:  # equal slices of whole 128-sample blocks
+            sizes = [-(-n // chunks // 128) * 128] * chunks
+        bounds, lo = [], 0
+        for sz in sizes:
+            if lo >= n:
+                break
+            bounds.append((lo, min(lo + sz, n)))
+            lo += sz
+        if lo < n:
+            bounds[-1] = (bounds[-1][0], n)
+        side.wait_stream(main)  # joins a stream capture in progress; orders the scatter behind whatever wrote table_grad last
+        for c, (lo, hi) in enumerate(bounds):
+            nerf_mod.mlp_backward(enc[lo:hi], dirs[lo:hi], self.mlp_flat, d_drgbs[lo:hi], d_weights=self.mlp_grad, d_enc=d_enc[lo:hi],
+                                  accumulate=c > 0)
+            done = torch.cuda.Event()
+            done.record(main)
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                encoders.hashgrid_backward(self.levels, xyzs[lo:hi], synthetic.BOUND, d_enc[lo:hi], out=self.table_grad, accumulate=c > 0)
+        main.wait_stream(side)
 
     def _step_body(self, perm, noises=None, bg=None, apply=True):
         if not self.fused_glue:

@@ -438,3 +438,32 @@ def test_persistent_frame_kernel_matches_the_loop_renderer(small_scene):
     empty = renderers.InferenceRenderer(model, cam, torch.zeros_like(bits))  # nothing occupied: every pixel is background
     rgb, _ = empty.render(small_scene.transforms[0])
     assert int(empty.counters[0]) == empty.N and int(empty.counters[1]) == 0 and bool((rgb == 255).all())
+
+
+def test_chunked_two_stream_backward_equals_single_pass(small_scene):
+    """Trainer._backward as a pipeline of 4 sample slices on two streams (MLP backward of slice c+1 beside the table scatter
+    of slice c, accumulating entry points) against the single pass: the same gradient sums, to atomic order."""
+    from jaxngp_b200 import nerf as nerf_mod, synthetic
+    from jaxngp_b200.trainer import Trainer
+    n_rays, total = 1 << 15, 1 << 18
+    tr = Trainer(device=DEV, n_rays=n_rays, total_samples=total, scene=small_scene, use_graph=False)
+    tr.grid.occupancy.copy_(small_scene.bitfield_gt)
+    tr.table.uniform_(-0.5, 0.5, generator=torch.Generator(device=DEV).manual_seed(3))
+    gen = torch.Generator(device=DEV).manual_seed(8)
+    perm = torch.randint(0, small_scene.n_pixels, (n_rays,), device=DEV, generator=gen, dtype=torch.int32)
+    _, _, _, _, _, _, xyzs, dirs, _, _, _ = tr._march_body(perm)
+    drgbs, enc = nerf_mod.fused_forward(tr.levels, xyzs, synthetic.BOUND, tr.table, dirs, tr.mlp_flat, want_enc=True)
+    d_drgbs = torch.randn(total, 4, device=DEV, generator=gen)
+    grads = {}
+    for chunks in (1, 4, 3):
+        tr.bwd_chunks = chunks
+        tr.flat_grads.fill_(7.0)  # must be overwritten, not added to
+        tr._backward(enc, dirs, xyzs, d_drgbs)
+        torch.cuda.synchronize()
+        grads[chunks] = tr.flat_grads.clone()
+    ref = grads[1]
+    assert float(ref[: tr.table_numel].abs().max()) > 0 and float(ref[tr.table_numel:tr.n_params].abs().max()) > 0
+    for chunks in (4, 3):
+        g = grads[chunks]
+        assert (g[: tr.table_numel] - ref[: tr.table_numel]).abs().max() <= 1e-4 * ref[: tr.table_numel].abs().max()
+        assert (g[tr.table_numel:tr.n_params] - ref[tr.table_numel:tr.n_params]).abs().max() <= 1e-4 * ref[tr.table_numel:tr.n_params].abs().max()
