@@ -235,6 +235,12 @@ typedef struct {
 } NgpNerfMlpDescriptor;
 void ngp_nerf_mlp_forward(cudaStream_t, void **, const char *, size_t);
 void ngp_nerf_mlp_backward(cudaStream_t, void **, const char *, size_t);
+/* MLP backward with the hash-table scatter of ngp_hashgrid_a1_backward fused behind it: the input gradient d_enc never
+ * leaves the SM (each thread scatters the fragment it holds).  descriptor: NgpHashGridA1Descriptor (n_points = samples;
+ * dim 3, L 16, F 2, power-of-two wrap_T).
+ * in : enc f32[n,32], dirs f32[n,3], weights f32[9408], d_drgbs f32[n,4], pos f32[n,3]
+ * out: d_weights f32[9408], d_table f32[rows,2] (zero-filled, then scatter-added) */
+void ngp_nerf_mlp_backward_scatter(cudaStream_t, void **, const char *, size_t);
 /* Same contract, but d_weights is ADDED to instead of defined (a batch processed in chunks: first chunk = the op above). */
 void ngp_nerf_mlp_backward_acc(cudaStream_t, void **, const char *, size_t);
 /* Same contract, weight gradients on mma.sync instead of tcgen05/TMEM (the cross-check arm of the tests). */

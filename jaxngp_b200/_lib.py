@@ -22,7 +22,7 @@ OPS = (
     "ngp_morton3d", "ngp_morton3d_invert", "ngp_integrate_rays", "ngp_integrate_rays_backward",
     "ngp_integrate_rays_inference", "ngp_hashgrid_encode", "ngp_hashgrid_encode_backward",
     "ngp_hashgrid_a1_forward", "ngp_hashgrid_a1_backward", "ngp_adam_step", "ngp_adam_step_exchange", "ngp_ogrid_sample_positions", "ngp_ogrid_decay_max", "ngp_ogrid_threshold", "ngp_nerf_mlp_forward", "ngp_nerf_mlp_backward", "ngp_nerf_mlp_backward_mma", "ngp_nerf_mlp_backward_tc", "ngp_nerf_fused_forward", "ngp_nerf_fused_forward_umma", "ngp_umma_selftest", "ngp_make_training_rays", "ngp_huber_loss_grad", "ngp_integrate_loss_fused",
-    "ngp_make_training_rays_rng", "ngp_philox_uniform", "ngp_ogrid_draw_cells", "ngp_u32_axpy", "ngp_render_frame", "ngp_nerf_mlp_backward_acc", "ngp_hashgrid_a1_backward_acc",
+    "ngp_make_training_rays_rng", "ngp_philox_uniform", "ngp_ogrid_draw_cells", "ngp_u32_axpy", "ngp_render_frame", "ngp_nerf_mlp_backward_acc", "ngp_hashgrid_a1_backward_acc", "ngp_nerf_mlp_backward_scatter",
 )
 #: the reference's ten registered targets (volume-rendering-jax lib/ffi.cc:25-51, jax-tcnn lib/ffi.cc:25-30)
 DROP_IN_TARGETS = ("pack_density_into_bits", "march_rays", "march_rays_inference", "morton3d", "morton3d_invert",

@@ -659,12 +659,56 @@ __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t a_addr, ui
                        accumulate || ks > 0);
 }
 
+// One (sample, level) of the hash-table scatter, from the MLP backward's own registers: the gradient pair (g0, g1) of
+// sample position p01 at level m goes to the 2^3 corner rows with the trilinear weights (hashgrid_a1_backward_kernel's
+// arithmetic; x-neighbour rows that are adjacent in memory share one 16-byte reduction).
+__device__ __forceinline__ void scatter_sample_level(float *__restrict__ d_table, const hg::LevelMeta &m, const float (&p01)[3],
+                                                     float g0, float g1) {
+    if (g0 == 0.f && g1 == 0.f) return;  // padded / masked samples carry exact zeros
+    uint32_t base[3];
+    float fr[3];
+    hg::a1_cell<3>(p01, m.scale, base, fr);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {  // corner c: x bit clear; its partner c + 4: x bit set
+        uint32_t va[3], vb[3];
+        float w = 1.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t bit = (c >> (2 - k)) & 1;
+            va[k] = base[k] + bit;
+            vb[k] = va[k];
+            if (k > 0) w *= bit ? fr[k] : 1.f - fr[k];
+        }
+        vb[0] = base[0] + 1u;
+        const float wa = w * (1.f - fr[0]), wb = w * fr[0];
+        uint32_t ra = hg::grid_row_unclamped<3, true>(va, m), rb = hg::grid_row_unclamped<3, true>(vb, m);
+        float a0 = wa * g0, a1 = wa * g1, b0 = wb * g0, b1 = wb * g1;
+        if (ra > m.last_row) { ra = m.last_row; a0 = a1 = 0.f; }  // XLA drops the update of an out-of-range row (hg::grid_row)
+        if (rb > m.last_row) { rb = m.last_row; b0 = b1 = 0.f; }
+        if ((ra ^ rb) == 1u) {
+            const bool a_hi = ra & 1u;
+            red_add_v4(d_table + (size_t)(ra & ~1u) * 2, a_hi ? b0 : a0, a_hi ? b1 : a1, a_hi ? a0 : b0, a_hi ? a1 : b1);
+        } else {
+            red_add_v2(d_table + (size_t)ra * 2, a0, a1);
+            red_add_v2(d_table + (size_t)rb * 2, b0, b1);
+        }
+    }
+}
+
+// kScatter: the input gradient never leaves the SM -- each thread scatters its fragment of d_enc (rows g, g + 8 of the
+// warp's 16 samples, levels t, t + 4, t + 8, t + 12) straight into the hash-table gradient (ngp_nerf_mlp_backward_scatter).
+template <bool kScatter>
 __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_umma_kernel(uint32_t n, const float *__restrict__ enc,
                                                                              const float *__restrict__ dirs,
                                                                              const float *__restrict__ weights,
                                                                              const float *__restrict__ d_drgbs,
                                                                              float *__restrict__ d_enc,
-                                                                             float *__restrict__ d_weights) {
+                                                                             float *__restrict__ d_weights,
+                                                                             const __grid_constant__ NgpHashGridA1Descriptor gd,
+                                                                             const float *__restrict__ pos,
+                                                                             float *__restrict__ d_table) {
+    __shared__ hg::LevelMeta s_meta[kScatter ? 16 : 1];
+    if (kScatter && threadIdx.x < 16) s_meta[threadIdx.x] = hg::a1_level(gd, threadIdx.x);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // aligned by an offset from the array (not through an integer round trip) so that the compiler keeps the
     // shared address space and emits LDS/STS rather than generic loads and stores
@@ -795,14 +839,31 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_umma_kernel(uin
             umma::commit(&bar_w0);
         }
         if (blk + gridDim.x < n_blocks) fetch(blk + gridDim.x);
-        // d_enc = d_a0 . W0^T -> global
+        // d_enc = d_a0 . W0^T -> global, or straight into the table gradient
         {
             float de[4][4];
             layer_backward<8, 4, S_W0>(a_d, sw + O_W0, de, g, t);
+            if (!kScatter) {
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                if (r_lo < n) *reinterpret_cast<float2 *>(d_enc + (size_t)r_lo * 32 + 8 * nt + 2 * t) = make_float2(de[nt][0], de[nt][1]);
-                if (r_hi < n) *reinterpret_cast<float2 *>(d_enc + (size_t)r_hi * 32 + 8 * nt + 2 * t) = make_float2(de[nt][2], de[nt][3]);
+                for (int nt = 0; nt < 4; ++nt) {
+                    if (r_lo < n) *reinterpret_cast<float2 *>(d_enc + (size_t)r_lo * 32 + 8 * nt + 2 * t) = make_float2(de[nt][0], de[nt][1]);
+                    if (r_hi < n) *reinterpret_cast<float2 *>(d_enc + (size_t)r_hi * 32 + 8 * nt + 2 * t) = make_float2(de[nt][2], de[nt][3]);
+                }
+            } else {
+                float xl[3] = {0.f, 0.f, 0.f}, xh[3] = {0.f, 0.f, 0.f}, pl[3], ph[3];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (r_lo < n) xl[k] = __ldg(pos + (size_t)r_lo * 3 + k);
+                    if (r_hi < n) xh[k] = __ldg(pos + (size_t)r_hi * 3 + k);
+                }
+                hg::unit_pos<3>(xl, gd.bound, pl);
+                hg::unit_pos<3>(xh, gd.bound, ph);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const hg::LevelMeta m = s_meta[4 * nt + t];  // column 8 nt + 2 t is feature 0 of level 4 nt + t
+                    if (r_lo < n) scatter_sample_level(d_table, m, pl, de[nt][0], de[nt][1]);
+                    if (r_hi < n) scatter_sample_level(d_table, m, ph, de[nt][2], de[nt][3]);
+                }
             }
         }
     }
@@ -904,12 +965,48 @@ static void launch_nerf_mlp_backward(cudaStream_t stream, void **buffers, const 
     if (d->n_samples == 0) return;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(nerf_mlp_backward_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdUmmaSmem);
+        cudaFuncSetAttribute(nerf_mlp_backward_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdUmmaSmem);
         configured = true;
     }
     const unsigned blocks = min(div_up(d->n_samples, kBlockSamples), 148u);
-    nerf_mlp_backward_umma_kernel<<<blocks, kThreads, kBwdUmmaSmem, stream>>>(d->n_samples, enc, dirs, weights, d_drgbs, d_enc, d_weights);
+    nerf_mlp_backward_umma_kernel<false><<<blocks, kThreads, kBwdUmmaSmem, stream>>>(d->n_samples, enc, dirs, weights, d_drgbs, d_enc, d_weights,
+                                                                                     NgpHashGridA1Descriptor{}, nullptr, nullptr);
     check_launch("nerf_mlp_backward");
+}
+
+// MLP backward with the hash-table scatter fused behind it: d_enc is never written, each thread scatters its fragment
+// (d_table is zero-filled here first, like ngp_hashgrid_a1_backward does).
+void ngp_nerf_mlp_backward_scatter(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {
+    using namespace ngp;
+    clear_error();
+    auto *gd = descriptor<NgpHashGridA1Descriptor>(opaque, opaque_len, "nerf_mlp_backward_scatter");
+    if (!gd) return;
+    BufferCursor b{buffers};
+    const float *enc = b.next<const float>();
+    const float *dirs = b.next<const float>();
+    const float *weights = b.next<const float>();
+    const float *d_drgbs = b.next<const float>();
+    const float *pos = b.next<const float>();
+    float *d_weights = b.next<float>();
+    float *d_table = b.next<float>();
+    if (gd->dim != 3 || gd->L != 16 || gd->F != 2 || gd->wrap_T == 0 || (gd->wrap_T & (gd->wrap_T - 1u)) != 0 ||
+        reinterpret_cast<uintptr_t>(d_table) % 16 != 0 || gd->offsets[gd->L] % 2 != 0 || gd->rows_per_group != 0) {
+        set_error(NGP_ERR_ARGUMENT, "nerf_mlp_backward_scatter: needs dim=3 L=16 F=2, power-of-two wrap_T and a 16-byte aligned gradient table "
+                  "of an even number of rows (got dim=%u L=%u F=%u wrap_T=%u); use nerf_mlp_backward + hashgrid_a1_backward", gd->dim, gd->L, gd->F, gd->wrap_T);
+        return;
+    }
+    NGP_CUDA_OK(cudaMemsetAsync(d_weights, 0, kGlobalWeights * sizeof(float), stream), "nerf_mlp_backward_scatter");
+    NGP_CUDA_OK(cudaMemsetAsync(d_table, 0, (size_t)gd->offsets[gd->L] * gd->F * sizeof(float), stream), "nerf_mlp_backward_scatter");
+    if (gd->n_points == 0) return;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(nerf_mlp_backward_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdUmmaSmem);
+        configured = true;
+    }
+    const unsigned blocks = min(div_up(gd->n_points, kBlockSamples), 148u);
+    nerf_mlp_backward_umma_kernel<true><<<blocks, kThreads, kBwdUmmaSmem, stream>>>(gd->n_points, enc, dirs, weights, d_drgbs, nullptr, d_weights, *gd, pos,
+                                                                                    d_table);
+    check_launch("nerf_mlp_backward_scatter");
 }
 
 void ngp_nerf_mlp_backward(cudaStream_t stream, void **buffers, const char *opaque, size_t opaque_len) {

@@ -21,6 +21,9 @@ def allreduce_flat_gradients(flat_grads: torch.Tensor, group=None) -> torch.Tens
 
 def shard_bounds(n_padded: int, rank: int, world_size: int):
     """[begin, end) of the flat parameter buffer owned by `rank` (n_padded is a multiple of 4 * world_size)."""
+    if n_padded % (4 * world_size) != 0:
+        raise ValueError(f"flat buffer length {n_padded} is not a multiple of 4 * world_size = {4 * world_size}: shards would be "
+                         "unaligned or leave a tail nobody owns (Trainer pads to lcm(32, 4 * world_size))")
     per = n_padded // world_size
     return rank * per, (rank + 1) * per
 

@@ -139,6 +139,16 @@ def mlp_backward(enc, dirs, weights, d_drgbs, d_weights=None, impl=None, d_enc=N
     return d_enc, d_weights
 
 
+def mlp_backward_scatter(lt, pos, bound: float, enc, dirs, weights, d_drgbs, d_weights, d_table, wrap: str = "jaxngp"):
+    """MLP backward with the hash-table scatter fused behind it (``ngp_nerf_mlp_backward_scatter``): the same sums as
+    ``mlp_backward`` followed by ``encoders.hashgrid_backward``, without d_enc ever leaving the SM.  Writes ``d_weights``
+    [9408] and ``d_table`` [rows, 2] (both defined by the call)."""
+    n = enc.shape[0]
+    _lib.call("ngp_nerf_mlp_backward_scatter", [enc, dirs, weights, d_drgbs, pos, d_weights, d_table],
+              encoders._a1_descriptor(lt, n, bound, wrap, torch.float32))
+    return d_weights, d_table
+
+
 class _FusedMLP(torch.autograd.Function):
     @staticmethod
     def forward(ctx, enc, dirs, weights):

@@ -109,6 +109,7 @@ class Trainer:
         # Measured on C2 (ms per step): 1 slice 0.562, 2 slices 0.533, 4 slices 0.552, 8 slices 0.658 -- each slice re-stages
         # the MLP kernel (weights, tensor memory, 9,408 atomics per CTA to flush), and beside the MLP's registers an SM
         # holds two scatter CTAs instead of five, so only part of the scatter hides; uneven splits measured worse.
+        self.bwd_fused_scatter = os.environ.get("NGP_B200_BWD_FUSED_SCATTER", "0") == "1"  # scatter from the MLP backward's registers
         self.bwd_chunks = int(os.environ.get("NGP_B200_BWD_CHUNKS", "2"))
         # optional explicit split in "waves" of 148 x 128 samples (one block per SM of the MLP kernel), e.g. "9,5"
         self.bwd_waves = [int(w) for w in os.environ.get("NGP_B200_BWD_WAVES", "").split(",") if w]
@@ -249,6 +250,9 @@ class Trainer:
         """MLP backward + hash-table scatter into the flat gradient buffer, as one pass or as the pipeline of ``bwd_chunks``
         slices described in ``__init__`` (per-sample work: any split of the sample array gives the same sums, to atomic order)."""
         n, chunks = xyzs.shape[0], self.bwd_chunks
+        if self.fused_mlp and self.bwd_fused_scatter and self.fused_encoder:
+            nerf_mod.mlp_backward_scatter(self.levels, xyzs, synthetic.BOUND, enc, dirs, self.mlp_flat, d_drgbs, self.mlp_grad, self.table_grad)
+            return
         if not self.fused_mlp or chunks <= 1 or n < 128 * 148 * chunks:
             d_enc, _ = nerf_mod.mlp_backward(enc, dirs, self.mlp_flat, d_drgbs, d_weights=self.mlp_grad)
             encoders.hashgrid_backward(self.levels, xyzs, synthetic.BOUND, d_enc, out=self.table_grad)

@@ -467,3 +467,31 @@ def test_chunked_two_stream_backward_equals_single_pass(small_scene):
         g = grads[chunks]
         assert (g[: tr.table_numel] - ref[: tr.table_numel]).abs().max() <= 1e-4 * ref[: tr.table_numel].abs().max()
         assert (g[tr.table_numel:tr.n_params] - ref[tr.table_numel:tr.n_params]).abs().max() <= 1e-4 * ref[tr.table_numel:tr.n_params].abs().max()
+
+
+def test_mlp_backward_with_fused_table_scatter_equals_the_two_ops():
+    """ngp_nerf_mlp_backward_scatter (the table scatter issued from the MLP backward's own d_enc fragments) against
+    nerf_mlp_backward + hashgrid_a1_backward: the same weight gradients (same kernel code) and the same table sums to
+    atomic order; cube-face points exercise the spill rows, a partial last block the row guards."""
+    from jaxngp_b200 import encoders as E, nerf as nerf_mod
+    gen = torch.Generator(device=DEV).manual_seed(23)
+    lt = E.make_level_table(16, 2 ** 19, 2, 16, 2048, 3)
+    w = (torch.rand(nerf_mod.MLP_NUMEL, device=DEV, generator=gen) - 0.5) * 0.6
+    table = (torch.rand(lt.rows, 2, device=DEV, generator=gen) - 0.5) * 2
+    for n in (77, 128 * 148 * 2 + 5):
+        pos = torch.rand(n, 3, device=DEV, generator=gen) * 2 - 1
+        pos[:32] = torch.tensor([1.0, -1.0, 0.999999], device=DEV)
+        dirs = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV, generator=gen), dim=-1)
+        enc = E.hashgrid_forward(lt, pos, 1.0, table)
+        d_out = torch.randn(n, 4, device=DEV, generator=gen)
+        d_out[n // 2: n // 2 + 10] = 0  # masked samples: exact zeros, nothing scattered
+        d_enc, d_w_ref = nerf_mod.mlp_backward(enc, dirs, w, d_out)
+        d_t_ref = E.hashgrid_backward(lt, pos, 1.0, d_enc)
+        d_w = torch.full((nerf_mod.MLP_NUMEL,), 3.0, device=DEV)
+        guard = torch.full((lt.rows + 1024, 2), 5.0, device=DEV)
+        d_t = guard[: lt.rows]
+        nerf_mod.mlp_backward_scatter(lt, pos, 1.0, enc, dirs, w, d_out, d_w, d_t)
+        torch.cuda.synchronize()
+        assert bool((guard[lt.rows:] == 5.0).all())
+        assert (d_w - d_w_ref).abs().max() <= 2e-4 * d_w_ref.abs().max()
+        assert (d_t - d_t_ref).abs().max() <= 1e-4 * d_t_ref.abs().max(), n
