@@ -30,7 +30,10 @@ constexpr int kMaxWorld = 8;
 constexpr int kThreads = 256;  // x 128 registers = half an SM: the next batch's march (or a second CTA) fits beside it.  (512 threads
                                // per CTA: the per-peer-load flavour alone drops from 0.156 to 0.108 ms at N = 2, but the march prefetched under
                                // the exchange no longer fits on the SM and the training step goes from 0.586 to 0.662 ms.)
-constexpr int kUnroll = 8;  // 8 x 16 B of remote requests per thread in flight: 4 MB per GPU against ~3 us of switch latency
+// 16-byte remote requests per thread in flight.  Per-peer loads want 8 (0.240 -> 0.156 ms at N = 2); the switch-reduced
+// flavour is no faster for it (0.158 / 0.157 ms) and the extra registers cost the overlapped march its place on the SM
+// (training step 0.572 -> 0.586 ms at N = 2), so it keeps 4.
+constexpr int kUnrollMultimem = 4, kUnrollPeer = 8;
 
 __device__ __forceinline__ uint32_t cas_release_sys(uint32_t *addr, uint32_t expect, uint32_t desired) {
     uint32_t old;
@@ -121,8 +124,10 @@ __global__ void __launch_bounds__(kThreads, 2) adam_exchange_kernel(
     float4 *m4 = reinterpret_cast<float4 *>(m), *v4 = reinterpret_cast<float4 *>(v);
     const size_t n4 = d.adam.n / 4;
     const size_t stride = (size_t)gridDim.x * kThreads;
+    constexpr int kUnroll = kMultimem ? kUnrollMultimem : kUnrollPeer;
+    constexpr int kLocal = 4;  // local state per pass
     for (size_t base = (size_t)blockIdx.x * kThreads + threadIdx.x; base < n4; base += stride * kUnroll) {
-        float4 g[kUnroll], p[kUnroll / 2], mm[kUnroll / 2], vv[kUnroll / 2];
+        float4 g[kUnroll], p[kLocal], mm[kLocal], vv[kLocal];
         // (2) all the remote requests of this round first: kUnroll x 16 B per thread in flight over the link
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
@@ -139,11 +144,11 @@ __global__ void __launch_bounds__(kThreads, 2) adam_exchange_kernel(
                 }
             }
         }
-        // local state and update in two halves: the registers of one half are free before the other half's loads
+        // local state and update kLocal at a time: the registers of one pass are free before the next pass's loads
 #pragma unroll
-        for (int h = 0; h < kUnroll; h += kUnroll / 2) {
+        for (int h = 0; h < kUnroll; h += kLocal) {
 #pragma unroll
-            for (int u = h; u < h + kUnroll / 2; ++u) {
+            for (int u = h; u < h + kLocal; ++u) {
                 const size_t i = base + u * stride;
                 if (i < n4) {
                     p[u - h] = p_own[i];
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 2) adam_exchange_kernel(
                 }
             }
 #pragma unroll
-            for (int u = h; u < h + kUnroll / 2; ++u) {
+            for (int u = h; u < h + kLocal; ++u) {
                 const size_t i = base + u * stride;
                 if (i < n4) {
                     const float wd = (i * 4 >= d.adam.decay_begin) ? d.adam.weight_decay : 0.f;
