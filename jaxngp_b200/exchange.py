@@ -35,8 +35,12 @@ def requested_mode(default="auto"):
     return mode
 
 
-def blocks_for(pad_bytes: int, world: int, want: int = 128) -> int:
-    """CTAs per launch: each needs ``world`` signal words above SIGNAL_BASE; at most one per SM (they spin on peers)."""
+def blocks_for(pad_bytes: int, world: int, want: int = 64) -> int:
+    """CTAs per launch: each needs ``world`` signal words above SIGNAL_BASE; at most one per SM (they spin on peers).
+
+    64 by default: the kernel is bound by requests in flight over the link, not by SMs, and the SMs it leaves alone run the
+    next batch's march beside it.  Training step on C2, ms, by CTA count: N = 8: 32 0.576, 64 0.578, 96 0.584, 128 0.596,
+    148 0.599; N = 2: 64 0.567, 128 0.571 (profiles/exchange_knobs_r02.txt)."""
     room = (pad_bytes // 4 - SIGNAL_BASE) // world
     if room < 1:
         raise _lib.NgpError(f"signal pad of {pad_bytes} bytes has no room above word {SIGNAL_BASE} for {world} ranks")

@@ -110,7 +110,10 @@ class Trainer:
         # the MLP kernel (weights, tensor memory, 9,408 atomics per CTA to flush), and beside the MLP's registers an SM
         # holds two scatter CTAs instead of five, so only part of the scatter hides; uneven splits measured worse.
         self.bwd_fused_scatter = os.environ.get("NGP_B200_BWD_FUSED_SCATTER", "0") == "1"  # scatter from the MLP backward's registers
-        self.bwd_chunks = int(os.environ.get("NGP_B200_BWD_CHUNKS", "2"))
+        # At more than one rank the step ends in the exchange kernel, under which the next batch's march already runs; the
+        # side stream then costs more than it hides (C2, ms per step, 1 slice / 2 slices: N = 2 0.564 / 0.571, N = 8 0.580 /
+        # 0.596), so the pipeline is the single-rank default only.
+        self.bwd_chunks = int(os.environ.get("NGP_B200_BWD_CHUNKS", "2" if world_size == 1 else "1"))
         # optional explicit split in "waves" of 148 x 128 samples (one block per SM of the MLP kernel), e.g. "9,5"
         self.bwd_waves = [int(w) for w in os.environ.get("NGP_B200_BWD_WAVES", "").split(",") if w]
         self._bwd_side = None

@@ -172,7 +172,7 @@ def test_adam_exchange_descriptor_and_argument_checks(monkeypatch, built_lib):
     monkeypatch.setenv("NGP_B200_EXCHANGE", "gloo")
     with pytest.raises(ValueError):
         X.requested_mode()
-    assert X.blocks_for(9216, 8) == 128 and X.blocks_for(9216, 2) == 128 and X.blocks_for(4096 + 4 * 8 * 5, 8) == 5
+    assert X.blocks_for(9216, 8) == 64 and X.blocks_for(9216, 2) == 64 and X.blocks_for(9216, 2, want=148) == 148 and X.blocks_for(4096 + 4 * 8 * 5, 8) == 5
     with pytest.raises(_lib.NgpError):
         X.blocks_for(4096, 8)
     with pytest.raises(_lib.NgpError):  # no process group on this host: the peer exchange refuses, nothing falls back
