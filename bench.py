@@ -351,7 +351,8 @@ def dominant_kernel_roofline(tr, perm, flush):
     P = tr.shard_hi - tr.shard_lo  # this rank's optimizer shard (all parameters on one GPU)
     # the step runs the backward as a pipeline of `bwd_chunks` slices (trainer._backward): the two backward kernels are
     # timed on the launch the step makes -- the first slice -- so that `achieved`, the ncu launch list and `traffic` agree
-    nb = -(-n // tr.bwd_chunks // 128) * 128 if (tr.bwd_chunks > 1 and n >= 128 * 148 * tr.bwd_chunks) else n
+    fused_bwd = bool(tr.fused_mlp and tr.bwd_fused_scatter and tr.fused_encoder)  # trainer._backward's first branch
+    nb = -(-n // tr.bwd_chunks // 128) * 128 if (not fused_bwd and tr.bwd_chunks > 1 and n >= 128 * 148 * tr.bwd_chunks) else n
     kernels = (
         # name, launch, algorithmic bytes per launch, note
         ("march_rays", march, N_RAYS * 45 + used * 36 + (synthetic.K * synthetic.G ** 3) // 8, "36 B/ray in, 9 B/ray + 36 B/sample out, bitfield"),
@@ -364,9 +365,15 @@ def dominant_kernel_roofline(tr, perm, flush):
          lambda: trainops.integrate_loss_fused(synthetic.NEAR, rs, rn, bg, dss, zs, drgbs, valid, perm, sc.rgbas_u8),
          used * 44 + N_RAYS * 70 + n * 16, "44 B/sample + 70 B/ray + zero-fill 16 B/slot"),
         ("nerf_mlp_backward", lambda: nerf_mod.mlp_backward(enc[:nb], dirs[:nb], tr.mlp_flat, d_drgbs[:nb]), nb * (128 + 12 + 16 + 128),
-         f"284 B/sample; 56 kFLOP/sample; one launch = {nb} sample slots (the step makes {-(-n // nb)} such launches)"),
+         f"284 B/sample; 56 kFLOP/sample; one launch = {nb} sample slots "
+         + ("(stand-alone op: the step runs the fused kernel below instead)" if fused_bwd else f"(the step makes {-(-n // nb)} such launches)")),
         ("hashgrid_a1_backward", lambda: encoders.hashgrid_backward(tr.levels, xyzs[:nb], 1.0, d_enc[:nb], out=tr.table_grad), nb * 1164 + tr.table_numel * 4,
          f"1164 B/point + table zero-fill; one launch = {nb} points (first of {-(-n // nb)} slices)"),
+        ("nerf_mlp_backward_scatter (replaces the two above in the step)" if fused_bwd else "nerf_mlp_backward_scatter",
+         lambda: nerf_mod.mlp_backward_scatter(tr.levels, xyzs, 1.0, enc, dirs, tr.mlp_flat, d_drgbs, tr.mlp_grad, tr.table_grad),
+         n * (128 + 12 + 16 + 12 + 1024) + tr.table_numel * 4,
+         "1192 B/sample (enc, dir, cotangent, position, 128 gradient rows of 8 B) + table zero-fill; 56 kFLOP/sample: MLP backward with "
+         "the table scatter issued from its d_enc fragments"),
         ("adam_step", lambda: _lib.call("ngp_adam_step", [tr.step_dev, tr.flat_params[tr.shard_lo:tr.shard_hi], tr.flat_grads[tr.shard_lo:tr.shard_hi], tr.adam_m, tr.adam_v], tr.adam_desc), P * 28, "28 B/param"),
     )
     res = {}
@@ -379,10 +386,14 @@ def dominant_kernel_roofline(tr, perm, flush):
                      "frac_of_hbm": round(nbytes / (t_ms * 1e-3) / 1e9 / hbm, 3), "per_unit": note}
     res["nerf_fused_forward"]["achieved_tflops"] = round(n * 18816 / (res["nerf_fused_forward"]["ms"] * 1e-3) / 1e12, 2)
     res["nerf_mlp_backward"]["achieved_tflops"] = round(nb * 56448 / (res["nerf_mlp_backward"]["ms"] * 1e-3) / 1e12, 2)
-    per_step = -(-n // nb)  # launches per step of the two sliced backward kernels; every other kernel runs once
+    fused_key = [k for k in res if k.startswith("nerf_mlp_backward_scatter")][0]
+    res[fused_key]["achieved_tflops"] = round(n * 56448 / (res[fused_key]["ms"] * 1e-3) / 1e12, 2)
+    per_step = 0 if fused_bwd else -(-n // nb)  # launches per step of the two separate backward kernels; every other kernel runs once
     for name in ("nerf_mlp_backward", "hashgrid_a1_backward"):
         res[name]["launches_per_step"] = per_step
         res[name]["ms_per_step"] = round(res[name]["ms"] * per_step, 4)
+    res[fused_key]["launches_per_step"] = 1 if fused_bwd else 0
+    res[fused_key]["ms_per_step"] = res[fused_key]["ms"] if fused_bwd else 0.0
     candidates = [k for k in res if k not in ("integrate_rays", "huber_loss_grad", "integrate_rays_backward")]  # replaced by the fused kernel in the step
     top = max(candidates, key=lambda k: res[k].get("ms_per_step", res[k]["ms"]))  # dominant = most time per step
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel: an ncu counter, so it cannot be taken
@@ -407,7 +418,7 @@ def dominant_kernel_roofline(tr, perm, flush):
         return {"bound": "tensor", "achieved": res[top]["achieved_tflops"], "peak": tpeak, "unit": "TFLOP/s",
                 "frac": round(res[top]["achieved_tflops"] / tpeak, 4), "peak_source": tsrc,
                 "flops_per_unit": "56,448 FLOP per sample slot (forward recompute 18,816 + input gradients + weight gradients), "
-                                  f"x {nb} slots per launch", **common}
+                                  f"x {n if top == fused_key else nb} slots per launch", **common}
     return {"bound": "hbm", "achieved": res[top]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
             "frac": res[top]["frac_of_hbm"], "peak_source": src, **common}
 

@@ -152,14 +152,32 @@ __device__ __forceinline__ void sh4_lane(float x, float y, float z, uint32_t t, 
     o[3] = t == 0 ? s9 : t == 1 ? s11 : t == 2 ? s13 : s15;
 }
 
+// Stage the 9,408 weights as tf32 bits in the padded shared layout.  Every thread issues ALL of its (up to 37) loads before
+// the first conversion: as five loops of load -> convert -> store this prologue was 38 dependent trips to L2 (~14 us, 9 % of
+// the backward kernel's stall samples).  The matrices start at multiples of kThreads floats, so for a given k every thread
+// is in the same matrix and the address arithmetic below resolves at compile time.
 __device__ __forceinline__ void load_weights(uint32_t *__restrict__ sw, const float *__restrict__ w) {
-    for (int i = threadIdx.x; i < 32 * 64; i += kThreads) sw[O_W0 + (i / 64) * S_W0 + i % 64] = tf32(__ldg(w + G_W0 + i));
-    for (int i = threadIdx.x; i < 64 * 16; i += kThreads) sw[O_W1 + (i / 16) * S_W1 + i % 16] = tf32(__ldg(w + G_W1 + i));
-    for (int i = threadIdx.x; i < 32 * 64; i += kThreads) sw[O_W2 + (i / 64) * S_W2 + i % 64] = tf32(__ldg(w + G_W2 + i));
-    for (int i = threadIdx.x; i < 64 * 64; i += kThreads) sw[O_W3 + (i / 64) * S_W3 + i % 64] = tf32(__ldg(w + G_W3 + i));
-    for (int i = threadIdx.x; i < 64 * 8; i += kThreads) {  // W4 padded from 3 to 8 output columns with zeros
-        const int r = i / 8, c = i % 8;
-        sw[O_W4 + r * S_W4 + c] = c < 3 ? tf32(__ldg(w + G_W4 + r * 3 + c)) : 0u;
+    static_assert(G_W1 % kThreads == 0 && G_W2 % kThreads == 0 && G_W3 % kThreads == 0 && G_W4 % kThreads == 0, "matrix boundaries");
+    constexpr int kPer = (kGlobalWeights + kThreads - 1) / kThreads;  // 37
+    const int tid = threadIdx.x;
+    if (tid >= kThreads) return;  // a kernel with extra (non-chain) warps: they do not take part
+    float v[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int i = tid + k * kThreads;
+        v[k] = i < kGlobalWeights ? __ldg(w + i) : 0.f;
+    }
+    // W4 is padded from 3 to 8 output columns with zeros
+    for (int j = tid; j < 64 * 5; j += kThreads) sw[O_W4 + (j / 5) * S_W4 + 3 + j % 5] = 0u;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int i = tid + k * kThreads;
+        const uint32_t x = tf32(v[k]);
+        if (k * kThreads < G_W1) sw[O_W0 + (i / 64) * S_W0 + i % 64] = x;
+        else if (k * kThreads < G_W2) sw[O_W1 + ((i - G_W1) / 16) * S_W1 + (i - G_W1) % 16] = x;
+        else if (k * kThreads < G_W3) sw[O_W2 + ((i - G_W2) / 64) * S_W2 + (i - G_W2) % 64] = x;
+        else if (k * kThreads < G_W4) sw[O_W3 + ((i - G_W3) / 64) * S_W3 + (i - G_W3) % 64] = x;
+        else if (i < kGlobalWeights) sw[O_W4 + ((i - G_W4) / 3) * S_W4 + (i - G_W4) % 3] = x;
     }
 }
 
@@ -190,7 +208,8 @@ __device__ __forceinline__ void warp_forward_from(const uint32_t *__restrict__ s
                                                   uint32_t row0, uint32_t n, const uint32_t (&a_in)[4][4],
                                                   const float *__restrict__ dirs, uint32_t g, uint32_t t, FwdState &st,
                                                   uint32_t (&a_h2)[8][4], float (&out_rgb)[1][4],
-                                                  uint32_t rows_per_group = 0, bool ok_lo_in = true, bool ok_hi_in = true) {
+                                                  uint32_t rows_per_group = 0, bool ok_lo_in = true, bool ok_hi_in = true,
+                                                  const float *__restrict__ pre_dirs = nullptr) {
     const uint32_t r_lo = row0 + g, r_hi = row0 + g + 8;
     const bool ok_lo = r_lo < n && ok_lo_in, ok_hi = r_hi < n && ok_hi_in;
     // grouped layout: one direction per group of rows (ray), else one per row
@@ -227,10 +246,13 @@ __device__ __forceinline__ void warp_forward_from(const uint32_t *__restrict__ s
     // direction encoding: SH degree 4 into columns 16..31 of hin
     {
         float sh_lo[4], sh_hi[4];
-        const float dx0 = ok_lo ? __ldg(dirs + (size_t)d_lo * 3 + 0) : 0.f, dy0 = ok_lo ? __ldg(dirs + (size_t)d_lo * 3 + 1) : 0.f,
-                    dz0 = ok_lo ? __ldg(dirs + (size_t)d_lo * 3 + 2) : 1.f;
-        const float dx1 = ok_hi ? __ldg(dirs + (size_t)d_hi * 3 + 0) : 0.f, dy1 = ok_hi ? __ldg(dirs + (size_t)d_hi * 3 + 1) : 0.f,
-                    dz1 = ok_hi ? __ldg(dirs + (size_t)d_hi * 3 + 2) : 1.f;
+        // pre_dirs: the six values below, already in registers (the backward kernel fetches them a block ahead)
+        const float dx0 = pre_dirs ? pre_dirs[0] : ok_lo ? __ldg(dirs + (size_t)d_lo * 3 + 0) : 0.f,
+                    dy0 = pre_dirs ? pre_dirs[1] : ok_lo ? __ldg(dirs + (size_t)d_lo * 3 + 1) : 0.f,
+                    dz0 = pre_dirs ? pre_dirs[2] : ok_lo ? __ldg(dirs + (size_t)d_lo * 3 + 2) : 1.f;
+        const float dx1 = pre_dirs ? pre_dirs[3] : ok_hi ? __ldg(dirs + (size_t)d_hi * 3 + 0) : 0.f,
+                    dy1 = pre_dirs ? pre_dirs[4] : ok_hi ? __ldg(dirs + (size_t)d_hi * 3 + 1) : 0.f,
+                    dz1 = pre_dirs ? pre_dirs[5] : ok_hi ? __ldg(dirs + (size_t)d_hi * 3 + 2) : 1.f;
         sh4_lane(dx0, dy0, dz0, t, sh_lo);
         sh4_lane(dx1, dy1, dz1, t, sh_hi);
         a_hin[2][0] = tf32(sh_lo[0]); a_hin[2][1] = tf32(sh_hi[0]); a_hin[2][2] = tf32(sh_lo[1]); a_hin[2][3] = tf32(sh_hi[1]);
@@ -697,8 +719,21 @@ __device__ __forceinline__ void scatter_sample_level(float *__restrict__ d_table
 
 // kScatter: the input gradient never leaves the SM -- each thread scatters its fragment of d_enc (rows g, g + 8 of the
 // warp's 16 samples, levels t, t + 4, t + 8, t + 12) straight into the hash-table gradient (ngp_nerf_mlp_backward_scatter).
+//
+// kBwdIssuerWarp: a ninth warp issues every weight-gradient MMA.  The chain warps never wait for each other -- each reads
+// and writes only its own 16 rows of the panels -- so what used to be five block-wide barriers per block (so that thread 0
+// could issue once every row was written) become non-blocking `bar.arrive`s on five named barriers the issuing warp
+// `bar.sync`s on in turn; warp 0 no longer carries the 80 MMA issues (and their descriptor arithmetic) of every block
+// with seven warps waiting for it at the next barrier.  A chain warp cannot lap the issuer: its next block starts with a
+// wait on bar_w0, which the issuer commits after the fifth barrier of this block.
+#ifndef NGP_BWD_ISSUER_WARP
+#define NGP_BWD_ISSUER_WARP 1
+#endif
+constexpr bool kBwdIssuerWarp = NGP_BWD_ISSUER_WARP != 0;
+constexpr int kBwdThreads = kThreads + (kBwdIssuerWarp ? 32 : 0);
+
 template <bool kScatter>
-__global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_umma_kernel(uint32_t n, const float *__restrict__ enc,
+__global__ void __launch_bounds__(kBwdThreads, 1) nerf_mlp_backward_umma_kernel(uint32_t n, const float *__restrict__ enc,
                                                                              const float *__restrict__ dirs,
                                                                              const float *__restrict__ weights,
                                                                              const float *__restrict__ d_drgbs,
@@ -719,7 +754,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_umma_kernel(uin
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, g = lane >> 2, t = lane & 3u;
 
     load_weights(sw, weights);
-    for (uint32_t i = tid; i < kPanel / 16; i += kThreads) reinterpret_cast<uint4 *>(panels + PB_S)[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = tid; i < kPanel / 16; i += kBwdThreads) reinterpret_cast<uint4 *>(panels + PB_S)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         umma::mbar_init(&bar_w4, 1);
         umma::mbar_init(&bar_w3, 1);
@@ -737,17 +772,75 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_umma_kernel(uin
 
     const uint32_t n_blocks = (n + kBlockSamples - 1) / kBlockSamples;
     uint32_t it = 0;
-    // this block's global inputs are fetched one block ahead (under the previous block's last layer)
-    uint32_t a_in[4][4];
-    float4 dd_lo = make_float4(0.f, 0.f, 0.f, 0.f), dd_hi = dd_lo;
-    auto fetch = [&](uint32_t blk) {
-        const uint32_t r_lo = blk * kBlockSamples + warp * 16 + g, r_hi = r_lo + 8;
-        load_enc_fragments(enc, r_lo, r_hi, r_lo < n, r_hi < n, t, a_in);
-        dd_lo = r_lo < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
-        dd_hi = r_hi < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_hi) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // the five weight-gradient products of a block, in the order their operands become complete
+    auto issue = [&](int k, bool acc) {
+        if (k == 0) {
+            issue_wgrad(tmem + T_W4, pa + PB_H2, pa + PB_S, kI32, acc);  // dW4 = h2^T . d_a3
+            umma::commit(&bar_w4);
+        } else if (k == 1) {
+            issue_wgrad(tmem + T_W3, pa + PB_H1, pa + PB_DA, kI64, acc);  // dW3 = h1^T . d_a2
+            umma::commit(&bar_w3);
+        } else if (k == 2) {
+            issue_wgrad(tmem + T_W2, pa + PB_H2, pa + PB_HIN, kI32, acc);  // dW2^T = d_a1^T . hin
+        } else if (k == 3) {
+            issue_wgrad(tmem + T_W1, pa + PB_H0, pa + PB_S, kI32, acc);  // dW1 = h0^T . d_x
+        } else {
+            issue_wgrad(tmem + T_W0, pa + PB_DA, pa + PB_ENC, kI32, acc);  // dW0^T = d_a0^T . enc
+            umma::commit(&bar_w0);
+        }
     };
-    if (blockIdx.x < n_blocks) fetch(blockIdx.x);
+    // a chain thread's panel rows of step k are written: make them visible to the tensor core and tell the issuer
+    auto publish = [&](int k, bool acc) {
+        umma::fence_smem_to_async();
+        if (kBwdIssuerWarp) {
+            asm volatile("bar.arrive %0, %1;" ::"r"(1 + k), "n"(kBwdThreads) : "memory");
+        } else {
+            __syncthreads();
+            if (tid == 0) {
+                umma::fence_after_sync();
+                issue(k, acc);
+            }
+        }
+    };
+    if (kBwdIssuerWarp && warp == kWarps) {
+        // the whole warp walks the barriers (bar.sync is warp-wide); lane 0 alone issues
+        for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "n"(kBwdThreads) : "memory");
+                umma::fence_after_sync();
+                if (lane == 0) issue(k, it > 0);
+                __syncwarp();
+            }
+        }
+    } else {
+    // A block's global inputs (enc fragments, output cotangents, directions) are fetched a WHOLE block ahead, into a
+    // second register set: with two warps per scheduler nothing else hides a trip to L2 or HBM (the loads issued under
+    // the previous block's last layer only, and the directions loaded where they are used, were the kernel's largest
+    // stall: long scoreboard 2.6 of 9.9 warp-cycles per issue)
+    struct Inputs {
+        uint32_t a_in[4][4];
+        float4 dd_lo, dd_hi;
+        float dir[6];
+    };
+    Inputs cur, nxt;
+    auto fetch = [&](uint32_t blk, Inputs &x) {
+        const uint32_t r_lo = blk * kBlockSamples + warp * 16 + g, r_hi = r_lo + 8;
+        load_enc_fragments(enc, r_lo, r_hi, r_lo < n, r_hi < n, t, x.a_in);
+        x.dd_lo = r_lo < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x.dd_hi = r_hi < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_hi) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            x.dir[k] = r_lo < n ? __ldg(dirs + (size_t)r_lo * 3 + k) : (k == 2 ? 1.f : 0.f);
+            x.dir[3 + k] = r_hi < n ? __ldg(dirs + (size_t)r_hi * 3 + k) : (k == 2 ? 1.f : 0.f);
+        }
+    };
+    if (blockIdx.x < n_blocks) fetch(blockIdx.x, cur);
+    else fetch(n_blocks, cur);  // out of range: zeros, so that no register is read uninitialised
     for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+        if (blk + gridDim.x < n_blocks) fetch(blk + gridDim.x, nxt);
+        uint32_t (&a_in)[4][4] = cur.a_in;
+        const float4 dd_lo = cur.dd_lo, dd_hi = cur.dd_hi;
         const uint32_t par = it & 1u;
         const bool acc = it > 0;
         const uint32_t base = blk * kBlockSamples, row0 = base + warp * 16;
@@ -758,7 +851,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_umma_kernel(uin
         FwdState st;
         uint32_t a_tmp[8][4];
         float rgb[1][4];
-        warp_forward_from<2, false>(sw, act, warp, row0, n, a_in, dirs, g, t, st, a_tmp, rgb);
+        warp_forward_from<2, false>(sw, act, warp, row0, n, a_in, dirs, g, t, st, a_tmp, rgb, 0, true, true, cur.dir);
 
         // ---- layer 4 delta: d_a3 = d_rgb * rgb * (1 - rgb), cols (2t, 2t+1) of the padded 8
         float d3[1][4];
@@ -774,13 +867,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_umma_kernel(uin
             a3[1][0] = a3[1][1] = a3[1][2] = a3[1][3] = 0u;  // columns 8..15 held d_x of the previous block
         }
         store_frag_panel<2>(panels + PB_S, a3, 0, warp, g, t);
-        umma::fence_smem_to_async();
-        __syncthreads();  // panels of the whole block are visible to the tensor core
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_wgrad(tmem + T_W4, pa + PB_H2, pa + PB_S, kI32, acc);  // dW4 = h2^T . d_a3
-            umma::commit(&bar_w4);
-        }
+        publish(0, acc);  // enc, h0, hin, h1, h2, d_a3 -> dW4
         // d_a2 = (d_a3 . W4^T) masked by h2 > 0
         uint32_t a_d[8][4];
         float dacc[8][4];
@@ -791,24 +878,13 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_umma_kernel(uin
             relu_mask_to_a<8>(panels + PB_H2, warp, g, t, dacc, a_d);
         }
         store_frag_panel<8>(panels + PB_DA, a_d, 0, warp, g, t);
-        umma::fence_smem_to_async();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_wgrad(tmem + T_W3, pa + PB_H1, pa + PB_DA, kI64, acc);  // dW3 = h1^T . d_a2
-            umma::commit(&bar_w3);
-        }
+        publish(1, acc);  // d_a2 -> dW3
         // d_a1 = (d_a2 . W3^T) masked by h1 > 0 -> takes over the h2 panels
         layer_backward<8, 8, S_W3>(a_d, sw + O_W3, dacc, g, t);
         relu_mask_to_a<8>(panels + PB_H1, warp, g, t, dacc, a_d);
         umma::mbar_wait(&bar_w4, par);
         store_frag_panel<8>(panels + PB_H2, a_d, 0, warp, g, t);
-        umma::fence_smem_to_async();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_wgrad(tmem + T_W2, pa + PB_H2, pa + PB_HIN, kI32, acc);  // dW2^T = d_a1^T . hin
-        }
+        publish(2, acc);  // d_a1 -> dW2
         // d_x = (d_a1 . W2^T)[:, :16] + d_density * exp(clip(x0, -15, 15)) on column 0 (nerfs.py:231-234)
         float dx[2][4];
         uint32_t a_dx[2][4];
@@ -820,25 +896,13 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_umma_kernel(uin
         c_to_a(dx[0], a_dx[0]);
         c_to_a(dx[1], a_dx[1]);
         store_frag_panel<2>(panels + PB_S, a_dx, 0, warp, g, t);
-        umma::fence_smem_to_async();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_wgrad(tmem + T_W1, pa + PB_H0, pa + PB_S, kI32, acc);  // dW1 = h0^T . d_x
-        }
+        publish(3, acc);  // d_x -> dW1
         // d_a0 = (d_x . W1^T) masked by h0 > 0 -> takes over the d_a2 panels
         layer_backward<2, 8, S_W1>(a_dx, sw + O_W1, dacc, g, t);
         relu_mask_to_a<8>(panels + PB_H0, warp, g, t, dacc, a_d);
         umma::mbar_wait(&bar_w3, par);
         store_frag_panel<8>(panels + PB_DA, a_d, 0, warp, g, t);
-        umma::fence_smem_to_async();
-        __syncthreads();
-        if (tid == 0) {
-            umma::fence_after_sync();
-            issue_wgrad(tmem + T_W0, pa + PB_DA, pa + PB_ENC, kI32, acc);  // dW0^T = d_a0^T . enc
-            umma::commit(&bar_w0);
-        }
-        if (blk + gridDim.x < n_blocks) fetch(blk + gridDim.x);
+        publish(4, acc);  // d_a0 -> dW0
         // d_enc = d_a0 . W0^T -> global, or straight into the table gradient
         {
             float de[4][4];
@@ -866,25 +930,36 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_umma_kernel(uin
                 }
             }
         }
+        cur = nxt;
     }
+    }  // chain warps
 
     // ---- flush the CTA's weight gradients: row m of an M = 64 accumulator sits in lane (m % 16) + 32 (m / 16)
-    if (it > 0) {
+    if (it > 0 && warp < kWarps) {
         umma::mbar_wait(&bar_w0, (it - 1u) & 1u);
         umma::fence_after_sync();
         const uint32_t q = warp & 3u, m = 16u * q + lane;
         const uint32_t taddr = tmem + ((32u * q) << 16);
         const bool mine = lane < 16u;
         uint32_t v[32];
-        if (warp < 4) {
+        // rows that are contiguous in the flat gradient go out as 16-byte reductions when the buffer allows it
+        const bool vec = (reinterpret_cast<uintptr_t>(d_weights) & 15u) == 0;
+        auto add_row = [&](float *dst, int count) {  // count: 32 or 16 consecutive floats from v[]
+            if (vec) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {  // dW3[m][32h + j]
-                umma::tmem_ld32(taddr + T_W3 + 32 * h, v);
-                umma::tmem_ld_wait();
-                if (mine)
+                for (int j = 0; j < 32; j += 4)
+                    if (j < count) red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(d_weights + G_W3 + m * 64 + 32 * h + j, __uint_as_float(v[j]));
+                for (int j = 0; j < 32; ++j)
+                    if (j < count) atomicAdd(dst + j, __uint_as_float(v[j]));
             }
+        };
+        // warps 0-3: dW3[:, :32] and dW0; warps 4-7: dW3[:, 32:], dW2, dW1, dW4
+        umma::tmem_ld32(taddr + T_W3 + (warp < 4 ? 0 : 32), v);
+        umma::tmem_ld_wait();
+        if (mine) add_row(d_weights + G_W3 + m * 64 + (warp < 4 ? 0 : 32), 32);
+        if (warp < 4) {
             umma::tmem_ld32(taddr + T_W0, v);  // dW0^T[m = out][j = in]
             umma::tmem_ld_wait();
             if (mine)
@@ -898,9 +973,7 @@ __global__ void __launch_bounds__(kThreads, 1) nerf_mlp_backward_umma_kernel(uin
                 for (int j = 0; j < 32; ++j) atomicAdd(d_weights + G_W2 + j * 64 + m, __uint_as_float(v[j]));
             umma::tmem_ld32(taddr + T_W1, v);  // dW1[m][j < 16]
             umma::tmem_ld_wait();
-            if (mine)
-#pragma unroll
-                for (int j = 0; j < 16; ++j) atomicAdd(d_weights + G_W1 + m * 16 + j, __uint_as_float(v[j]));
+            if (mine) add_row(d_weights + G_W1 + m * 16, 16);
             umma::tmem_ld32(taddr + T_W4, v);  // dW4[m][j < 3]
             umma::tmem_ld_wait();
             if (mine)
@@ -969,7 +1042,7 @@ static void launch_nerf_mlp_backward(cudaStream_t stream, void **buffers, const 
         configured = true;
     }
     const unsigned blocks = min(div_up(d->n_samples, kBlockSamples), 148u);
-    nerf_mlp_backward_umma_kernel<false><<<blocks, kThreads, kBwdUmmaSmem, stream>>>(d->n_samples, enc, dirs, weights, d_drgbs, d_enc, d_weights,
+    nerf_mlp_backward_umma_kernel<false><<<blocks, kBwdThreads, kBwdUmmaSmem, stream>>>(d->n_samples, enc, dirs, weights, d_drgbs, d_enc, d_weights,
                                                                                      NgpHashGridA1Descriptor{}, nullptr, nullptr);
     check_launch("nerf_mlp_backward");
 }
@@ -1004,7 +1077,7 @@ void ngp_nerf_mlp_backward_scatter(cudaStream_t stream, void **buffers, const ch
         configured = true;
     }
     const unsigned blocks = min(div_up(gd->n_points, kBlockSamples), 148u);
-    nerf_mlp_backward_umma_kernel<true><<<blocks, kThreads, kBwdUmmaSmem, stream>>>(gd->n_points, enc, dirs, weights, d_drgbs, nullptr, d_weights, *gd, pos,
+    nerf_mlp_backward_umma_kernel<true><<<blocks, kBwdThreads, kBwdUmmaSmem, stream>>>(gd->n_points, enc, dirs, weights, d_drgbs, nullptr, d_weights, *gd, pos,
                                                                                     d_table);
     check_launch("nerf_mlp_backward_scatter");
 }

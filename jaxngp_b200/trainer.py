@@ -103,17 +103,17 @@ class Trainer:
         self.fused_glue = fused_mlp if fused_glue is None else fused_glue
         self.prefetch_march_ctas_per_sm = 1
         self.fused_loss = True  # ngp_integrate_loss_fused instead of integrate_rays / huber_loss_grad / integrate_rays_backward
-        # The backward as a two-stream software pipeline over `bwd_chunks` slices of the sample array: the MLP backward of
-        # slice c+1 (latency-bound: one 225 KB CTA per SM, a quarter of the issue slots) runs while the table scatter of
-        # slice c (bound by the L2's reduction rate, 1 KB of shared memory per CTA) fills the same SMs beside it.
-        # Measured on C2 (ms per step): 1 slice 0.562, 2 slices 0.533, 4 slices 0.552, 8 slices 0.658 -- each slice re-stages
-        # the MLP kernel (weights, tensor memory, 9,408 atomics per CTA to flush), and beside the MLP's registers an SM
-        # holds two scatter CTAs instead of five, so only part of the scatter hides; uneven splits measured worse.
-        self.bwd_fused_scatter = os.environ.get("NGP_B200_BWD_FUSED_SCATTER", "0") == "1"  # scatter from the MLP backward's registers
-        # At more than one rank the step ends in the exchange kernel, under which the next batch's march already runs; the
-        # side stream then costs more than it hides (C2, ms per step, 1 slice / 2 slices: N = 2 0.564 / 0.571, N = 8 0.580 /
-        # 0.596), so the pipeline is the single-rank default only.
-        self.bwd_chunks = int(os.environ.get("NGP_B200_BWD_CHUNKS", "2" if world_size == 1 else "1"))
+        # The backward, three arrangements (C2, ms per step at N = 1 / N = 2, `profiles/backward_knobs_r02.txt`):
+        #   * fused scatter (default where the fused encoder applies): ONE kernel, `ngp_nerf_mlp_backward_scatter` -- the table
+        #     scatter is issued from the MLP backward's own d_enc fragments, d_enc never exists in memory: 0.497 / 0.511;
+        #   * one pass: `ngp_nerf_mlp_backward` then `ngp_hashgrid_a1_backward`: 0.517 / 0.519;
+        #   * a two-stream pipeline over `bwd_chunks` slices of the sample array (the MLP backward of slice c+1 beside the
+        #     table scatter of slice c): 0.545 / 0.546 with 2 slices, 0.547 with 3, 0.574 with 4.
+        # Before the MLP backward got its issuing warp (csrc/mlp.cu) the order was the reverse (pipeline 0.533, one pass
+        # 0.562, fused 0.528): the kernel now keeps 288 x 160 registers, so fewer scatter CTAs fit beside it, and the
+        # 37 us it no longer spends are worth more than the overlap was.
+        self.bwd_fused_scatter = os.environ.get("NGP_B200_BWD_FUSED_SCATTER", "1") == "1"
+        self.bwd_chunks = int(os.environ.get("NGP_B200_BWD_CHUNKS", "1"))
         # optional explicit split in "waves" of 148 x 128 samples (one block per SM of the MLP kernel), e.g. "9,5"
         self.bwd_waves = [int(w) for w in os.environ.get("NGP_B200_BWD_WAVES", "").split(",") if w]
         self._bwd_side = None

@@ -441,8 +441,9 @@ def test_persistent_frame_kernel_matches_the_loop_renderer(small_scene):
 
 
 def test_chunked_two_stream_backward_equals_single_pass(small_scene):
-    """Trainer._backward as a pipeline of 4 sample slices on two streams (MLP backward of slice c+1 beside the table scatter
-    of slice c, accumulating entry points) against the single pass: the same gradient sums, to atomic order."""
+    """Trainer._backward in its three arrangements: the default (one kernel, table scatter fused behind the MLP backward), and
+    a pipeline of 4 / 3 sample slices on two streams (MLP backward of slice c+1 beside the table scatter of slice c,
+    accumulating entry points), against the single pass of the two ops: the same gradient sums, to atomic order."""
     from jaxngp_b200 import nerf as nerf_mod, synthetic
     from jaxngp_b200.trainer import Trainer
     n_rays, total = 1 << 15, 1 << 18
@@ -455,15 +456,17 @@ def test_chunked_two_stream_backward_equals_single_pass(small_scene):
     drgbs, enc = nerf_mod.fused_forward(tr.levels, xyzs, synthetic.BOUND, tr.table, dirs, tr.mlp_flat, want_enc=True)
     d_drgbs = torch.randn(total, 4, device=DEV, generator=gen)
     grads = {}
-    for chunks in (1, 4, 3):
-        tr.bwd_chunks = chunks
+    assert tr.bwd_fused_scatter and tr.bwd_chunks == 1  # the defaults: one kernel for MLP backward + table scatter
+    for chunks in ("fused", 1, 4, 3):
+        tr.bwd_fused_scatter = chunks == "fused"
+        tr.bwd_chunks = 1 if chunks == "fused" else chunks
         tr.flat_grads.fill_(7.0)  # must be overwritten, not added to
         tr._backward(enc, dirs, xyzs, d_drgbs)
         torch.cuda.synchronize()
         grads[chunks] = tr.flat_grads.clone()
     ref = grads[1]
     assert float(ref[: tr.table_numel].abs().max()) > 0 and float(ref[tr.table_numel:tr.n_params].abs().max()) > 0
-    for chunks in (4, 3):
+    for chunks in ("fused", 4, 3):
         g = grads[chunks]
         assert (g[: tr.table_numel] - ref[: tr.table_numel]).abs().max() <= 1e-4 * ref[: tr.table_numel].abs().max()
         assert (g[tr.table_numel:tr.n_params] - ref[tr.table_numel:tr.n_params]).abs().max() <= 1e-4 * ref[tr.table_numel:tr.n_params].abs().max()

@@ -12,7 +12,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KEYS = {"march_rays_kernel": "march_rays", "nerf_fused_forward_kernel": "nerf_fused_forward", "integrate_loss_fused_kernel": "integrate_loss_fused (replaces the three above in the step)",
-        "nerf_mlp_backward_umma_kernel": "nerf_mlp_backward", "hashgrid_a1_backward_kernel": "hashgrid_a1_backward", "adam_kernel": "adam_step"}
+        "nerf_mlp_backward_umma_kernel<(bool)0>": "nerf_mlp_backward", "nerf_mlp_backward_umma_kernel<(bool)1>": "nerf_mlp_backward_scatter (replaces the two above in the step)",
+        "nerf_mlp_backward_umma_kernel<0>": "nerf_mlp_backward", "nerf_mlp_backward_umma_kernel<1>": "nerf_mlp_backward_scatter (replaces the two above in the step)", "hashgrid_a1_backward_kernel": "hashgrid_a1_backward", "adam_kernel": "adam_step"}
 raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
