@@ -717,6 +717,53 @@ __device__ __forceinline__ void scatter_sample_level(float *__restrict__ d_table
     }
 }
 
+// Flush a CTA's weight-gradient accumulators (tensor memory, M = 64: row m sits in lane (m % 16) + 32 (m / 16)) into the flat
+// gradient with reductions; called by warps 0..7 once the last MMA has completed.
+__device__ __forceinline__ void flush_weight_gradients(uint32_t tmem, uint32_t warp, uint32_t lane, float *__restrict__ d_weights) {
+    const uint32_t q = warp & 3u, m = 16u * q + lane;
+    const uint32_t taddr = tmem + ((32u * q) << 16);
+    const bool mine = lane < 16u;
+    uint32_t v[32];
+    // rows that are contiguous in the flat gradient go out as 16-byte reductions when the buffer allows it
+    const bool vec = (reinterpret_cast<uintptr_t>(d_weights) & 15u) == 0;
+    auto add_row = [&](float *dst, int count) {  // count: 32 or 16 consecutive floats from v[]
+        if (vec) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                if (j < count) red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < count) atomicAdd(dst + j, __uint_as_float(v[j]));
+        }
+    };
+    // warps 0-3: dW3[:, :32] and dW0; warps 4-7: dW3[:, 32:], dW2, dW1, dW4
+    umma::tmem_ld32(taddr + T_W3 + (warp < 4 ? 0 : 32), v);
+    umma::tmem_ld_wait();
+    if (mine) add_row(d_weights + G_W3 + m * 64 + (warp < 4 ? 0 : 32), 32);
+    if (warp < 4) {
+        umma::tmem_ld32(taddr + T_W0, v);  // dW0^T[m = out][j = in]
+        umma::tmem_ld_wait();
+        if (mine)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(d_weights + G_W0 + j * 64 + m, __uint_as_float(v[j]));
+    } else {
+        umma::tmem_ld32(taddr + T_W2, v);  // dW2^T[m = out][j = in]
+        umma::tmem_ld_wait();
+        if (mine)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(d_weights + G_W2 + j * 64 + m, __uint_as_float(v[j]));
+        umma::tmem_ld32(taddr + T_W1, v);  // dW1[m][j < 16]
+        umma::tmem_ld_wait();
+        if (mine) add_row(d_weights + G_W1 + m * 16, 16);
+        umma::tmem_ld32(taddr + T_W4, v);  // dW4[m][j < 3]
+        umma::tmem_ld_wait();
+        if (mine)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) atomicAdd(d_weights + G_W4 + m * 3 + j, __uint_as_float(v[j]));
+    }
+}
+
 // kScatter: the input gradient never leaves the SM -- each thread scatters its fragment of d_enc (rows g, g + 8 of the
 // warp's 16 samples, levels t, t + 4, t + 8, t + 12) straight into the hash-table gradient (ngp_nerf_mlp_backward_scatter).
 //
@@ -934,56 +981,363 @@ __global__ void __launch_bounds__(kBwdThreads, 1) nerf_mlp_backward_umma_kernel(
     }
     }  // chain warps
 
-    // ---- flush the CTA's weight gradients: row m of an M = 64 accumulator sits in lane (m % 16) + 32 (m / 16)
+    // ---- flush the CTA's weight gradients
     if (it > 0 && warp < kWarps) {
         umma::mbar_wait(&bar_w0, (it - 1u) & 1u);
         umma::fence_after_sync();
-        const uint32_t q = warp & 3u, m = 16u * q + lane;
-        const uint32_t taddr = tmem + ((32u * q) << 16);
-        const bool mine = lane < 16u;
-        uint32_t v[32];
-        // rows that are contiguous in the flat gradient go out as 16-byte reductions when the buffer allows it
-        const bool vec = (reinterpret_cast<uintptr_t>(d_weights) & 15u) == 0;
-        auto add_row = [&](float *dst, int count) {  // count: 32 or 16 consecutive floats from v[]
-            if (vec) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    if (j < count) red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < count) atomicAdd(dst + j, __uint_as_float(v[j]));
-            }
-        };
-        // warps 0-3: dW3[:, :32] and dW0; warps 4-7: dW3[:, 32:], dW2, dW1, dW4
-        umma::tmem_ld32(taddr + T_W3 + (warp < 4 ? 0 : 32), v);
-        umma::tmem_ld_wait();
-        if (mine) add_row(d_weights + G_W3 + m * 64 + (warp < 4 ? 0 : 32), 32);
-        if (warp < 4) {
-            umma::tmem_ld32(taddr + T_W0, v);  // dW0^T[m = out][j = in]
-            umma::tmem_ld_wait();
-            if (mine)
-#pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(d_weights + G_W0 + j * 64 + m, __uint_as_float(v[j]));
-        } else {
-            umma::tmem_ld32(taddr + T_W2, v);  // dW2^T[m = out][j = in]
-            umma::tmem_ld_wait();
-            if (mine)
-#pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(d_weights + G_W2 + j * 64 + m, __uint_as_float(v[j]));
-            umma::tmem_ld32(taddr + T_W1, v);  // dW1[m][j < 16]
-            umma::tmem_ld_wait();
-            if (mine) add_row(d_weights + G_W1 + m * 16, 16);
-            umma::tmem_ld32(taddr + T_W4, v);  // dW4[m][j < 3]
-            umma::tmem_ld_wait();
-            if (mine)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) atomicAdd(d_weights + G_W4 + m * 3 + j, __uint_as_float(v[j]));
-        }
+        flush_weight_gradients(tmem, warp, lane, d_weights);
     }
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+}
+
+// ---------------------------------------------------------------- backward, sixteen chain warps (column-split pairs)
+// The kernel above keeps ONE 225 KB block per SM, i.e. two chain warps per scheduler, and its profile is all latency
+// (issue slots 20 % used, tensor pipe 25 %).  The panels cannot shrink, so this kernel doubles the warps over the SAME
+// panels instead: warps p and p + 8 share row tile p (16 samples) and each computes HALF the output columns of every
+// layer.  A layer's output goes into the MN-major panels anyway (the weight gradients read it there); the partner's half
+// comes back from the panel as A fragments after a 64-thread named barrier (eight pair barriers per block), the own
+// half never leaves the registers.  Per warp and block: 148 MMAs instead of 288 (layer 4 and the SH basis are done by
+// both warps), 26 + 26 extra 8-byte shared loads, and half the accumulator registers.  Barrier ids: 0 block, 1-5 issuer,
+// 6-13 pairs.
+// MEASURED (C2 batch, L2 flushed): correct on its first run, and SLOWER than the eight-warp kernel -- 0.153 ms against 0.132 ms
+// alone, 0.286 against 0.265 ms with the table scatter fused in, training step 0.504 against 0.498 ms: eight exchanges per
+// block (store, 64-thread barrier, load) sit on every warp's critical path and cost more than four warps per scheduler
+// hide.  It stays as the opt-in arm (NGP_B200_MLP_BWD_SPLIT=1) with its parity tests.
+constexpr int kSplitChainWarps = 16;
+constexpr int kSplitThreads = (kSplitChainWarps + 1) * 32;  // 544: sixteen chain warps + the issuing warp
+
+template <int NT>
+__device__ __forceinline__ void zero_acc(float (&acc)[NT][4]) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+}
+// acc[16 x 8 NT] += a[16 x 8 KT] . W[8 KT rows][8 NT cols]; W points at the first of those rows and columns
+template <int KT, int NT, int STRIDE>
+__device__ __forceinline__ void fwd_acc(float (&acc)[NT][4], const uint32_t (&a)[KT][4], const uint32_t *__restrict__ W, uint32_t g, uint32_t t) {
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+        const uint32_t *w0 = W + (8 * kt + 2 * t) * STRIDE + g;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(acc[nt], a[kt], w0[8 * nt], w0[STRIDE + 8 * nt]);
+    }
+}
+// acc[16 x 8 NT] += a[16 x 8 KT] . W^T; W points at row (first output column) and column (first k) of the stored [in][out] matrix
+template <int KT, int NT, int STRIDE>
+__device__ __forceinline__ void bwd_acc(float (&acc)[NT][4], const uint32_t (&a)[KT][4], const uint32_t *__restrict__ W, uint32_t g, uint32_t t) {
+    const uint32_t *w0 = W + g * STRIDE + 2 * t;
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const uint2 b = *reinterpret_cast<const uint2 *>(w0 + 8 * nt * STRIDE + 8 * kt);
+            mma_tf32(acc[nt], a[kt], b.x, b.y);
+        }
+    }
+}
+// inverse of store_frag_panel: A fragments of columns col0 .. col0 + 8 NT of row tile `tile`
+template <int NT>
+__device__ __forceinline__ void load_frag_panel(const uint8_t *__restrict__ panel, uint32_t (&a)[NT][4], int col0, uint32_t tile, uint32_t g, uint32_t t) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const uint32_t off = panel_frag_offset(tile, g, t, col0 + 8 * nt);
+        const uint2 lo = *reinterpret_cast<const uint2 *>(panel + off);
+        const uint2 hi = *reinterpret_cast<const uint2 *>(panel + off + 1024u);
+        a[nt][0] = lo.x; a[nt][2] = lo.y; a[nt][1] = hi.x; a[nt][3] = hi.y;
+    }
+}
+// ReLU mask from the activation's panel columns col0.. (own rows), then accumulator -> A fragments
+template <int NT>
+__device__ __forceinline__ void mask_to_a(const uint8_t *__restrict__ panel, int col0, uint32_t tile, uint32_t g, uint32_t t,
+                                          float (&dacc)[NT][4], uint32_t (&a_d)[NT][4]) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const uint32_t off = panel_frag_offset(tile, g, t, col0 + 8 * nt);
+        const float2 lo = *reinterpret_cast<const float2 *>(panel + off);
+        const float2 hi = *reinterpret_cast<const float2 *>(panel + off + 1024u);
+        dacc[nt][0] = lo.x > 0.f ? dacc[nt][0] : 0.f;
+        dacc[nt][1] = lo.y > 0.f ? dacc[nt][1] : 0.f;
+        dacc[nt][2] = hi.x > 0.f ? dacc[nt][2] : 0.f;
+        dacc[nt][3] = hi.y > 0.f ? dacc[nt][3] : 0.f;
+        c_to_a(dacc[nt], a_d[nt]);
+    }
+}
+template <int NT>
+__device__ __forceinline__ void relu_to_a(float (&acc)[NT][4], uint32_t (&a)[NT][4]) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = fmaxf(acc[nt][i], 0.f);
+        c_to_a(acc[nt], a[nt]);
+    }
+}
+
+template <bool kScatter>
+__global__ void __launch_bounds__(kSplitThreads, 1) nerf_mlp_backward_split_kernel(uint32_t n, const float *__restrict__ enc,
+                                                                                    const float *__restrict__ dirs,
+                                                                                    const float *__restrict__ weights,
+                                                                                    const float *__restrict__ d_drgbs,
+                                                                                    float *__restrict__ d_enc,
+                                                                                    float *__restrict__ d_weights,
+                                                                                    const __grid_constant__ NgpHashGridA1Descriptor gd,
+                                                                                    const float *__restrict__ pos,
+                                                                                    float *__restrict__ d_table) {
+    __shared__ hg::LevelMeta s_meta[kScatter ? 16 : 1];
+    if (kScatter && threadIdx.x < 16) s_meta[threadIdx.x] = hg::a1_level(gd, threadIdx.x);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *panels = smem_raw + ((1024u - (umma::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint32_t *sw = reinterpret_cast<uint32_t *>(panels + kPanelBytes);
+    __shared__ uint64_t bar_w4, bar_w3, bar_w0;
+    __shared__ uint32_t tmem_slot;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, g = lane >> 2, t = lane & 3u;
+
+    load_weights(sw, weights);  // threads 0..255
+    for (uint32_t i = tid; i < kPanel / 16; i += kSplitThreads) reinterpret_cast<uint4 *>(panels + PB_S)[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) {
+        umma::mbar_init(&bar_w4, 1);
+        umma::mbar_init(&bar_w3, 1);
+        umma::mbar_init(&bar_w0, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 0) umma::tmem_alloc(&tmem_slot, kTmemCols);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t pa = umma::smem_u32(panels);
+    constexpr uint32_t kI32 = umma::make_idesc(64, 32, true, true), kI64 = umma::make_idesc(64, 64, true, true);
+
+    const uint32_t n_blocks = (n + kBlockSamples - 1) / kBlockSamples;
+    uint32_t it = 0;
+    if (warp == kSplitChainWarps) {
+        // ---- issuing warp: the five weight-gradient products of a block, each once every chain warp has published its rows
+        for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+            const bool acc = it > 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + k), "n"(kSplitThreads) : "memory");
+                umma::fence_after_sync();
+                if (lane == 0) {
+                    if (k == 0) {
+                        issue_wgrad(tmem + T_W4, pa + PB_H2, pa + PB_S, kI32, acc);  // dW4 = h2^T . d_a3
+                        umma::commit(&bar_w4);
+                    } else if (k == 1) {
+                        issue_wgrad(tmem + T_W3, pa + PB_H1, pa + PB_DA, kI64, acc);  // dW3 = h1^T . d_a2
+                        umma::commit(&bar_w3);
+                    } else if (k == 2) {
+                        issue_wgrad(tmem + T_W2, pa + PB_H2, pa + PB_HIN, kI32, acc);  // dW2^T = d_a1^T . hin
+                    } else if (k == 3) {
+                        issue_wgrad(tmem + T_W1, pa + PB_H0, pa + PB_S, kI32, acc);  // dW1 = h0^T . d_x
+                    } else {
+                        issue_wgrad(tmem + T_W0, pa + PB_DA, pa + PB_ENC, kI32, acc);  // dW0^T = d_a0^T . enc
+                        umma::commit(&bar_w0);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---- chain warps: row tile p, column half h
+        const uint32_t p = warp & 7u, h = warp >> 3, o = 1u - h;
+        auto publish = [&](int k) {
+            umma::fence_smem_to_async();
+            asm volatile("bar.arrive %0, %1;" ::"r"(1 + k), "n"(kSplitThreads) : "memory");
+        };
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(6u + p) : "memory"); };
+        const uint32_t *W0 = sw + O_W0, *W1 = sw + O_W1, *W2 = sw + O_W2, *W3 = sw + O_W3, *W4 = sw + O_W4;
+
+        uint32_t a_in[4][4];
+        float4 dd_lo = make_float4(0.f, 0.f, 0.f, 0.f), dd_hi = dd_lo;
+        float dir[6] = {0.f, 0.f, 1.f, 0.f, 0.f, 1.f};
+        auto fetch = [&](uint32_t blk) {
+            const uint32_t r_lo = blk * kBlockSamples + p * 16 + g, r_hi = r_lo + 8;
+            load_enc_fragments(enc, r_lo, r_hi, r_lo < n, r_hi < n, t, a_in);
+            dd_lo = r_lo < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
+            dd_hi = r_hi < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_hi) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                dir[k] = r_lo < n ? __ldg(dirs + (size_t)r_lo * 3 + k) : (k == 2 ? 1.f : 0.f);
+                dir[3 + k] = r_hi < n ? __ldg(dirs + (size_t)r_hi * 3 + k) : (k == 2 ? 1.f : 0.f);
+            }
+        };
+        if (blockIdx.x < n_blocks) fetch(blockIdx.x);
+        for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x, ++it) {
+            const uint32_t par = it & 1u;
+            const uint32_t r_lo = blk * kBlockSamples + p * 16 + g, r_hi = r_lo + 8;
+            if (it > 0) umma::mbar_wait(&bar_w0, par ^ 1u);  // the previous block's weight gradients have read every panel
+            // enc columns 16 h .. 16 h + 15 of the tile -> panel (the partner stores the other half)
+            if (h == 0) store_frag_panel<2>(panels + PB_ENC, reinterpret_cast<const uint32_t(&)[2][4]>(a_in[0]), 0, p, g, t);
+            else store_frag_panel<2>(panels + PB_ENC, reinterpret_cast<const uint32_t(&)[2][4]>(a_in[2]), 16, p, g, t);
+
+            uint32_t a_own[4][4], a_oth[4][4];
+            float acc[4][4];
+            // layer 0: 32 -> 64, ReLU; own columns 32 h ..
+            zero_acc(acc);
+            fwd_acc<4, 4, S_W0>(acc, a_in, W0 + 32 * h, g, t);
+            relu_to_a(acc, a_own);
+            store_frag_panel<4>(panels + PB_H0, a_own, 32 * h, p, g, t);
+            pair_sync();
+            load_frag_panel<4>(panels + PB_H0, a_oth, 32 * o, p, g, t);
+            // layer 1: 64 -> 16; own columns 8 h ..; x0 (column 0) lives with h == 0
+            uint32_t a_x[1][4], a_xo[1][4], a_sh[2][4];
+            float x0_lo, x0_hi;
+            {
+                float x[1][4];
+                zero_acc(x);
+                fwd_acc<4, 1, S_W1>(x, a_own, W1 + 32 * h * S_W1 + 8 * h, g, t);
+                fwd_acc<4, 1, S_W1>(x, a_oth, W1 + 32 * o * S_W1 + 8 * h, g, t);
+                x0_lo = x[0][0];
+                x0_hi = x[0][2];
+                c_to_a(x[0], a_x[0]);
+                float sh_lo[4], sh_hi[4];
+                sh4_lane(dir[0], dir[1], dir[2], t, sh_lo);
+                sh4_lane(dir[3], dir[4], dir[5], t, sh_hi);
+                a_sh[0][0] = tf32(sh_lo[0]); a_sh[0][1] = tf32(sh_hi[0]); a_sh[0][2] = tf32(sh_lo[1]); a_sh[0][3] = tf32(sh_hi[1]);
+                a_sh[1][0] = tf32(sh_lo[2]); a_sh[1][1] = tf32(sh_hi[2]); a_sh[1][2] = tf32(sh_lo[3]); a_sh[1][3] = tf32(sh_hi[3]);
+            }
+            store_frag_panel<1>(panels + PB_HIN, a_x, 8 * h, p, g, t);
+            if (h == 0) store_frag_panel<1>(panels + PB_HIN, reinterpret_cast<const uint32_t(&)[1][4]>(a_sh[0]), 16, p, g, t);
+            else store_frag_panel<1>(panels + PB_HIN, reinterpret_cast<const uint32_t(&)[1][4]>(a_sh[1]), 24, p, g, t);
+            pair_sync();
+            load_frag_panel<1>(panels + PB_HIN, a_xo, 8 * o, p, g, t);
+            // layer 2: 32 -> 64, ReLU
+            zero_acc(acc);
+            fwd_acc<1, 4, S_W2>(acc, a_x, W2 + 8 * h * S_W2 + 32 * h, g, t);
+            fwd_acc<1, 4, S_W2>(acc, a_xo, W2 + 8 * o * S_W2 + 32 * h, g, t);
+            fwd_acc<2, 4, S_W2>(acc, a_sh, W2 + 16 * S_W2 + 32 * h, g, t);
+            relu_to_a(acc, a_own);
+            store_frag_panel<4>(panels + PB_H1, a_own, 32 * h, p, g, t);
+            pair_sync();
+            load_frag_panel<4>(panels + PB_H1, a_oth, 32 * o, p, g, t);
+            // layer 3: 64 -> 64, ReLU
+            zero_acc(acc);
+            fwd_acc<4, 4, S_W3>(acc, a_own, W3 + 32 * h * S_W3 + 32 * h, g, t);
+            fwd_acc<4, 4, S_W3>(acc, a_oth, W3 + 32 * o * S_W3 + 32 * h, g, t);
+            relu_to_a(acc, a_own);
+            store_frag_panel<4>(panels + PB_H2, a_own, 32 * h, p, g, t);
+            pair_sync();
+            load_frag_panel<4>(panels + PB_H2, a_oth, 32 * o, p, g, t);
+            // layer 4: 64 -> 3 (padded to 8), sigmoid -- both warps of the pair; then d_a3 = d_rgb * rgb * (1 - rgb)
+            uint32_t a3[1][4];
+            {
+                float rgb[1][4];
+                zero_acc(rgb);
+                fwd_acc<4, 1, S_W4>(rgb, a_own, W4 + 32 * h * S_W4, g, t);
+                fwd_acc<4, 1, S_W4>(rgb, a_oth, W4 + 32 * o * S_W4, g, t);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rgb[0][i] = 1.f / (1.f + expf(-rgb[0][i]));
+                const float dr_lo0 = t == 0 ? dd_lo.y : t == 1 ? dd_lo.w : 0.f, dr_lo1 = t == 0 ? dd_lo.z : 0.f;
+                const float dr_hi0 = t == 0 ? dd_hi.y : t == 1 ? dd_hi.w : 0.f, dr_hi1 = t == 0 ? dd_hi.z : 0.f;
+                float d3[4];
+                d3[0] = dr_lo0 * rgb[0][0] * (1.f - rgb[0][0]);
+                d3[1] = dr_lo1 * rgb[0][1] * (1.f - rgb[0][1]);
+                d3[2] = dr_hi0 * rgb[0][2] * (1.f - rgb[0][2]);
+                d3[3] = dr_hi1 * rgb[0][3] * (1.f - rgb[0][3]);
+                c_to_a(d3, a3[0]);
+            }
+            {   // PB_S: columns 0..7 = d_a3 (h == 0), columns 8..15 = zeros (they held d_x of the previous block; h == 1)
+                uint32_t z[1][4] = {{0u, 0u, 0u, 0u}};
+                if (h == 0) store_frag_panel<1>(panels + PB_S, a3, 0, p, g, t);
+                else store_frag_panel<1>(panels + PB_S, z, 8, p, g, t);
+            }
+            publish(0);  // enc, h0, hin, h1, h2, d_a3 -> dW4
+            // d_a2 = (d_a3 . W4^T) masked by h2 > 0; own columns 32 h ..
+            zero_acc(acc);
+            bwd_acc<1, 4, S_W4>(acc, a3, W4 + 32 * h * S_W4, g, t);
+            mask_to_a<4>(panels + PB_H2, 32 * h, p, g, t, acc, a_own);
+            store_frag_panel<4>(panels + PB_DA, a_own, 32 * h, p, g, t);
+            publish(1);  // d_a2 -> dW3
+            pair_sync();
+            load_frag_panel<4>(panels + PB_DA, a_oth, 32 * o, p, g, t);
+            // d_a1 = (d_a2 . W3^T) masked by h1 > 0 -> takes over the h2 panels
+            zero_acc(acc);
+            bwd_acc<4, 4, S_W3>(acc, a_own, W3 + 32 * h * S_W3 + 32 * h, g, t);
+            bwd_acc<4, 4, S_W3>(acc, a_oth, W3 + 32 * h * S_W3 + 32 * o, g, t);
+            mask_to_a<4>(panels + PB_H1, 32 * h, p, g, t, acc, a_own);
+            umma::mbar_wait(&bar_w4, par);
+            store_frag_panel<4>(panels + PB_H2, a_own, 32 * h, p, g, t);
+            publish(2);  // d_a1 -> dW2
+            pair_sync();
+            load_frag_panel<4>(panels + PB_H2, a_oth, 32 * o, p, g, t);
+            // d_x = (d_a1 . W2^T)[:, :16] + d_density * exp(clip(x0, -15, 15)) on column 0 (nerfs.py:231-234); own columns 8 h ..
+            {
+                float dx[1][4];
+                zero_acc(dx);
+                bwd_acc<4, 1, S_W2>(dx, a_own, W2 + 8 * h * S_W2 + 32 * h, g, t);
+                bwd_acc<4, 1, S_W2>(dx, a_oth, W2 + 8 * h * S_W2 + 32 * o, g, t);
+                if (h == 0 && t == 0) {
+                    dx[0][0] += dd_lo.x * expf(fminf(fmaxf(x0_lo, -15.f), 15.f));
+                    dx[0][2] += dd_hi.x * expf(fminf(fmaxf(x0_hi, -15.f), 15.f));
+                }
+                c_to_a(dx[0], a_x[0]);
+            }
+            store_frag_panel<1>(panels + PB_S, a_x, 8 * h, p, g, t);
+            publish(3);  // d_x -> dW1
+            pair_sync();
+            load_frag_panel<1>(panels + PB_S, a_xo, 8 * o, p, g, t);
+            // d_a0 = (d_x . W1^T) masked by h0 > 0 -> takes over the d_a2 panels
+            zero_acc(acc);
+            bwd_acc<1, 4, S_W1>(acc, a_x, W1 + 32 * h * S_W1 + 8 * h, g, t);
+            bwd_acc<1, 4, S_W1>(acc, a_xo, W1 + 32 * h * S_W1 + 8 * o, g, t);
+            mask_to_a<4>(panels + PB_H0, 32 * h, p, g, t, acc, a_own);
+            umma::mbar_wait(&bar_w3, par);
+            store_frag_panel<4>(panels + PB_DA, a_own, 32 * h, p, g, t);
+            publish(4);  // d_a0 -> dW0
+            pair_sync();
+            load_frag_panel<4>(panels + PB_DA, a_oth, 32 * o, p, g, t);
+            if (blk + gridDim.x < n_blocks) fetch(blk + gridDim.x);
+            // d_enc = d_a0 . W0^T; own columns 16 h .. 16 h + 15 -> global, or straight into the table gradient
+            {
+                float de[2][4];
+                zero_acc(de);
+                bwd_acc<4, 2, S_W0>(de, a_own, W0 + 16 * h * S_W0 + 32 * h, g, t);
+                bwd_acc<4, 2, S_W0>(de, a_oth, W0 + 16 * h * S_W0 + 32 * o, g, t);
+                if (!kScatter) {
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        if (r_lo < n) *reinterpret_cast<float2 *>(d_enc + (size_t)r_lo * 32 + 16 * h + 8 * nt + 2 * t) = make_float2(de[nt][0], de[nt][1]);
+                        if (r_hi < n) *reinterpret_cast<float2 *>(d_enc + (size_t)r_hi * 32 + 16 * h + 8 * nt + 2 * t) = make_float2(de[nt][2], de[nt][3]);
+                    }
+                } else {
+                    float xl[3] = {0.f, 0.f, 0.f}, xh[3] = {0.f, 0.f, 0.f}, pl[3], ph[3];
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        if (r_lo < n) xl[k] = __ldg(pos + (size_t)r_lo * 3 + k);
+                        if (r_hi < n) xh[k] = __ldg(pos + (size_t)r_hi * 3 + k);
+                    }
+                    hg::unit_pos<3>(xl, gd.bound, pl);
+                    hg::unit_pos<3>(xh, gd.bound, ph);
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const hg::LevelMeta m = s_meta[8 * h + 4 * nt + t];  // column 16 h + 8 nt + 2 t is feature 0 of that level
+                        if (r_lo < n) scatter_sample_level(d_table, m, pl, de[nt][0], de[nt][1]);
+                        if (r_hi < n) scatter_sample_level(d_table, m, ph, de[nt][2], de[nt][3]);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- flush the CTA's weight gradients
+    if (it > 0 && warp < kWarps) {
+        umma::mbar_wait(&bar_w0, (it - 1u) & 1u);
+        umma::fence_after_sync();
+        flush_weight_gradients(tmem, warp, lane, d_weights);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, kTmemCols);
+}
+
+
+// which backward kernel a launch takes: eight chain warps (default) or sixteen in column-split pairs (NGP_B200_MLP_BWD_SPLIT=1);
+// read per launch so that a test or an A/B run can switch inside one process
+static bool backward_split() {
+    const char *e = getenv("NGP_B200_MLP_BWD_SPLIT");
+    return e && e[0] == '1';
 }
 
 constexpr size_t kFwdSmem = kWeightFloats * sizeof(uint32_t);
@@ -1039,11 +1393,16 @@ static void launch_nerf_mlp_backward(cudaStream_t stream, void **buffers, const 
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(nerf_mlp_backward_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdUmmaSmem);
+        cudaFuncSetAttribute(nerf_mlp_backward_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdUmmaSmem);
         configured = true;
     }
     const unsigned blocks = min(div_up(d->n_samples, kBlockSamples), 148u);
-    nerf_mlp_backward_umma_kernel<false><<<blocks, kBwdThreads, kBwdUmmaSmem, stream>>>(d->n_samples, enc, dirs, weights, d_drgbs, d_enc, d_weights,
-                                                                                     NgpHashGridA1Descriptor{}, nullptr, nullptr);
+    if (backward_split())
+        nerf_mlp_backward_split_kernel<false><<<blocks, kSplitThreads, kBwdUmmaSmem, stream>>>(d->n_samples, enc, dirs, weights, d_drgbs, d_enc, d_weights,
+                                                                                            NgpHashGridA1Descriptor{}, nullptr, nullptr);
+    else
+        nerf_mlp_backward_umma_kernel<false><<<blocks, kBwdThreads, kBwdUmmaSmem, stream>>>(d->n_samples, enc, dirs, weights, d_drgbs, d_enc, d_weights,
+                                                                                         NgpHashGridA1Descriptor{}, nullptr, nullptr);
     check_launch("nerf_mlp_backward");
 }
 
@@ -1074,11 +1433,16 @@ void ngp_nerf_mlp_backward_scatter(cudaStream_t stream, void **buffers, const ch
     static bool configured = false;
     if (!configured) {
         cudaFuncSetAttribute(nerf_mlp_backward_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdUmmaSmem);
+        cudaFuncSetAttribute(nerf_mlp_backward_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdUmmaSmem);
         configured = true;
     }
     const unsigned blocks = min(div_up(gd->n_points, kBlockSamples), 148u);
-    nerf_mlp_backward_umma_kernel<true><<<blocks, kBwdThreads, kBwdUmmaSmem, stream>>>(gd->n_points, enc, dirs, weights, d_drgbs, nullptr, d_weights, *gd, pos,
-                                                                                    d_table);
+    if (backward_split())
+        nerf_mlp_backward_split_kernel<true><<<blocks, kSplitThreads, kBwdUmmaSmem, stream>>>(gd->n_points, enc, dirs, weights, d_drgbs, nullptr, d_weights, *gd,
+                                                                                           pos, d_table);
+    else
+        nerf_mlp_backward_umma_kernel<true><<<blocks, kBwdThreads, kBwdUmmaSmem, stream>>>(gd->n_points, enc, dirs, weights, d_drgbs, nullptr, d_weights, *gd, pos,
+                                                                                        d_table);
     check_launch("nerf_mlp_backward_scatter");
 }
 

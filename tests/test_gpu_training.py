@@ -180,12 +180,17 @@ def test_fused_integrate_loss_matches_the_three_ops(small_scene):
         assert float(d_ref.abs().max()) > 0
 
 
+@pytest.mark.parametrize("split", ["1", "0"])
 @pytest.mark.parametrize("n", [100, 128 * 148 * 3 + 77, (1 << 18) + 5])
-def test_mlp_backward_tcgen05_wgrad_matches_mma_sync_arm(n):
-    """The two backward kernels share the per-warp register chain (d_enc: same bits) and differ in where the weight
-    gradients are reduced: tcgen05.mma into TMEM accumulators that live across the CTA's blocks vs mma.sync into
-    registers.  Several blocks per CTA exercise the accumulate flag, the panel reuse barriers and both parities."""
+def test_mlp_backward_tcgen05_wgrad_matches_mma_sync_arm(n, split, monkeypatch):
+    """The backward kernels against the all-mma.sync arm.  split = 0: eight chain warps, the same per-warp register chain
+    (d_enc: same bits; the default); they differ in where the weight gradients are reduced: tcgen05.mma into TMEM accumulators
+    that live across the CTA's blocks vs mma.sync into registers.  split = 1 (opt-in): sixteen chain warps in column-split pairs
+    that exchange half of every layer through the panels -- the k halves are summed in a different order, so d_enc agrees to
+    tf32 rounding, not bit for bit.  Several blocks per CTA exercise the accumulate flag, the panel reuse barriers, the pair
+    barriers and both parities."""
     from jaxngp_b200 import nerf as nerf_mod
+    monkeypatch.setenv("NGP_B200_MLP_BWD_SPLIT", split)
     gen = torch.Generator(device=DEV).manual_seed(11)
     model = nerf_mod.NeRF(bound=1.0, device=DEV, generator=gen, T=2 ** 14)
     w = model.mlp_flat.detach().clone()
@@ -196,7 +201,11 @@ def test_mlp_backward_tcgen05_wgrad_matches_mma_sync_arm(n):
         g_enc_a, g_w_a = nerf_mod.mlp_backward(enc, dirs, w, d_out, impl="umma")
         g_enc_b, g_w_b = nerf_mod.mlp_backward(enc, dirs, w, d_out, impl="mma")
         torch.cuda.synchronize()
-        assert (g_enc_a != g_enc_b).float().mean() <= 1e-5, rep
+        if split == "0":
+            assert (g_enc_a != g_enc_b).float().mean() <= 1e-5, rep
+        else:
+            assert (g_enc_a - g_enc_b).abs().max() <= 5e-3 * g_enc_b.abs().max(), (rep, (g_enc_a - g_enc_b).abs().max(), g_enc_b.abs().max())
+            assert (g_enc_a - g_enc_b).abs().mean() <= 1e-4 * g_enc_b.abs().max(), rep
         assert (g_w_a - g_w_b).abs().max() <= 2e-4 * g_w_b.abs().max(), (rep, (g_w_a - g_w_b).abs().max(), g_w_b.abs().max())
 
 
@@ -472,11 +481,13 @@ def test_chunked_two_stream_backward_equals_single_pass(small_scene):
         assert (g[tr.table_numel:tr.n_params] - ref[tr.table_numel:tr.n_params]).abs().max() <= 1e-4 * ref[tr.table_numel:tr.n_params].abs().max()
 
 
-def test_mlp_backward_with_fused_table_scatter_equals_the_two_ops():
+@pytest.mark.parametrize("split", ["1", "0"])
+def test_mlp_backward_with_fused_table_scatter_equals_the_two_ops(split, monkeypatch):
     """ngp_nerf_mlp_backward_scatter (the table scatter issued from the MLP backward's own d_enc fragments) against
     nerf_mlp_backward + hashgrid_a1_backward: the same weight gradients (same kernel code) and the same table sums to
     atomic order; cube-face points exercise the spill rows, a partial last block the row guards."""
     from jaxngp_b200 import encoders as E, nerf as nerf_mod
+    monkeypatch.setenv("NGP_B200_MLP_BWD_SPLIT", split)  # both ops below take the same kernel family
     gen = torch.Generator(device=DEV).manual_seed(23)
     lt = E.make_level_table(16, 2 ** 19, 2, 16, 2048, 3)
     w = (torch.rand(nerf_mod.MLP_NUMEL, device=DEV, generator=gen) - 0.5) * 0.6

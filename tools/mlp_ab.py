@@ -44,6 +44,13 @@ def main():
     d_out = torch.randn_like(drgbs)
     for impl in sys.argv[1:] or ("umma", "mma"):
         res[f"mlp_backward_{impl}_ms"] = timed(lambda: nerf_mod.mlp_backward(enc, dirs, tr.mlp_flat, d_out, impl=impl))
+    # the two kernels behind "umma" (sixteen chain warps in column-split pairs / eight), alone and with the table scatter fused in
+    for split in ("0", "1"):
+        os.environ["NGP_B200_MLP_BWD_SPLIT"] = split
+        res[f"mlp_backward_split{split}_ms"] = timed(lambda: nerf_mod.mlp_backward(enc, dirs, tr.mlp_flat, d_out, impl="umma"))
+        res[f"mlp_backward_scatter_split{split}_ms"] = timed(lambda: nerf_mod.mlp_backward_scatter(
+            tr.levels, xyzs, 1.0, enc, dirs, tr.mlp_flat, d_out, tr.mlp_grad, tr.table_grad))
+    del os.environ["NGP_B200_MLP_BWD_SPLIT"]
     print(json.dumps(res))
 
 
