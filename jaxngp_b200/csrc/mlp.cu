@@ -717,6 +717,55 @@ __device__ __forceinline__ void scatter_sample_level(float *__restrict__ d_table
     }
 }
 
+// Two CONSECUTIVE samples of a ray at one level (a thread of the eight-warp backward kernel holds rows 2g and 2g + 1 of its
+// warp's tile): when both fall into the same cell -- nearly always at the coarse levels, where a cell spans tens of march
+// steps -- their eight corner rows are the same rows, and one set of reductions carries both (the weights differ, the sums
+// are formed in registers).  Otherwise two ordinary scatters.  Same sums as scatter_sample_level on each, to rounding order.
+__device__ __forceinline__ void scatter_pair_level(float *__restrict__ d_table, const hg::LevelMeta &m, const float (&pa)[3],
+                                                   const float (&pb)[3], float a0, float a1, float b0, float b1) {
+    const bool has_a = a0 != 0.f || a1 != 0.f, has_b = b0 != 0.f || b1 != 0.f;  // padded / masked samples carry exact zeros
+    if (!has_a && !has_b) return;
+    uint32_t base[3], base_b[3];
+    float fa[3], fb[3];
+    hg::a1_cell<3>(pa, m.scale, base, fa);
+    hg::a1_cell<3>(pb, m.scale, base_b, fb);
+    const bool same = base[0] == base_b[0] && base[1] == base_b[1] && base[2] == base_b[2];
+    if (!same || !has_a) {  // b on its own (also when a is empty: then b's cell is the one to scatter into)
+        scatter_sample_level(d_table, m, pb, b0, b1);
+        if (!has_a) return;
+        b0 = b1 = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {  // corner c: x bit clear; its partner c + 4: x bit set
+        uint32_t va[3], vb[3];
+        float wa = 1.f, wb = 1.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t bit = (c >> (2 - k)) & 1;
+            va[k] = base[k] + bit;
+            vb[k] = va[k];
+            if (k > 0) {
+                wa *= bit ? fa[k] : 1.f - fa[k];
+                wb *= bit ? fb[k] : 1.f - fb[k];
+            }
+        }
+        vb[0] = base[0] + 1u;
+        // corner with the x bit clear (rows ra) and set (rows rb): contributions of sample a and sample b
+        const float wa0 = wa * (1.f - fa[0]), wa1 = wa * fa[0], wb0 = wb * (1.f - fb[0]), wb1 = wb * fb[0];
+        uint32_t ra = hg::grid_row_unclamped<3, true>(va, m), rb = hg::grid_row_unclamped<3, true>(vb, m);
+        float x0 = wa0 * a0 + wb0 * b0, x1 = wa0 * a1 + wb0 * b1, y0 = wa1 * a0 + wb1 * b0, y1 = wa1 * a1 + wb1 * b1;
+        if (ra > m.last_row) { ra = m.last_row; x0 = x1 = 0.f; }  // XLA drops the update of an out-of-range row (hg::grid_row)
+        if (rb > m.last_row) { rb = m.last_row; y0 = y1 = 0.f; }
+        if ((ra ^ rb) == 1u) {
+            const bool a_hi = ra & 1u;
+            red_add_v4(d_table + (size_t)(ra & ~1u) * 2, a_hi ? y0 : x0, a_hi ? y1 : x1, a_hi ? x0 : y0, a_hi ? x1 : y1);
+        } else {
+            red_add_v2(d_table + (size_t)ra * 2, x0, x1);
+            red_add_v2(d_table + (size_t)rb * 2, y0, y1);
+        }
+    }
+}
+
 // Flush a CTA's weight-gradient accumulators (tensor memory, M = 64: row m sits in lane (m % 16) + 32 (m / 16)) into the flat
 // gradient with reductions; called by warps 0..7 once the last MMA has completed.
 __device__ __forceinline__ void flush_weight_gradients(uint32_t tmem, uint32_t warp, uint32_t lane, float *__restrict__ d_weights) {
@@ -862,9 +911,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) nerf_mlp_backward_umma_kernel(
         }
     } else {
     // A block's global inputs (enc fragments, output cotangents, directions) are fetched a WHOLE block ahead, into a
-    // second register set: with two warps per scheduler nothing else hides a trip to L2 or HBM (the loads issued under
-    // the previous block's last layer only, and the directions loaded where they are used, were the kernel's largest
-    // stall: long scoreboard 2.6 of 9.9 warp-cycles per issue)
+    // second register set: with two warps per scheduler nothing else hides a trip to L2 or HBM.  (Measured alone this
+    // changed nothing -- the long-scoreboard samples turned out to be the weight-staging prologue -- but it costs nothing
+    // either: one block per SM leaves the registers free.)
     struct Inputs {
         uint32_t a_in[4][4];
         float4 dd_lo, dd_hi;
@@ -872,7 +921,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) nerf_mlp_backward_umma_kernel(
     };
     Inputs cur, nxt;
     auto fetch = [&](uint32_t blk, Inputs &x) {
-        const uint32_t r_lo = blk * kBlockSamples + warp * 16 + g, r_hi = r_lo + 8;
+        // fragment rows g and g + 8 of the warp's tile hold samples 2g and 2g + 1: any assignment of the tile's 16 samples to
+        // its rows gives the same sums, and this one puts two CONSECUTIVE samples of a ray into each thread for the scatter
+        const uint32_t r_lo = blk * kBlockSamples + warp * 16 + 2 * g, r_hi = r_lo + 1;
         load_enc_fragments(enc, r_lo, r_hi, r_lo < n, r_hi < n, t, x.a_in);
         x.dd_lo = r_lo < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_lo) : make_float4(0.f, 0.f, 0.f, 0.f);
         x.dd_hi = r_hi < n ? __ldg(reinterpret_cast<const float4 *>(d_drgbs) + r_hi) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -891,7 +942,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) nerf_mlp_backward_umma_kernel(
         const uint32_t par = it & 1u;
         const bool acc = it > 0;
         const uint32_t base = blk * kBlockSamples, row0 = base + warp * 16;
-        const uint32_t r_lo = row0 + g, r_hi = row0 + g + 8;
+        const uint32_t r_lo = row0 + 2 * g, r_hi = r_lo + 1;  // see fetch
         if (it > 0) umma::mbar_wait(&bar_w0, par ^ 1u);  // the previous block's wgrad MMAs have read every panel
         store_frag_panel<4>(panels + PB_ENC, a_in, 0, warp, g, t);
         // ---- forward recompute; h0, hin, h1, h2 of the CTA's 128 samples -> panels
@@ -972,8 +1023,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) nerf_mlp_backward_umma_kernel(
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
                     const hg::LevelMeta m = s_meta[4 * nt + t];  // column 8 nt + 2 t is feature 0 of level 4 nt + t
-                    if (r_lo < n) scatter_sample_level(d_table, m, pl, de[nt][0], de[nt][1]);
-                    if (r_hi < n) scatter_sample_level(d_table, m, ph, de[nt][2], de[nt][3]);
+                    // rows beyond n carry exact zeros (their cotangents were loaded as zeros): nothing is scattered for them
+                    scatter_pair_level(d_table, m, pl, ph, de[nt][0], de[nt][1], de[nt][2], de[nt][3]);
                 }
             }
         }

@@ -494,6 +494,13 @@ def test_mlp_backward_with_fused_table_scatter_equals_the_two_ops(split, monkeyp
     table = (torch.rand(lt.rows, 2, device=DEV, generator=gen) - 0.5) * 2
     for n in (77, 128 * 148 * 2 + 5):
         pos = torch.rand(n, 3, device=DEV, generator=gen) * 2 - 1
+        # the second half as march samples: runs of 64 points 0.0034 apart along random directions, so that consecutive
+        # samples share cells at the coarse levels (the merged path of the pair scatter) and split at the fine ones
+        k = torch.arange(n - n // 2, device=DEV)
+        run = k // 64
+        o = (torch.rand(int(run.max()) + 1, 3, device=DEV, generator=gen) - 0.5)
+        d = torch.nn.functional.normalize(torch.randn(int(run.max()) + 1, 3, device=DEV, generator=gen), dim=-1)
+        pos[n // 2:] = (o[run] + d[run] * (k % 64).to(torch.float32)[:, None] * 0.0034).clamp(-1, 1)
         pos[:32] = torch.tensor([1.0, -1.0, 0.999999], device=DEV)
         dirs = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV, generator=gen), dim=-1)
         enc = E.hashgrid_forward(lt, pos, 1.0, table)
