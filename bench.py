@@ -413,12 +413,25 @@ def dominant_kernel_roofline(tr, perm, flush):
               "note": "each kernel timed alone with an L2 flush before every launch (isolated times sum to more than the "
                       "graph-replayed step, whose kernels find their inputs in L2); limiter per kernel in DESIGN.md section 5",
               "kernels": res}
-    if "achieved_tflops" in res[top]:  # the dense contraction (fused MLP): tensor roofline; its HBM fraction is in `kernels`
+    if "achieved_tflops" in res[top]:
+        # A kernel that both contracts and streams: the roof that bounds it is the lower of the two at its arithmetic
+        # intensity (algorithmic FLOP / algorithmic byte against the machine balance, tensor peak / HBM peak).  The MLP
+        # backward alone (199 FLOP/B) sits under the tensor roof; with the table scatter fused in (41 FLOP/B: 1192 B per
+        # sample) it sits under the HBM roof.  Both fractions are reported either way.
         tpeak, tsrc = tensor_peak_tf32()
-        return {"bound": "tensor", "achieved": res[top]["achieved_tflops"], "peak": tpeak, "unit": "TFLOP/s",
-                "frac": round(res[top]["achieved_tflops"] / tpeak, 4), "peak_source": tsrc,
+        slots = n if top == fused_key else nb
+        intensity = slots * 56448 / res[top]["algorithmic_bytes"]
+        balance = tpeak * 1e12 / (hbm * 1e9)
+        both = {"frac_of_tensor_peak": round(res[top]["achieved_tflops"] / tpeak, 4), "frac_of_hbm_peak": res[top]["frac_of_hbm"],
+                "arithmetic_intensity_flop_per_byte": round(intensity, 1), "machine_balance_flop_per_byte": round(balance, 1),
+                "tensor_peak_tflops": tpeak, "tensor_peak_source": tsrc, "hbm_peak_gbs": hbm, "hbm_peak_source": src,
                 "flops_per_unit": "56,448 FLOP per sample slot (forward recompute 18,816 + input gradients + weight gradients), "
-                                  f"x {n if top == fused_key else nb} slots per launch", **common}
+                                  f"x {slots} slots per launch"}
+        if intensity >= balance:
+            return {"bound": "tensor", "achieved": res[top]["achieved_tflops"], "peak": tpeak, "unit": "TFLOP/s",
+                    "frac": both["frac_of_tensor_peak"], "peak_source": tsrc, **both, **common}
+        return {"bound": "hbm", "achieved": res[top]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
+                "frac": res[top]["frac_of_hbm"], "peak_source": src, **both, **common}
     return {"bound": "hbm", "achieved": res[top]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
             "frac": res[top]["frac_of_hbm"], "peak_source": src, **common}
 
