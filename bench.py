@@ -323,6 +323,21 @@ def time_once(fn, flush):
     return e0.elapsed_time(e1)
 
 
+def pick_roof(flops, nbytes, ms, tensor_peak_tflops, hbm_peak_gbs):
+    """Roofline object of a kernel that both contracts (`flops` algorithmic FLOP per launch) and streams (`nbytes`
+    algorithmic bytes per launch) and takes `ms`: the roof that bounds it is the lower one at its arithmetic intensity,
+    i.e. the tensor roof iff flops / nbytes >= tensor peak / HBM peak.  Both fractions are reported either way."""
+    tflops, gbs = flops / (ms * 1e-3) / 1e12, nbytes / (ms * 1e-3) / 1e9
+    intensity, balance = flops / nbytes, tensor_peak_tflops * 1e12 / (hbm_peak_gbs * 1e9)
+    both = {"frac_of_tensor_peak": round(tflops / tensor_peak_tflops, 4), "frac_of_hbm_peak": round(gbs / hbm_peak_gbs, 4),
+            "arithmetic_intensity_flop_per_byte": round(intensity, 1), "machine_balance_flop_per_byte": round(balance, 1),
+            "tensor_peak_tflops": tensor_peak_tflops, "hbm_peak_gbs": hbm_peak_gbs}
+    if intensity >= balance:
+        return {"bound": "tensor", "achieved": round(tflops, 2), "peak": tensor_peak_tflops, "unit": "TFLOP/s",
+                "frac": both["frac_of_tensor_peak"], **both}
+    return {"bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak_gbs, "unit": "GB/s", "frac": both["frac_of_hbm_peak"], **both}
+
+
 def dominant_kernel_roofline(tr, perm, flush):
     """Times every kernel of the step alone, on the step's own tensors, with CUDA events on the launching
     stream and an L2 flush before each launch, then reports the roofline of the slowest one.
@@ -419,19 +434,15 @@ def dominant_kernel_roofline(tr, perm, flush):
         # backward alone (199 FLOP/B) sits under the tensor roof; with the table scatter fused in (41 FLOP/B: 1192 B per
         # sample) it sits under the HBM roof.  Both fractions are reported either way.
         tpeak, tsrc = tensor_peak_tf32()
-        slots = n if top == fused_key else nb
-        intensity = slots * 56448 / res[top]["algorithmic_bytes"]
-        balance = tpeak * 1e12 / (hbm * 1e9)
-        both = {"frac_of_tensor_peak": round(res[top]["achieved_tflops"] / tpeak, 4), "frac_of_hbm_peak": res[top]["frac_of_hbm"],
-                "arithmetic_intensity_flop_per_byte": round(intensity, 1), "machine_balance_flop_per_byte": round(balance, 1),
-                "tensor_peak_tflops": tpeak, "tensor_peak_source": tsrc, "hbm_peak_gbs": hbm, "hbm_peak_source": src,
-                "flops_per_unit": "56,448 FLOP per sample slot (forward recompute 18,816 + input gradients + weight gradients), "
-                                  f"x {slots} slots per launch"}
-        if intensity >= balance:
-            return {"bound": "tensor", "achieved": res[top]["achieved_tflops"], "peak": tpeak, "unit": "TFLOP/s",
-                    "frac": both["frac_of_tensor_peak"], "peak_source": tsrc, **both, **common}
-        return {"bound": "hbm", "achieved": res[top]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
-                "frac": res[top]["frac_of_hbm"], "peak_source": src, **both, **common}
+        slots = nb if top == "nerf_mlp_backward" else n
+        per_slot = 18816 if top == "nerf_fused_forward" else 56448
+        roof = pick_roof(slots * per_slot, res[top]["algorithmic_bytes"], res[top]["ms"], tpeak, hbm)
+        roof["peak_source"] = tsrc if roof["bound"] == "tensor" else src
+        roof.update({"tensor_peak_source": tsrc, "hbm_peak_source": src,
+                     "flops_per_unit": ("18,816 FLOP per sample slot (five dense layers), " if per_slot == 18816 else
+                                        "56,448 FLOP per sample slot (forward recompute 18,816 + input gradients + weight gradients), ")
+                                       + f"x {slots} slots per launch"})
+        return {**roof, **common}
     return {"bound": "hbm", "achieved": res[top]["achieved_gbs"], "peak": hbm, "unit": "GB/s",
             "frac": res[top]["frac_of_hbm"], "peak_source": src, **common}
 

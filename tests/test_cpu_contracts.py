@@ -177,3 +177,19 @@ def test_adam_exchange_descriptor_and_argument_checks(monkeypatch, built_lib):
         X.blocks_for(4096, 8)
     with pytest.raises(_lib.NgpError):  # no process group on this host: the peer exchange refuses, nothing falls back
         X.PeerExchange(1 << 12, 0, 2, "cpu")
+
+
+def test_bench_roof_is_chosen_by_arithmetic_intensity():
+    """bench.pick_roof: a kernel that contracts and streams is held to the lower roof at its FLOP/byte.  The MLP backward alone
+    (56,448 FLOP over 284 B per sample) sits under the tensor roof, the step's backward with the table scatter fused in
+    (1192 B per sample + the table zero-fill) under the HBM roof; `frac` is always achieved / peak of the roof named."""
+    import bench
+    n, tpeak, hbm = 1 << 18, 842.8, 6543.7
+    a = bench.pick_roof(n * 56448, n * 284, 0.132, tpeak, hbm)
+    assert a["bound"] == "tensor" and a["unit"] == "TFLOP/s" and abs(a["achieved"] - n * 56448 / 0.132e-3 / 1e12) < 0.01
+    assert abs(a["frac"] - a["achieved"] / tpeak) < 1e-3 and a["frac"] == a["frac_of_tensor_peak"]
+    b = bench.pick_roof(n * 56448, n * 1192 + 48_784_960, 0.204, tpeak, hbm)
+    assert b["bound"] == "hbm" and b["unit"] == "GB/s" and abs(b["frac"] - b["achieved"] / hbm) < 1e-3
+    assert b["arithmetic_intensity_flop_per_byte"] < b["machine_balance_flop_per_byte"] < a["arithmetic_intensity_flop_per_byte"]
+    for r in (a, b):
+        assert 0 < r["frac_of_tensor_peak"] < 1 and 0 < r["frac_of_hbm_peak"] < 1
