@@ -101,7 +101,10 @@ class Trainer:
         self.levels = self.nerf.position_encoder.levels
         self.fused_mlp = fused_mlp
         self.fused_glue = fused_mlp if fused_glue is None else fused_glue
-        self.prefetch_march_ctas_per_sm = 1
+        # Persistent CTAs per SM of the prefetched march (0 = a full grid).  It runs beneath the step's other kernels and must be
+        # done before the next step needs it: C2 at N = 1, ms per step: 1 -> 0.498 (the march was the critical path), 2 -> 0.444,
+        # 3 -> 0.449, 4 -> 0.471, full grid -> 0.470 (`profiles/backward_knobs_r02.txt`).  More than one rank: full grid, as measured.
+        self.prefetch_march_ctas_per_sm = int(os.environ.get("NGP_B200_MARCH_CTAS_PER_SM", "2" if world_size == 1 else "0"))
         self.fused_loss = True  # ngp_integrate_loss_fused instead of integrate_rays / huber_loss_grad / integrate_rays_backward
         # The backward, three arrangements (C2, ms per step at N = 1 / N = 2, `profiles/backward_knobs_r02.txt`):
         #   * fused scatter (default where the fused encoder applies): ONE kernel, `ngp_nerf_mlp_backward_scatter` -- the table
@@ -440,7 +443,7 @@ class Trainer:
                 mg = torch.cuda.CUDAGraph()
                 # the captured march runs underneath the step's other kernels: a small persistent grid keeps it from
                 # crowding them out of the SMs (its tiles are taken by ticket, so any grid size does all the work)
-                _lib.lib().ngp_b200_set_march_ctas_per_sm(self.prefetch_march_ctas_per_sm if self.world_size == 1 else 0)
+                _lib.lib().ngp_b200_set_march_ctas_per_sm(self.prefetch_march_ctas_per_sm)
                 try:
                     with torch.cuda.graph(mg, stream=self._side):
                         marched = self._march_body(self._static_perm[slot])

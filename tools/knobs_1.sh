@@ -1,13 +1,10 @@
-# the single-GPU training step under a few settings of the backward pipeline: bash tools/knobs_1.sh
+# the single-GPU training step under a few runtime settings: bash tools/knobs_1.sh
 mkdir -p gpurun_out/knobs
 run() {
   tag=$1; shift
   env "$@" timeout 200 python bench.py --steps 20 --warmup 5 --no-extras --no-ref-gpu > gpurun_out/knobs/$tag.log 2>&1
   echo "$tag rc=$? $(grep -h '^{"metric' gpurun_out/knobs/$tag.log | tail -1 | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print(d["ms_per_step"], d["timing"]["ms_per_step_min"], d["e2e"]["ms_per_step"])')"
 }
-run c1 NGP_B200_BWD_CHUNKS=1
-run c2 NGP_B200_BWD_CHUNKS=2
-run c3 NGP_B200_BWD_CHUNKS=3
-run c4 NGP_B200_BWD_CHUNKS=4
-run fused NGP_B200_BWD_FUSED_SCATTER=1
-run c2b NGP_B200_BWD_CHUNKS=2
+run march2 NGP_B200_MARCH_CTAS_PER_SM=2
+run march0 NGP_B200_MARCH_CTAS_PER_SM=0
+run march1 NGP_B200_MARCH_CTAS_PER_SM=1
